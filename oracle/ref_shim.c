@@ -1,0 +1,521 @@
+/* oracle/ref_shim.c — TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A thin ctypes-friendly C surface over the UNMODIFIED reference (compiled from
+ * /root/reference into oracle/_ref/liblongtail_ref.a by oracle/Makefile).  It lets
+ * tests/ and bench.py's cpu_baseline / --impl reference leg run the reference's own
+ * chunker, hashes, codecs and the Longtail_CreateVersionIndex / Longtail_CreateMissingContent /
+ * Longtail_WriteContent verbs on in-memory assets, exactly as cmd/main.c:UpSync wires them
+ * (cmd/main.c:972-1153): bikeshed JobAPI, HPCDC chunker, BLAKE3/BLAKE2/Meow hash,
+ * full compression registry, compressblockstore on top of a capturing sink or
+ * fsblockstore->memstorage.
+ *
+ * Everything here is this repository's own code; the reference is only #included and linked.
+ */
+#include "src/longtail.h"
+#include "lib/bikeshed/longtail_bikeshed.h"
+#include "lib/blake2/longtail_blake2.h"
+#include "lib/blake3/longtail_blake3.h"
+#include "lib/meowhash/longtail_meowhash.h"
+#include "lib/hpcdcchunker/longtail_hpcdcchunker.h"
+#include "lib/lz4/longtail_lz4.h"
+#include "lib/zstd/longtail_zstd.h"
+#include "lib/brotli/longtail_brotli.h"
+#include "lib/compressblockstore/longtail_compressblockstore.h"
+#include "lib/compressionregistry/longtail_full_compression_registry.h"
+#include "lib/fsblockstore/longtail_fsblockstore.h"
+#include "lib/memstorage/longtail_memstorage.h"
+#include "lib/longtail_platform.h"
+
+#include <errno.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define REF_EXPORT __attribute__((visibility("default")))
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+REF_EXPORT void ref_free(void* p) { free(p); }
+REF_EXPORT uint32_t ref_cpu_count(void) { return Longtail_GetCPUCount(); }
+
+/* ---------------------------------------------------------------- hashes */
+
+static struct Longtail_HashAPI* make_hash(uint32_t hash_type)
+{
+    if (hash_type == Longtail_GetBlake3HashType()) return Longtail_CreateBlake3HashAPI();
+    if (hash_type == Longtail_GetBlake2HashType()) return Longtail_CreateBlake2HashAPI();
+    if (hash_type == Longtail_GetMeowHashType()) return Longtail_CreateMeowHashAPI();
+    return 0;
+}
+
+REF_EXPORT uint32_t ref_hash_type_blake3(void) { return Longtail_GetBlake3HashType(); }
+REF_EXPORT uint32_t ref_hash_type_blake2(void) { return Longtail_GetBlake2HashType(); }
+REF_EXPORT uint32_t ref_hash_type_meow(void) { return Longtail_GetMeowHashType(); }
+
+REF_EXPORT int ref_hash_buffer(uint32_t hash_type, const void* data, uint32_t len, uint64_t* out_hash)
+{
+    struct Longtail_HashAPI* h = make_hash(hash_type);
+    if (!h) return EINVAL;
+    int err = h->HashBuffer(h, len, data, out_hash);
+    SAFE_DISPOSE_API(h);
+    return err;
+}
+
+/* hash `count` segments (offset,len) of one buffer; used to check per-chunk hashes in bulk */
+REF_EXPORT int ref_hash_segments(uint32_t hash_type, const uint8_t* base, uint64_t count,
+                                 const uint64_t* offsets, const uint32_t* lens, uint64_t* out_hashes)
+{
+    struct Longtail_HashAPI* h = make_hash(hash_type);
+    if (!h) return EINVAL;
+    int err = 0;
+    for (uint64_t i = 0; i < count && !err; ++i)
+        err = h->HashBuffer(h, lens[i], base + offsets[i], &out_hashes[i]);
+    SAFE_DISPOSE_API(h);
+    return err;
+}
+
+/* ---------------------------------------------------------------- chunker */
+
+struct mem_feeder
+{
+    const uint8_t* data;
+    uint64_t size;
+    uint64_t off;
+};
+
+static int mem_feed(void* context, Longtail_ChunkerAPI_HChunker chunker, uint32_t requested, char* buffer, uint32_t* out_size)
+{
+    (void)chunker;
+    struct mem_feeder* f = (struct mem_feeder*)context;
+    uint64_t n = f->size - f->off;
+    if (n > requested) n = requested;
+    memcpy(buffer, f->data + f->off, n);
+    f->off += n;
+    *out_size = (uint32_t)n;
+    return 0;
+}
+
+/* Longtail_ChunkerAPI.NextChunk over a memory buffer until ESPIPE (the path DynamicChunking
+ * takes, src/longtail.c:2231-2296).  Writes chunk lengths; returns 0 or errno. */
+REF_EXPORT int ref_hpcdc_chunk(const uint8_t* data, uint64_t size, uint32_t min, uint32_t avg, uint32_t max,
+                               uint32_t* out_lens, uint64_t cap, uint64_t* out_count)
+{
+    struct Longtail_ChunkerAPI* api = Longtail_CreateHPCDCChunkerAPI();
+    if (!api) return ENOMEM;
+    Longtail_ChunkerAPI_HChunker c;
+    int err = api->CreateChunker(api, min, avg, max, &c);
+    if (err) { SAFE_DISPOSE_API(api); return err; }
+    struct mem_feeder f = {data, size, 0};
+    uint64_t n = 0;
+    uint64_t expect_off = 0;
+    for (;;)
+    {
+        struct Longtail_Chunker_ChunkRange r;
+        err = api->NextChunk(api, c, mem_feed, &f, &r);
+        if (err == ESPIPE) { err = 0; break; }
+        if (err) break;
+        if (r.offset != expect_off) { err = EFAULT; break; }
+        if (n >= cap) { err = ENOSPC; break; }
+        out_lens[n++] = r.len;
+        expect_off += r.len;
+    }
+    *out_count = n;
+    api->DisposeChunker(api, c);
+    SAFE_DISPOSE_API(api);
+    return err;
+}
+
+/* ---------------------------------------------------------------- codecs */
+
+static struct Longtail_CompressionAPI* make_codec(uint32_t type, uint32_t* settings)
+{
+    struct Longtail_CompressionAPI* c = Longtail_CompressionRegistry_CreateForLZ4(type, settings);
+    if (c) return c;
+    c = Longtail_CompressionRegistry_CreateForZstd(type, settings);
+    if (c) return c;
+    return Longtail_CompressionRegistry_CreateForBrotli(type, settings);
+}
+
+REF_EXPORT uint64_t ref_compress_bound(uint32_t compression_type, uint64_t size)
+{
+    uint32_t settings = 0;
+    struct Longtail_CompressionAPI* c = make_codec(compression_type, &settings);
+    if (!c) return 0;
+    uint64_t r = c->GetMaxCompressedSize(c, settings, size);
+    SAFE_DISPOSE_API(c);
+    return r;
+}
+
+REF_EXPORT int ref_compress(uint32_t compression_type, const void* src, uint64_t size, void* dst, uint64_t cap, uint64_t* out_size)
+{
+    uint32_t settings = 0;
+    struct Longtail_CompressionAPI* c = make_codec(compression_type, &settings);
+    if (!c) return EINVAL;
+    size_t n = 0;
+    int err = c->Compress(c, settings, (const char*)src, (char*)dst, size, cap, &n);
+    *out_size = n;
+    SAFE_DISPOSE_API(c);
+    return err;
+}
+
+REF_EXPORT int ref_decompress(uint32_t compression_type, const void* src, uint64_t size, void* dst, uint64_t cap, uint64_t* out_size)
+{
+    uint32_t settings = 0;
+    struct Longtail_CompressionAPI* c = make_codec(compression_type, &settings);
+    if (!c) return EINVAL;
+    size_t n = 0;
+    int err = c->Decompress(c, (const char*)src, (char*)dst, size, cap, &n);
+    *out_size = n;
+    SAFE_DISPOSE_API(c);
+    return err;
+}
+
+/* ---------------------------------------------------------------- asset storage
+ * A read-only Longtail_StorageAPI over caller-owned host buffers (the five functions the
+ * hot path uses: ConcatPath, OpenReadFile, GetSize, Read, CloseFile — SURVEY.md §8b). */
+
+struct asset_set
+{
+    uint32_t count;
+    const char** paths;
+    const uint8_t** datas;
+    const uint64_t* sizes;
+    uint32_t* slots; /* open addressing: path hash -> index+1 */
+    uint32_t slot_mask;
+};
+
+struct asset_storage
+{
+    struct Longtail_StorageAPI api;
+    struct asset_set set;
+};
+
+static uint64_t fnv1a(const char* s)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    while (*s) { h ^= (uint8_t)*s++; h *= 0x100000001b3ull; }
+    return h;
+}
+
+static void asset_storage_dispose(struct Longtail_API* api)
+{
+    struct asset_storage* s = (struct asset_storage*)api;
+    free(s->set.slots);
+    free(s);
+}
+
+static char* asset_concat(struct Longtail_StorageAPI* api, const char* root, const char* sub)
+{
+    (void)api;
+    size_t a = strlen(root), b = strlen(sub);
+    char* p = (char*)Longtail_Alloc("ref_shim", a + b + 2);
+    memcpy(p, root, a);
+    p[a] = '/';
+    memcpy(p + a + 1, sub, b + 1);
+    return p;
+}
+
+static int asset_open(struct Longtail_StorageAPI* api, const char* path, Longtail_StorageAPI_HOpenFile* out)
+{
+    struct asset_storage* s = (struct asset_storage*)api;
+    const char* rel = strchr(path, '/'); /* root is a single component without '/' */
+    if (!rel) return ENOENT;
+    ++rel;
+    uint64_t h = fnv1a(rel);
+    for (uint32_t i = (uint32_t)h & s->set.slot_mask;; i = (i + 1) & s->set.slot_mask)
+    {
+        uint32_t v = s->set.slots[i];
+        if (!v) return ENOENT;
+        if (strcmp(s->set.paths[v - 1], rel) == 0)
+        {
+            *out = (Longtail_StorageAPI_HOpenFile)(uintptr_t)v;
+            return 0;
+        }
+    }
+}
+
+static int asset_size(struct Longtail_StorageAPI* api, Longtail_StorageAPI_HOpenFile f, uint64_t* out)
+{
+    struct asset_storage* s = (struct asset_storage*)api;
+    *out = s->set.sizes[(uintptr_t)f - 1];
+    return 0;
+}
+
+static int asset_read(struct Longtail_StorageAPI* api, Longtail_StorageAPI_HOpenFile f, uint64_t offset, uint64_t length, void* output)
+{
+    struct asset_storage* s = (struct asset_storage*)api;
+    uint32_t i = (uint32_t)((uintptr_t)f - 1);
+    if (offset + length > s->set.sizes[i]) return EIO;
+    memcpy(output, s->set.datas[i] + offset, length);
+    return 0;
+}
+
+static void asset_close(struct Longtail_StorageAPI* api, Longtail_StorageAPI_HOpenFile f) { (void)api; (void)f; }
+
+static struct Longtail_StorageAPI* make_asset_storage(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes)
+{
+    struct asset_storage* s = (struct asset_storage*)calloc(1, sizeof(*s));
+    s->api.m_API.Dispose = asset_storage_dispose;
+    s->api.OpenReadFile = asset_open;
+    s->api.GetSize = asset_size;
+    s->api.Read = asset_read;
+    s->api.CloseFile = asset_close;
+    s->api.ConcatPath = asset_concat;
+    s->set.count = count;
+    s->set.paths = paths;
+    s->set.datas = datas;
+    s->set.sizes = sizes;
+    uint32_t n = 16;
+    while (n < count * 2u) n <<= 1;
+    s->set.slot_mask = n - 1;
+    s->set.slots = (uint32_t*)calloc(n, sizeof(uint32_t));
+    for (uint32_t a = 0; a < count; ++a)
+    {
+        uint32_t i = (uint32_t)fnv1a(paths[a]) & s->set.slot_mask;
+        while (s->set.slots[i]) i = (i + 1) & s->set.slot_mask;
+        s->set.slots[i] = a + 1;
+    }
+    return &s->api;
+}
+
+/* Longtail_FileInfos laid out the way Longtail_GetFilesRecursively2 produces it
+ * (src/longtail.c:1435-1655): one allocation, paths NUL-terminated back to back. */
+static struct Longtail_FileInfos* make_file_infos(uint32_t count, const char** paths, const uint64_t* sizes, const uint16_t* perms)
+{
+    size_t path_bytes = 0;
+    for (uint32_t i = 0; i < count; ++i) path_bytes += strlen(paths[i]) + 1;
+    size_t total = sizeof(struct Longtail_FileInfos) + count * (sizeof(uint64_t) + sizeof(uint32_t) + sizeof(uint16_t)) + path_bytes + 16;
+    char* mem = (char*)calloc(1, total);
+    struct Longtail_FileInfos* fi = (struct Longtail_FileInfos*)mem;
+    char* p = mem + sizeof(*fi);
+    fi->m_Count = count;
+    fi->m_PathDataSize = (uint32_t)path_bytes;
+    fi->m_Sizes = (uint64_t*)p; p += count * sizeof(uint64_t);
+    fi->m_PathStartOffsets = (uint32_t*)p; p += count * sizeof(uint32_t);
+    fi->m_Permissions = (uint16_t*)p; p += count * sizeof(uint16_t);
+    fi->m_PathData = p;
+    uint32_t off = 0;
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        size_t n = strlen(paths[i]) + 1;
+        memcpy(fi->m_PathData + off, paths[i], n);
+        fi->m_PathStartOffsets[i] = off;
+        fi->m_Sizes[i] = sizes[i];
+        fi->m_Permissions[i] = perms ? perms[i] : 0644;
+        off += (uint32_t)n;
+    }
+    return fi;
+}
+
+/* ---------------------------------------------------------------- CreateVersionIndex */
+
+/* Runs the reference Longtail_CreateVersionIndex (src/longtail.c:2808) with
+ * `workers` bikeshed worker threads (0 = calling thread only, test.cpp:2061) and returns the
+ * serialised index (Longtail_WriteVersionIndexToBuffer, src/longtail.c:3415).  *out_seconds is the
+ * wall time of the verb alone. */
+REF_EXPORT int ref_create_version_index(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
+                                        const uint16_t* perms, const uint32_t* tags, uint32_t hash_type,
+                                        uint32_t target_chunk_size, uint32_t workers,
+                                        void** out_buf, uint64_t* out_size, double* out_seconds)
+{
+    struct Longtail_HashAPI* hash = make_hash(hash_type);
+    if (!hash) return EINVAL;
+    struct Longtail_JobAPI* job = Longtail_CreateBikeshedJobAPI(workers, 0);
+    struct Longtail_ChunkerAPI* chunker = Longtail_CreateHPCDCChunkerAPI();
+    struct Longtail_StorageAPI* storage = make_asset_storage(count, paths, datas, sizes);
+    struct Longtail_FileInfos* fi = make_file_infos(count, paths, sizes, perms);
+    struct Longtail_VersionIndex* vi = 0;
+    double t0 = now_s();
+    int err = Longtail_CreateVersionIndex(storage, hash, chunker, job, 0, 0, 0, "root", fi, tags, target_chunk_size, 0, &vi);
+    double t1 = now_s();
+    if (out_seconds) *out_seconds = t1 - t0;
+    if (!err && out_buf)
+    {
+        void* buf = 0;
+        size_t size = 0;
+        err = Longtail_WriteVersionIndexToBuffer(vi, &buf, &size);
+        if (!err)
+        {
+            *out_buf = malloc(size ? size : 1);
+            memcpy(*out_buf, buf, size);
+            *out_size = size;
+            Longtail_Free(buf);
+        }
+    }
+    Longtail_Free(vi);
+    free(fi);
+    SAFE_DISPOSE_API(storage);
+    SAFE_DISPOSE_API(chunker);
+    SAFE_DISPOSE_API(job);
+    SAFE_DISPOSE_API(hash);
+    return err;
+}
+
+/* ---------------------------------------------------------------- WriteContent with a capturing sink */
+
+struct captured_block
+{
+    uint64_t hash;
+    void* data;
+    size_t size;
+};
+
+struct capture_store
+{
+    struct Longtail_BlockStoreAPI api;
+    pthread_mutex_t lock;
+    struct captured_block* blocks;
+    uint32_t count, cap;
+    int keep_bytes;
+    uint64_t total_bytes;
+};
+
+static void capture_dispose(struct Longtail_API* api)
+{
+    struct capture_store* s = (struct capture_store*)api;
+    for (uint32_t i = 0; i < s->count; ++i) free(s->blocks[i].data);
+    free(s->blocks);
+    pthread_mutex_destroy(&s->lock);
+    free(s);
+}
+
+static int capture_put(struct Longtail_BlockStoreAPI* api, struct Longtail_StoredBlock* block, struct Longtail_AsyncPutStoredBlockAPI* async)
+{
+    struct capture_store* s = (struct capture_store*)api;
+    void* buf = 0;
+    size_t size = 0;
+    int err = Longtail_WriteStoredBlockToBuffer(block, &buf, &size);
+    if (!err)
+    {
+        pthread_mutex_lock(&s->lock);
+        if (s->count == s->cap)
+        {
+            s->cap = s->cap ? s->cap * 2 : 64;
+            s->blocks = (struct captured_block*)realloc(s->blocks, s->cap * sizeof(*s->blocks));
+        }
+        struct captured_block* b = &s->blocks[s->count++];
+        b->hash = *block->m_BlockIndex->m_BlockHash;
+        b->size = size;
+        b->data = 0;
+        if (s->keep_bytes)
+        {
+            b->data = malloc(size);
+            memcpy(b->data, buf, size);
+        }
+        s->total_bytes += size;
+        pthread_mutex_unlock(&s->lock);
+        Longtail_Free(buf);
+    }
+    async->OnComplete(async, err);
+    return 0;
+}
+
+static int capture_flush(struct Longtail_BlockStoreAPI* api, struct Longtail_AsyncFlushAPI* async)
+{
+    (void)api;
+    if (async) async->OnComplete(async, 0);
+    return 0;
+}
+
+static struct capture_store* make_capture_store(int keep_bytes)
+{
+    struct capture_store* s = (struct capture_store*)calloc(1, sizeof(*s));
+    s->api.m_API.Dispose = capture_dispose;
+    s->api.PutStoredBlock = capture_put;
+    s->api.Flush = capture_flush;
+    s->keep_bytes = keep_bytes;
+    pthread_mutex_init(&s->lock, 0);
+    return s;
+}
+
+/* Reference upsync of a fresh store (cmd/main.c:1052-1153 with an empty existing store index):
+ * CreateVersionIndex -> CreateMissingContent(empty) -> WriteContent into
+ * compressblockstore(full registry) -> capturing sink.
+ *
+ * Output buffer (malloc'd): u32 block_count, then per block IN STORE-INDEX ORDER
+ * { u64 block_hash, u64 size, u8 serialised_stored_block[size] } (Longtail_WriteStoredBlockToBuffer),
+ * followed by the serialised VersionIndex { u64 size, bytes }.  With keep_bytes == 0 only sizes are
+ * recorded (timing runs).  seconds[0..2] = CreateVersionIndex, CreateMissingContent, WriteContent. */
+REF_EXPORT int ref_upsync(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
+                          const uint16_t* perms, const uint32_t* tags, uint32_t hash_type,
+                          uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block,
+                          uint32_t workers, int keep_bytes,
+                          void** out_buf, uint64_t* out_size, double* seconds, uint64_t* out_stored_bytes)
+{
+    struct Longtail_HashAPI* hash = make_hash(hash_type);
+    if (!hash) return EINVAL;
+    struct Longtail_JobAPI* job = Longtail_CreateBikeshedJobAPI(workers, 0);
+    struct Longtail_ChunkerAPI* chunker = Longtail_CreateHPCDCChunkerAPI();
+    struct Longtail_StorageAPI* storage = make_asset_storage(count, paths, datas, sizes);
+    struct Longtail_FileInfos* fi = make_file_infos(count, paths, sizes, perms);
+    struct Longtail_CompressionRegistryAPI* registry = Longtail_CreateFullCompressionRegistry();
+    struct capture_store* sink = make_capture_store(keep_bytes);
+    struct Longtail_BlockStoreAPI* store = Longtail_CreateCompressBlockStoreAPI(&sink->api, registry);
+    struct Longtail_VersionIndex* vi = 0;
+    struct Longtail_StoreIndex* empty = 0;
+    struct Longtail_StoreIndex* missing = 0;
+
+    double t0 = now_s();
+    int err = Longtail_CreateVersionIndex(storage, hash, chunker, job, 0, 0, 0, "root", fi, tags, target_chunk_size, 0, &vi);
+    double t1 = now_s();
+    if (!err) err = Longtail_CreateStoreIndexFromBlocks(0, 0, &empty);
+    double t2 = now_s();
+    if (!err) err = Longtail_CreateMissingContent(hash, empty, vi, max_block_size, max_chunks_per_block, &missing);
+    double t3 = now_s();
+    if (!err) err = Longtail_WriteContent(storage, store, job, 0, 0, 0, missing, vi, "root");
+    double t4 = now_s();
+    if (seconds) { seconds[0] = t1 - t0; seconds[1] = t3 - t2; seconds[2] = t4 - t3; }
+    if (out_stored_bytes) *out_stored_bytes = sink->total_bytes;
+
+    if (!err && out_buf)
+    {
+        void* vbuf = 0;
+        size_t vsize = 0;
+        err = Longtail_WriteVersionIndexToBuffer(vi, &vbuf, &vsize);
+        if (!err)
+        {
+            uint32_t block_count = *missing->m_BlockCount;
+            size_t total = 4 + 8 + vsize;
+            for (uint32_t i = 0; i < sink->count; ++i) total += 16 + (keep_bytes ? sink->blocks[i].size : 0);
+            uint8_t* out = (uint8_t*)malloc(total);
+            uint8_t* p = out;
+            memcpy(p, &block_count, 4); p += 4;
+            for (uint32_t b = 0; b < block_count && !err; ++b)
+            {
+                uint64_t h = missing->m_BlockHashes[b];
+                uint32_t j = 0;
+                while (j < sink->count && sink->blocks[j].hash != h) ++j;
+                if (j == sink->count) { err = ENOENT; break; }
+                uint64_t sz = sink->blocks[j].size;
+                memcpy(p, &h, 8); p += 8;
+                memcpy(p, &sz, 8); p += 8;
+                if (keep_bytes) { memcpy(p, sink->blocks[j].data, sz); p += sz; }
+            }
+            uint64_t vs = vsize;
+            memcpy(p, &vs, 8); p += 8;
+            memcpy(p, vbuf, vsize); p += vsize;
+            *out_buf = out;
+            *out_size = (uint64_t)(p - out);
+            Longtail_Free(vbuf);
+        }
+    }
+    Longtail_Free(missing);
+    Longtail_Free(empty);
+    Longtail_Free(vi);
+    free(fi);
+    SAFE_DISPOSE_API(store);
+    SAFE_DISPOSE_API(&sink->api);
+    SAFE_DISPOSE_API(registry);
+    SAFE_DISPOSE_API(storage);
+    SAFE_DISPOSE_API(chunker);
+    SAFE_DISPOSE_API(job);
+    SAFE_DISPOSE_API(hash);
+    return err;
+}

@@ -1,0 +1,144 @@
+"""Pins the CPU restatement (oracle/lt_oracle.c) — against the reference's own golden vectors and
+KATs, against fixtures generated from the unmodified reference (tests/golden/golden.json), and,
+when oracle/_ref/libref_shim.so is present, byte-for-byte against the reference itself."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from synth import chunker_params, small_tree, synth_bytes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+
+# reference test/test.cpp:3422-3445 (ChunkerLargeFile): min/avg/max 16384/65536/262144 over testdata/chunker.input
+GOLDEN_CHUNKS = [81590, 46796, 36543, 83172, 76749, 79550, 41484, 20326, 31652, 19995, 103873, 38087, 38377, 23449,
+                 47321, 86692, 28268, 65465, 33255, 65932]
+KAT_STRING = b"This is the first test string which is fairly long and should - reconstructed properly, than you very much\0"
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def test_chunker_golden_vector(oracle):
+    data = np.fromfile(os.path.join(HERE, "golden", "chunker.input"), dtype=np.uint8)
+    assert data.size == 1048576
+    assert oracle.chunk(data, 16384, 65536, 262144).tolist() == GOLDEN_CHUNKS
+
+
+def test_hash_kats(oracle):
+    assert oracle.hash(ol.HASH_BLAKE3, KAT_STRING) == 0xD38BBE79F1F03FDA  # test.cpp:472
+    assert oracle.hash(ol.HASH_BLAKE2, KAT_STRING) == 0xD336E5AFA4FA1F4D  # test.cpp:460
+
+
+def test_discriminator(oracle):
+    assert oracle.discriminator(32768) == 24680
+    assert oracle.discriminator(65536) == 49535
+
+
+def test_lz4_size_pin(oracle):
+    # test.cpp:2185-2192: 1147 x 0x0d + 4711 x 0x4d compresses to 38 bytes of LZ4 payload
+    data = np.concatenate([np.full(1147, 0x0D, np.uint8), np.full(4711, 0x4D, np.uint8)])
+    comp = oracle.lz4_compress(data)
+    assert len(comp) == 38
+    assert oracle.lz4_decompress(comp, data.size) == data.tobytes()
+
+
+@pytest.mark.parametrize("case", GOLDEN["chunker"], ids=lambda c: "%s-%d-t%d" % (c["kind"], c["n"], c["target"]))
+def test_chunker_fixtures(oracle, case):
+    mn, av, mx = chunker_params(case["target"])
+    lens = oracle.chunk(synth_bytes(case["seed"], case["n"], case["kind"]), mn, av, mx)
+    assert lens.size == case["count"]
+    assert lens[:8].tolist() == case["first"]
+    assert sha(lens.astype("<u4").tobytes()) == case["sha256"]
+    assert int(lens.sum()) == case["n"]
+
+
+@pytest.mark.parametrize("case", GOLDEN["hash"], ids=lambda c: str(c["n"]))
+def test_hash_fixtures(oracle, case):
+    x = synth_bytes(100 + case["n"], case["n"])
+    assert "%016x" % oracle.hash(ol.HASH_BLAKE3, x) == case["blk3"]
+    assert "%016x" % oracle.hash(ol.HASH_BLAKE2, x) == case["blk2"]
+
+
+@pytest.mark.parametrize("case", GOLDEN["lz4"], ids=lambda c: "%s-%d" % (c["kind"], c["n"]))
+def test_lz4_fixtures(oracle, case):
+    x = synth_bytes(200 + case["n"], case["n"], case["kind"])
+    comp = oracle.lz4_compress(x)
+    assert len(comp) == case["size"]
+    assert sha(comp) == case["sha256"]
+    assert oracle.lz4_decompress(comp, x.size) == x.tobytes()
+
+
+def _tree(target):
+    assets = small_tree(target)
+    tags = [ol.COMP_LZ4 if i % 3 else 0 for i in range(len(assets))]
+    perms = [0o644 + i for i in range(len(assets))]
+    return assets, tags, perms
+
+
+@pytest.mark.parametrize("case", GOLDEN["version_index"], ids=lambda c: "t%d-%s" % (c["target"], c["hash"]))
+def test_version_index_fixtures(oracle, case):
+    assets, tags, perms = _tree(case["target"])
+    ht = {"blk3": ol.HASH_BLAKE3, "blk2": ol.HASH_BLAKE2}[case["hash"]]
+    v = oracle.create_version_index(assets, case["target"], hash_type=ht, tags=tags, perms=perms)
+    assert len(v) == case["size"]
+    assert sha(v) == case["sha256"]
+
+
+@pytest.mark.parametrize("case", GOLDEN["upsync"], ids=lambda c: "t%d" % c["target"])
+def test_upsync_fixtures(oracle, case):
+    assets, tags, perms = _tree(case["target"])
+    blocks, v = oracle.upsync(assets, case["target"], max_block_size=case["max_block_size"],
+                              max_chunks_per_block=case["max_chunks_per_block"], tags=tags, perms=perms)
+    assert len(blocks) == case["blocks"]
+    assert sha(v) == case["version_sha256"]
+    assert sha(b"".join(h.to_bytes(8, "little") + b for h, b in blocks)) == case["blocks_sha256"]
+
+
+# ---------------------------------------------------------------- live differential vs the unmodified reference
+
+
+def test_reference_matches_its_own_vectors(reference):
+    if reference is None:
+        pytest.skip("oracle/_ref/libref_shim.so not built (needs /root/reference)")
+    data = np.fromfile(os.path.join(HERE, "golden", "chunker.input"), dtype=np.uint8)
+    assert reference.chunk(data, 16384, 65536, 262144).tolist() == GOLDEN_CHUNKS
+    assert reference.hash(ol.HASH_BLAKE3, KAT_STRING) == 0xD38BBE79F1F03FDA
+    assert reference.hash(ol.HASH_BLAKE2, KAT_STRING) == 0xD336E5AFA4FA1F4D
+    assert reference.hash(ol.HASH_MEOW, KAT_STRING) == 0x4EDC68DAC105C4EE  # test.cpp:484
+
+
+@pytest.mark.parametrize("seed,n,target,kind", [(21, 6 << 20, 65536, "rand"), (22, 3 << 20, 32768, "text"), (23, 1 << 20, 2048, "nib"),
+                                                (24, 700001, 512, "p7"), (25, 65536 * 3, 64, "rand")])
+def test_chunker_vs_reference(oracle, reference, seed, n, target, kind):
+    if reference is None:
+        pytest.skip("reference not built")
+    x = synth_bytes(seed, n, kind)
+    mn, av, mx = chunker_params(target)
+    assert oracle.chunk(x, mn, av, mx).tolist() == reference.chunk(x, mn, av, mx).tolist()
+
+
+@pytest.mark.parametrize("n,kind", [(70000, "text"), (65546, "nib"), (65547, "nib"), (2 << 20, "text"), (9 << 20, "nib"), (1 << 20, "rand")])
+def test_lz4_vs_reference(oracle, reference, n, kind):
+    if reference is None:
+        pytest.skip("reference not built")
+    x = synth_bytes(300 + n, n, kind)
+    assert oracle.lz4_compress(x) == reference.compress(ol.COMP_LZ4, x)
+
+
+def test_upsync_vs_reference_default_params(oracle, reference):
+    if reference is None:
+        pytest.skip("reference not built")
+    assets = [("big/f%03d.bin" % i, synth_bytes(400 + i, 150000 + 410000 * i, "rand" if i % 2 else "nib")) for i in range(10)]
+    assets.append(("big/f003_copy.bin", assets[3][1].copy()))
+    assets.sort(key=lambda a: a[0].encode())
+    tags = [ol.COMP_LZ4] * len(assets)
+    ours = oracle.upsync(assets, 32768, tags=tags)
+    theirs = reference.upsync(assets, 32768, tags=tags, workers=3)
+    assert ours[1] == theirs[1]
+    assert ours[0] == theirs[0]
