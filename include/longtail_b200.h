@@ -1,0 +1,174 @@
+/* longtail_b200.h — C ABI of liblongtail_b200.so: the B200 (sm_100a) implementation of longtail's
+ * chunk -> hash -> compress indexing hot path.
+ *
+ * Plain C: pointers, sizes and errno-style int returns (0 = success), exactly like the reference's own
+ * API (src/longtail.h).  No CUDA or torch types appear in any signature; device memory is passed as
+ * `void*` / `const uint8_t*` device addresses (cudaMalloc'd by the caller, by torch, or by
+ * lt_b200_device_alloc).
+ *
+ * Layers, bottom up:
+ *   1. device primitives over data already resident in HBM      (lt_b200_chunk_ranges, lt_b200_hash_segments, ...)
+ *   2. batched verbs replacing the reference's job fan-out       (lt_b200_index_assets ~ ChunkAssets + CreateVersionIndex)
+ *   3. drop-in Longtail_*API objects and verbs                   (include/longtail_b200_api.h)
+ *
+ * Reference interfaces replaced (all paths relative to the reference tree):
+ *   lt_b200_chunk_ranges        <- Longtail_ChunkerAPI.NextChunk loop, lib/hpcdcchunker/longtail_hpcdcchunker.c:225-310,
+ *                                  driven per part by DynamicChunking, src/longtail.c:1989-2311
+ *   lt_b200_hash_segments       <- Longtail_HashAPI.HashBuffer, src/longtail.h:209-217 (lib/blake3/longtail_blake3.c:81-102)
+ *   lt_b200_index_*             <- ChunkAssets + Longtail_CreateVersionIndex, src/longtail.c:2343-2550, :2808-3017
+ */
+#ifndef LONGTAIL_B200_H
+#define LONGTAIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LT_B200_EXPORT __attribute__((visibility("default")))
+#else
+#define LT_B200_EXPORT
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LT_B200_HASH_BLAKE3 0x626c6b33u /* 'blk3', lib/blake3/longtail_blake3.c:6 */
+#define LT_B200_HASH_BLAKE2 0x626c6b32u /* 'blk2', lib/blake2/longtail_blake2.c:9 */
+#define LT_B200_HASH_MEOW 0x6d656f77u   /* 'meow', lib/meowhash/longtail_meowhash.c:7 */
+
+typedef struct lt_b200_context lt_b200_context;
+
+/* ---- context: one per GPU (one process per GPU in multi-GPU runs) */
+LT_B200_EXPORT int lt_b200_context_create(int device_ordinal, lt_b200_context** out_context);
+LT_B200_EXPORT void lt_b200_context_destroy(lt_b200_context* context);
+/* text of the last failure on this context ("" when none); valid until the next call */
+LT_B200_EXPORT const char* lt_b200_last_error(const lt_b200_context* context);
+/* number of kernel launches issued by this context since creation (bench.py reports it as gpu_launches) */
+LT_B200_EXPORT uint64_t lt_b200_launch_count(const lt_b200_context* context);
+/* blocks until all work queued by this context is done */
+LT_B200_EXPORT int lt_b200_synchronize(lt_b200_context* context);
+/* the CUDA stream (cudaStream_t as void*) this context launches on — for CUDA-event timing by the caller */
+LT_B200_EXPORT void* lt_b200_stream(lt_b200_context* context);
+
+/* Optional per-kernel timing with CUDA events on the context stream (what bench.py's roofline block reads).
+ * `bytes` is the algorithmic byte count the launches covered (asset bytes for the scan and the leaf hash). */
+enum
+{
+    LT_B200_KERNEL_HPCDC_SCAN = 0,
+    LT_B200_KERNEL_HPCDC_WALK = 1,
+    LT_B200_KERNEL_BLAKE3_LEAVES = 2,
+    LT_B200_KERNEL_BLAKE3_MERGE = 3,
+    LT_B200_KERNEL_COUNT = 8
+};
+LT_B200_EXPORT int lt_b200_profile_enable(lt_b200_context* context, int on);
+LT_B200_EXPORT int lt_b200_profile_reset(lt_b200_context* context);
+LT_B200_EXPORT int lt_b200_profile_read(lt_b200_context* context, uint32_t kernel, double* out_ms, uint64_t* out_launches, uint64_t* out_bytes);
+
+/* ---- device memory helpers (so that C callers need no CUDA headers) */
+LT_B200_EXPORT int lt_b200_device_alloc(lt_b200_context* context, uint64_t bytes, void** out_device_ptr);
+LT_B200_EXPORT int lt_b200_device_free(lt_b200_context* context, void* device_ptr);
+LT_B200_EXPORT int lt_b200_host_alloc_pinned(lt_b200_context* context, uint64_t bytes, void** out_host_ptr);
+LT_B200_EXPORT int lt_b200_host_free_pinned(lt_b200_context* context, void* host_ptr);
+LT_B200_EXPORT int lt_b200_copy_to_device(lt_b200_context* context, void* device_dst, const void* host_src, uint64_t bytes);
+LT_B200_EXPORT int lt_b200_copy_to_host(lt_b200_context* context, void* host_dst, const void* device_src, uint64_t bytes);
+
+/* Deterministic synthetic asset bytes written straight into HBM (include/lt_synth.h).  Bench/test input only. */
+struct lt_b200_synth_spec
+{
+    uint64_t seed;
+    uint32_t shared_permille;
+    uint32_t pool_segments;
+    uint32_t class_mode;
+    uint32_t reserved;
+};
+LT_B200_EXPORT int lt_b200_synth_fill(lt_b200_context* context, void* device_dst, uint64_t bytes, const struct lt_b200_synth_spec* spec,
+                                      uint64_t asset_id, uint64_t asset_offset);
+
+/* ---- layer 1: device primitives */
+
+/* One range = one chunker instance = one "part" of the reference (src/longtail.c:2396-2457): bytes
+ * [arena_offset, arena_offset + size) of the device arena.  arena_offset must be a multiple of 16. */
+struct lt_b200_range
+{
+    uint64_t arena_offset;
+    uint32_t size; /* < 2^31 */
+    uint32_t tag;  /* carried to every chunk of the range (asset compression tag) */
+};
+
+/* Result of chunk + hash over a list of ranges.  Arrays live in pinned host memory owned by the context and
+ * stay valid until the next lt_b200_chunk_ranges call on it; the device copies stay resident for
+ * lt_b200_finalize_index / lt_b200_write_blocks. */
+struct lt_b200_chunk_table
+{
+    uint32_t range_count;
+    uint32_t chunk_count;               /* total over all ranges */
+    const uint32_t* range_chunk_counts; /* [range_count] */
+    const uint64_t* chunk_hashes;       /* [chunk_count] in range order, then stream order */
+    const uint32_t* chunk_sizes;        /* [chunk_count] */
+    const uint32_t* chunk_tags;         /* [chunk_count] */
+    const uint64_t* chunk_offsets;      /* [chunk_count] arena offset of each chunk */
+};
+
+/* Content-defined chunking (HPCDC) of every range followed by the hash of every chunk.
+ * min/avg/max as computed by the caller from target_chunk_size (src/longtail.c:1985-1987); returns EINVAL for
+ * parameter combinations the reference asserts on (longtail_hpcdcchunker.c:146-150).
+ * want_host = 0 skips the device->host copy of the table (out_table then only carries the counts). */
+LT_B200_EXPORT int lt_b200_chunk_ranges(lt_b200_context* context, const uint8_t* device_arena, uint64_t arena_size,
+                                        const struct lt_b200_range* ranges, uint32_t range_count,
+                                        uint32_t min_chunk_size, uint32_t avg_chunk_size, uint32_t max_chunk_size,
+                                        uint32_t hash_type, int want_host, struct lt_b200_chunk_table* out_table);
+
+/* HashAPI.HashBuffer over `count` segments [offsets[i], offsets[i]+sizes[i]) of one device buffer.  offsets/sizes/out are
+ * HOST arrays. */
+LT_B200_EXPORT int lt_b200_hash_segments(lt_b200_context* context, uint32_t hash_type, const uint8_t* device_base, uint64_t base_size,
+                                         const uint64_t* offsets, const uint32_t* sizes, uint32_t count, uint64_t* out_hashes);
+
+/* ---- layer 2: batched verbs */
+
+/* Input of the index build: what Longtail_FileInfos + optional_asset_tags carry (src/longtail.h:1684-1692) plus, per asset,
+ * how many chunks its ranges produced. */
+struct lt_b200_assets
+{
+    uint32_t asset_count;
+    uint32_t path_data_size;            /* bytes in path_data, NUL terminators included */
+    const uint64_t* sizes;              /* [asset_count] */
+    const uint32_t* path_start_offsets; /* [asset_count] */
+    const uint16_t* permissions;        /* [asset_count] */
+    const char* path_data;              /* relative paths, NUL terminated, directories end with '/' */
+};
+
+/* Builds the serialised VersionIndex (src/longtail.c:2566-2584 layout, Longtail_WriteVersionIndexToBuffer :3415-3439) from a
+ * chunk table: per-asset content hashes (:2518-2537), path hashes (:1281-1297), first-occurrence dedup (:2952-2970) and the
+ * zero-parse layout (:2709-2806), all on the device.
+ *
+ * chunk arrays are HOST pointers covering all assets in asset order (chunk_count entries; asset a owns
+ * asset_chunk_counts[a] consecutive entries) — after a multi-GPU allgather they are the merged table.  Pass NULL for
+ * chunk_hashes/sizes/tags to use the table still resident on the device from the last lt_b200_chunk_ranges call.
+ * *out_buffer points at pinned host memory owned by the context, valid until the next index call on it (the drop-in
+ * verb copies it into Longtail_Alloc memory); do not free it. */
+LT_B200_EXPORT int lt_b200_build_version_index(lt_b200_context* context, const struct lt_b200_assets* assets,
+                                               const uint32_t* asset_chunk_counts, uint32_t chunk_count,
+                                               const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
+                                               uint32_t hash_type, uint32_t target_chunk_size,
+                                               const void** out_buffer, uint64_t* out_size);
+
+/* Whole CreateVersionIndex over assets resident in one device arena: splits every asset into parts of
+ * target_chunk_size*1024 bytes (src/longtail.c:2396-2437), chunks + hashes them and builds the index.
+ * asset_arena_offsets[a] (multiples of 16) locate asset a's bytes in the arena; asset_tags may be NULL. */
+LT_B200_EXPORT int lt_b200_index_device_assets(lt_b200_context* context, const uint8_t* device_arena, uint64_t arena_size,
+                                               const struct lt_b200_assets* assets, const uint64_t* asset_arena_offsets,
+                                               const uint32_t* asset_tags, uint32_t hash_type, uint32_t target_chunk_size,
+                                               const void** out_buffer, uint64_t* out_size);
+
+/* Same, with asset bytes in HOST memory (asset_data[a] may be pageable or pinned): host->device copies are part of the
+ * call and are pipelined against the kernels in batches of whole parts. */
+LT_B200_EXPORT int lt_b200_index_host_assets(lt_b200_context* context, const struct lt_b200_assets* assets,
+                                             const uint8_t* const* asset_data, const uint32_t* asset_tags,
+                                             uint32_t hash_type, uint32_t target_chunk_size,
+                                             const void** out_buffer, uint64_t* out_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LONGTAIL_B200_H */

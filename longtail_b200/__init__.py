@@ -1,0 +1,265 @@
+"""longtail_b200 — B200 (sm_100a) implementation of longtail's chunk -> hash -> compress indexing path.
+
+This package is a thin ctypes mirror of the C ABI in include/longtail_b200.h (the product is the CUDA
+library ``longtail_b200/_lib/liblongtail_b200.so``).  There is no CPU fallback: importing works anywhere,
+but creating a :class:`Context` without the built library or without a CUDA device raises.
+"""
+import ctypes as C
+import errno
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblongtail_b200.so")
+
+HASH_BLAKE3 = 0x626C6B33  # 'blk3'
+HASH_BLAKE2 = 0x626C6B32  # 'blk2'
+HASH_MEOW = 0x6D656F77  # 'meow'
+COMPRESSION_LZ4 = 0x6C7A3432  # 'lz42'
+
+_lib = None
+
+
+class LongtailB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s (errno %d %s)" % (message, code, errno.errorcode.get(code, "?")))
+        self.errno = code
+
+
+class Range(C.Structure):
+    _fields_ = [("arena_offset", C.c_uint64), ("size", C.c_uint32), ("tag", C.c_uint32)]
+
+
+class ChunkTable(C.Structure):
+    _fields_ = [("range_count", C.c_uint32), ("chunk_count", C.c_uint32), ("range_chunk_counts", C.POINTER(C.c_uint32)),
+                ("chunk_hashes", C.POINTER(C.c_uint64)), ("chunk_sizes", C.POINTER(C.c_uint32)),
+                ("chunk_tags", C.POINTER(C.c_uint32)), ("chunk_offsets", C.POINTER(C.c_uint64))]
+
+
+class Assets(C.Structure):
+    _fields_ = [("asset_count", C.c_uint32), ("path_data_size", C.c_uint32), ("sizes", C.POINTER(C.c_uint64)),
+                ("path_start_offsets", C.POINTER(C.c_uint32)), ("permissions", C.POINTER(C.c_uint16)), ("path_data", C.c_char_p)]
+
+
+class SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("shared_permille", C.c_uint32), ("pool_segments", C.c_uint32),
+                ("class_mode", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def load_library():
+    """dlopen the CUDA library; raises when it has not been built (python -m longtail_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LongtailB200Error(errno.ENOENT, "liblongtail_b200.so is not built: run `python -m longtail_b200.build` "
+                                              "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.lt_b200_last_error.restype = C.c_char_p
+    lib.lt_b200_last_error.argtypes = [C.c_void_p]
+    lib.lt_b200_launch_count.restype = C.c_uint64
+    lib.lt_b200_launch_count.argtypes = [C.c_void_p]
+    lib.lt_b200_stream.restype = C.c_void_p
+    lib.lt_b200_stream.argtypes = [C.c_void_p]
+    lib.lt_b200_context_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.lt_b200_context_destroy.argtypes = [C.c_void_p]
+    lib.lt_b200_synchronize.argtypes = [C.c_void_p]
+    lib.lt_b200_device_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lt_b200_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lt_b200_host_alloc_pinned.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lt_b200_host_free_pinned.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lt_b200_copy_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.lt_b200_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.lt_b200_synth_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SynthSpec), C.c_uint64, C.c_uint64]
+    lib.lt_b200_chunk_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Range), C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.c_uint32, C.c_int, C.POINTER(ChunkTable)]
+    lib.lt_b200_hash_segments.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.lt_b200_build_version_index.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.lt_b200_index_device_assets.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Assets), C.c_void_p, C.c_void_p, C.c_uint32,
+                                                C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.lt_b200_index_host_assets.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    _lib = lib
+    return lib
+
+
+def chunker_params(target_chunk_size):
+    """min/avg/max of the reference driver (src/longtail.c:1985-1987, GetMinChunkSize() == 48)"""
+    t = int(target_chunk_size)
+    return max(48, t // 8), max(48, t // 2), max(48, t * 2)
+
+
+class AssetList:
+    """what Longtail_FileInfos carries (src/longtail.h:1684-1692): relative paths (dirs end in '/'), sizes, permissions"""
+
+    def __init__(self, paths, sizes, permissions=None):
+        self.paths = [p if isinstance(p, bytes) else p.encode() for p in paths]
+        self.count = len(self.paths)
+        self.sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        self.permissions = np.ascontiguousarray(permissions if permissions is not None else [0o644] * self.count, dtype=np.uint16)
+        offs, blob, o = [], bytearray(), 0
+        for p in self.paths:
+            offs.append(o)
+            blob += p + b"\0"
+            o += len(p) + 1
+        self.path_data = bytes(blob)
+        self.path_start_offsets = np.ascontiguousarray(offs, dtype=np.uint32)
+        assert self.sizes.size == self.count and self.permissions.size == self.count
+
+    def as_struct(self):
+        a = Assets()
+        a.asset_count = self.count
+        a.path_data_size = len(self.path_data)
+        a.sizes = self.sizes.ctypes.data_as(C.POINTER(C.c_uint64))
+        a.path_start_offsets = self.path_start_offsets.ctypes.data_as(C.POINTER(C.c_uint32))
+        a.permissions = self.permissions.ctypes.data_as(C.POINTER(C.c_uint16))
+        a.path_data = self.path_data
+        return a
+
+
+class Context:
+    """one per GPU; mirrors lt_b200_context"""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        err = self.lib.lt_b200_context_create(int(device), C.byref(h))
+        if err:
+            raise LongtailB200Error(err, "lt_b200_context_create(device %d) failed: no usable CUDA device (no CPU fallback)" % device)
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.lt_b200_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, err, what):
+        if err:
+            raise LongtailB200Error(err, "%s: %s" % (what, self.lib.lt_b200_last_error(self.handle).decode()))
+
+    # ---- plumbing
+    @property
+    def stream(self):
+        return self.lib.lt_b200_stream(self.handle)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.lt_b200_launch_count(self.handle))
+
+    def synchronize(self):
+        self._check(self.lib.lt_b200_synchronize(self.handle), "synchronize")
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.lt_b200_device_alloc(self.handle, int(nbytes), C.byref(p)), "device_alloc")
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(self.lib.lt_b200_device_free(self.handle, C.c_void_p(ptr)), "device_free")
+
+    def pinned_alloc(self, nbytes):
+        """-> numpy uint8 view over pinned host memory (keep the returned array alive; free with pinned_free(arr))"""
+        p = C.c_void_p()
+        self._check(self.lib.lt_b200_host_alloc_pinned(self.handle, int(nbytes), C.byref(p)), "host_alloc_pinned")
+        arr = np.ctypeslib.as_array((C.c_uint8 * max(int(nbytes), 1)).from_address(p.value))[:int(nbytes)]
+        arr.flags.writeable = True
+        return arr
+
+    def pinned_free(self, arr):
+        self._check(self.lib.lt_b200_host_free_pinned(self.handle, C.c_void_p(arr.ctypes.data)), "host_free_pinned")
+
+    def to_device(self, dptr, host_array):
+        a = np.ascontiguousarray(host_array)
+        self._check(self.lib.lt_b200_copy_to_device(self.handle, C.c_void_p(dptr), a.ctypes.data_as(C.c_void_p), a.nbytes), "copy_to_device")
+
+    def to_host(self, dptr, nbytes):
+        out = np.empty(int(nbytes), dtype=np.uint8)
+        self._check(self.lib.lt_b200_copy_to_host(self.handle, out.ctypes.data_as(C.c_void_p), C.c_void_p(dptr), int(nbytes)), "copy_to_host")
+        return out
+
+    def synth_fill(self, dptr, nbytes, seed, asset_id=0, offset=0, shared_permille=0, pool_segments=1, class_mode=0):
+        spec = SynthSpec(int(seed), int(shared_permille), int(pool_segments), int(class_mode), 0)
+        self._check(self.lib.lt_b200_synth_fill(self.handle, C.c_void_p(dptr), int(nbytes), C.byref(spec), int(asset_id), int(offset)), "synth_fill")
+
+    # ---- layer 1
+    def chunk_ranges(self, dptr, arena_size, ranges, min_size, avg_size, max_size, hash_type=HASH_BLAKE3, want_host=True):
+        """ranges: iterable of (arena_offset, size[, tag]).  Returns dict of numpy arrays (copies)."""
+        rs = (Range * max(len(ranges), 1))()
+        for i, r in enumerate(ranges):
+            rs[i].arena_offset, rs[i].size, rs[i].tag = int(r[0]), int(r[1]), int(r[2]) if len(r) > 2 else 0
+        t = ChunkTable()
+        self._check(self.lib.lt_b200_chunk_ranges(self.handle, C.c_void_p(dptr), int(arena_size), rs, len(ranges), int(min_size), int(avg_size),
+                                                  int(max_size), int(hash_type), 1 if want_host else 0, C.byref(t)), "chunk_ranges")
+        out = {"chunk_count": int(t.chunk_count),
+               "range_chunk_counts": np.ctypeslib.as_array(t.range_chunk_counts, (max(t.range_count, 1),))[:t.range_count].copy()
+               if t.range_count else np.zeros(0, np.uint32)}
+        if want_host and t.chunk_count:
+            n = t.chunk_count
+            out["hashes"] = np.ctypeslib.as_array(t.chunk_hashes, (n,)).copy()
+            out["sizes"] = np.ctypeslib.as_array(t.chunk_sizes, (n,)).copy()
+            out["tags"] = np.ctypeslib.as_array(t.chunk_tags, (n,)).copy()
+            out["offsets"] = np.ctypeslib.as_array(t.chunk_offsets, (n,)).copy()
+        elif want_host:
+            out.update(hashes=np.zeros(0, np.uint64), sizes=np.zeros(0, np.uint32), tags=np.zeros(0, np.uint32), offsets=np.zeros(0, np.uint64))
+        return out
+
+    def hash_segments(self, dptr, base_size, offsets, sizes, hash_type=HASH_BLAKE3):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+        out = np.zeros(offsets.size, dtype=np.uint64)
+        self._check(self.lib.lt_b200_hash_segments(self.handle, int(hash_type), C.c_void_p(dptr), int(base_size), offsets.ctypes.data_as(C.c_void_p),
+                                                   sizes.ctypes.data_as(C.c_void_p), offsets.size, out.ctypes.data_as(C.c_void_p)), "hash_segments")
+        return out
+
+    # ---- layer 2
+    def _result(self, buf, size, copy):
+        raw = (C.c_uint8 * max(size.value, 1)).from_address(buf.value)
+        return bytes(raw[:size.value]) if copy else memoryview(raw)[:size.value]
+
+    def build_version_index(self, assets, asset_chunk_counts, chunk_hashes=None, chunk_sizes=None, chunk_tags=None, chunk_count=None,
+                            hash_type=HASH_BLAKE3, target_chunk_size=32768, copy=True):
+        st = assets.as_struct()
+        counts = np.ascontiguousarray(asset_chunk_counts, dtype=np.uint32)
+        buf, size = C.c_void_p(), C.c_uint64(0)
+        if chunk_hashes is None:
+            n = int(chunk_count if chunk_count is not None else counts.sum())
+            args = (None, None, None)
+        else:
+            h = np.ascontiguousarray(chunk_hashes, dtype=np.uint64)
+            s = np.ascontiguousarray(chunk_sizes, dtype=np.uint32)
+            t = np.ascontiguousarray(chunk_tags, dtype=np.uint32)
+            n = h.size
+            args = (h.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
+        self._check(self.lib.lt_b200_build_version_index(self.handle, C.byref(st), counts.ctypes.data_as(C.c_void_p), n, args[0], args[1], args[2],
+                                                         int(hash_type), int(target_chunk_size), C.byref(buf), C.byref(size)), "build_version_index")
+        return self._result(buf, size, copy)
+
+    def index_device_assets(self, dptr, arena_size, assets, arena_offsets, tags=None, hash_type=HASH_BLAKE3, target_chunk_size=32768, copy=True):
+        st = assets.as_struct()
+        offs = np.ascontiguousarray(arena_offsets, dtype=np.uint64)
+        tg = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint32)
+        buf, size = C.c_void_p(), C.c_uint64(0)
+        self._check(self.lib.lt_b200_index_device_assets(self.handle, C.c_void_p(dptr), int(arena_size), C.byref(st), offs.ctypes.data_as(C.c_void_p),
+                                                         None if tg is None else tg.ctypes.data_as(C.c_void_p), int(hash_type),
+                                                         int(target_chunk_size), C.byref(buf), C.byref(size)), "index_device_assets")
+        return self._result(buf, size, copy)
+
+    def index_host_assets(self, assets, datas, tags=None, hash_type=HASH_BLAKE3, target_chunk_size=32768, copy=True):
+        """datas: list of contiguous uint8 numpy arrays (pinned for full PCIe speed), one per asset"""
+        st = assets.as_struct()
+        keep = [np.ascontiguousarray(d, dtype=np.uint8) for d in datas]
+        ptrs = (C.c_void_p * max(len(keep), 1))(*[d.ctypes.data if d.size else None for d in keep])
+        tg = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint32)
+        buf, size = C.c_void_p(), C.c_uint64(0)
+        self._check(self.lib.lt_b200_index_host_assets(self.handle, C.byref(st), ptrs, None if tg is None else tg.ctypes.data_as(C.c_void_p),
+                                                       int(hash_type), int(target_chunk_size), C.byref(buf), C.byref(size)), "index_host_assets")
+        return self._result(buf, size, copy)

@@ -1,0 +1,887 @@
+// capi.cu — the C ABI of liblongtail_b200.so (include/longtail_b200.h): context, workspace and the batched verbs.
+//
+// This file holds host logic only; every byte of asset data is touched by the kernels in hpcdc.cu / blake3.cu / util.cu.
+// There is deliberately no CPU fallback: without a CUDA device every entry point fails with ENODEV.
+#include "../../include/longtail_b200.h"
+#include "lt_kernels.h"
+
+#include <errno.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+using namespace ltb;
+
+namespace {
+
+const uint32_t k_hpcdc_table[256] = {
+#include "hpcdc_table.inc"
+};
+
+enum WsSlot
+{
+    WS_PARTS, WS_TILE_DESC, WS_TILE_COUNT, WS_TILE_SLOTS, WS_CAND, WS_STAGE_OFF, WS_STAGE_LEN, WS_PART_COUNT, WS_PART_BASE,
+    WS_SCAN_TMP, WS_CHUNK_OFF, WS_CHUNK_LEN, WS_CHUNK_TAG, WS_CHUNK_HASH, WS_LEAF_COUNT, WS_LEAF_PREFIX, WS_CVS,
+    WS_SEG_OFF, WS_SEG_LEN, WS_SEG_HASH, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS,
+    WS_TAB_HASH, WS_TAB_LEN, WS_TAB_TAG,
+    WS_DEDUP_KEYS, WS_DEDUP_VALS, WS_DEDUP_FIRST, WS_DEDUP_ISFIRST, WS_DEDUP_UIDX, WS_ACI, WS_UHASH, WS_ULEN, WS_UTAG,
+    WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
+    WS_COUNT
+};
+
+enum HostSlot
+{
+    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_COUNT
+};
+
+struct Buf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct lt_b200_context
+{
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t compute_done[2] = {nullptr, nullptr};
+    uint32_t* d_table = nullptr;
+    Buf ws[WS_COUNT];
+    Buf hs[HS_COUNT];
+    uint64_t launches = 0;
+    char err[512] = {0};
+    // chunk table left resident by the last lt_b200_chunk_ranges call
+    uint32_t table_chunks = 0;
+    // optional per-kernel CUDA-event timing (lt_b200_profile_*)
+    bool prof_on = false;
+    struct Span { cudaEvent_t a, b; int id; uint64_t bytes; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[LT_B200_KERNEL_COUNT] = {0};
+    uint64_t prof_launches[LT_B200_KERNEL_COUNT] = {0};
+    uint64_t prof_bytes[LT_B200_KERNEL_COUNT] = {0};
+};
+
+namespace {
+
+int fail(lt_b200_context* c, int code, const char* fmt, ...)
+{
+    if (c)
+    {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int cuda_fail(lt_b200_context* c, cudaError_t e, const char* what)
+{
+    return fail(c, e == cudaErrorMemoryAllocation ? ENOMEM : EIO, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(c, e__, #call);   \
+    } while (0)
+
+#define TRY(call)                  \
+    do {                           \
+        int r__ = (call);          \
+        if (r__) return r__;       \
+    } while (0)
+
+int ws_reserve(lt_b200_context* c, int slot, size_t bytes)
+{
+    Buf& b = c->ws[slot];
+    if (b.cap >= bytes && b.p) return 0;
+    if (b.p)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        want = bytes ? bytes : 256;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) { b.p = nullptr; return cuda_fail(c, e, "cudaMalloc(workspace)"); }
+    b.cap = want;
+    return 0;
+}
+
+template <typename T>
+T* ws(lt_b200_context* c, int slot) { return static_cast<T*>(c->ws[slot].p); }
+
+int hs_reserve(lt_b200_context* c, int slot, size_t bytes)
+{
+    Buf& b = c->hs[slot];
+    if (b.cap >= bytes && b.p) return 0;
+    if (b.p)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFreeHost(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    CU(cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return 0;
+}
+
+template <typename T>
+T* hs(lt_b200_context* c, int slot) { return static_cast<T*>(c->hs[slot].p); }
+
+cudaEvent_t prof_event(lt_b200_context* c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+// brackets the next kernel launch(es) on the context stream with CUDA events when profiling is on
+struct ProfScope
+{
+    lt_b200_context* c;
+    size_t idx;
+    bool on;
+    ProfScope(lt_b200_context* ctx, int id, uint64_t bytes) : c(ctx), idx(0), on(ctx->prof_on)
+    {
+        if (!on) return;
+        lt_b200_context::Span s = {prof_event(c), prof_event(c), id, bytes};
+        cudaEventRecord(s.a, c->stream);
+        idx = c->spans.size();
+        c->spans.push_back(s);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->spans[idx].b, c->stream); }
+};
+
+void prof_collect(lt_b200_context* c)
+{
+    for (auto& s : c->spans)
+    {
+        float ms = 0;
+        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
+        {
+            c->prof_ms[s.id] += ms;
+            c->prof_launches[s.id] += 1;
+            c->prof_bytes[s.id] += s.bytes;
+        }
+        c->event_pool.push_back(s.a);
+        c->event_pool.push_back(s.b);
+    }
+    c->spans.clear();
+    cudaGetLastError();
+}
+
+uint32_t inverse_mod_2_32(uint32_t odd)
+{
+    uint32_t x = odd; // correct to 3 bits; each Newton step doubles the precision
+    for (int i = 0; i < 5; ++i) x *= 2u - odd * x;
+    return x;
+}
+
+int make_chunk_params(lt_b200_context* c, uint32_t mn, uint32_t av, uint32_t mx, ChunkParams* cp)
+{
+    // lib/hpcdcchunker/longtail_hpcdcchunker.c:146-150
+    if (mn < (uint32_t)SCAN_WINDOW || mn > mx || mn > av || av > mx) return fail(c, EINVAL, "invalid chunker parameters %u/%u/%u", mn, av, mx);
+    const double a = (double)av;
+    const uint32_t d = (uint32_t)(a / (-1.42888852e-7 * a + 1.33237515)); // :126-129, evaluated in double like the reference
+    if (d == 0) return fail(c, EINVAL, "discriminator is zero for avg %u", av);
+    uint32_t odd = d;
+    while (!(odd & 1u)) odd >>= 1;
+    cp->min = mn;
+    cp->avg = av;
+    cp->max = mx;
+    cp->d = d;
+    cp->d_odd_inv = inverse_mod_2_32(odd);
+    cp->d_odd_thr = 0xffffffffu / odd;
+    uint32_t expect = (uint32_t)SCAN_TILE / d + 1;
+    uint32_t slots = (8 * expect + 32 + 31) & ~31u;
+    if (slots > 8192) slots = 8192;
+    cp->slots = slots;
+    return 0;
+}
+
+// hash segments whose offsets / lengths already sit in device memory; result stays on the device
+int hash_segments_device(lt_b200_context* c, uint32_t hash_type, const uint8_t* d_base, uint64_t base_size, const uint64_t* d_off,
+                         const uint32_t* d_len, uint32_t count, uint64_t upper_leaves, int slot_leaf_count, int slot_leaf_prefix,
+                         int slot_cvs, uint64_t* d_hash_out, uint64_t payload_bytes = 0)
+{
+    if (hash_type != LT_B200_HASH_BLAKE3) return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation yet", hash_type);
+    if (!count) return 0;
+    TRY(ws_reserve(c, slot_leaf_count, sizeof(uint32_t) * (size_t)count));
+    TRY(ws_reserve(c, slot_leaf_prefix, sizeof(uint32_t) * ((size_t)count + 1)));
+    TRY(ws_reserve(c, WS_SCAN_TMP, sizeof(uint32_t) * scan_tmp_words(count)));
+    TRY(ws_reserve(c, slot_cvs, 32 * (size_t)upper_leaves));
+    launch_leaf_counts(d_len, count, ws<uint32_t>(c, slot_leaf_count), c->stream);
+    launch_exclusive_scan(ws<uint32_t>(c, slot_leaf_count), count, ws<uint32_t>(c, slot_leaf_prefix), ws<uint32_t>(c, WS_SCAN_TMP), c->stream);
+    c->launches += 4;
+    uint32_t total_leaves = 0;
+    CU(cudaMemcpyAsync(&total_leaves, ws<uint32_t>(c, slot_leaf_prefix) + count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if ((uint64_t)total_leaves > upper_leaves) return fail(c, EFAULT, "leaf count %u exceeds bound %llu", total_leaves, (unsigned long long)upper_leaves);
+    uint64_t seg_bytes = (uint64_t)total_leaves * 1024; // upper bound; callers that know the exact byte count pass it instead
+    if (payload_bytes) seg_bytes = payload_bytes;
+    {
+        ProfScope ps(c, LT_B200_KERNEL_BLAKE3_LEAVES, seg_bytes);
+        launch_blake3_leaves(d_base, base_size, d_off, d_len, ws<uint32_t>(c, slot_leaf_prefix), count, total_leaves,
+                             ws<uint32_t>(c, slot_cvs), d_hash_out, c->stream);
+    }
+    {
+        ProfScope ps(c, LT_B200_KERNEL_BLAKE3_MERGE, (uint64_t)total_leaves * 32);
+        launch_blake3_merge(d_len, ws<uint32_t>(c, slot_leaf_prefix), count, ws<uint32_t>(c, slot_cvs), d_hash_out, c->stream);
+    }
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+} // namespace
+
+// ================================================================ context
+
+extern "C" int lt_b200_context_create(int device_ordinal, lt_b200_context** out_context)
+{
+    if (!out_context) return EINVAL;
+    *out_context = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device_ordinal < 0 || device_ordinal >= n)
+    {
+        cudaGetLastError();
+        return ENODEV; // no CUDA device: there is no CPU fallback by design
+    }
+    lt_b200_context* c = new (std::nothrow) lt_b200_context();
+    if (!c) return ENOMEM;
+    c->device = device_ordinal;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&c->d_table, sizeof(k_hpcdc_table)) != cudaSuccess ||
+        cudaMemcpy(c->d_table, k_hpcdc_table, sizeof(k_hpcdc_table), cudaMemcpyHostToDevice) != cudaSuccess)
+    {
+        cudaGetLastError();
+        delete c;
+        return EIO;
+    }
+    for (int i = 0; i < 2; ++i)
+    {
+        cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    *out_context = c;
+    return 0;
+}
+
+extern "C" void lt_b200_context_destroy(lt_b200_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    prof_collect(c);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    for (Buf& b : c->ws) if (b.p) cudaFree(b.p);
+    for (Buf& b : c->hs) if (b.p) cudaFreeHost(b.p);
+    if (c->d_table) cudaFree(c->d_table);
+    for (int i = 0; i < 2; ++i)
+    {
+        if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
+        if (c->compute_done[i]) cudaEventDestroy(c->compute_done[i]);
+    }
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+extern "C" const char* lt_b200_last_error(const lt_b200_context* c) { return c ? c->err : "no context"; }
+extern "C" uint64_t lt_b200_launch_count(const lt_b200_context* c) { return c ? c->launches : 0; }
+extern "C" void* lt_b200_stream(lt_b200_context* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int lt_b200_synchronize(lt_b200_context* c)
+{
+    if (!c) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lt_b200_profile_enable(lt_b200_context* c, int on)
+{
+    if (!c) return EINVAL;
+    c->prof_on = on != 0;
+    return 0;
+}
+
+extern "C" int lt_b200_profile_reset(lt_b200_context* c)
+{
+    if (!c) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    for (int i = 0; i < LT_B200_KERNEL_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; c->prof_bytes[i] = 0; }
+    return 0;
+}
+
+extern "C" int lt_b200_profile_read(lt_b200_context* c, uint32_t kernel, double* out_ms, uint64_t* out_launches, uint64_t* out_bytes)
+{
+    if (!c || kernel >= LT_B200_KERNEL_COUNT) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    if (out_ms) *out_ms = c->prof_ms[kernel];
+    if (out_launches) *out_launches = c->prof_launches[kernel];
+    if (out_bytes) *out_bytes = c->prof_bytes[kernel];
+    return 0;
+}
+
+extern "C" int lt_b200_device_alloc(lt_b200_context* c, uint64_t bytes, void** out)
+{
+    if (!c || !out) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return 0;
+}
+
+extern "C" int lt_b200_device_free(lt_b200_context* c, void* p)
+{
+    if (!c) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(p));
+    return 0;
+}
+
+extern "C" int lt_b200_host_alloc_pinned(lt_b200_context* c, uint64_t bytes, void** out)
+{
+    if (!c || !out) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+extern "C" int lt_b200_host_free_pinned(lt_b200_context* c, void* p)
+{
+    if (!c) return EINVAL;
+    CU(cudaFreeHost(p));
+    return 0;
+}
+
+extern "C" int lt_b200_copy_to_device(lt_b200_context* c, void* dst, const void* src, uint64_t bytes)
+{
+    if (!c) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lt_b200_copy_to_host(lt_b200_context* c, void* dst, const void* src, uint64_t bytes)
+{
+    if (!c) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lt_b200_synth_fill(lt_b200_context* c, void* dst, uint64_t bytes, const lt_b200_synth_spec* spec, uint64_t asset_id, uint64_t offset)
+{
+    if (!c || !spec || (offset & 15u)) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    lt_synth_spec_dev s = {spec->seed, spec->shared_permille, spec->pool_segments, spec->class_mode, 0};
+    launch_synth_fill(static_cast<uint8_t*>(dst), bytes, s, asset_id, offset, c->stream);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ================================================================ layer 1
+
+extern "C" int lt_b200_chunk_ranges(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, const lt_b200_range* ranges,
+                                    uint32_t range_count, uint32_t mn, uint32_t av, uint32_t mx, uint32_t hash_type, int want_host,
+                                    lt_b200_chunk_table* out)
+{
+    if (!c || !out || (range_count && !ranges)) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    memset(out, 0, sizeof(*out));
+    c->table_chunks = 0;
+    ChunkParams cp;
+    TRY(make_chunk_params(c, mn, av, mx, &cp));
+    if (hash_type != LT_B200_HASH_BLAKE3) return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation yet", hash_type);
+    if (((uintptr_t)d_arena) & 15u) return fail(c, EINVAL, "device arena must be 16-byte aligned");
+    out->range_count = range_count;
+    if (!range_count) return 0;
+
+    // part descriptors (host) -> device
+    TRY(hs_reserve(c, HS_PARTS, sizeof(PartDesc) * (size_t)range_count));
+    PartDesc* h_parts = hs<PartDesc>(c, HS_PARTS);
+    uint64_t tiles = 0, stage = 0, bytes = 0;
+    for (uint32_t r = 0; r < range_count; ++r)
+    {
+        const lt_b200_range& rg = ranges[r];
+        if ((rg.arena_offset & 15u) || rg.size >= 0x80000000u || rg.arena_offset + rg.size > arena_size)
+            return fail(c, EINVAL, "range %u (offset %llu size %u) is misaligned or outside the arena", r, (unsigned long long)rg.arena_offset, rg.size);
+        PartDesc& p = h_parts[r];
+        p.data_off = rg.arena_offset;
+        p.size = rg.size;
+        p.tile_start = (uint32_t)tiles;
+        p.chunk_start = (uint32_t)stage;
+        p.asset = r;
+        p.tag = rg.tag;
+        p.pad = 0;
+        tiles += (rg.size + (uint32_t)SCAN_TILE - 1) / (uint32_t)SCAN_TILE;
+        stage += rg.size / mn + 2;
+        bytes += rg.size;
+    }
+    if (tiles >= 0xffffffffull || stage >= 0xffffffffull) return fail(c, E2BIG, "batch too large: %llu tiles, %llu chunk slots", (unsigned long long)tiles, (unsigned long long)stage);
+    const uint32_t num_tiles = (uint32_t)tiles;
+
+    TRY(ws_reserve(c, WS_PARTS, sizeof(PartDesc) * (size_t)range_count));
+    TRY(ws_reserve(c, WS_TILE_DESC, sizeof(uint2) * (size_t)num_tiles));
+    TRY(ws_reserve(c, WS_TILE_COUNT, sizeof(uint32_t) * (size_t)num_tiles));
+    TRY(ws_reserve(c, WS_TILE_SLOTS, sizeof(uint32_t) * (size_t)num_tiles * cp.slots));
+    TRY(ws_reserve(c, WS_CAND, sizeof(uint32_t) * (size_t)num_tiles * cp.slots));
+    TRY(ws_reserve(c, WS_STAGE_OFF, sizeof(uint64_t) * (size_t)stage));
+    TRY(ws_reserve(c, WS_STAGE_LEN, sizeof(uint32_t) * (size_t)stage));
+    TRY(ws_reserve(c, WS_PART_COUNT, sizeof(uint32_t) * (size_t)range_count));
+    TRY(ws_reserve(c, WS_PART_BASE, sizeof(uint32_t) * ((size_t)range_count + 1)));
+    TRY(ws_reserve(c, WS_SCAN_TMP, sizeof(uint32_t) * scan_tmp_words(range_count)));
+
+    CU(cudaMemcpyAsync(ws<PartDesc>(c, WS_PARTS), h_parts, sizeof(PartDesc) * (size_t)range_count, cudaMemcpyHostToDevice, c->stream));
+    launch_tile_desc(ws<PartDesc>(c, WS_PARTS), range_count, ws<uint2>(c, WS_TILE_DESC), c->stream);
+    {
+        ProfScope ps(c, LT_B200_KERNEL_HPCDC_SCAN, bytes);
+        CU(launch_hpcdc_scan(d_arena, ws<PartDesc>(c, WS_PARTS), ws<uint2>(c, WS_TILE_DESC), num_tiles, cp, c->d_table,
+                             ws<uint32_t>(c, WS_TILE_COUNT), ws<uint32_t>(c, WS_TILE_SLOTS), c->sm_count, c->stream));
+    }
+    {
+        ProfScope ps(c, LT_B200_KERNEL_HPCDC_WALK, (uint64_t)num_tiles * 4);
+        launch_hpcdc_walk(d_arena, ws<PartDesc>(c, WS_PARTS), range_count, cp, c->d_table, ws<uint32_t>(c, WS_TILE_COUNT),
+                          ws<uint32_t>(c, WS_TILE_SLOTS), ws<uint32_t>(c, WS_CAND), ws<uint64_t>(c, WS_STAGE_OFF),
+                          ws<uint32_t>(c, WS_STAGE_LEN), ws<uint32_t>(c, WS_PART_COUNT), c->stream);
+    }
+    launch_exclusive_scan(ws<uint32_t>(c, WS_PART_COUNT), range_count, ws<uint32_t>(c, WS_PART_BASE), ws<uint32_t>(c, WS_SCAN_TMP), c->stream);
+    c->launches += 6;
+
+    TRY(hs_reserve(c, HS_RANGE_COUNTS, sizeof(uint32_t) * ((size_t)range_count + 1)));
+    uint32_t* h_counts = hs<uint32_t>(c, HS_RANGE_COUNTS);
+    CU(cudaMemcpyAsync(h_counts, ws<uint32_t>(c, WS_PART_COUNT), sizeof(uint32_t) * (size_t)range_count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_counts + range_count, ws<uint32_t>(c, WS_PART_BASE) + range_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    const uint32_t chunk_count = h_counts[range_count];
+    out->chunk_count = chunk_count;
+    out->range_chunk_counts = h_counts;
+    if (!chunk_count) return 0;
+
+    TRY(ws_reserve(c, WS_CHUNK_OFF, sizeof(uint64_t) * (size_t)chunk_count));
+    TRY(ws_reserve(c, WS_CHUNK_LEN, sizeof(uint32_t) * (size_t)chunk_count));
+    TRY(ws_reserve(c, WS_CHUNK_TAG, sizeof(uint32_t) * (size_t)chunk_count));
+    TRY(ws_reserve(c, WS_CHUNK_HASH, sizeof(uint64_t) * (size_t)chunk_count));
+    launch_compact_chunks(ws<PartDesc>(c, WS_PARTS), range_count, ws<uint32_t>(c, WS_PART_COUNT), ws<uint32_t>(c, WS_PART_BASE),
+                          ws<uint64_t>(c, WS_STAGE_OFF), ws<uint32_t>(c, WS_STAGE_LEN), ws<uint64_t>(c, WS_CHUNK_OFF),
+                          ws<uint32_t>(c, WS_CHUNK_LEN), ws<uint32_t>(c, WS_CHUNK_TAG), c->stream);
+    c->launches += 1;
+    TRY(hash_segments_device(c, hash_type, d_arena, arena_size, ws<uint64_t>(c, WS_CHUNK_OFF), ws<uint32_t>(c, WS_CHUNK_LEN), chunk_count,
+                             bytes / 1024 + chunk_count, WS_LEAF_COUNT, WS_LEAF_PREFIX, WS_CVS, ws<uint64_t>(c, WS_CHUNK_HASH), bytes));
+    c->table_chunks = chunk_count;
+    if (want_host)
+    {
+        TRY(hs_reserve(c, HS_CHUNK_HASH, sizeof(uint64_t) * (size_t)chunk_count));
+        TRY(hs_reserve(c, HS_CHUNK_LEN, sizeof(uint32_t) * (size_t)chunk_count));
+        TRY(hs_reserve(c, HS_CHUNK_TAG, sizeof(uint32_t) * (size_t)chunk_count));
+        TRY(hs_reserve(c, HS_CHUNK_OFF, sizeof(uint64_t) * (size_t)chunk_count));
+        CU(cudaMemcpyAsync(hs<void>(c, HS_CHUNK_HASH), ws<void>(c, WS_CHUNK_HASH), sizeof(uint64_t) * (size_t)chunk_count, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(hs<void>(c, HS_CHUNK_LEN), ws<void>(c, WS_CHUNK_LEN), sizeof(uint32_t) * (size_t)chunk_count, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(hs<void>(c, HS_CHUNK_TAG), ws<void>(c, WS_CHUNK_TAG), sizeof(uint32_t) * (size_t)chunk_count, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(hs<void>(c, HS_CHUNK_OFF), ws<void>(c, WS_CHUNK_OFF), sizeof(uint64_t) * (size_t)chunk_count, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        out->chunk_hashes = hs<uint64_t>(c, HS_CHUNK_HASH);
+        out->chunk_sizes = hs<uint32_t>(c, HS_CHUNK_LEN);
+        out->chunk_tags = hs<uint32_t>(c, HS_CHUNK_TAG);
+        out->chunk_offsets = hs<uint64_t>(c, HS_CHUNK_OFF);
+    }
+    return 0;
+}
+
+extern "C" int lt_b200_hash_segments(lt_b200_context* c, uint32_t hash_type, const uint8_t* d_base, uint64_t base_size,
+                                     const uint64_t* offsets, const uint32_t* sizes, uint32_t count, uint64_t* out_hashes)
+{
+    if (!c || (count && (!offsets || !sizes || !out_hashes))) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    if (!count) return 0;
+    if (((uintptr_t)d_base) & 15u) return fail(c, EINVAL, "device buffer must be 16-byte aligned");
+    uint64_t upper = count;
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        if (offsets[i] + sizes[i] > base_size) return fail(c, EINVAL, "segment %u outside the buffer", i);
+        upper += sizes[i] / 1024;
+    }
+    TRY(ws_reserve(c, WS_SEG_OFF, sizeof(uint64_t) * (size_t)count));
+    TRY(ws_reserve(c, WS_SEG_LEN, sizeof(uint32_t) * (size_t)count));
+    TRY(ws_reserve(c, WS_SEG_HASH, sizeof(uint64_t) * (size_t)count));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_OFF), offsets, sizeof(uint64_t) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_LEN), sizes, sizeof(uint32_t) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    TRY(hash_segments_device(c, hash_type, d_base, base_size, ws<uint64_t>(c, WS_SEG_OFF), ws<uint32_t>(c, WS_SEG_LEN), count, upper,
+                             WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, ws<uint64_t>(c, WS_SEG_HASH)));
+    CU(cudaMemcpyAsync(out_hashes, ws<void>(c, WS_SEG_HASH), sizeof(uint64_t) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ================================================================ layer 2
+
+namespace {
+
+// device-side table to index: [d_hash, d_len, d_tag] x chunk_count already resident
+int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, const uint32_t* asset_chunk_counts, uint32_t chunk_count,
+                                  const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t hash_type,
+                                  uint32_t target_chunk_size, const void** out_buffer, uint64_t* out_size)
+{
+    const uint32_t A = a->asset_count;
+    // ---- per-asset segments: content hash over the asset's chunk-hash array (src/longtail.c:2518-2537) and path hash over
+    // strlen(path) bytes (src/longtail.c:1281-1297).  Both are HashBuffer calls -> same segment kernel.
+    TRY(hs_reserve(c, HS_SEG, (sizeof(uint64_t) + sizeof(uint32_t)) * 2 * (size_t)(A + 1) + sizeof(uint32_t) * (size_t)(A + 1)));
+    uint64_t* h_off = hs<uint64_t>(c, HS_SEG);
+    uint32_t* h_len = reinterpret_cast<uint32_t*>(h_off + 2 * (size_t)(A + 1));
+    uint32_t* h_starts = h_len + 2 * (size_t)(A + 1);
+    uint64_t run = 0;
+    uint64_t upper = 2ull * A;
+    for (uint32_t i = 0; i < A; ++i)
+    {
+        h_starts[i] = (uint32_t)run;
+        h_off[i] = run * 8;
+        h_len[i] = asset_chunk_counts[i] * 8u;
+        upper += h_len[i] / 1024;
+        run += asset_chunk_counts[i];
+        const char* path = a->path_data + a->path_start_offsets[i];
+        h_off[A + i] = a->path_start_offsets[i];
+        h_len[A + i] = (uint32_t)strlen(path);
+        upper += h_len[A + i] / 1024;
+    }
+    if (run != chunk_count) return fail(c, EINVAL, "asset chunk counts sum to %llu, table has %u", (unsigned long long)run, chunk_count);
+
+    const size_t path_bytes = ((size_t)a->path_data_size + 15) & ~(size_t)15;
+    TRY(ws_reserve(c, WS_PATHS, path_bytes + 16));
+    TRY(ws_reserve(c, WS_SEG_OFF, sizeof(uint64_t) * 2 * (size_t)(A + 1)));
+    TRY(ws_reserve(c, WS_SEG_LEN, sizeof(uint32_t) * 2 * (size_t)(A + 1)));
+    TRY(ws_reserve(c, WS_SEG_HASH, sizeof(uint64_t) * 2 * (size_t)(A + 1)));
+    uint64_t* d_seg_hash = ws<uint64_t>(c, WS_SEG_HASH);
+    if (A)
+    {
+        CU(cudaMemcpyAsync(ws<void>(c, WS_PATHS), a->path_data, a->path_data_size, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_OFF), h_off, sizeof(uint64_t) * 2 * (size_t)A, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_LEN), h_len, sizeof(uint32_t) * 2 * (size_t)A, cudaMemcpyHostToDevice, c->stream));
+        // content hashes: base = the chunk-hash array itself (any valid pointer when there are no chunks at all)
+        const uint8_t* hash_bytes = chunk_count ? reinterpret_cast<const uint8_t*>(d_hash) : ws<uint8_t>(c, WS_PATHS);
+        TRY(hash_segments_device(c, hash_type, hash_bytes, 8ull * chunk_count, ws<uint64_t>(c, WS_SEG_OFF),
+                                 ws<uint32_t>(c, WS_SEG_LEN), A, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, d_seg_hash));
+        TRY(hash_segments_device(c, hash_type, ws<uint8_t>(c, WS_PATHS), a->path_data_size, ws<uint64_t>(c, WS_SEG_OFF) + A,
+                                 ws<uint32_t>(c, WS_SEG_LEN) + A, A, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, d_seg_hash + A));
+    }
+
+    // ---- first-occurrence dedup (src/longtail.c:2952-2970)
+    uint32_t unique = 0;
+    if (chunk_count)
+    {
+        uint32_t cap = 1024;
+        while (cap < 2ull * chunk_count && cap < 0x80000000u) cap <<= 1;
+        TRY(ws_reserve(c, WS_DEDUP_KEYS, sizeof(uint64_t) * (size_t)cap));
+        TRY(ws_reserve(c, WS_DEDUP_VALS, sizeof(uint32_t) * ((size_t)cap + 1)));
+        TRY(ws_reserve(c, WS_DEDUP_FIRST, sizeof(uint32_t) * (size_t)chunk_count));
+        TRY(ws_reserve(c, WS_DEDUP_ISFIRST, sizeof(uint32_t) * (size_t)chunk_count));
+        TRY(ws_reserve(c, WS_DEDUP_UIDX, sizeof(uint32_t) * ((size_t)chunk_count + 1)));
+        TRY(ws_reserve(c, WS_SCAN_TMP, sizeof(uint32_t) * scan_tmp_words(chunk_count)));
+        TRY(ws_reserve(c, WS_ACI, sizeof(uint32_t) * (size_t)chunk_count));
+        TRY(ws_reserve(c, WS_UHASH, sizeof(uint64_t) * (size_t)chunk_count));
+        TRY(ws_reserve(c, WS_ULEN, sizeof(uint32_t) * (size_t)chunk_count));
+        TRY(ws_reserve(c, WS_UTAG, sizeof(uint32_t) * (size_t)chunk_count));
+        DedupBuffers db;
+        db.keys = ws<uint64_t>(c, WS_DEDUP_KEYS);
+        db.vals = ws<uint32_t>(c, WS_DEDUP_VALS);
+        db.capacity = cap;
+        db.first = ws<uint32_t>(c, WS_DEDUP_FIRST);
+        db.is_first = ws<uint32_t>(c, WS_DEDUP_ISFIRST);
+        db.uidx = ws<uint32_t>(c, WS_DEDUP_UIDX);
+        CU(cudaMemsetAsync(db.keys, 0xff, sizeof(uint64_t) * (size_t)cap, c->stream));
+        CU(cudaMemsetAsync(db.vals, 0xff, sizeof(uint32_t) * ((size_t)cap + 1), c->stream));
+        launch_dedup_insert(d_hash, chunk_count, db, c->stream);
+        launch_dedup_lookup(d_hash, chunk_count, db, c->stream);
+        launch_exclusive_scan(db.is_first, chunk_count, db.uidx, ws<uint32_t>(c, WS_SCAN_TMP), c->stream);
+        launch_dedup_emit(d_hash, d_len, d_tag, chunk_count, db, ws<uint32_t>(c, WS_ACI), ws<uint64_t>(c, WS_UHASH), ws<uint32_t>(c, WS_ULEN),
+                          ws<uint32_t>(c, WS_UTAG), c->stream);
+        c->launches += 6;
+        CU(cudaMemcpyAsync(&unique, db.uidx + chunk_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+    }
+
+    // ---- serialised layout, assembled in device memory then copied out once (src/longtail.c:2566-2584)
+    const size_t total = 24 + (size_t)A * (8 + 8 + 8 + 4 + 4 + 4 + 2) + 4 * (size_t)chunk_count + 16 * (size_t)unique + a->path_data_size;
+    TRY(ws_reserve(c, WS_INDEX_OUT, total + 16));
+    TRY(hs_reserve(c, HS_INDEX_OUT, total + 16));
+    TRY(hs_reserve(c, HS_SMALL, 64));
+    uint8_t* d_out = ws<uint8_t>(c, WS_INDEX_OUT);
+    uint32_t* hdr = hs<uint32_t>(c, HS_SMALL);
+    hdr[0] = 2; // Longtail_CurrentVersionIndexVersion, src/longtail.c:16-22
+    hdr[1] = hash_type;
+    hdr[2] = target_chunk_size;
+    hdr[3] = A;
+    hdr[4] = unique;
+    hdr[5] = chunk_count;
+    size_t o = 0;
+    auto put_h = [&](const void* src, size_t n) -> cudaError_t {
+        cudaError_t e = n ? cudaMemcpyAsync(d_out + o, src, n, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+        o += n;
+        return e;
+    };
+    auto put_d = [&](const void* src, size_t n) -> cudaError_t {
+        cudaError_t e = n ? cudaMemcpyAsync(d_out + o, src, n, cudaMemcpyDeviceToDevice, c->stream) : cudaSuccess;
+        o += n;
+        return e;
+    };
+    CU(put_h(hdr, 24));
+    CU(put_d(d_seg_hash + A, 8 * (size_t)A));                       // m_PathHashes
+    CU(put_d(d_seg_hash, 8 * (size_t)A));                           // m_ContentHashes
+    CU(put_h(a->sizes, 8 * (size_t)A));                             // m_AssetSizes
+    CU(put_h(asset_chunk_counts, 4 * (size_t)A));                   // m_AssetChunkCounts
+    CU(put_h(h_starts, 4 * (size_t)A));                             // m_AssetChunkIndexStarts
+    CU(put_d(ws<void>(c, WS_ACI), 4 * (size_t)chunk_count));        // m_AssetChunkIndexes
+    CU(put_d(ws<void>(c, WS_UHASH), 8 * (size_t)unique));           // m_ChunkHashes
+    CU(put_d(ws<void>(c, WS_ULEN), 4 * (size_t)unique));            // m_ChunkSizes
+    CU(put_d(ws<void>(c, WS_UTAG), 4 * (size_t)unique));            // m_ChunkTags
+    CU(put_h(a->path_start_offsets, 4 * (size_t)A));                // m_NameOffsets
+    CU(put_h(a->permissions, 2 * (size_t)A));                       // m_Permissions
+    CU(put_h(a->path_data, a->path_data_size));                     // m_NameData
+    if (o != total) return fail(c, EFAULT, "index layout mismatch %zu != %zu", o, total);
+    CU(cudaMemcpyAsync(hs<void>(c, HS_INDEX_OUT), d_out, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out_buffer = hs<void>(c, HS_INDEX_OUT);
+    *out_size = total;
+    return 0;
+}
+
+int validate_assets(lt_b200_context* c, const lt_b200_assets* a)
+{
+    if (!a) return EINVAL;
+    if (a->asset_count && (!a->sizes || !a->path_start_offsets || !a->permissions || !a->path_data)) return fail(c, EINVAL, "incomplete asset description");
+    for (uint32_t i = 0; i < a->asset_count; ++i)
+        if (a->path_start_offsets[i] >= a->path_data_size) return fail(c, EINVAL, "asset %u path offset outside path data", i);
+    return 0;
+}
+
+void target_to_params(uint32_t t, uint32_t* mn, uint32_t* av, uint32_t* mx)
+{
+    // src/longtail.c:1985-1987 with ChunkerAPI.GetMinChunkSize() == 48 (lib/hpcdcchunker/longtail_hpcdcchunker.c:332-346)
+    *mn = t / 8 < 48 ? 48 : t / 8;
+    *av = t / 2 < 48 ? 48 : t / 2;
+    *mx = (uint64_t)t * 2 < 48 ? 48 : t * 2;
+}
+
+} // namespace
+
+extern "C" int lt_b200_build_version_index(lt_b200_context* c, const lt_b200_assets* a, const uint32_t* asset_chunk_counts,
+                                           uint32_t chunk_count, const uint64_t* chunk_hashes, const uint32_t* chunk_sizes,
+                                           const uint32_t* chunk_tags, uint32_t hash_type, uint32_t target_chunk_size,
+                                           const void** out_buffer, uint64_t* out_size)
+{
+    if (!c || !out_buffer || !out_size) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    TRY(validate_assets(c, a));
+    if (a->asset_count && !asset_chunk_counts) return EINVAL;
+    if (!chunk_hashes)
+    {
+        if (chunk_count != c->table_chunks) return fail(c, EINVAL, "no resident chunk table of %u chunks (have %u)", chunk_count, c->table_chunks);
+        return build_index_from_device_table(c, a, asset_chunk_counts, chunk_count, ws<uint64_t>(c, WS_CHUNK_HASH), ws<uint32_t>(c, WS_CHUNK_LEN),
+                                             ws<uint32_t>(c, WS_CHUNK_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+    }
+    if (chunk_count && (!chunk_sizes || !chunk_tags)) return EINVAL;
+    TRY(ws_reserve(c, WS_TAB_HASH, sizeof(uint64_t) * (size_t)chunk_count + 16));
+    TRY(ws_reserve(c, WS_TAB_LEN, sizeof(uint32_t) * (size_t)chunk_count + 16));
+    TRY(ws_reserve(c, WS_TAB_TAG, sizeof(uint32_t) * (size_t)chunk_count + 16));
+    if (chunk_count)
+    {
+        CU(cudaMemcpyAsync(ws<void>(c, WS_TAB_HASH), chunk_hashes, sizeof(uint64_t) * (size_t)chunk_count, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_TAB_LEN), chunk_sizes, sizeof(uint32_t) * (size_t)chunk_count, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_TAB_TAG), chunk_tags, sizeof(uint32_t) * (size_t)chunk_count, cudaMemcpyHostToDevice, c->stream));
+    }
+    return build_index_from_device_table(c, a, asset_chunk_counts, chunk_count, ws<uint64_t>(c, WS_TAB_HASH), ws<uint32_t>(c, WS_TAB_LEN),
+                                         ws<uint32_t>(c, WS_TAB_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+}
+
+extern "C" int lt_b200_index_device_assets(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, const lt_b200_assets* a,
+                                           const uint64_t* asset_arena_offsets, const uint32_t* asset_tags, uint32_t hash_type,
+                                           uint32_t target_chunk_size, const void** out_buffer, uint64_t* out_size)
+{
+    if (!c || !out_buffer || !out_size) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    TRY(validate_assets(c, a));
+    if (a->asset_count && !asset_arena_offsets) return EINVAL;
+    if (target_chunk_size == 0 || target_chunk_size > (1u << 20)) return fail(c, EINVAL, "target_chunk_size %u outside (0, 1 MiB]", target_chunk_size);
+    uint32_t mn, av, mx;
+    target_to_params(target_chunk_size, &mn, &av, &mx);
+    const uint64_t part_size = (uint64_t)target_chunk_size * 1024; // src/longtail.c:2396
+    std::vector<lt_b200_range> ranges;
+    std::vector<uint32_t> first_range(a->asset_count + 1);
+    for (uint32_t i = 0; i < a->asset_count; ++i)
+    {
+        first_range[i] = (uint32_t)ranges.size();
+        const uint64_t size = a->sizes[i];
+        const uint64_t parts = 1 + size / part_size; // :2402 — a trailing empty part produces no chunks and is skipped here
+        for (uint64_t p = 0; p < parts; ++p)
+        {
+            const uint64_t start = p * part_size;
+            const uint64_t n = size - start > part_size ? part_size : size - start;
+            if (!n) continue;
+            lt_b200_range r = {asset_arena_offsets[i] + start, (uint32_t)n, asset_tags ? asset_tags[i] : 0u};
+            ranges.push_back(r);
+        }
+    }
+    first_range[a->asset_count] = (uint32_t)ranges.size();
+    lt_b200_chunk_table table;
+    TRY(lt_b200_chunk_ranges(c, d_arena, arena_size, ranges.data(), (uint32_t)ranges.size(), mn, av, mx, hash_type, 0, &table));
+    std::vector<uint32_t> asset_chunks(a->asset_count);
+    for (uint32_t i = 0; i < a->asset_count; ++i)
+    {
+        uint32_t n = 0;
+        for (uint32_t r = first_range[i]; r < first_range[i + 1]; ++r) n += table.range_chunk_counts[r];
+        asset_chunks[i] = n;
+    }
+    return build_index_from_device_table(c, a, asset_chunks.data(), table.chunk_count, ws<uint64_t>(c, WS_CHUNK_HASH), ws<uint32_t>(c, WS_CHUNK_LEN),
+                                         ws<uint32_t>(c, WS_CHUNK_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+}
+
+extern "C" int lt_b200_index_host_assets(lt_b200_context* c, const lt_b200_assets* a, const uint8_t* const* asset_data,
+                                         const uint32_t* asset_tags, uint32_t hash_type, uint32_t target_chunk_size,
+                                         const void** out_buffer, uint64_t* out_size)
+{
+    if (!c || !out_buffer || !out_size) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    TRY(validate_assets(c, a));
+    if (a->asset_count && !asset_data) return EINVAL;
+    if (target_chunk_size == 0 || target_chunk_size > (1u << 20)) return fail(c, EINVAL, "target_chunk_size %u outside (0, 1 MiB]", target_chunk_size);
+    uint32_t mn, av, mx;
+    target_to_params(target_chunk_size, &mn, &av, &mx);
+    const uint64_t part_size = (uint64_t)target_chunk_size * 1024;
+
+    // the job list of ChunkAssets (src/longtail.c:2399-2457), empty parts dropped
+    struct Job { uint32_t asset; uint64_t start; uint32_t size; };
+    std::vector<Job> jobs;
+    uint64_t total_bytes = 0;
+    for (uint32_t i = 0; i < a->asset_count; ++i)
+    {
+        const uint64_t size = a->sizes[i];
+        const uint64_t parts = 1 + size / part_size;
+        for (uint64_t p = 0; p < parts; ++p)
+        {
+            const uint64_t start = p * part_size;
+            const uint64_t n = size - start > part_size ? part_size : size - start;
+            if (n) jobs.push_back({i, start, (uint32_t)n});
+        }
+        total_bytes += size;
+    }
+    // batches of whole jobs, double-buffered device arenas: copy of batch k+1 overlaps the kernels of batch k
+    const uint64_t batch_bytes = 1ull << 30 > part_size ? 1ull << 30 : part_size;
+    const uint64_t arena_cap = batch_bytes + (uint64_t)jobs.size() * 0 + 4096;
+    uint64_t max_chunks = total_bytes / mn + 2 * (uint64_t)jobs.size() + 16;
+    TRY(ws_reserve(c, WS_ACC_HASH, sizeof(uint64_t) * (size_t)max_chunks));
+    TRY(ws_reserve(c, WS_ACC_LEN, sizeof(uint32_t) * (size_t)max_chunks));
+    TRY(ws_reserve(c, WS_ACC_TAG, sizeof(uint32_t) * (size_t)max_chunks));
+    std::vector<uint32_t> asset_chunks(a->asset_count, 0);
+
+    struct Batch { size_t first, last; std::vector<lt_b200_range> ranges; uint64_t bytes; };
+    auto plan = [&](size_t first) {
+        Batch b;
+        b.first = first;
+        b.bytes = 0;
+        size_t j = first;
+        while (j < jobs.size())
+        {
+            uint64_t padded = ((uint64_t)jobs[j].size + 255) & ~255ull;
+            if (b.bytes + padded > batch_bytes && j > first) break;
+            lt_b200_range r = {b.bytes, jobs[j].size, asset_tags ? asset_tags[jobs[j].asset] : 0u};
+            b.ranges.push_back(r);
+            b.bytes += padded;
+            ++j;
+        }
+        b.last = j;
+        return b;
+    };
+    auto upload = [&](const Batch& b, int which) -> int {
+        TRY(ws_reserve(c, which ? WS_ARENA_B : WS_ARENA_A, arena_cap > b.bytes + 4096 ? arena_cap : b.bytes + 4096));
+        uint8_t* d = ws<uint8_t>(c, which ? WS_ARENA_B : WS_ARENA_A);
+        CU(cudaStreamWaitEvent(c->copy_stream, c->compute_done[which], 0)); // the arena's previous batch has been consumed
+        for (size_t j = b.first; j < b.last; ++j)
+            CU(cudaMemcpyAsync(d + b.ranges[j - b.first].arena_offset, asset_data[jobs[j].asset] + jobs[j].start, jobs[j].size,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->copy_done[which], c->copy_stream));
+        return 0;
+    };
+
+    uint64_t acc = 0;
+    if (!jobs.empty())
+    {
+        // make the events "signalled" for the first use
+        CU(cudaEventRecord(c->compute_done[0], c->stream));
+        CU(cudaEventRecord(c->compute_done[1], c->stream));
+        Batch cur = plan(0);
+        int which = 0;
+        TRY(upload(cur, which));
+        while (true)
+        {
+            Batch next;
+            const bool has_next = cur.last < jobs.size();
+            if (has_next)
+            {
+                next = plan(cur.last);
+                TRY(upload(next, which ^ 1));
+            }
+            CU(cudaStreamWaitEvent(c->stream, c->copy_done[which], 0));
+            const uint8_t* d = ws<uint8_t>(c, which ? WS_ARENA_B : WS_ARENA_A);
+            lt_b200_chunk_table table;
+            TRY(lt_b200_chunk_ranges(c, d, c->ws[which ? WS_ARENA_B : WS_ARENA_A].cap, cur.ranges.data(), (uint32_t)cur.ranges.size(), mn, av, mx,
+                                     hash_type, 0, &table));
+            CU(cudaEventRecord(c->compute_done[which], c->stream));
+            if (acc + table.chunk_count > max_chunks) return fail(c, EFAULT, "chunk accumulation overflow");
+            if (table.chunk_count)
+            {
+                CU(cudaMemcpyAsync(ws<uint64_t>(c, WS_ACC_HASH) + acc, ws<void>(c, WS_CHUNK_HASH), sizeof(uint64_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaMemcpyAsync(ws<uint32_t>(c, WS_ACC_LEN) + acc, ws<void>(c, WS_CHUNK_LEN), sizeof(uint32_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaMemcpyAsync(ws<uint32_t>(c, WS_ACC_TAG) + acc, ws<void>(c, WS_CHUNK_TAG), sizeof(uint32_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            for (size_t j = cur.first; j < cur.last; ++j) asset_chunks[jobs[j].asset] += table.range_chunk_counts[j - cur.first];
+            acc += table.chunk_count;
+            if (!has_next) break;
+            cur = std::move(next);
+            which ^= 1;
+        }
+    }
+    if (acc > 0xffffffffull) return fail(c, E2BIG, "more than 2^32 chunks");
+    return build_index_from_device_table(c, a, asset_chunks.data(), (uint32_t)acc, ws<uint64_t>(c, WS_ACC_HASH), ws<uint32_t>(c, WS_ACC_LEN),
+                                         ws<uint32_t>(c, WS_ACC_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+}

@@ -1,0 +1,59 @@
+// lt_kernels.h — host-callable launchers of the sm_100a kernels (internal to liblongtail_b200.so)
+#pragma once
+
+#include "lt_device.cuh"
+
+namespace ltb {
+
+// ---- hpcdc.cu
+void launch_tile_desc(const PartDesc* d_parts, uint32_t part_count, uint2* d_tile_desc, cudaStream_t st);
+cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint2* d_tile_desc, uint32_t num_tiles,
+                              const ChunkParams& cp, const uint32_t* d_table, uint32_t* d_tile_count, uint32_t* d_tile_slots,
+                              int sm_count, cudaStream_t st);
+void launch_hpcdc_walk(const uint8_t* d_arena, const PartDesc* d_parts, uint32_t part_count, const ChunkParams& cp,
+                       const uint32_t* d_table, const uint32_t* d_tile_count, const uint32_t* d_tile_slots, uint32_t* d_cand,
+                       uint64_t* d_stage_off, uint32_t* d_stage_len, uint32_t* d_part_chunk_count, cudaStream_t st);
+void launch_compact_chunks(const PartDesc* d_parts, uint32_t part_count, const uint32_t* d_part_chunk_count,
+                           const uint32_t* d_part_chunk_base, const uint64_t* d_stage_off, const uint32_t* d_stage_len,
+                           uint64_t* d_chunk_off, uint32_t* d_chunk_len, uint32_t* d_chunk_tag, cudaStream_t st);
+
+// ---- blake3.cu : hash `count` byte segments [off, off+len) of `base` (device memory of `base_size` bytes)
+// leaf_prefix has count+1 entries: exclusive prefix of max(1, ceil(len/1024)); cvs holds 8 u32 per leaf.
+void launch_leaf_counts(const uint32_t* d_len, uint32_t count, uint32_t* d_leaf_count, cudaStream_t st);
+void launch_blake3_leaves(const uint8_t* d_base, uint64_t base_size, const uint64_t* d_off, const uint32_t* d_len,
+                          const uint32_t* d_leaf_prefix, uint32_t count, uint32_t total_leaves, uint32_t* d_cvs,
+                          uint64_t* d_hash_out, cudaStream_t st);
+void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, uint32_t count, uint32_t* d_cvs, uint64_t* d_hash_out,
+                         cudaStream_t st);
+
+// ---- util.cu
+// exclusive prefix sum of count u32 values into out[0..count]; out[count] = total.  tmp: >= scan_tmp_words(count) u32.
+size_t scan_tmp_words(uint32_t count);
+void launch_exclusive_scan(const uint32_t* d_in, uint32_t count, uint32_t* d_out, uint32_t* d_tmp, cudaStream_t st);
+
+// first-occurrence dedup of chunk hashes (src/longtail.c:2952-2970)
+struct DedupBuffers
+{
+    uint64_t* keys;     // [capacity] open-addressing table, capacity is a power of two >= 2 * count
+    uint32_t* vals;     // [capacity] smallest ordinal seen for the key
+    uint32_t capacity;
+    uint32_t* first;    // [count]   ordinal of the first occurrence of chunk i's hash
+    uint32_t* is_first; // [count]   1 when chunk i is that first occurrence
+    uint32_t* uidx;     // [count+1] exclusive scan of is_first
+};
+void launch_dedup_insert(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st);
+void launch_dedup_lookup(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st);
+void launch_dedup_emit(const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, const DedupBuffers& b,
+                       uint32_t* d_asset_chunk_index, uint64_t* d_unique_hash, uint32_t* d_unique_len, uint32_t* d_unique_tag,
+                       cudaStream_t st);
+void launch_fill_u32(uint32_t* d, uint32_t value, size_t count, cudaStream_t st);
+
+// ---- synth.cu : deterministic synthetic asset bytes (include/lt_synth.h)
+struct lt_synth_spec_dev
+{
+    uint64_t seed;
+    uint32_t shared_permille, pool_segments, class_mode, reserved;
+};
+void launch_synth_fill(uint8_t* d_dst, uint64_t len, const lt_synth_spec_dev& spec, uint64_t asset_id, uint64_t offset, cudaStream_t st);
+
+} // namespace ltb

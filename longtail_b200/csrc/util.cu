@@ -1,0 +1,256 @@
+// util.cu — device-wide exclusive scan, first-occurrence dedup table, synthetic asset fill.
+#include "lt_device.cuh"
+#include "lt_kernels.h"
+#include "../../include/lt_synth.h"
+
+namespace ltb {
+
+// ---------------------------------------------------------------- exclusive scan (u32)
+
+namespace {
+constexpr int PS_THREADS = 256;
+constexpr int PS_ITEMS = 8;
+constexpr int PS_BLOCK = PS_THREADS * PS_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* s_warp, uint32_t* out_total)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w)
+    {
+        uint32_t t = s_warp[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    __syncthreads();
+    *out_total = total;
+    return base + incl - v;
+}
+} // namespace
+
+__global__ void __launch_bounds__(PS_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint32_t count, uint32_t* __restrict__ block_sums)
+{
+    __shared__ uint32_t s_warp[PS_THREADS / 32];
+    const uint32_t first = blockIdx.x * PS_BLOCK + threadIdx.x * PS_ITEMS;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i)
+        if (first + i < count) v += in[first + i];
+    uint32_t total;
+    block_exclusive(v, s_warp, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: in-place exclusive scan of block_sums[0..nblocks), total appended at [nblocks]
+__global__ void __launch_bounds__(1024) k_scan_tops(uint32_t* __restrict__ block_sums, uint32_t nblocks)
+{
+    __shared__ uint32_t s_warp[32];
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < nblocks; b += 1024)
+    {
+        uint32_t i = b + threadIdx.x;
+        uint32_t v = i < nblocks ? block_sums[i] : 0;
+        uint32_t total;
+        uint32_t ex = block_exclusive(v, s_warp, &total);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) block_sums[nblocks] = carry;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) k_scan_final(const uint32_t* __restrict__ in, uint32_t count, const uint32_t* __restrict__ block_sums,
+                                                           uint32_t nblocks, uint32_t* __restrict__ out)
+{
+    __shared__ uint32_t s_warp[PS_THREADS / 32];
+    const uint32_t first = blockIdx.x * PS_BLOCK + threadIdx.x * PS_ITEMS;
+    uint32_t item[PS_ITEMS];
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i)
+    {
+        item[i] = first + i < count ? in[first + i] : 0;
+        v += item[i];
+    }
+    uint32_t total;
+    uint32_t run = block_sums[blockIdx.x] + block_exclusive(v, s_warp, &total);
+#pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i)
+    {
+        if (first + i < count) out[first + i] = run;
+        run += item[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[count] = block_sums[nblocks];
+}
+
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
+size_t scan_tmp_words(uint32_t count) { return (size_t)(count + PS_BLOCK - 1) / PS_BLOCK + 2; }
+
+void launch_exclusive_scan(const uint32_t* d_in, uint32_t count, uint32_t* d_out, uint32_t* d_tmp, cudaStream_t st)
+{
+    if (count == 0)
+    {
+        k_set_u32<<<1, 1, 0, st>>>(d_out, 0);
+        return;
+    }
+    const uint32_t nblocks = (count + PS_BLOCK - 1) / PS_BLOCK;
+    k_scan_reduce<<<nblocks, PS_THREADS, 0, st>>>(d_in, count, d_tmp);
+    k_scan_tops<<<1, 1024, 0, st>>>(d_tmp, nblocks);
+    k_scan_final<<<nblocks, PS_THREADS, 0, st>>>(d_in, count, d_tmp, nblocks, d_out);
+}
+
+__global__ void k_fill_u32(uint32_t* __restrict__ d, uint32_t value, size_t count)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) d[i] = value;
+}
+
+void launch_fill_u32(uint32_t* d, uint32_t value, size_t count, cudaStream_t st)
+{
+    if (!count) return;
+    size_t blocks = (count + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_fill_u32<<<(unsigned)blocks, 256, 0, st>>>(d, value, count);
+}
+
+// ---------------------------------------------------------------- first-occurrence dedup
+// The reference keeps, for every distinct chunk hash, the first occurrence in asset/part/chunk order
+// (src/longtail.c:2952-2970, LookupTable_PutUnique).  Order-independent restatement: the representative of a
+// hash is the occurrence with the smallest ordinal -> atomicMin into an open-addressing table.
+
+namespace {
+constexpr uint64_t DEDUP_EMPTY = 0xffffffffffffffffull;
+__device__ __forceinline__ uint32_t dedup_slot(uint64_t key, uint32_t mask)
+{
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+}
+} // namespace
+
+__global__ void k_dedup_insert(const uint64_t* __restrict__ hash, uint32_t count, uint64_t* keys, uint32_t* vals, uint32_t capacity)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t key = hash[i];
+    if (key == DEDUP_EMPTY)
+    {
+        atomicMin(&vals[capacity], i); // the one key that cannot live in the table has a side slot
+        return;
+    }
+    const uint32_t mask = capacity - 1;
+    for (uint32_t s = dedup_slot(key, mask);; s = (s + 1) & mask)
+    {
+        unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&keys[s]), (unsigned long long)DEDUP_EMPTY, (unsigned long long)key);
+        if (prev == DEDUP_EMPTY || prev == key)
+        {
+            atomicMin(&vals[s], i);
+            return;
+        }
+    }
+}
+
+__global__ void k_dedup_lookup(const uint64_t* __restrict__ hash, uint32_t count, const uint64_t* __restrict__ keys,
+                               const uint32_t* __restrict__ vals, uint32_t capacity, uint32_t* __restrict__ first,
+                               uint32_t* __restrict__ is_first)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t key = hash[i];
+    uint32_t f;
+    if (key == DEDUP_EMPTY)
+        f = vals[capacity];
+    else
+    {
+        const uint32_t mask = capacity - 1;
+        uint32_t s = dedup_slot(key, mask);
+        while (keys[s] != key) s = (s + 1) & mask;
+        f = vals[s];
+    }
+    first[i] = f;
+    is_first[i] = f == i ? 1u : 0u;
+}
+
+__global__ void k_dedup_emit(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ len, const uint32_t* __restrict__ tag,
+                             uint32_t count, const uint32_t* __restrict__ first, const uint32_t* __restrict__ is_first,
+                             const uint32_t* __restrict__ uidx, uint32_t* __restrict__ asset_chunk_index,
+                             uint64_t* __restrict__ unique_hash, uint32_t* __restrict__ unique_len, uint32_t* __restrict__ unique_tag)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    asset_chunk_index[i] = uidx[first[i]];
+    if (is_first[i])
+    {
+        const uint32_t u = uidx[i];
+        unique_hash[u] = hash[i];
+        unique_len[u] = len[i];
+        unique_tag[u] = tag[i]; // tag of the first occurrence (src/longtail.c:2962)
+    }
+}
+
+void launch_dedup_insert(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st)
+{
+    if (!count) return;
+    k_dedup_insert<<<(count + 255) / 256, 256, 0, st>>>(d_hash, count, b.keys, b.vals, b.capacity);
+}
+
+void launch_dedup_lookup(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st)
+{
+    if (!count) return;
+    k_dedup_lookup<<<(count + 255) / 256, 256, 0, st>>>(d_hash, count, b.keys, b.vals, b.capacity, b.first, b.is_first);
+}
+
+void launch_dedup_emit(const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, const DedupBuffers& b,
+                       uint32_t* d_asset_chunk_index, uint64_t* d_unique_hash, uint32_t* d_unique_len, uint32_t* d_unique_tag,
+                       cudaStream_t st)
+{
+    if (!count) return;
+    k_dedup_emit<<<(count + 255) / 256, 256, 0, st>>>(d_hash, d_len, d_tag, count, b.first, b.is_first, b.uidx, d_asset_chunk_index,
+                                                      d_unique_hash, d_unique_len, d_unique_tag);
+}
+
+// ---------------------------------------------------------------- synthetic assets (bench / test inputs only)
+
+__global__ void k_synth_fill(uint8_t* __restrict__ dst, uint64_t len, lt_synth_spec spec, uint64_t asset_id, uint64_t offset)
+{
+    const uint64_t blocks = (len + 15) / 16;
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; b < blocks; b += stride)
+    {
+        const uint64_t off = offset + b * 16;
+        uint64_t key, base;
+        uint32_t cls;
+        lt_synth_segment(&spec, asset_id, off, &key, &base, &cls);
+        uint8_t tmp[16];
+        lt_synth_block16(key, (base + off % LT_SYNTH_SEGMENT_BYTES) / 16, cls, tmp);
+        if (b * 16 + 16 <= len && (((uintptr_t)dst) & 15) == 0)
+            *reinterpret_cast<uint4*>(dst + b * 16) = *reinterpret_cast<uint4*>(tmp);
+        else
+            for (uint64_t i = 0; i < 16 && b * 16 + i < len; ++i) dst[b * 16 + i] = tmp[i];
+    }
+}
+
+void launch_synth_fill(uint8_t* d_dst, uint64_t len, const lt_synth_spec_dev& s, uint64_t asset_id, uint64_t offset, cudaStream_t st)
+{
+    if (!len) return;
+    lt_synth_spec spec;
+    spec.seed = s.seed;
+    spec.shared_permille = s.shared_permille;
+    spec.pool_segments = s.pool_segments;
+    spec.class_mode = s.class_mode;
+    spec.reserved = 0;
+    uint64_t blocks = ((len + 15) / 16 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_synth_fill<<<(unsigned)blocks, 256, 0, st>>>(d_dst, len, spec, asset_id, offset);
+}
+
+} // namespace ltb
