@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of BASELINE.json: GiB/s of CreateVersionIndex (content-defined chunking + BLAKE3
+per chunk + dedup + VersionIndex) and the fraction of the HBM-read roofline.
+
+Workload (config.workload): BASELINE.json configs[1] — "1xB200: chunk+BLAKE3 only (no compression) on one 64 GiB synthetic
+file, 64 KiB target chunk size" (SURVEY.md §8d config 2): uniform-random bytes from the counter-based generator of
+include/lt_synth.h (seed 1), target_chunk_size 65536, tag 0.  With N GPUs every rank indexes its own 64 GiB file (weak
+scaling); the per-rank chunk tables are merged with one allgather and rank 0 builds the VersionIndex of all N files.
+
+A step = one full pass: chunk + hash every part, merge, content hashes, dedup, serialised VersionIndex copied to the host.
+  value  inputs already resident in HBM (CUDA events on the context stream, max over ranks)
+  e2e    the same verb through the C ABI with the asset bytes in pinned HOST memory, host->device copies inside the timing
+  roofline / cpu_baseline  as the task contract describes; see DESIGN.md §Measurement
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libref_shim.so: Longtail_CreateVersionIndex with the bikeshed
+JobAPI on all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GIB = 1 << 30
+TARGET_CHUNK_SIZE = 65536
+SEED = 1
+METRIC = "GiB/s end-to-end chunk+hash (CreateVersionIndex); % HBM roofline"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gib", type=float, default=64.0, help="size of the synthetic file per GPU (GiB)")
+    ap.add_argument("--e2e-gib", type=float, default=None, help="size of the host-resident file for the e2e leg (default: --gib, bounded by host RAM)")
+    ap.add_argument("--cpu-gib", type=float, default=8.0, help="bounded sample for the CPU baseline / the reference arm")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_sample(nbytes, threads):
+    """the first nbytes of the synthetic file, generated on the host (oracle/_ref/libsynth_host.so)"""
+    import ctypes as C
+
+    import numpy as np
+
+    import longtail_b200
+    path = os.path.join(ROOT, "oracle", "_ref", "libsynth_host.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    lib = C.CDLL(path)
+    buf = np.empty(nbytes, dtype=np.uint8)
+    spec = longtail_b200.SynthSpec(SEED, 0, 1, 0, 0)
+    lib.synth_fill_mt(C.byref(spec), C.c_uint64(0), C.c_uint64(0), buf.ctypes.data_as(C.c_void_p), C.c_uint64(nbytes), C.c_uint32(threads))
+    return buf
+
+
+def reference_pass(ref, data, workers):
+    """one Longtail_CreateVersionIndex of the unmodified reference over `data` as a single asset; -> seconds (wall, inside C)"""
+    _, secs = ref.create_version_index([("f00000.bin", data)], TARGET_CHUNK_SIZE, workers=workers, want_seconds=True)
+    return secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    ref = ol.Reference()
+    if not ref.available:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_shim.so missing (built from /root/reference by `make -C oracle ref`)"}))
+        return
+    cores = ref.cpu_count()
+    nbytes = int(args.cpu_gib * GIB)
+    data = host_sample(nbytes, cores)
+    for _ in range(args.warmup):
+        reference_pass(ref, data, cores)
+    t = [reference_pass(ref, data, cores) for _ in range(args.steps)]
+    total = sum(t)
+    value = nbytes * args.steps / total / GIB
+    sample = "first %.1f GiB of the %.0f GiB file, Longtail_CreateVersionIndex, bikeshed %d workers + caller" % (args.cpu_gib, args.gib, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "configs[1]: chunk+BLAKE3, one %.0f GiB synthetic file, target_chunk_size 65536 (CPU sample: %s)" % (args.gib, sample)},
+        "cpu_baseline": {"value": round(value, 4), "unit": "GiB/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import longtail_b200
+    from longtail_b200 import distributed as ltd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = longtail_b200.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    nbytes = int(args.gib * GIB)
+    part = TARGET_CHUNK_SIZE * 1024
+    mn, av, mx = longtail_b200.chunker_params(TARGET_CHUNK_SIZE)
+    arena = ctx.device_alloc(nbytes + 4096)
+    ctx.synth_fill(arena, nbytes, seed=SEED, asset_id=rank)
+    ctx.synchronize()
+
+    # the whole job: N files of nbytes each; this rank owns file `rank`
+    all_assets = longtail_b200.AssetList(["f%05d.bin" % r for r in range(world)], [nbytes] * world)
+    my_asset = longtail_b200.AssetList(["f%05d.bin" % rank], [nbytes])
+    jobs = ltd.plan_jobs([nbytes] * world, TARGET_CHUNK_SIZE)
+    my_jobs = [j for j in jobs if j[0] == rank]
+    ranges = [(start, size, 0) for _, start, size in my_jobs]
+    index_bytes = [0]
+
+    def step_resident():
+        if world == 1:
+            v = ctx.index_device_assets(arena, nbytes + 4096, my_asset, [0], None, target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
+            index_bytes[0] = len(v)
+            return v
+        t = ctx.chunk_ranges(arena, nbytes + 4096, ranges, mn, av, mx, want_host=False)
+        dh, ds, dt, n = ctx.resident_table()
+        with torch.cuda.stream(stream):
+            counts = torch.as_tensor(t["range_chunk_counts"].astype(np.int64), device="cuda")
+            hashes = torch.as_tensor(ltd.DeviceArray(dh, n, "<i8"), device="cuda")
+            sizes = torch.as_tensor(ltd.DeviceArray(ds, n, "<i4"), device="cuda")
+            tags = torch.as_tensor(ltd.DeviceArray(dt, n, "<i4"), device="cuda")
+            jc, gh, gs, gt = ltd.allgather_tables(counts, hashes, sizes, tags)
+            stream.synchronize()
+            if rank == 0:
+                acc = ltd.asset_chunk_counts(jobs, jc.cpu().numpy(), world)
+                v = ctx.build_version_index_device(all_assets, acc, gh.numel(), gh.data_ptr(), gs.data_ptr(), gt.data_ptr(),
+                                                   target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
+                index_bytes[0] = len(v)
+                return v
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """-> (device ms over `steps` calls of fn, max over ranks)"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- parity spot check before anything is timed: first 2 parts against the CPU checker
+    parity = "skipped"
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        check_n = min(nbytes, 2 * part)
+        got = ctx.chunk_ranges(arena, nbytes + 4096, [(o, min(part, check_n - o), 0) for o in range(0, check_n, part)], mn, av, mx)
+        host = ctx.to_host(arena, check_n)
+        ref = ol.Reference()
+        checker = ref if ref.available else ol.Oracle()
+        exp = np.concatenate([checker.chunk(host[o:o + part], mn, av, mx) for o in range(0, check_n, part)])
+        offs = np.concatenate([[0], np.cumsum(exp.astype(np.uint64))[:-1]]).astype(np.uint64)
+        ok = got["sizes"].tolist() == exp.tolist() and got["hashes"].tolist() == checker.hash_segments(ol.HASH_BLAKE3, host, offs, exp).tolist()
+        parity = ("bit-exact vs %s on the first %d MiB" % ("reference" if ref.available else "oracle", check_n >> 20)) if ok else "MISMATCH"
+        if not ok:
+            raise SystemExit("parity check failed: the CUDA path differs from the CPU checker")
+
+    # ---- resident-in-HBM measurement
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = ctx.launch_count
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.finish() if rank == 0 else None
+    ctx.profile_enable(False)
+    prof = ctx.profile_read()
+    launches = ctx.launch_count - launches0
+    value = world * nbytes * args.steps / (ms / 1e3) / GIB
+
+    # ---- end to end from pinned host memory
+    e2e = None
+    host_buf = None
+    if not args.no_e2e:
+        import psutil
+        avail = psutil.virtual_memory().available
+        want = args.e2e_gib if args.e2e_gib is not None else args.gib
+        e2e_bytes = int(min(want * GIB, 0.7 * avail / max(world, 1))) // part * part
+        e2e_bytes = max(e2e_bytes, part)
+        host_buf = ctx.pinned_alloc(e2e_bytes)
+        ctx.lib.lt_b200_copy_to_host(ctx.handle, host_buf.ctypes.data, arena, e2e_bytes)
+        e2e_asset = longtail_b200.AssetList(["f%05d.bin" % rank], [e2e_bytes])
+
+        def step_e2e():
+            v = ctx.index_host_assets(e2e_asset, [host_buf], None, target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
+            index_bytes[0] = len(v)
+
+        for _ in range(1):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(world * e2e_bytes * args.steps / float(wall.item()) / GIB, 3), "unit": "GiB/s",
+               "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": index_bytes[0],
+               "note": "lt_b200_index_host_assets over a %.1f GiB pinned host buffer per GPU, wall clock" % (e2e_bytes / GIB)}
+
+    # ---- CPU baseline (rank 0, N == 1): the unmodified reference on a bounded sample of the same bytes
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_lib as ol
+        ref = ol.Reference()
+        cpu_bytes = int(min(args.cpu_gib * GIB, nbytes))
+        if host_buf is not None and host_buf.size >= cpu_bytes:
+            sample = host_buf[:cpu_bytes]
+        else:
+            sample = ctx.to_host(arena, cpu_bytes)
+        if ref.available:
+            cores = ref.cpu_count()
+            secs = reference_pass(ref, sample, cores)
+            cpu = {"value": round(cpu_bytes / secs / GIB, 4), "unit": "GiB/s", "cores": cores, "kind": "reference",
+                   "sample": "first %.1f GiB of the file, Longtail_CreateVersionIndex, bikeshed %d workers + caller, 1 pass" % (cpu_bytes / GIB, cores)}
+        else:
+            o = ol.Oracle()
+            small = sample[:min(cpu_bytes, 1 << 30)]
+            t0 = time.perf_counter()
+            o.create_version_index([("f00000.bin", small)], TARGET_CHUNK_SIZE)
+            secs = time.perf_counter() - t0
+            cpu = {"value": round(small.size / secs / GIB, 4), "unit": "GiB/s", "cores": 1, "kind": "port",
+                   "sample": "first %.1f GiB of the file, oracle/lt_oracle.c single thread" % (small.size / GIB)}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # dominant kernel = the one with the largest share of device time
+        name = max(prof, key=lambda k: prof[k][0])
+        kms, kn, kbytes = prof[name]
+        achieved = (kbytes / max(kn, 1)) / ((kms / max(kn, 1)) / 1e3) / 1e9 if kms > 0 else 0.0
+        shares = {k: round(v[0] / (ms / 1.0), 4) for k, v in prof.items()}
+        per_kernel = {k: {"ms_per_launch": round(v[0] / max(v[1], 1), 4), "launches": v[1],
+                          "GBps": round((v[2] / max(v[1], 1)) / ((v[0] / max(v[1], 1)) / 1e3) / 1e9, 1) if v[0] > 0 else None} for k, v in prof.items()}
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "GiB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: chunk+BLAKE3 (no compression), one %.0f GiB synthetic file per GPU, target_chunk_size 65536"
+                                   % args.gib, "bytes_per_gpu": nbytes, "l2": "inputs (%.0f GiB) far larger than L2; no flush needed" % args.gib,
+                       "parity": parity, "index_bytes": index_bytes[0]},
+            "hbm_roofline_frac_whole_step": round(value * GIB / 1e9 / world / peak, 4),
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "share_of_step": shares, "per_kernel": per_kernel,
+                         "note": "algorithmic bytes = 1 B read per asset byte (SURVEY.md §8d); both hot kernels are integer-issue bound, see DESIGN.md"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if host_buf is not None:
+        ctx.pinned_free(host_buf)
+    ctx.device_free(arena)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

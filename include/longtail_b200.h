@@ -153,6 +153,18 @@ LT_B200_EXPORT int lt_b200_build_version_index(lt_b200_context* context, const s
                                                uint32_t hash_type, uint32_t target_chunk_size,
                                                const void** out_buffer, uint64_t* out_size);
 
+/* Device addresses of the chunk table left resident by the last lt_b200_chunk_ranges call (u64 hashes, u32 sizes, u32 tags),
+ * e.g. to hand them to an NCCL allgather without a host round trip. */
+LT_B200_EXPORT int lt_b200_resident_table(lt_b200_context* context, void** out_device_hashes, void** out_device_sizes,
+                                          void** out_device_tags, uint32_t* out_chunk_count);
+
+/* lt_b200_build_version_index with the (merged) chunk table given as DEVICE arrays. */
+LT_B200_EXPORT int lt_b200_build_version_index_device(lt_b200_context* context, const struct lt_b200_assets* assets,
+                                                      const uint32_t* asset_chunk_counts, uint32_t chunk_count,
+                                                      const void* device_chunk_hashes, const void* device_chunk_sizes,
+                                                      const void* device_chunk_tags, uint32_t hash_type, uint32_t target_chunk_size,
+                                                      const void** out_buffer, uint64_t* out_size);
+
 /* Whole CreateVersionIndex over assets resident in one device arena: splits every asset into parts of
  * target_chunk_size*1024 bytes (src/longtail.c:2396-2437), chunks + hashes them and builds the index.
  * asset_arena_offsets[a] (multiples of 16) locate asset a's bytes in the arena; asset_tags may be NULL. */

@@ -81,8 +81,17 @@ def load_library():
                                                 C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.lt_b200_index_host_assets.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                               C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.lt_b200_resident_table.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    lib.lt_b200_build_version_index_device.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                       C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.lt_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.lt_b200_profile_reset.argtypes = [C.c_void_p]
+    lib.lt_b200_profile_read.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
+
+
+KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge"}
 
 
 def chunker_params(target_chunk_size):
@@ -189,6 +198,37 @@ class Context:
     def synth_fill(self, dptr, nbytes, seed, asset_id=0, offset=0, shared_permille=0, pool_segments=1, class_mode=0):
         spec = SynthSpec(int(seed), int(shared_permille), int(pool_segments), int(class_mode), 0)
         self._check(self.lib.lt_b200_synth_fill(self.handle, C.c_void_p(dptr), int(nbytes), C.byref(spec), int(asset_id), int(offset)), "synth_fill")
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.lt_b200_profile_enable(self.handle, 1 if on else 0), "profile_enable")
+
+    def profile_reset(self):
+        self._check(self.lib.lt_b200_profile_reset(self.handle), "profile_reset")
+
+    def profile_read(self):
+        """-> {kernel name: (total ms, launches, algorithmic bytes)} accumulated since the last reset"""
+        out = {}
+        for k, name in KERNEL_NAMES.items():
+            ms, n, b = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+            self._check(self.lib.lt_b200_profile_read(self.handle, k, C.byref(ms), C.byref(n), C.byref(b)), "profile_read")
+            out[name] = (ms.value, int(n.value), int(b.value))
+        return out
+
+    def resident_table(self):
+        """device addresses (hashes u64, sizes u32, tags u32) and length of the table left by the last chunk_ranges call"""
+        h, s, t, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32(0)
+        self._check(self.lib.lt_b200_resident_table(self.handle, C.byref(h), C.byref(s), C.byref(t), C.byref(n)), "resident_table")
+        return h.value, s.value, t.value, int(n.value)
+
+    def build_version_index_device(self, assets, asset_chunk_counts, chunk_count, d_hashes, d_sizes, d_tags, hash_type=HASH_BLAKE3,
+                                   target_chunk_size=32768, copy=True):
+        st = assets.as_struct()
+        counts = np.ascontiguousarray(asset_chunk_counts, dtype=np.uint32)
+        buf, size = C.c_void_p(), C.c_uint64(0)
+        self._check(self.lib.lt_b200_build_version_index_device(self.handle, C.byref(st), counts.ctypes.data_as(C.c_void_p), int(chunk_count),
+                                                                C.c_void_p(d_hashes), C.c_void_p(d_sizes), C.c_void_p(d_tags), int(hash_type),
+                                                                int(target_chunk_size), C.byref(buf), C.byref(size)), "build_version_index_device")
+        return self._result(buf, size, copy)
 
     # ---- layer 1
     def chunk_ranges(self, dptr, arena_size, ranges, min_size, avg_size, max_size, hash_type=HASH_BLAKE3, want_host=True):

@@ -214,8 +214,8 @@ int make_chunk_params(lt_b200_context* c, uint32_t mn, uint32_t av, uint32_t mx,
     cp->d_odd_inv = inverse_mod_2_32(odd);
     cp->d_odd_thr = 0xffffffffu / odd;
     uint32_t expect = (uint32_t)SCAN_TILE / d + 1;
-    uint32_t slots = (8 * expect + 32 + 31) & ~31u;
-    if (slots > 8192) slots = 8192;
+    uint32_t slots = (6 * expect + 2 + 7) & ~7u;
+    if (slots > 4096) slots = 4096;
     cp->slots = slots;
     return 0;
 }
@@ -458,7 +458,7 @@ extern "C" int lt_b200_chunk_ranges(lt_b200_context* c, const uint8_t* d_arena, 
     const uint32_t num_tiles = (uint32_t)tiles;
 
     TRY(ws_reserve(c, WS_PARTS, sizeof(PartDesc) * (size_t)range_count));
-    TRY(ws_reserve(c, WS_TILE_DESC, sizeof(uint2) * (size_t)num_tiles));
+    TRY(ws_reserve(c, WS_TILE_DESC, sizeof(uint32_t) * (size_t)num_tiles));
     TRY(ws_reserve(c, WS_TILE_COUNT, sizeof(uint32_t) * (size_t)num_tiles));
     TRY(ws_reserve(c, WS_TILE_SLOTS, sizeof(uint32_t) * (size_t)num_tiles * cp.slots));
     TRY(ws_reserve(c, WS_CAND, sizeof(uint32_t) * (size_t)num_tiles * cp.slots));
@@ -469,10 +469,10 @@ extern "C" int lt_b200_chunk_ranges(lt_b200_context* c, const uint8_t* d_arena, 
     TRY(ws_reserve(c, WS_SCAN_TMP, sizeof(uint32_t) * scan_tmp_words(range_count)));
 
     CU(cudaMemcpyAsync(ws<PartDesc>(c, WS_PARTS), h_parts, sizeof(PartDesc) * (size_t)range_count, cudaMemcpyHostToDevice, c->stream));
-    launch_tile_desc(ws<PartDesc>(c, WS_PARTS), range_count, ws<uint2>(c, WS_TILE_DESC), c->stream);
+    launch_tile_part(ws<PartDesc>(c, WS_PARTS), range_count, num_tiles, ws<uint32_t>(c, WS_TILE_DESC), c->stream);
     {
         ProfScope ps(c, LT_B200_KERNEL_HPCDC_SCAN, bytes);
-        CU(launch_hpcdc_scan(d_arena, ws<PartDesc>(c, WS_PARTS), ws<uint2>(c, WS_TILE_DESC), num_tiles, cp, c->d_table,
+        CU(launch_hpcdc_scan(d_arena, ws<PartDesc>(c, WS_PARTS), ws<uint32_t>(c, WS_TILE_DESC), num_tiles, cp, c->d_table,
                              ws<uint32_t>(c, WS_TILE_COUNT), ws<uint32_t>(c, WS_TILE_SLOTS), c->sm_count, c->stream));
     }
     {
@@ -730,6 +730,32 @@ extern "C" int lt_b200_build_version_index(lt_b200_context* c, const lt_b200_ass
     }
     return build_index_from_device_table(c, a, asset_chunk_counts, chunk_count, ws<uint64_t>(c, WS_TAB_HASH), ws<uint32_t>(c, WS_TAB_LEN),
                                          ws<uint32_t>(c, WS_TAB_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+}
+
+extern "C" int lt_b200_resident_table(lt_b200_context* c, void** out_hashes, void** out_sizes, void** out_tags, uint32_t* out_count)
+{
+    if (!c || !out_hashes || !out_sizes || !out_tags || !out_count) return EINVAL;
+    *out_hashes = ws<void>(c, WS_CHUNK_HASH);
+    *out_sizes = ws<void>(c, WS_CHUNK_LEN);
+    *out_tags = ws<void>(c, WS_CHUNK_TAG);
+    *out_count = c->table_chunks;
+    return 0;
+}
+
+extern "C" int lt_b200_build_version_index_device(lt_b200_context* c, const lt_b200_assets* a, const uint32_t* asset_chunk_counts,
+                                                  uint32_t chunk_count, const void* d_hashes, const void* d_sizes, const void* d_tags,
+                                                  uint32_t hash_type, uint32_t target_chunk_size, const void** out_buffer, uint64_t* out_size)
+{
+    if (!c || !out_buffer || !out_size) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    TRY(validate_assets(c, a));
+    if (a->asset_count && !asset_chunk_counts) return EINVAL;
+    if (chunk_count && (!d_hashes || !d_sizes || !d_tags)) return EINVAL;
+    if (((uintptr_t)d_hashes) & 15u) return fail(c, EINVAL, "device hash array must be 16-byte aligned");
+    return build_index_from_device_table(c, a, asset_chunk_counts, chunk_count, static_cast<const uint64_t*>(d_hashes),
+                                         static_cast<const uint32_t*>(d_sizes), static_cast<const uint32_t*>(d_tags), hash_type,
+                                         target_chunk_size, out_buffer, out_size);
 }
 
 extern "C" int lt_b200_index_device_assets(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, const lt_b200_assets* a,

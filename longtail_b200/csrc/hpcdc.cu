@@ -3,10 +3,10 @@
 // Re-design of lib/hpcdcchunker/longtail_hpcdcchunker.c:225-310 (Longtail_HPCDCNextChunk) as driven by
 // src/longtail.c:2231-2296 (DynamicChunking) for a whole batch of parts at once:
 //
-//   k_tile_desc   tile -> (part, tile-in-part) table for the batch
+//   k_tile_part   tile -> part table for the batch
 //   k_hpcdc_scan  every position's 48-byte Buzhash (the window hash is a pure function of the trailing 48
 //                 bytes) is evaluated once; positions with hash % d == d-1 ("candidates") are
-//                 written per 64 KiB tile, sorted, to a small slot list
+//                 written per 8 KiB tile (one warp per tile), sorted, to a small slot list
 //   k_hpcdc_walk  one CTA per part: compacts the part's candidates and walks the min / max selection rule
 //                 (:257-264 left <= min, :285 lim = min(left, max), first hit in [min+1, lim]) sequentially
 //                 over the sparse list, 32 candidates per step
@@ -17,46 +17,57 @@
 
 namespace ltb {
 
-__global__ void k_tile_desc(const PartDesc* __restrict__ parts, uint32_t part_count, uint2* __restrict__ tile_desc)
+// tile -> part lookup table for the batch (binary search over the parts' first-tile indices)
+__global__ void k_tile_part(const PartDesc* __restrict__ parts, uint32_t part_count, uint32_t num_tiles, uint32_t* __restrict__ tile_part)
 {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= part_count) return;
-    PartDesc pd = parts[p];
-    uint32_t n = (pd.size + SCAN_TILE - 1) / SCAN_TILE;
-    for (uint32_t t = 0; t < n; ++t) tile_desc[pd.tile_start + t] = make_uint2(p, t);
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    uint32_t lo = 0, hi = part_count; // parts[lo].tile_start <= t < parts[hi].tile_start (hi == part_count: +inf)
+    while (hi - lo > 1)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&parts[mid].tile_start) <= t) lo = mid; else hi = mid;
+    }
+    // empty parts share their tile_start with the next part: the search lands on the last of them, step back is not needed
+    // because `<=` always prefers the right-most part with tile_start <= t, which is the one that owns tiles
+    tile_part[t] = lo;
 }
 
-// exact re-evaluation of one 16-byte group after the fast divisibility filter fired (rare)
-__device__ __noinline__ void scan_group_exact(uint32_t in_addr, uint32_t out_addr, uint32_t h, uint32_t d,
-                                              const uint32_t* __restrict__ g_table, uint32_t* bitmap_row, uint32_t first_bit)
+// Re-evaluation of one 8-byte group after the group-level divisibility filter fired (about one group in 400 at the
+// default parameters).  Runs divergent, so it is kept short: same table lookups as the main loop, the filter again per byte
+// and the true `%` only where the filter passes.
+__device__ __noinline__ void scan_group_exact(uint32_t in_addr, uint32_t out_addr, uint32_t h, uint32_t d, uint32_t d_odd_inv,
+                                              uint32_t d_odd_thr, uint32_t tab_lane, uint32_t bitmap_row, uint32_t first_bit)
 {
-    for (uint32_t k = 0; k < 16; ++k)
+#pragma unroll 4
+    for (uint32_t k = 0; k < 8; ++k)
     {
         uint32_t in, out;
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(in) : "r"(in_addr + k));
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(out) : "r"(out_addr + k));
-        h = rotl32(h, 1) ^ rotl32(__ldg(&g_table[out]), 16) ^ __ldg(&g_table[in]); // longtail_hpcdcchunker.c:295-297
-        if (h % d == d - 1)                                                       // :298
+        h = rotl32(h, 1) ^ lds32(tab_lane + 128u + (out << 8)) ^ lds32(tab_lane + (in << 8)); // longtail_hpcdcchunker.c:295-297
+        if (h * d_odd_inv + d_odd_inv <= d_odd_thr && h % d == d - 1)                          // :298
         {
             uint32_t bit = first_bit + k;
-            bitmap_row[bit >> 5] |= 1u << (bit & 31);
+            uint32_t a = bitmap_row + (bit >> 5) * 4u;
+            uint32_t v = lds32(a) | (1u << (bit & 31));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
         }
     }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
-k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ parts, const uint2* __restrict__ tile_desc,
+k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ parts, const uint32_t* __restrict__ tile_part,
              uint32_t num_tiles, ChunkParams cp, const uint32_t* __restrict__ g_table,
              uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_slots)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t* s_table = reinterpret_cast<uint32_t*>(smem);
-    uint8_t* s_rows = smem + SCAN_TABLE_BYTES;
-    uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(smem + SCAN_TABLE_BYTES + 2 * SCAN_ROWS_BYTES);
-    uint32_t* s_warp = s_bitmap + SCAN_THREADS * (SCAN_SEG / 32);
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t lane4 = (tid & 31u) * 4u;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane4 = lane * 4u;
 
     // bank-replicated substitution table: entry v occupies 256 B = 32 lanes x T[v] then 32 lanes x rotl(T[v],16),
     // so lane l always reads bank l and a lookup is conflict free for any byte values
@@ -65,51 +76,59 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
         uint32_t t = __ldg(&g_table[i >> 6]);
         s_table[i] = (i & 32u) ? rotl32(t, 16) : t;
     }
-    for (uint32_t i = tid; i < SCAN_THREADS * (SCAN_SEG / 32); i += SCAN_THREADS) s_bitmap[i] = 0;
+    uint8_t* s_mine = smem + SCAN_TABLE_BYTES + warp * SCAN_WARP_BYTES;
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_mine + SCAN_ROWS_BYTES) + lane * (SCAN_SEG / 32);
+#pragma unroll
+    for (int w = 0; w < SCAN_SEG / 32; ++w) s_bits[w] = 0;
+    __syncthreads(); // the only block-wide barrier: the table is ready
 
-    const uint32_t rows_addr = smem_u32(s_rows);
+    const uint32_t tab = smem_u32(s_table);
+    const uint32_t rows = smem_u32(s_mine);
+    const uint32_t my = rows + (lane + 1u) * SCAN_ROW;
+    const uint32_t prev = my - SCAN_ROW + (SCAN_SEG - SCAN_WINDOW);
+    const uint32_t bits_addr = smem_u32(s_bits);
+    const uint32_t stride = gridDim.x * SCAN_WARPS;
 
-    auto issue_tile = [&](uint32_t tile, uint32_t buf) {
-        const uint2 td = tile_desc[tile];
-        const PartDesc pd = parts[td.x];
-        const uint32_t tile_off = td.y * (uint32_t)SCAN_TILE;
+    uint32_t tile = blockIdx.x * SCAN_WARPS + warp;
+    uint32_t part_idx = tile < num_tiles ? __ldg(&tile_part[tile]) : 0u;
+    for (; tile < num_tiles; tile += stride)
+    {
+        const PartDesc pd = parts[part_idx];
+        const uint32_t tip = tile - pd.tile_start;
+        const uint32_t tile_off = tip * (uint32_t)SCAN_TILE;
         const uint8_t* src = arena + pd.data_off + tile_off;
-        const uint32_t dst = rows_addr + buf * SCAN_ROWS_BYTES;
+        // stage the tile: 512 sixteen-byte pieces, consecutive lanes fetch consecutive pieces (coalesced); bytes past the
+        // end of the part are zero-filled
 #pragma unroll 4
-        for (uint32_t i = tid; i < SCAN_TILE / 16; i += SCAN_THREADS)
+        for (uint32_t i = lane; i < SCAN_TILE / 16; i += 32)
         {
             uint32_t off = tile_off + i * 16u;
             uint32_t nb = pd.size > off ? min(16u, pd.size - off) : 0u;
-            cp_async16(dst + ((i >> 4) + 1u) * SCAN_ROW + (i & 15u) * 16u, nb ? src + i * 16u : arena, nb);
+            cp_async16(rows + ((i >> 4) + 1u) * SCAN_ROW + (i & 15u) * 16u, nb ? src + i * 16u : arena, nb);
         }
-        if (tid < 3)
+        if (lane < 3)
         {
             // 48-byte halo in front of the tile; a part's first tile sees zeros (those positions can never be cuts:
             // a cut needs at least min >= 48 bytes of the same part in front of it)
-            cp_async16(dst + (SCAN_SEG - SCAN_WINDOW) + tid * 16u, td.y ? src - SCAN_WINDOW + tid * 16u : arena, td.y ? 16u : 0u);
+            cp_async16(rows + (SCAN_SEG - SCAN_WINDOW) + lane * 16u, tip ? src - SCAN_WINDOW + lane * 16u : arena, tip ? 16u : 0u);
         }
         cp_async_commit();
-    };
-
-    uint32_t tile = blockIdx.x;
-    uint32_t buf = 0;
-    if (tile < num_tiles) issue_tile(tile, 0);
-
-    for (; tile < num_tiles; tile += gridDim.x, buf ^= 1u)
-    {
-        const uint32_t next = tile + gridDim.x;
+        // while the copy is in flight: pull the next tile of this warp towards L2 and fetch its descriptor
+        const uint32_t next = tile + stride;
+        uint32_t next_part = 0;
         if (next < num_tiles)
         {
-            issue_tile(next, buf ^ 1u);
-            cp_async_wait<1>();
+            next_part = __ldg(&tile_part[next]);
+            const uint64_t noff = (uint64_t)tile_off + (uint64_t)stride * SCAN_TILE + lane * 256u;
+            if (noff + 256u <= pd.size) // only when the next tile lies in the same part (the common case)
+            {
+                const uint8_t* nsrc = arena + pd.data_off + noff;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 128u));
+            }
         }
-        else
-            cp_async_wait<0>();
-        __syncthreads();
-
-        const uint32_t my = rows_addr + buf * SCAN_ROWS_BYTES + (tid + 1u) * SCAN_ROW;
-        const uint32_t prev = my - SCAN_ROW + (SCAN_SEG - SCAN_WINDOW);
-        const uint32_t tab = smem_u32(s_table);
+        cp_async_wait<0>();
+        __syncwarp();
 
         // seed: hash of the 48 bytes in front of my segment (longtail_hpcdcchunker.c:273-279)
         uint32_t h = 0;
@@ -126,7 +145,6 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
             }
         }
 
-        uint32_t* my_bits = s_bitmap + tid * (SCAN_SEG / 32);
 #pragma unroll 2
         for (int j = 0; j < SCAN_SEG / 16; ++j)
         {
@@ -136,75 +154,74 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
             const uint4 cout = lds128(out_addr);
             const uint32_t wi[4] = {cin.x, cin.y, cin.z, cin.w};
             const uint32_t wo[4] = {cout.x, cout.y, cout.z, cout.w};
-            const uint32_t h0 = h;
-            uint32_t best = 0xffffffffu;
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
+            for (int g = 0; g < 2; ++g)
             {
-                const uint32_t sel = 0x5504 | ((k & 3) << 4);
-                uint32_t tin = lds32(tab + __byte_perm(wi[k >> 2], lane4, sel));
-                uint32_t tout = lds32(tab + 128u + __byte_perm(wo[k >> 2], lane4, sel));
-                h = rotl32(h, 1) ^ tout ^ tin;              // :295-297 with rotl(T[out],48&31) pre-rotated in the table
-                best = min(best, h * cp.d_odd_inv + cp.d_odd_inv); // (h+1)/odd(d) exact-division test, superset of :298
+                const uint32_t h0 = h;
+                uint32_t best = 0xffffffffu;
+#pragma unroll
+                for (int k = 8 * g; k < 8 * g + 8; ++k)
+                {
+                    const uint32_t sel = 0x5504 | ((k & 3) << 4);
+                    uint32_t tin = lds32(tab + __byte_perm(wi[k >> 2], lane4, sel));
+                    uint32_t tout = lds32(tab + 128u + __byte_perm(wo[k >> 2], lane4, sel));
+                    h = rotl32(h, 1) ^ tout ^ tin;              // :295-297 with rotl(T[out],48&31) pre-rotated in the table
+                    best = min(best, h * cp.d_odd_inv + cp.d_odd_inv); // (h+1)/odd(d) exact-division test, superset of :298
+                }
+                if (best <= cp.d_odd_thr)
+                    scan_group_exact(in_addr + 8 * g, out_addr + 8 * g, h0, cp.d, cp.d_odd_inv, cp.d_odd_thr, tab + lane4, bits_addr, 16 * j + 8 * g);
             }
-            if (best <= cp.d_odd_thr) scan_group_exact(in_addr, out_addr, h0, cp.d, g_table, my_bits, 16 * j);
         }
-        __syncthreads();
+        __syncwarp(); // every lane is done with the rows: the next iteration may overwrite them
 
-        // ordered compaction of this tile's candidate bits into its slot list
-        const uint2 td = tile_desc[tile];
-        const uint32_t part_size = parts[td.x].size;
-        const uint32_t seg_first = td.y * (uint32_t)SCAN_TILE + tid * SCAN_SEG; // part-relative position of my first byte
+        // ordered compaction of this tile's candidate bits into its slot list (lane order == position order)
+        const uint32_t seg_first = tile_off + lane * SCAN_SEG; // part-relative position of my first byte
         uint32_t words[SCAN_SEG / 32];
         uint32_t cnt = 0;
 #pragma unroll
         for (int w = 0; w < SCAN_SEG / 32; ++w)
         {
-            uint32_t v = my_bits[w];
-            my_bits[w] = 0;
+            uint32_t v = s_bits[w];
             // a cut after byte q is position q+1; keep it only inside the part
             uint32_t first = seg_first + 32 * w + 1;
-            if (first > part_size) v = 0;
-            else if (first + 31 > part_size) v &= (1u << (part_size - first + 1)) - 1u;
+            if (first > pd.size) v = 0;
+            else if (first + 31 > pd.size) v &= (1u << (pd.size - first + 1)) - 1u;
             words[w] = v;
             cnt += __popc(v);
         }
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((tid & 31) >= o) incl += t;
-        }
-        if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-        __syncthreads();
-        uint32_t base = incl - cnt;
+        const uint32_t any = __ballot_sync(0xffffffffu, cnt != 0);
         uint32_t total = 0;
-#pragma unroll
-        for (int w = 0; w < SCAN_THREADS / 32; ++w)
+        if (any)
         {
-            uint32_t v = s_warp[w];
-            if (w < (int)(tid >> 5)) base += v;
-            total += v;
-        }
-        if (cnt)
-        {
-            uint32_t* out = tile_slots + (size_t)tile * cp.slots;
+            uint32_t incl = cnt;
 #pragma unroll
-            for (int w = 0; w < SCAN_SEG / 32; ++w)
+            for (int o = 1; o < 32; o <<= 1)
             {
-                uint32_t v = words[w];
-                while (v)
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = incl - cnt;
+            if (cnt)
+            {
+                uint32_t* out = tile_slots + (size_t)tile * cp.slots;
+#pragma unroll
+                for (int w = 0; w < SCAN_SEG / 32; ++w)
                 {
-                    uint32_t b = __ffs(v) - 1;
-                    v &= v - 1;
-                    if (base < cp.slots) out[base] = seg_first + 32 * w + b + 1;
-                    ++base;
+                    uint32_t v = words[w];
+                    s_bits[w] = 0;
+                    while (v)
+                    {
+                        uint32_t b = __ffs(v) - 1;
+                        v &= v - 1;
+                        if (base < cp.slots) out[base] = seg_first + 32 * w + b + 1;
+                        ++base;
+                    }
                 }
             }
         }
-        if (tid == 0) tile_count[tile] = total;
-        __syncthreads();
+        if (lane == 0) tile_count[tile] = total;
+        part_idx = next_part;
     }
 }
 
@@ -365,13 +382,13 @@ __global__ void k_compact_chunks(const PartDesc* __restrict__ parts, const uint3
 
 // ---------------------------------------------------------------- host launchers
 
-void launch_tile_desc(const PartDesc* d_parts, uint32_t part_count, uint2* d_tile_desc, cudaStream_t st)
+void launch_tile_part(const PartDesc* d_parts, uint32_t part_count, uint32_t num_tiles, uint32_t* d_tile_part, cudaStream_t st)
 {
-    if (!part_count) return;
-    k_tile_desc<<<(part_count + 127) / 128, 128, 0, st>>>(d_parts, part_count, d_tile_desc);
+    if (!part_count || !num_tiles) return;
+    k_tile_part<<<(num_tiles + 255) / 256, 256, 0, st>>>(d_parts, part_count, num_tiles, d_tile_part);
 }
 
-cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint2* d_tile_desc, uint32_t num_tiles,
+cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint32_t* d_tile_part, uint32_t num_tiles,
                               const ChunkParams& cp, const uint32_t* d_table, uint32_t* d_tile_count, uint32_t* d_tile_slots,
                               int sm_count, cudaStream_t st)
 {
@@ -383,8 +400,9 @@ cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, c
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    uint32_t grid = num_tiles < (uint32_t)sm_count ? num_tiles : (uint32_t)sm_count;
-    k_hpcdc_scan<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(d_arena, d_parts, d_tile_desc, num_tiles, cp, d_table, d_tile_count, d_tile_slots);
+    uint32_t grid = (num_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
+    if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
+    k_hpcdc_scan<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(d_arena, d_parts, d_tile_part, num_tiles, cp, d_table, d_tile_count, d_tile_slots);
     return cudaGetLastError();
 }
 

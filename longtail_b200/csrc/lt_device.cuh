@@ -7,17 +7,20 @@
 namespace ltb {
 
 // ---------------------------------------------------------------- geometry of the Buzhash scan
-// One CTA scans one tile.  Every thread owns SCAN_SEG contiguous bytes; rows are padded by 16 B in
-// shared memory so that the 32 lanes' 16-byte reads fall into distinct bank groups.
-constexpr int SCAN_THREADS = 256;
+// One WARP scans one tile, independently of every other warp (no block barriers in the steady state).  Every lane owns
+// SCAN_SEG contiguous bytes; rows are padded by 16 B in shared memory so that the 32 lanes' 16-byte reads fall into
+// distinct bank groups.  16 warps and the 64 KiB bank-replicated table share one SM.
+constexpr int SCAN_WARPS = 16;
+constexpr int SCAN_THREADS = SCAN_WARPS * 32;
 constexpr int SCAN_SEG = 256;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_SEG; // 65536 bytes of asset data per tile
+constexpr int SCAN_TILE = 32 * SCAN_SEG;           // 8192 bytes of asset data per (warp) tile
 constexpr int SCAN_ROW = SCAN_SEG + 16;
 constexpr int SCAN_WINDOW = 48;                    // lib/hpcdcchunker/longtail_hpcdcchunker.c:12
 constexpr int SCAN_TABLE_BYTES = 256 * 256;        // 256 entries x (32 lanes x T, 32 lanes x rotl16(T))
-constexpr int SCAN_ROWS_BYTES = (SCAN_THREADS + 1) * SCAN_ROW;
-constexpr int SCAN_BITMAP_BYTES = SCAN_THREADS * (SCAN_SEG / 32) * 4;
-constexpr int SCAN_SMEM_BYTES = SCAN_TABLE_BYTES + 2 * SCAN_ROWS_BYTES + SCAN_BITMAP_BYTES + 64;
+constexpr int SCAN_ROWS_BYTES = 33 * SCAN_ROW;     // halo row + 32 lane rows
+constexpr int SCAN_BITMAP_BYTES = 32 * (SCAN_SEG / 32) * 4;
+constexpr int SCAN_WARP_BYTES = SCAN_ROWS_BYTES + SCAN_BITMAP_BYTES;
+constexpr int SCAN_SMEM_BYTES = SCAN_TABLE_BYTES + SCAN_WARPS * SCAN_WARP_BYTES;
 
 constexpr uint32_t CAND_OVERFLOW = 0x80000000u;    // dense-list marker: tile whose slot list overflowed
 

@@ -6,8 +6,8 @@
 namespace ltb {
 
 // ---- hpcdc.cu
-void launch_tile_desc(const PartDesc* d_parts, uint32_t part_count, uint2* d_tile_desc, cudaStream_t st);
-cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint2* d_tile_desc, uint32_t num_tiles,
+void launch_tile_part(const PartDesc* d_parts, uint32_t part_count, uint32_t num_tiles, uint32_t* d_tile_part, cudaStream_t st);
+cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint32_t* d_tile_part, uint32_t num_tiles,
                               const ChunkParams& cp, const uint32_t* d_table, uint32_t* d_tile_count, uint32_t* d_tile_slots,
                               int sm_count, cudaStream_t st);
 void launch_hpcdc_walk(const uint8_t* d_arena, const PartDesc* d_parts, uint32_t part_count, const ChunkParams& cp,
