@@ -66,7 +66,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -79,6 +79,7 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
+        # under load = the SM clock samples of the upper half (idle samples before the first step would drag the median down)
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
         mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
         reasons = set()
@@ -234,14 +235,15 @@ def run_b200(args):
             raise SystemExit("parity check failed: the CUDA path differs from the CPU checker")
 
     # ---- resident-in-HBM measurement
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)  # let nvidia-smi come up; it then samples through the warm-up and the timed region
     for _ in range(max(args.warmup, 3)):
         step_resident()
     launches0 = ctx.launch_count
     ctx.profile_reset()
     ctx.profile_enable(True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ms = timed(step_resident, args.steps)
     clocks = sampler.finish() if rank == 0 else None
     ctx.profile_enable(False)

@@ -22,11 +22,15 @@ constexpr uint32_t IV0 = 0x6A09E667u, IV1 = 0xBB67AE85u, IV2 = 0x3C6EF372u, IV3 
 constexpr uint32_t IV4 = 0x510E527Fu, IV5 = 0x9B05688Cu, IV6 = 0x1F83D9ABu, IV7 = 0x5BE0CD19u; // ext/blake3_impl.h:76-78
 constexpr uint32_t F_CHUNK_START = 1, F_CHUNK_END = 2, F_PARENT = 4, F_ROOT = 8;                // ext/blake3_impl.h:13-21
 
-#define B3_G(a, b, c, d, x, y)                        \
-    a = a + b + (x); d = __byte_perm(d ^ a, 0, 0x1032); \
-    c = c + d;       b = rotr32(b ^ c, 12);            \
-    a = a + b + (y); d = __byte_perm(d ^ a, 0, 0x0321); \
-    c = c + d;       b = rotr32(b ^ c, 7);
+// The G function is 14 integer ops; IADD3 / LOP3 / SHF / PRMT all issue on the ALU pipe, which saturates first
+// (profiles/r01b_leaves_ncu.txt: ALU 94.7 %, FMA 11 %).  Every addition is therefore written as x * one + y with `one` an
+// opaque kernel argument (== 1), which ptxas must keep as IMAD on the FMA pipe: 8 ALU + 6 FMA ops per G instead of 10 + 2.
+#define B3_ADD(x, y) ((x) * one + (y))
+#define B3_G(a, b, c, d, x, y)                                          \
+    a = B3_ADD(b, a); a = B3_ADD((x), a); d = __byte_perm(d ^ a, 0, 0x1032); \
+    c = B3_ADD(d, c);                     b = rotr32(b ^ c, 12);            \
+    a = B3_ADD(b, a); a = B3_ADD((y), a); d = __byte_perm(d ^ a, 0, 0x0321); \
+    c = B3_ADD(d, c);                     b = rotr32(b ^ c, 7);
 
 #define B3_ROUND(m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11, m12, m13, m14, m15) \
     B3_G(v0, v4, v8, v12, m0, m1)   B3_G(v1, v5, v9, v13, m2, m3)                        \
@@ -36,7 +40,7 @@ constexpr uint32_t F_CHUNK_START = 1, F_CHUNK_END = 2, F_PARENT = 4, F_ROOT = 8;
 
 // cv <- first 8 words of compress(cv, m, counter, block_len, flags)   (ext/blake3_portable.c:46-122)
 __device__ __forceinline__ void b3_compress(uint32_t (&cv)[8], const uint32_t (&m)[16], uint32_t counter_lo,
-                                            uint32_t block_len, uint32_t flags)
+                                            uint32_t block_len, uint32_t flags, uint32_t one)
 {
     uint32_t v0 = cv[0], v1 = cv[1], v2 = cv[2], v3 = cv[3], v4 = cv[4], v5 = cv[5], v6 = cv[6], v7 = cv[7];
     uint32_t v8 = IV0, v9 = IV1, v10 = IV2, v11 = IV3, v12 = counter_lo, v13 = 0, v14 = block_len, v15 = flags;
@@ -71,7 +75,7 @@ __global__ void k_leaf_counts(const uint32_t* __restrict__ len, uint32_t count, 
 __global__ void __launch_bounds__(LEAF_THREADS, 3)
 k_blake3_leaves(const uint8_t* __restrict__ base, uint64_t base_size, const uint64_t* __restrict__ seg_off,
                 const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ leaf_prefix, uint32_t seg_count,
-                uint32_t total_leaves, uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out)
+                uint32_t total_leaves, uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out, uint32_t one)
 {
     __shared__ __align__(16) uint8_t s_stage[LEAF_WARPS][2][LEAF_STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31u;
@@ -112,32 +116,43 @@ k_blake3_leaves(const uint8_t* __restrict__ base, uint64_t base_size, const uint
     const uint64_t first_piece = addr & ~(uint64_t)15;
     const uint64_t my_end = addr + len;
 
-    // the warp copies, for each lane q, the five 16-byte pieces covering q's next 64 bytes; piece ids are spread over
-    // lanes so that consecutive lanes fetch consecutive 16 bytes (coalesced 80-byte runs)
-    auto issue = [&](uint32_t j, uint32_t st) {
+    // The warp copies, for each lane q, the five 16-byte pieces covering q's next 64 bytes; piece ids are spread over lanes
+    // so that consecutive lanes fetch consecutive 16 bytes (coalesced 80-byte runs).  Which piece a lane fetches does not
+    // depend on the block index, so source pointer / bytes-left / destination are set up once and advanced by 64 per block.
+    const uint8_t* p_src[5];
+    int32_t p_left[5];
+    uint32_t p_dst[5];
+#pragma unroll
+    for (uint32_t r = 0; r < 5; ++r)
+    {
+        const uint32_t id = r * 32u + lane;
+        const uint32_t q = id / 5u, k = id - q * 5u;
+        const uint64_t q_first = __shfl_sync(0xffffffffu, first_piece, q);
+        const uint64_t q_end = __shfl_sync(0xffffffffu, my_end, q);
+        const uint64_t src = q_first + (uint64_t)k * 16u;
+        p_src[r] = base + src;
+        p_left[r] = (int32_t)(int64_t)(q_end - src); // <= 1024 + 15; <= 0 when the piece holds nothing of the leaf
+        p_dst[r] = stage0 + q * LEAF_LANE_BYTES + k * 16u;
+    }
+    auto issue = [&](uint32_t st) {
 #pragma unroll
         for (uint32_t r = 0; r < 5; ++r)
         {
-            const uint32_t id = r * 32u + lane;
-            const uint32_t q = id / 5u, k = id - q * 5u;
-            const uint64_t q_first = __shfl_sync(0xffffffffu, first_piece, q);
-            const uint64_t q_end = __shfl_sync(0xffffffffu, my_end, q);
-            const uint64_t src = q_first + (uint64_t)j * 64u + (uint64_t)k * 16u;
-            uint32_t nb = 0;
-            if (src < q_end) nb = (uint32_t)min((uint64_t)16, base_size - src);
-            cp_async16(stage0 + st * LEAF_STAGE_BYTES + q * LEAF_LANE_BYTES + k * 16u, base + (nb ? src : 0), nb);
+            if (p_left[r] > 0) cp_async16(p_dst[r] + st * LEAF_STAGE_BYTES, p_src[r], (uint32_t)min(p_left[r], 16));
+            p_src[r] += 64;
+            p_left[r] -= 64;
         }
         cp_async_commit();
     };
 
     uint32_t cv[8] = {IV0, IV1, IV2, IV3, IV4, IV5, IV6, IV7};
-    if (max_blocks > 0) issue(0, 0);
+    if (max_blocks > 0) issue(0);
     for (uint32_t j = 0; j < max_blocks; ++j)
     {
         const uint32_t st = j & 1u;
         if (j + 1 < max_blocks)
         {
-            issue(j + 1, st ^ 1u);
+            issue(st ^ 1u);
             cp_async_wait<1>();
         }
         else
@@ -165,7 +180,7 @@ k_blake3_leaves(const uint8_t* __restrict__ base, uint64_t base_size, const uint
             }
             uint32_t flags = (j == 0 ? F_CHUNK_START : 0u);
             if (j == nblocks - 1) flags |= F_CHUNK_END | (single ? F_ROOT : 0u);
-            b3_compress(cv, m, leaf_in_seg, nb, flags);
+            b3_compress(cv, m, leaf_in_seg, nb, flags, one);
         }
         __syncwarp(); // everyone is done reading stage st before it is refilled two iterations later
     }
@@ -186,7 +201,7 @@ constexpr int MERGE_THREADS = 128;
 
 __global__ void __launch_bounds__(MERGE_THREADS)
 k_blake3_merge(const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ leaf_prefix, uint32_t seg_count,
-               uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out)
+               uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out, uint32_t one)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t seg = blockIdx.x * (MERGE_THREADS / 32) + (threadIdx.x >> 5);
@@ -209,7 +224,7 @@ k_blake3_merge(const uint32_t* __restrict__ seg_len, const uint32_t* __restrict_
                 uint4 a0 = node[4 * i], a1 = node[4 * i + 1], b0 = node[4 * i + 2], b1 = node[4 * i + 3];
                 m[0] = a0.x; m[1] = a0.y; m[2] = a0.z; m[3] = a0.w; m[4] = a1.x; m[5] = a1.y; m[6] = a1.z; m[7] = a1.w;
                 m[8] = b0.x; m[9] = b0.y; m[10] = b0.z; m[11] = b0.w; m[12] = b1.x; m[13] = b1.y; m[14] = b1.z; m[15] = b1.w;
-                b3_compress(cv, m, 0, 64, flags); // parent node: key = IV, counter 0 (ext/blake3.c:89-116)
+                b3_compress(cv, m, 0, 64, flags, one); // parent node: key = IV, counter 0 (ext/blake3.c:89-116)
             }
             __syncwarp(); // all loads of this batch happen before any store of it (in-place levels)
             if (i < pairs)
@@ -248,7 +263,7 @@ void launch_blake3_leaves(const uint8_t* d_base, uint64_t base_size, const uint6
     if (!count || !total_leaves) return;
     const uint32_t leaves_per_block = LEAF_WARPS * 32;
     k_blake3_leaves<<<(total_leaves + leaves_per_block - 1) / leaves_per_block, LEAF_THREADS, 0, st>>>(
-        d_base, base_size, d_off, d_len, d_leaf_prefix, count, total_leaves, d_cvs, d_hash_out);
+        d_base, base_size, d_off, d_len, d_leaf_prefix, count, total_leaves, d_cvs, d_hash_out, 1u);
 }
 
 void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, uint32_t count, uint32_t* d_cvs, uint64_t* d_hash_out,
@@ -256,7 +271,7 @@ void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, u
 {
     if (!count) return;
     const uint32_t segs_per_block = MERGE_THREADS / 32;
-    k_blake3_merge<<<(count + segs_per_block - 1) / segs_per_block, MERGE_THREADS, 0, st>>>(d_len, d_leaf_prefix, count, d_cvs, d_hash_out);
+    k_blake3_merge<<<(count + segs_per_block - 1) / segs_per_block, MERGE_THREADS, 0, st>>>(d_len, d_leaf_prefix, count, d_cvs, d_hash_out, 1u);
 }
 
 } // namespace ltb

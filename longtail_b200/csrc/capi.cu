@@ -54,6 +54,7 @@ struct lt_b200_context
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaEvent_t compute_done[2] = {nullptr, nullptr};
     uint32_t* d_table = nullptr;
+    ScanLayout scan_layout = {0, 0, 0};
     Buf ws[WS_COUNT];
     Buf hs[HS_COUNT];
     uint64_t launches = 0;
@@ -288,6 +289,12 @@ extern "C" int lt_b200_context_create(int device_ordinal, lt_b200_context** out_
         cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming);
     }
     c->sm_count = prop.multiProcessorCount;
+    if (make_scan_layout(&c->scan_layout, c->stream) != cudaSuccess)
+    {
+        cudaGetLastError();
+        lt_b200_context_destroy(c);
+        return ENOTSUP; // the device cannot hold the scan kernel's shared-memory layout (not a B200-class part)
+    }
     *out_context = c;
     return 0;
 }
@@ -473,7 +480,7 @@ extern "C" int lt_b200_chunk_ranges(lt_b200_context* c, const uint8_t* d_arena, 
     {
         ProfScope ps(c, LT_B200_KERNEL_HPCDC_SCAN, bytes);
         CU(launch_hpcdc_scan(d_arena, ws<PartDesc>(c, WS_PARTS), ws<uint32_t>(c, WS_TILE_DESC), num_tiles, cp, c->d_table,
-                             ws<uint32_t>(c, WS_TILE_COUNT), ws<uint32_t>(c, WS_TILE_SLOTS), c->sm_count, c->stream));
+                             ws<uint32_t>(c, WS_TILE_COUNT), ws<uint32_t>(c, WS_TILE_SLOTS), c->scan_layout, c->sm_count, c->stream));
     }
     {
         ProfScope ps(c, LT_B200_KERNEL_HPCDC_WALK, (uint64_t)num_tiles * 4);

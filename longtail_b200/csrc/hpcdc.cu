@@ -56,13 +56,17 @@ __device__ __noinline__ void scan_group_exact(uint32_t in_addr, uint32_t out_add
     }
 }
 
+// Shared-memory layout (ScanLayout, computed on the host from the probed base of the dynamic window): the 64 KiB table is
+// placed at a shared address that is a multiple of 64 KiB, so that "table base + byte * 256 + lane * 4" is produced by the
+// single PRMT that extracts the byte — no address add per lookup.  `warps_before` per-warp buffers sit in front of the
+// table, the rest behind it.
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ parts, const uint32_t* __restrict__ tile_part,
              uint32_t num_tiles, ChunkParams cp, const uint32_t* __restrict__ g_table,
-             uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_slots)
+             uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_slots, ScanLayout lay)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint32_t* s_table = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* s_table = reinterpret_cast<uint32_t*>(smem + lay.table_off);
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
@@ -76,13 +80,15 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
         uint32_t t = __ldg(&g_table[i >> 6]);
         s_table[i] = (i & 32u) ? rotl32(t, 16) : t;
     }
-    uint8_t* s_mine = smem + SCAN_TABLE_BYTES + warp * SCAN_WARP_BYTES;
+    uint8_t* s_mine = smem + (warp < lay.warps_before ? warp * SCAN_WARP_BYTES
+                                                      : lay.table_off + SCAN_TABLE_BYTES + (warp - lay.warps_before) * SCAN_WARP_BYTES);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_mine + SCAN_ROWS_BYTES) + lane * (SCAN_SEG / 32);
 #pragma unroll
     for (int w = 0; w < SCAN_SEG / 32; ++w) s_bits[w] = 0;
     __syncthreads(); // the only block-wide barrier: the table is ready
 
-    const uint32_t tab = smem_u32(s_table);
+    const uint32_t tab = smem_u32(s_table);   // multiple of 65536 by construction
+    const uint32_t tab_lane = tab | lane4;     // bytes 2..3: table base, byte 1: free for the data byte, byte 0: lane * 4
     const uint32_t rows = smem_u32(s_mine);
     const uint32_t my = rows + (lane + 1u) * SCAN_ROW;
     const uint32_t prev = my - SCAN_ROW + (SCAN_SEG - SCAN_WINDOW);
@@ -140,8 +146,8 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
 #pragma unroll
             for (int k = 0; k < 16; ++k)
             {
-                uint32_t idx = __byte_perm(ws[k >> 2], lane4, 0x5504 | ((k & 3) << 4));
-                h ^= rotl32(lds32(tab + idx), (47 - (16 * j + k)) & 31);
+                uint32_t idx = __byte_perm(ws[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4));
+                h ^= rotl32(lds32(idx), (47 - (16 * j + k)) & 31);
             }
         }
 
@@ -162,14 +168,14 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
 #pragma unroll
                 for (int k = 8 * g; k < 8 * g + 8; ++k)
                 {
-                    const uint32_t sel = 0x5504 | ((k & 3) << 4);
-                    uint32_t tin = lds32(tab + __byte_perm(wi[k >> 2], lane4, sel));
-                    uint32_t tout = lds32(tab + 128u + __byte_perm(wo[k >> 2], lane4, sel));
+                    const uint32_t sel = 0x7604 | ((k & 3) << 4);
+                    uint32_t tin = lds32(__byte_perm(wi[k >> 2], tab_lane, sel));
+                    uint32_t tout = lds32_off128(__byte_perm(wo[k >> 2], tab_lane, sel));
                     h = rotl32(h, 1) ^ tout ^ tin;              // :295-297 with rotl(T[out],48&31) pre-rotated in the table
                     best = min(best, h * cp.d_odd_inv + cp.d_odd_inv); // (h+1)/odd(d) exact-division test, superset of :298
                 }
                 if (best <= cp.d_odd_thr)
-                    scan_group_exact(in_addr + 8 * g, out_addr + 8 * g, h0, cp.d, cp.d_odd_inv, cp.d_odd_thr, tab + lane4, bits_addr, 16 * j + 8 * g);
+                    scan_group_exact(in_addr + 8 * g, out_addr + 8 * g, h0, cp.d, cp.d_odd_inv, cp.d_odd_thr, tab_lane, bits_addr, 16 * j + 8 * g);
             }
         }
         __syncwarp(); // every lane is done with the rows: the next iteration may overwrite them
@@ -388,21 +394,52 @@ void launch_tile_part(const PartDesc* d_parts, uint32_t part_count, uint32_t num
     k_tile_part<<<(num_tiles + 255) / 256, 256, 0, st>>>(d_parts, part_count, num_tiles, d_tile_part);
 }
 
+__global__ void k_probe_dynamic_smem_base(uint32_t* out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    *out = smem_u32(smem);
+}
+
+// finds where the 64 KiB-aligned table fits inside the dynamic shared window of this device
+cudaError_t make_scan_layout(ScanLayout* lay, cudaStream_t st)
+{
+    uint32_t* d_base = nullptr;
+    uint32_t base = 0;
+    cudaError_t e = cudaMalloc(&d_base, sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    k_probe_dynamic_smem_base<<<1, 32, 1024, st>>>(d_base);
+    e = cudaMemcpyAsync(&base, d_base, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_base);
+    if (e != cudaSuccess) return e;
+    int dev = 0, max_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    uint32_t best_total = 0xffffffffu;
+    for (uint32_t k = 0; k <= (uint32_t)SCAN_WARPS; ++k)
+    {
+        uint32_t t0 = (base + k * SCAN_WARP_BYTES + 65535u) & ~65535u; // shared address of the table
+        uint32_t total = t0 - base + SCAN_TABLE_BYTES + (SCAN_WARPS - k) * SCAN_WARP_BYTES;
+        if (total < best_total)
+        {
+            best_total = total;
+            lay->warps_before = k;
+            lay->table_off = t0 - base;
+            lay->total_bytes = total;
+        }
+    }
+    if (best_total > (uint32_t)max_optin) return cudaErrorInvalidConfiguration;
+    return cudaFuncSetAttribute(k_hpcdc_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay->total_bytes);
+}
+
 cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint32_t* d_tile_part, uint32_t num_tiles,
                               const ChunkParams& cp, const uint32_t* d_table, uint32_t* d_tile_count, uint32_t* d_tile_slots,
-                              int sm_count, cudaStream_t st)
+                              const ScanLayout& lay, int sm_count, cudaStream_t st)
 {
     if (!num_tiles) return cudaSuccess;
-    static bool configured = false;
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(k_hpcdc_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     uint32_t grid = (num_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
     if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-    k_hpcdc_scan<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(d_arena, d_parts, d_tile_part, num_tiles, cp, d_table, d_tile_count, d_tile_slots);
+    k_hpcdc_scan<<<grid, SCAN_THREADS, lay.total_bytes, st>>>(d_arena, d_parts, d_tile_part, num_tiles, cp, d_table, d_tile_count, d_tile_slots, lay);
     return cudaGetLastError();
 }
 

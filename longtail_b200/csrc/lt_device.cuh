@@ -22,6 +22,13 @@ constexpr int SCAN_BITMAP_BYTES = 32 * (SCAN_SEG / 32) * 4;
 constexpr int SCAN_WARP_BYTES = SCAN_ROWS_BYTES + SCAN_BITMAP_BYTES;
 constexpr int SCAN_SMEM_BYTES = SCAN_TABLE_BYTES + SCAN_WARPS * SCAN_WARP_BYTES;
 
+struct ScanLayout
+{
+    uint32_t table_off;    // offset of the table inside the dynamic shared window (its shared ADDRESS is a multiple of 64 KiB)
+    uint32_t warps_before; // how many per-warp buffers lie in front of the table
+    uint32_t total_bytes;  // dynamic shared memory to request
+};
+
 constexpr uint32_t CAND_OVERFLOW = 0x80000000u;    // dense-list marker: tile whose slot list overflowed
 
 struct PartDesc
@@ -52,6 +59,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32_off128(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+128];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr)

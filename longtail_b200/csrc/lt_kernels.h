@@ -9,7 +9,8 @@ namespace ltb {
 void launch_tile_part(const PartDesc* d_parts, uint32_t part_count, uint32_t num_tiles, uint32_t* d_tile_part, cudaStream_t st);
 cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint32_t* d_tile_part, uint32_t num_tiles,
                               const ChunkParams& cp, const uint32_t* d_table, uint32_t* d_tile_count, uint32_t* d_tile_slots,
-                              int sm_count, cudaStream_t st);
+                              const ScanLayout& lay, int sm_count, cudaStream_t st);
+cudaError_t make_scan_layout(ScanLayout* lay, cudaStream_t st);
 void launch_hpcdc_walk(const uint8_t* d_arena, const PartDesc* d_parts, uint32_t part_count, const ChunkParams& cp,
                        const uint32_t* d_table, const uint32_t* d_tile_count, const uint32_t* d_tile_slots, uint32_t* d_cand,
                        uint64_t* d_stage_off, uint32_t* d_stage_len, uint32_t* d_part_chunk_count, cudaStream_t st);
