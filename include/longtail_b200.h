@@ -180,6 +180,22 @@ LT_B200_EXPORT int lt_b200_index_host_assets(lt_b200_context* context, const str
                                              uint32_t hash_type, uint32_t target_chunk_size,
                                              const void** out_buffer, uint64_t* out_size);
 
+/* Same, with the asset bytes pulled through a callback: the library hands out batches of read jobs whose destinations are
+ * pinned staging buffers it owns; the callee fills them (in parallel if it likes — the drop-in verb fans them out over the
+ * caller's Longtail_JobAPI) and returns 0 or an errno, which aborts the call.  While batch k+1 is being read on the host,
+ * batch k is already on its way to the device. */
+struct lt_b200_read_job
+{
+    uint32_t asset_index;
+    uint32_t size;
+    uint64_t offset; /* byte offset inside the asset */
+    void* dst;
+};
+typedef int (*lt_b200_read_batch_func)(void* user, const struct lt_b200_read_job* jobs, uint32_t job_count);
+LT_B200_EXPORT int lt_b200_index_stream_assets(lt_b200_context* context, const struct lt_b200_assets* assets, const uint32_t* asset_tags,
+                                               uint32_t hash_type, uint32_t target_chunk_size, lt_b200_read_batch_func read_batch,
+                                               void* user, const void** out_buffer, uint64_t* out_size);
+
 #ifdef __cplusplus
 }
 #endif

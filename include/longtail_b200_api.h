@@ -1,0 +1,66 @@
+/* longtail_b200_api.h — drop-in Longtail_*API objects and batched verbs backed by the B200 kernels.
+ *
+ * Everything here speaks longtail's own plugin ABI (include/longtail_abi.h == reference src/longtail.h), so the objects
+ * can be handed to the unmodified reference core (Longtail_CreateVersionIndex, Longtail_WriteContent, the registries,
+ * cmd/main.c:UpSync) exactly where the reference's own backends go:
+ *
+ *   Longtail_CreateB200ChunkerAPI()        replaces Longtail_CreateHPCDCChunkerAPI()   lib/hpcdcchunker/longtail_hpcdcchunker.c:563
+ *   Longtail_CreateB200Blake3HashAPI()     replaces Longtail_CreateBlake3HashAPI()     lib/blake3/longtail_blake3.c:104
+ *   Longtail_B200_CreateVersionIndex()     replaces Longtail_CreateVersionIndex()      src/longtail.c:2808   (same parameter list)
+ *
+ * Error behaviour follows the reference: errno-style ints, 0 = success, ESPIPE from NextChunk at end of stream
+ * (lib/hpcdcchunker/longtail_hpcdcchunker.c:420-423), objects freed through m_API.Dispose (SAFE_DISPOSE_API).
+ * Objects returned here are allocated with the host's Longtail_Alloc when liblongtail is present in the process
+ * (resolved with dlsym at first use) and with malloc otherwise, so that Longtail_Free / SAFE_DISPOSE_API on the
+ * caller's side does the right thing in both settings.
+ */
+#ifndef LONGTAIL_B200_API_H
+#define LONGTAIL_B200_API_H
+
+#include "longtail_abi.h"
+#include "longtail_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Device used by the objects created below (default 0).  Call before the first Create*; returns EBUSY afterwards. */
+LT_B200_EXPORT int Longtail_B200_SetDevice(int device_ordinal);
+
+/* ChunkerAPI (src/longtail.h:586-594).  GetMinChunkSize reports 48.  The first NextChunk on a handle drains the feeder
+ * (one part of at most target_chunk_size*1024 bytes, src/longtail.c:2396), runs the scan + selection + BLAKE3 kernels once
+ * over it and serves the remaining NextChunk calls — and the HashBuffer calls of the B200 HashAPI on those very ranges —
+ * from the result.  NextChunkFromBuffer is not on the CreateVersionIndex path (src/longtail.c:2453 forces the feeder
+ * branch) and returns ENOTSUP. */
+LT_B200_EXPORT struct Longtail_ChunkerAPI* Longtail_CreateB200ChunkerAPI(void);
+
+/* HashAPI (src/longtail.h:209-217), identifier 'blk3'.  HashBuffer on a range handed out by a B200 chunker returns the
+ * hash computed in the chunker's pass; any other buffer is hashed on the GPU on the spot (correct, but one round trip per
+ * call — the batched verb below is the fast path). */
+LT_B200_EXPORT struct Longtail_HashAPI* Longtail_CreateB200Blake3HashAPI(void);
+
+/* Longtail_CreateVersionIndex with the reference's parameter list (src/longtail.h:1134-1147).  storage_api supplies the
+ * bytes (ConcatPath / OpenReadFile / Read / CloseFile, exactly the calls DynamicChunking makes); job_api, when given, runs
+ * the storage reads of one batch in parallel while the GPU works on the previous batch.  hash_api / chunker_api only select
+ * the algorithms (GetIdentifier must be 'blk3'; the chunker must report a minimum of 48): the work is done by
+ * lt_b200_index_host_assets' kernels, not by calling back into them.  enable_file_map is ignored, as in the reference.
+ * *out_version_index is allocated with Longtail_Alloc (see above) and is released by the caller with Longtail_Free. */
+LT_B200_EXPORT int Longtail_B200_CreateVersionIndex(
+    struct Longtail_StorageAPI* storage_api,
+    struct Longtail_HashAPI* hash_api,
+    struct Longtail_ChunkerAPI* chunker_api,
+    struct Longtail_JobAPI* job_api,
+    struct Longtail_ProgressAPI* progress_api,
+    struct Longtail_CancelAPI* optional_cancel_api,
+    Longtail_CancelAPI_HCancelToken optional_cancel_token,
+    const char* root_path,
+    const struct Longtail_FileInfos* file_infos,
+    const uint32_t* optional_asset_tags,
+    uint32_t target_chunk_size,
+    int enable_file_map,
+    struct Longtail_VersionIndex** out_version_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LONGTAIL_B200_API_H */

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "liblongtail_b200.so")
-CUDA_SOURCES = ["hpcdc.cu", "blake3.cu", "util.cu", "capi.cu"]
+CUDA_SOURCES = ["hpcdc.cu", "blake3.cu", "util.cu", "capi.cu", "longtail_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
               "-Xptxas", "-v"]
 
@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in CUDA_SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        o = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
             cmd = [_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError("nvcc failed for %s" % src)
     if rebuilt or not os.path.exists(LIB):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         subprocess.run(cmd, check=True)
     return LIB
 

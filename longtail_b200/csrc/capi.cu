@@ -34,7 +34,7 @@ enum WsSlot
 
 enum HostSlot
 {
-    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_COUNT
+    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_COUNT
 };
 
 struct Buf
@@ -899,6 +899,116 @@ extern "C" int lt_b200_index_host_assets(lt_b200_context* c, const lt_b200_asset
             lt_b200_chunk_table table;
             TRY(lt_b200_chunk_ranges(c, d, c->ws[which ? WS_ARENA_B : WS_ARENA_A].cap, cur.ranges.data(), (uint32_t)cur.ranges.size(), mn, av, mx,
                                      hash_type, 0, &table));
+            CU(cudaEventRecord(c->compute_done[which], c->stream));
+            if (acc + table.chunk_count > max_chunks) return fail(c, EFAULT, "chunk accumulation overflow");
+            if (table.chunk_count)
+            {
+                CU(cudaMemcpyAsync(ws<uint64_t>(c, WS_ACC_HASH) + acc, ws<void>(c, WS_CHUNK_HASH), sizeof(uint64_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaMemcpyAsync(ws<uint32_t>(c, WS_ACC_LEN) + acc, ws<void>(c, WS_CHUNK_LEN), sizeof(uint32_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaMemcpyAsync(ws<uint32_t>(c, WS_ACC_TAG) + acc, ws<void>(c, WS_CHUNK_TAG), sizeof(uint32_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            for (size_t j = cur.first; j < cur.last; ++j) asset_chunks[jobs[j].asset] += table.range_chunk_counts[j - cur.first];
+            acc += table.chunk_count;
+            if (!has_next) break;
+            cur = std::move(next);
+            which ^= 1;
+        }
+    }
+    if (acc > 0xffffffffull) return fail(c, E2BIG, "more than 2^32 chunks");
+    return build_index_from_device_table(c, a, asset_chunks.data(), (uint32_t)acc, ws<uint64_t>(c, WS_ACC_HASH), ws<uint32_t>(c, WS_ACC_LEN),
+                                         ws<uint32_t>(c, WS_ACC_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+}
+
+extern "C" int lt_b200_index_stream_assets(lt_b200_context* c, const lt_b200_assets* a, const uint32_t* asset_tags, uint32_t hash_type,
+                                           uint32_t target_chunk_size, lt_b200_read_batch_func read_batch, void* user,
+                                           const void** out_buffer, uint64_t* out_size)
+{
+    if (!c || !out_buffer || !out_size || !read_batch) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    TRY(validate_assets(c, a));
+    if (target_chunk_size == 0 || target_chunk_size > (1u << 20)) return fail(c, EINVAL, "target_chunk_size %u outside (0, 1 MiB]", target_chunk_size);
+    uint32_t mn, av, mx;
+    target_to_params(target_chunk_size, &mn, &av, &mx);
+    const uint64_t part_size = (uint64_t)target_chunk_size * 1024;
+
+    struct Job { uint32_t asset; uint64_t start; uint32_t size; };
+    std::vector<Job> jobs;
+    uint64_t total_bytes = 0;
+    for (uint32_t i = 0; i < a->asset_count; ++i)
+    {
+        const uint64_t size = a->sizes[i];
+        const uint64_t parts = 1 + size / part_size; // src/longtail.c:2402
+        for (uint64_t p = 0; p < parts; ++p)
+        {
+            const uint64_t start = p * part_size;
+            const uint64_t n = size - start > part_size ? part_size : size - start;
+            if (n) jobs.push_back({i, start, (uint32_t)n});
+        }
+        total_bytes += size;
+    }
+    const uint64_t batch_bytes = 1ull << 30 > part_size ? 1ull << 30 : part_size;
+    const uint64_t max_chunks = total_bytes / mn + 2 * (uint64_t)jobs.size() + 16;
+    TRY(ws_reserve(c, WS_ACC_HASH, sizeof(uint64_t) * (size_t)max_chunks));
+    TRY(ws_reserve(c, WS_ACC_LEN, sizeof(uint32_t) * (size_t)max_chunks));
+    TRY(ws_reserve(c, WS_ACC_TAG, sizeof(uint32_t) * (size_t)max_chunks));
+    std::vector<uint32_t> asset_chunks(a->asset_count, 0);
+
+    struct Batch { size_t first = 0, last = 0; std::vector<lt_b200_range> ranges; uint64_t bytes = 0; };
+    auto plan = [&](size_t first) {
+        Batch b;
+        b.first = first;
+        size_t j = first;
+        while (j < jobs.size())
+        {
+            const uint64_t padded = ((uint64_t)jobs[j].size + 255) & ~255ull;
+            if (b.bytes + padded > batch_bytes && j > first) break;
+            b.ranges.push_back({b.bytes, jobs[j].size, asset_tags ? asset_tags[jobs[j].asset] : 0u});
+            b.bytes += padded;
+            ++j;
+        }
+        b.last = j;
+        return b;
+    };
+    // host reads into pinned staging `which`, then the batch is queued for the device on the copy stream
+    std::vector<lt_b200_read_job> read_jobs;
+    auto read_and_upload = [&](const Batch& b, int which) -> int {
+        const size_t need = (size_t)(batch_bytes > b.bytes ? batch_bytes : b.bytes) + 4096;
+        TRY(hs_reserve(c, which ? HS_STAGE_B : HS_STAGE_A, need));
+        TRY(ws_reserve(c, which ? WS_ARENA_B : WS_ARENA_A, need));
+        uint8_t* h = hs<uint8_t>(c, which ? HS_STAGE_B : HS_STAGE_A);
+        read_jobs.clear();
+        for (size_t j = b.first; j < b.last; ++j)
+            read_jobs.push_back({jobs[j].asset, jobs[j].size, jobs[j].start, h + b.ranges[j - b.first].arena_offset});
+        int err = read_batch(user, read_jobs.data(), (uint32_t)read_jobs.size());
+        if (err) return fail(c, err, "read callback failed with %d", err);
+        CU(cudaStreamWaitEvent(c->copy_stream, c->compute_done[which], 0));
+        CU(cudaMemcpyAsync(ws<uint8_t>(c, which ? WS_ARENA_B : WS_ARENA_A), h, b.bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->copy_done[which], c->copy_stream));
+        return 0;
+    };
+
+    uint64_t acc = 0;
+    if (!jobs.empty())
+    {
+        CU(cudaEventRecord(c->compute_done[0], c->stream));
+        CU(cudaEventRecord(c->compute_done[1], c->stream));
+        Batch cur = plan(0);
+        int which = 0;
+        TRY(read_and_upload(cur, which));
+        while (true)
+        {
+            Batch next;
+            const bool has_next = cur.last < jobs.size();
+            if (has_next)
+            {
+                next = plan(cur.last);
+                TRY(read_and_upload(next, which ^ 1)); // host reads batch k+1 while batch k travels over PCIe
+            }
+            CU(cudaStreamWaitEvent(c->stream, c->copy_done[which], 0));
+            lt_b200_chunk_table table;
+            TRY(lt_b200_chunk_ranges(c, ws<uint8_t>(c, which ? WS_ARENA_B : WS_ARENA_A), c->ws[which ? WS_ARENA_B : WS_ARENA_A].cap, cur.ranges.data(),
+                                     (uint32_t)cur.ranges.size(), mn, av, mx, hash_type, 0, &table));
             CU(cudaEventRecord(c->compute_done[which], c->stream));
             if (acc + table.chunk_count > max_chunks) return fail(c, EFAULT, "chunk accumulation overflow");
             if (table.chunk_count)

@@ -1,0 +1,208 @@
+/* dropin_test.c — the B200 backends inside the UNMODIFIED reference pipeline.
+ *
+ * Built by oracle/Makefile (target `dropin`) against the reference's own src/longtail.h and liblongtail_ref.a, linked with
+ * liblongtail_b200.so.  Needs a GPU to run.  Checks, on an in-memory tree written through the reference's memstorage:
+ *   0. include/longtail_abi.h has the same struct layout as src/longtail.h (abi_table.c compiled both ways)
+ *   1. reference Longtail_CreateVersionIndex with the reference backends                      -> baseline bytes
+ *   2. reference Longtail_CreateVersionIndex with Longtail_CreateB200ChunkerAPI + B200 HashAPI -> identical bytes
+ *   3. Longtail_B200_CreateVersionIndex (same parameter list)                                 -> identical bytes
+ *   4. the reference's ChunkerLargeFile golden vector (test/test.cpp:3363-3465) through the B200 ChunkerAPI
+ */
+#define LONGTAIL_B200_USE_LONGTAIL_H
+#include "longtail.h"
+#include "longtail_b200_api.h"
+#include "../lib/bikeshed/longtail_bikeshed.h"
+#include "../lib/blake3/longtail_blake3.h"
+#include "../lib/hpcdcchunker/longtail_hpcdcchunker.h"
+#include "../lib/memstorage/longtail_memstorage.h"
+
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct abi_entry { const char* name; unsigned long value; };
+extern const struct abi_entry abi_table_b200[];
+extern const struct abi_entry abi_table_reference[];
+
+static int failures = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { ++failures; printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } } while (0)
+
+static uint64_t mix(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static void fill(uint8_t* p, size_t n, uint64_t seed, int low_entropy)
+{
+    for (size_t i = 0; i < n; ++i)
+    {
+        uint8_t b = (uint8_t)(mix(seed * 0x9E3779B97F4A7C15ull + i / 8) >> (8 * (i % 8)));
+        p[i] = low_entropy ? (b & 0x0f) : b;
+    }
+}
+
+static int write_file(struct Longtail_StorageAPI* st, const char* path, const uint8_t* data, size_t n)
+{
+    char* parent = st->GetParentPath(st, path);
+    if (parent) { /* create parents bottom-up */
+        char tmp[512]; size_t len = strlen(parent);
+        for (size_t i = 1; i <= len; ++i) if (parent[i] == '/' || parent[i] == 0) { memcpy(tmp, parent, i); tmp[i] = 0; st->CreateDir(st, tmp); }
+        Longtail_Free(parent);
+    }
+    Longtail_StorageAPI_HOpenFile f;
+    int err = st->OpenWriteFile(st, path, n, &f);
+    if (err) return err;
+    if (n) err = st->Write(st, f, 0, n, data);
+    st->CloseFile(st, f);
+    return err;
+}
+
+static int serialise(struct Longtail_VersionIndex* v, void** buf, size_t* size) { return Longtail_WriteVersionIndexToBuffer(v, buf, size); }
+
+struct feed { const uint8_t* data; uint64_t size, off; };
+static int feed_func(void* ctx, Longtail_ChunkerAPI_HChunker c, uint32_t requested, char* buffer, uint32_t* out)
+{
+    (void)c;
+    struct feed* f = (struct feed*)ctx;
+    uint64_t n = f->size - f->off;
+    if (n > requested) n = requested;
+    memcpy(buffer, f->data + f->off, n);
+    f->off += n;
+    *out = (uint32_t)n;
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    /* 0. ABI layout */
+    for (int i = 0; abi_table_reference[i].name; ++i)
+    {
+        CHECK(strcmp(abi_table_reference[i].name, abi_table_b200[i].name) == 0, "abi table order");
+        CHECK(abi_table_reference[i].value == abi_table_b200[i].value, "%s: reference %lu, longtail_abi.h %lu", abi_table_reference[i].name,
+              abi_table_reference[i].value, abi_table_b200[i].value);
+    }
+    printf("abi: %s\n", failures ? "MISMATCH" : "identical layout");
+    if (argc > 1 && strcmp(argv[1], "--abi-only") == 0) return failures ? 1 : 0;
+
+    const uint32_t target = argc > 2 ? (uint32_t)atoi(argv[2]) : 4096;
+    struct Longtail_StorageAPI* storage = Longtail_CreateInMemStorageAPI();
+    struct Longtail_JobAPI* jobs = Longtail_CreateBikeshedJobAPI(3, 0);
+    const size_t part = (size_t)target * 1024;
+    const struct { const char* path; size_t size; int low; } files[] = {
+        {"root/a/empty.bin", 0, 0}, {"root/a/one.bin", 1, 0}, {"root/a/48.bin", 48, 0}, {"root/a/49.bin", 49, 0},
+        {"root/b/exact.bin", part, 0}, {"root/b/two.bin", part + 12345, 0}, {"root/b/three.bin", 2 * part + 777, 1},
+        {"root/c/dup1.bin", 300000, 0}, {"root/d/dup2.bin", 300000, 0}, {"root/e/low.bin", 500000, 1}, {"root/z.txt", 100000, 1}};
+    for (size_t i = 0; i < sizeof(files) / sizeof(files[0]); ++i)
+    {
+        uint8_t* d = (uint8_t*)malloc(files[i].size ? files[i].size : 1);
+        fill(d, files[i].size, strstr(files[i].path, "dup") ? 99 : 7 + i, files[i].low);
+        CHECK(write_file(storage, files[i].path, d, files[i].size) == 0, "write %s", files[i].path);
+        free(d);
+    }
+    struct Longtail_FileInfos* infos = 0;
+    CHECK(Longtail_GetFilesRecursively2(storage, jobs, 0, 0, 0, "root", &infos) == 0, "GetFilesRecursively2");
+    uint32_t* tags = (uint32_t*)malloc(sizeof(uint32_t) * infos->m_Count);
+    for (uint32_t i = 0; i < infos->m_Count; ++i) tags[i] = (i % 2) ? 0x6c7a3432u : 0u;
+
+    struct Longtail_HashAPI* ref_hash = Longtail_CreateBlake3HashAPI();
+    struct Longtail_ChunkerAPI* ref_chunker = Longtail_CreateHPCDCChunkerAPI();
+    struct Longtail_HashAPI* b200_hash = Longtail_CreateB200Blake3HashAPI();
+    struct Longtail_ChunkerAPI* b200_chunker = Longtail_CreateB200ChunkerAPI();
+    CHECK(b200_hash && b200_chunker, "B200 API objects");
+
+    /* 1. baseline */
+    struct Longtail_VersionIndex* v_ref = 0;
+    CHECK(Longtail_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v_ref) == 0, "reference CreateVersionIndex");
+    void* b_ref = 0; size_t n_ref = 0;
+    serialise(v_ref, &b_ref, &n_ref);
+
+    /* 2. the reference core driving the B200 ChunkerAPI / HashAPI objects */
+    struct Longtail_VersionIndex* v_obj = 0;
+    int err = Longtail_CreateVersionIndex(storage, b200_hash, b200_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v_obj);
+    CHECK(err == 0, "reference core + B200 objects: %d", err);
+    if (!err)
+    {
+        void* b = 0; size_t n = 0;
+        serialise(v_obj, &b, &n);
+        CHECK(n == n_ref && memcmp(b, b_ref, n) == 0, "VersionIndex through B200 API objects differs (%zu vs %zu bytes)", n, n_ref);
+        printf("reference core + B200 ChunkerAPI/HashAPI: %zu bytes %s\n", n, (n == n_ref && memcmp(b, b_ref, n) == 0) ? "identical" : "DIFFERENT");
+        Longtail_Free(b);
+        Longtail_Free(v_obj);
+    }
+
+    /* 3. the batched verb with the reference's parameter list */
+    struct Longtail_VersionIndex* v_verb = 0;
+    err = Longtail_B200_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v_verb);
+    CHECK(err == 0, "Longtail_B200_CreateVersionIndex: %d", err);
+    if (!err)
+    {
+        void* b = 0; size_t n = 0;
+        serialise(v_verb, &b, &n);
+        CHECK(n == n_ref && memcmp(b, b_ref, n) == 0, "VersionIndex of Longtail_B200_CreateVersionIndex differs (%zu vs %zu bytes)", n, n_ref);
+        printf("Longtail_B200_CreateVersionIndex: %zu bytes %s\n", n, (n == n_ref && memcmp(b, b_ref, n) == 0) ? "identical" : "DIFFERENT");
+        Longtail_Free(b);
+        Longtail_Free(v_verb);
+    }
+
+    /* 4. golden chunker vector through the B200 ChunkerAPI */
+    if (argc > 1)
+    {
+        FILE* f = fopen(argv[1], "rb");
+        CHECK(f != 0, "open %s", argv[1]);
+        if (f)
+        {
+            static const uint32_t expected[20] = {81590, 46796, 36543, 83172, 76749, 79550, 41484, 20326, 31652, 19995, 103873, 38087, 38377, 23449,
+                                                  47321, 86692, 28268, 65465, 33255, 65932};
+            uint8_t* data = (uint8_t*)malloc(1048576);
+            size_t got = fread(data, 1, 1048576, f);
+            fclose(f);
+            struct feed fd = {data, got, 0};
+            Longtail_ChunkerAPI_HChunker c;
+            CHECK(b200_chunker->CreateChunker(b200_chunker, 16384, 65536, 262144, &c) == 0, "CreateChunker");
+            struct Longtail_Chunker_ChunkRange r;
+            uint64_t off = 0;
+            for (int i = 0; i < 20; ++i)
+            {
+                CHECK(b200_chunker->NextChunk(b200_chunker, c, feed_func, &fd, &r) == 0, "NextChunk %d", i);
+                CHECK(r.offset == off && r.len == expected[i], "chunk %d: offset %llu len %u", i, (unsigned long long)r.offset, r.len);
+                uint64_t h1 = 0, h2 = 0;
+                ref_hash->HashBuffer(ref_hash, r.len, r.buf, &h1);
+                b200_hash->HashBuffer(b200_hash, r.len, r.buf, &h2);
+                CHECK(h1 == h2, "chunk %d hash", i);
+                off += r.len;
+            }
+            CHECK(b200_chunker->NextChunk(b200_chunker, c, feed_func, &fd, &r) == ESPIPE, "ESPIPE at end");
+            CHECK(r.buf == 0 && r.offset == 1048576 && r.len == 0, "end range");
+            b200_chunker->DisposeChunker(b200_chunker, c);
+            free(data);
+            printf("golden chunker vector through Longtail_CreateB200ChunkerAPI: %s\n", failures ? "see failures" : "20/20");
+        }
+    }
+    /* generic HashBuffer (not a chunker range) incl. the KAT of test/test.cpp:465-474 and the empty buffer */
+    {
+        const char* s = "This is the first test string which is fairly long and should - reconstructed properly, than you very much";
+        uint64_t h = 0;
+        CHECK(b200_hash->HashBuffer(b200_hash, (uint32_t)strlen(s) + 1, s, &h) == 0 && h == 0xd38bbe79f1f03fdaull, "blake3 KAT %llx", (unsigned long long)h);
+        uint64_t e1 = 0, e2 = 0;
+        ref_hash->HashBuffer(ref_hash, 0, s, &e1);
+        b200_hash->HashBuffer(b200_hash, 0, s, &e2);
+        CHECK(e1 == e2, "empty hash");
+        CHECK(b200_hash->GetIdentifier(b200_hash) == ref_hash->GetIdentifier(ref_hash), "identifier");
+    }
+
+    Longtail_Free(b_ref);
+    Longtail_Free(v_ref);
+    free(tags);
+    Longtail_Free(infos);
+    SAFE_DISPOSE_API(b200_chunker);
+    SAFE_DISPOSE_API(b200_hash);
+    SAFE_DISPOSE_API(ref_chunker);
+    SAFE_DISPOSE_API(ref_hash);
+    SAFE_DISPOSE_API(jobs);
+    SAFE_DISPOSE_API(storage);
+    printf("%s (%d failures)\n", failures ? "DROPIN FAILED" : "DROPIN OK", failures);
+    return failures ? 1 : 0;
+}
