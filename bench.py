@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-gib", type=float, default=8.0, help="bounded sample for the CPU baseline / the reference arm")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="small sizes only: compare the final VersionIndex with the CPU checker, byte for byte")
     return ap.parse_args()
 
 
@@ -91,8 +92,8 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def host_sample(nbytes, threads):
-    """the first nbytes of the synthetic file, generated on the host (oracle/_ref/libsynth_host.so)"""
+def host_sample(nbytes, threads, asset_id=0):
+    """the first nbytes of synthetic file `asset_id`, generated on the host (oracle/_ref/libsynth_host.so)"""
     import ctypes as C
 
     import numpy as np
@@ -104,7 +105,7 @@ def host_sample(nbytes, threads):
     lib = C.CDLL(path)
     buf = np.empty(nbytes, dtype=np.uint8)
     spec = longtail_b200.SynthSpec(SEED, 0, 1, 0, 0)
-    lib.synth_fill_mt(C.byref(spec), C.c_uint64(0), C.c_uint64(0), buf.ctypes.data_as(C.c_void_p), C.c_uint64(nbytes), C.c_uint32(threads))
+    lib.synth_fill_mt(C.byref(spec), C.c_uint64(asset_id), C.c_uint64(0), buf.ctypes.data_as(C.c_void_p), C.c_uint64(nbytes), C.c_uint32(threads))
     return buf
 
 
@@ -233,6 +234,19 @@ def run_b200(args):
         parity = ("bit-exact vs %s on the first %d MiB" % ("reference" if ref.available else "oracle", check_n >> 20)) if ok else "MISMATCH"
         if not ok:
             raise SystemExit("parity check failed: the CUDA path differs from the CPU checker")
+
+    if args.verify:
+        v = step_resident()
+        if rank == 0:
+            import oracle_lib as ol
+            ref = ol.Reference()
+            checker = ref if ref.available else ol.Oracle()
+            assets = [("f%05d.bin" % r, host_sample(nbytes, 8, asset_id=r)) for r in range(world)]
+            want = checker.create_version_index(assets, TARGET_CHUNK_SIZE)
+            if bytes(v) != want:
+                raise SystemExit("VERIFY FAILED: VersionIndex of %d GPUs differs from the CPU checker" % world)
+            print("verify ok: %d-byte VersionIndex of %d file(s) identical to the %s" % (len(want), world, "reference" if ref.available else "oracle"), file=sys.stderr)
+            parity += "; full VersionIndex verified"
 
     # ---- resident-in-HBM measurement
     sampler = ClockSampler(local_rank)
