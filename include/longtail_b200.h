@@ -36,6 +36,7 @@ extern "C" {
 #define LT_B200_HASH_BLAKE3 0x626c6b33u /* 'blk3', lib/blake3/longtail_blake3.c:6 */
 #define LT_B200_HASH_BLAKE2 0x626c6b32u /* 'blk2', lib/blake2/longtail_blake2.c:9 */
 #define LT_B200_HASH_MEOW 0x6d656f77u   /* 'meow', lib/meowhash/longtail_meowhash.c:7 */
+#define LT_B200_COMPRESSION_LZ4 0x6c7a3432u /* 'lz42', lib/lz4/longtail_lz4.c:10 */
 
 typedef struct lt_b200_context lt_b200_context;
 
@@ -59,6 +60,8 @@ enum
     LT_B200_KERNEL_HPCDC_WALK = 1,
     LT_B200_KERNEL_BLAKE3_LEAVES = 2,
     LT_B200_KERNEL_BLAKE3_MERGE = 3,
+    LT_B200_KERNEL_GATHER = 4,
+    LT_B200_KERNEL_LZ4 = 5,
     LT_B200_KERNEL_COUNT = 8
 };
 LT_B200_EXPORT int lt_b200_profile_enable(lt_b200_context* context, int on);
@@ -179,6 +182,36 @@ LT_B200_EXPORT int lt_b200_index_host_assets(lt_b200_context* context, const str
                                              const uint8_t* const* asset_data, const uint32_t* asset_tags,
                                              uint32_t hash_type, uint32_t target_chunk_size,
                                              const void** out_buffer, uint64_t* out_size);
+
+/* ---- the WriteContent half: block packing, block hashes, payload gather, compression, StoredBlock serialisation
+ *
+ * Replaces, for chunks whose bytes are resident in a device arena: Longtail_CreateStoreIndex's packing
+ * (src/longtail.c:6745-6880), Longtail_CreateBlockIndex (:3712-3770), WriteContentBlockJob's payload gather (:4559-4758) and
+ * compressblockstore's CompressBlock (lib/compressblockstore/longtail_compressblockstore.c:67-141) with the LZ4 backend
+ * (lib/lz4/longtail_lz4.c:52-77).  `chunk_*` are HOST arrays listing the chunks to store, in store order (for a fresh store:
+ * the unique chunks of the VersionIndex in order — DiffHashes keeps that order, src/longtail.c:6718-6740).
+ * Every finished block is handed to `sink` in store order as the exact byte image Longtail_WriteStoredBlockToBuffer
+ * (src/longtail.c:4111-4150) would produce; the memory is only valid during the call.  Tags: 0 = stored raw, 'lz42' = LZ4;
+ * anything else returns ENOTSUP. */
+struct lt_b200_stored_block_view
+{
+    uint64_t block_hash;
+    const void* data;          /* serialised stored block: block index + payload */
+    uint64_t size;
+    uint32_t chunk_count;
+    uint32_t tag;
+    uint32_t raw_payload_size; /* uncompressed payload bytes (what compressblockstore's stats count) */
+    uint32_t first_chunk;      /* index of the block's first chunk in the caller's arrays */
+};
+typedef int (*lt_b200_block_sink)(void* user, const struct lt_b200_stored_block_view* block);
+LT_B200_EXPORT int lt_b200_write_blocks_device(lt_b200_context* context, const uint8_t* device_arena, uint64_t arena_size,
+                                               uint32_t chunk_count, const uint64_t* chunk_hashes, const uint32_t* chunk_sizes,
+                                               const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
+                                               uint32_t max_block_size, uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user);
+
+/* Arena offsets of the unique chunks (first occurrences, VersionIndex order) found by the last lt_b200_index_device_assets
+ * call on this context — the `chunk_arena_offsets` of a fresh-store lt_b200_write_blocks_device. */
+LT_B200_EXPORT int lt_b200_unique_chunk_offsets(lt_b200_context* context, uint64_t* out_offsets, uint32_t count);
 
 /* Same, with the asset bytes pulled through a callback: the library hands out batches of read jobs whose destinations are
  * pinned staging buffers it owns; the callee fills them (in parallel if it likes — the drop-in verb fans them out over the

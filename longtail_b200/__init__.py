@@ -42,6 +42,14 @@ class Assets(C.Structure):
                 ("path_start_offsets", C.POINTER(C.c_uint32)), ("permissions", C.POINTER(C.c_uint16)), ("path_data", C.c_char_p)]
 
 
+class StoredBlockView(C.Structure):
+    _fields_ = [("block_hash", C.c_uint64), ("data", C.c_void_p), ("size", C.c_uint64), ("chunk_count", C.c_uint32), ("tag", C.c_uint32),
+                ("raw_payload_size", C.c_uint32), ("first_chunk", C.c_uint32)]
+
+
+BLOCK_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(StoredBlockView))
+
+
 class SynthSpec(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("shared_permille", C.c_uint32), ("pool_segments", C.c_uint32),
                 ("class_mode", C.c_uint32), ("reserved", C.c_uint32)]
@@ -84,6 +92,9 @@ def load_library():
     lib.lt_b200_resident_table.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
     lib.lt_b200_build_version_index_device.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                        C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.lt_b200_write_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_uint32, C.c_uint32, C.c_uint32, BLOCK_SINK, C.c_void_p]
+    lib.lt_b200_unique_chunk_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.lt_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.lt_b200_profile_reset.argtypes = [C.c_void_p]
     lib.lt_b200_profile_read.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -91,7 +102,37 @@ def load_library():
     return lib
 
 
-KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge"}
+KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks"}
+
+
+def parse_version_index(buf):
+    """-> dict of numpy views over a serialised VersionIndex (src/longtail.c:2566-2584 layout)"""
+    b = np.frombuffer(buf, dtype=np.uint8)
+    hdr = b[:24].view("<u4")
+    A, Cn, I = int(hdr[3]), int(hdr[4]), int(hdr[5])
+    o = 24
+    out = {"version": int(hdr[0]), "hash_id": int(hdr[1]), "target_chunk_size": int(hdr[2]), "asset_count": A, "chunk_count": Cn,
+           "asset_chunk_index_count": I}
+
+    def take(name, n, dt):
+        nonlocal o
+        size = n * np.dtype(dt).itemsize
+        out[name] = b[o:o + size].view(dt)
+        o += size
+
+    take("path_hashes", A, "<u8")
+    take("content_hashes", A, "<u8")
+    take("asset_sizes", A, "<u8")
+    take("asset_chunk_counts", A, "<u4")
+    take("asset_chunk_index_starts", A, "<u4")
+    take("asset_chunk_indexes", I, "<u4")
+    take("chunk_hashes", Cn, "<u8")
+    take("chunk_sizes", Cn, "<u4")
+    take("chunk_tags", Cn, "<u4")
+    take("name_offsets", A, "<u4")
+    take("permissions", A, "<u2")
+    out["name_data"] = bytes(b[o:])
+    return out
 
 
 def chunker_params(target_chunk_size):
@@ -259,6 +300,32 @@ class Context:
         self._check(self.lib.lt_b200_hash_segments(self.handle, int(hash_type), C.c_void_p(dptr), int(base_size), offsets.ctypes.data_as(C.c_void_p),
                                                    sizes.ctypes.data_as(C.c_void_p), offsets.size, out.ctypes.data_as(C.c_void_p)), "hash_segments")
         return out
+
+    # ---- the WriteContent half
+    def unique_chunk_offsets(self, count):
+        out = np.zeros(int(count), dtype=np.uint64)
+        self._check(self.lib.lt_b200_unique_chunk_offsets(self.handle, out.ctypes.data_as(C.c_void_p), int(count)), "unique_chunk_offsets")
+        return out
+
+    def write_blocks_device(self, dptr, arena_size, chunk_hashes, chunk_sizes, chunk_tags, chunk_offsets, max_block_size=8388608,
+                            max_chunks_per_block=1024, hash_type=HASH_BLAKE3, keep_bytes=True):
+        """-> list of (block_hash, serialised stored block bytes | size) in store order"""
+        h = np.ascontiguousarray(chunk_hashes, dtype=np.uint64)
+        s = np.ascontiguousarray(chunk_sizes, dtype=np.uint32)
+        t = np.ascontiguousarray(chunk_tags, dtype=np.uint32)
+        o = np.ascontiguousarray(chunk_offsets, dtype=np.uint64)
+        blocks = []
+
+        def sink(_user, view):
+            v = view.contents
+            blocks.append((int(v.block_hash), C.string_at(v.data, v.size) if keep_bytes else int(v.size)))
+            return 0
+
+        cb = BLOCK_SINK(sink)
+        self._check(self.lib.lt_b200_write_blocks_device(self.handle, C.c_void_p(dptr), int(arena_size), h.size, h.ctypes.data_as(C.c_void_p),
+                                                         s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                                                         int(hash_type), int(max_block_size), int(max_chunks_per_block), cb, None), "write_blocks_device")
+        return blocks
 
     # ---- layer 2
     def _result(self, buf, size, copy):

@@ -29,12 +29,14 @@ enum WsSlot
     WS_TAB_HASH, WS_TAB_LEN, WS_TAB_TAG,
     WS_DEDUP_KEYS, WS_DEDUP_VALS, WS_DEDUP_FIRST, WS_DEDUP_ISFIRST, WS_DEDUP_UIDX, WS_ACI, WS_UHASH, WS_ULEN, WS_UTAG,
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
+    WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
+    WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN,
     WS_COUNT
 };
 
 enum HostSlot
 {
-    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_COUNT
+    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_BLK_META, HS_BLK_OUT_LEN, HS_BLK_STAGE, HS_COUNT
 };
 
 struct Buf
@@ -61,6 +63,8 @@ struct lt_b200_context
     char err[512] = {0};
     // chunk table left resident by the last lt_b200_chunk_ranges call
     uint32_t table_chunks = 0;
+    uint32_t unique_chunks = 0; // entries of WS_UHASH/ULEN/UTAG/UOFF left by the last index build (UOFF only for resident arenas)
+    bool unique_offsets_valid = false;
     // optional per-kernel CUDA-event timing (lt_b200_profile_*)
     bool prof_on = false;
     struct Span { cudaEvent_t a, b; int id; uint64_t bytes; };
@@ -565,8 +569,10 @@ namespace {
 // device-side table to index: [d_hash, d_len, d_tag] x chunk_count already resident
 int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, const uint32_t* asset_chunk_counts, uint32_t chunk_count,
                                   const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t hash_type,
-                                  uint32_t target_chunk_size, const void** out_buffer, uint64_t* out_size)
+                                  uint32_t target_chunk_size, const void** out_buffer, uint64_t* out_size, const uint64_t* d_chunk_off = nullptr)
 {
+    c->unique_chunks = 0;
+    c->unique_offsets_valid = false;
     const uint32_t A = a->asset_count;
     // ---- per-asset segments: content hash over the asset's chunk-hash array (src/longtail.c:2518-2537) and path hash over
     // strlen(path) bytes (src/longtail.c:1281-1297).  Both are HashBuffer calls -> same segment kernel.
@@ -625,6 +631,7 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
         TRY(ws_reserve(c, WS_UHASH, sizeof(uint64_t) * (size_t)chunk_count));
         TRY(ws_reserve(c, WS_ULEN, sizeof(uint32_t) * (size_t)chunk_count));
         TRY(ws_reserve(c, WS_UTAG, sizeof(uint32_t) * (size_t)chunk_count));
+        TRY(ws_reserve(c, WS_UOFF, sizeof(uint64_t) * (size_t)chunk_count));
         DedupBuffers db;
         db.keys = ws<uint64_t>(c, WS_DEDUP_KEYS);
         db.vals = ws<uint32_t>(c, WS_DEDUP_VALS);
@@ -638,7 +645,7 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
         launch_dedup_lookup(d_hash, chunk_count, db, c->stream);
         launch_exclusive_scan(db.is_first, chunk_count, db.uidx, ws<uint32_t>(c, WS_SCAN_TMP), c->stream);
         launch_dedup_emit(d_hash, d_len, d_tag, chunk_count, db, ws<uint32_t>(c, WS_ACI), ws<uint64_t>(c, WS_UHASH), ws<uint32_t>(c, WS_ULEN),
-                          ws<uint32_t>(c, WS_UTAG), c->stream);
+                          ws<uint32_t>(c, WS_UTAG), d_chunk_off, ws<uint64_t>(c, WS_UOFF), c->stream);
         c->launches += 6;
         CU(cudaMemcpyAsync(&unique, db.uidx + chunk_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -687,6 +694,8 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
     CU(cudaStreamSynchronize(c->stream));
     *out_buffer = hs<void>(c, HS_INDEX_OUT);
     *out_size = total;
+    c->unique_chunks = unique;
+    c->unique_offsets_valid = d_chunk_off != nullptr;
     return 0;
 }
 
@@ -805,7 +814,8 @@ extern "C" int lt_b200_index_device_assets(lt_b200_context* c, const uint8_t* d_
         asset_chunks[i] = n;
     }
     return build_index_from_device_table(c, a, asset_chunks.data(), table.chunk_count, ws<uint64_t>(c, WS_CHUNK_HASH), ws<uint32_t>(c, WS_CHUNK_LEN),
-                                         ws<uint32_t>(c, WS_CHUNK_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+                                         ws<uint32_t>(c, WS_CHUNK_TAG), hash_type, target_chunk_size, out_buffer, out_size,
+                                         ws<uint64_t>(c, WS_CHUNK_OFF));
 }
 
 extern "C" int lt_b200_index_host_assets(lt_b200_context* c, const lt_b200_assets* a, const uint8_t* const* asset_data,
@@ -1027,4 +1037,226 @@ extern "C" int lt_b200_index_stream_assets(lt_b200_context* c, const lt_b200_ass
     if (acc > 0xffffffffull) return fail(c, E2BIG, "more than 2^32 chunks");
     return build_index_from_device_table(c, a, asset_chunks.data(), (uint32_t)acc, ws<uint64_t>(c, WS_ACC_HASH), ws<uint32_t>(c, WS_ACC_LEN),
                                          ws<uint32_t>(c, WS_ACC_TAG), hash_type, target_chunk_size, out_buffer, out_size);
+}
+
+// ================================================================ block build + compress (the WriteContent half)
+
+extern "C" int lt_b200_unique_chunk_offsets(lt_b200_context* c, uint64_t* out_offsets, uint32_t count)
+{
+    if (!c || (count && !out_offsets)) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    if (!c->unique_offsets_valid || count != c->unique_chunks)
+        return fail(c, EINVAL, "no resident unique-chunk offsets for %u chunks (have %u, valid %d)", count, c->unique_chunks, (int)c->unique_offsets_valid);
+    if (!count) return 0;
+    CU(cudaMemcpyAsync(out_offsets, ws<void>(c, WS_UOFF), sizeof(uint64_t) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
+                                           const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
+                                           const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
+                                           uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user)
+{
+    if (!c || !sink || (chunk_count && (!chunk_hashes || !chunk_sizes || !chunk_arena_offsets))) return EINVAL;
+    if (max_chunks_per_block == 0) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    if (hash_type != LT_B200_HASH_BLAKE3) return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation yet", hash_type);
+    if (!chunk_count) return 0;
+
+    // ---- Longtail_CreateStoreIndex's greedy packing (src/longtail.c:6796-6860): in order; a block closes on a tag change, at
+    // max_chunks_per_block chunks, or when the next chunk would exceed max_block_size + max_block_size/10
+    struct Block { uint32_t first, count, raw, tag; };
+    std::vector<Block> blocks;
+    const uint64_t limit = (uint64_t)max_block_size + max_block_size / 10;
+    for (uint32_t i = 0; i < chunk_count;)
+    {
+        Block b = {i, 1, chunk_sizes[i], chunk_tags ? chunk_tags[i] : 0u};
+        if (b.tag != 0 && b.tag != LT_B200_COMPRESSION_LZ4) return fail(c, ENOTSUP, "compression type 0x%08x has no device implementation yet", b.tag);
+        if (chunk_arena_offsets[i] + chunk_sizes[i] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", i);
+        while (i + b.count < chunk_count)
+        {
+            const uint32_t j = i + b.count;
+            if ((chunk_tags ? chunk_tags[j] : 0u) != b.tag) break;
+            if (b.count == max_chunks_per_block) break;
+            if ((uint64_t)b.raw + chunk_sizes[j] > limit) break;
+            if (chunk_arena_offsets[j] + chunk_sizes[j] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", j);
+            b.raw += chunk_sizes[j];
+            ++b.count;
+        }
+        blocks.push_back(b);
+        i += b.count;
+    }
+    const uint32_t nblocks = (uint32_t)blocks.size();
+
+    // ---- block hashes = HashBuffer over each block's chunk-hash array (Longtail_CreateBlockIndex, src/longtail.c:3712-3770)
+    TRY(ws_reserve(c, WS_BLK_HASHES, sizeof(uint64_t) * (size_t)chunk_count + 16));
+    TRY(ws_reserve(c, WS_BLK_SEG_OFF, sizeof(uint64_t) * (size_t)nblocks));
+    TRY(ws_reserve(c, WS_BLK_SEG_LEN, sizeof(uint32_t) * (size_t)nblocks));
+    TRY(ws_reserve(c, WS_BLK_HASH_OUT, sizeof(uint64_t) * (size_t)nblocks));
+    TRY(hs_reserve(c, HS_BLK_META, (sizeof(uint64_t) * 2 + sizeof(uint32_t)) * (size_t)nblocks + 64));
+    uint64_t* h_seg_off = hs<uint64_t>(c, HS_BLK_META);
+    uint64_t* h_blk_hash = h_seg_off + nblocks;
+    uint32_t* h_seg_len = reinterpret_cast<uint32_t*>(h_blk_hash + nblocks);
+    uint64_t upper = nblocks;
+    for (uint32_t b = 0; b < nblocks; ++b)
+    {
+        h_seg_off[b] = 8ull * blocks[b].first;
+        h_seg_len[b] = 8u * blocks[b].count;
+        upper += h_seg_len[b] / 1024;
+    }
+    CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_HASHES), chunk_hashes, sizeof(uint64_t) * (size_t)chunk_count, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_SEG_OFF), h_seg_off, sizeof(uint64_t) * (size_t)nblocks, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_SEG_LEN), h_seg_len, sizeof(uint32_t) * (size_t)nblocks, cudaMemcpyHostToDevice, c->stream));
+    TRY(hash_segments_device(c, hash_type, ws<uint8_t>(c, WS_BLK_HASHES), 8ull * chunk_count, ws<uint64_t>(c, WS_BLK_SEG_OFF),
+                             ws<uint32_t>(c, WS_BLK_SEG_LEN), nblocks, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS,
+                             ws<uint64_t>(c, WS_BLK_HASH_OUT)));
+    CU(cudaMemcpyAsync(h_blk_hash, ws<void>(c, WS_BLK_HASH_OUT), sizeof(uint64_t) * (size_t)nblocks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+
+    // ---- batches of blocks bounded by a device-memory budget: gather -> LZ4 -> copy out -> sink, in store order
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = (uint64_t)(free_b * 0.4);
+    if (budget > (24ull << 30)) budget = 24ull << 30;
+    if (budget < (64ull << 20)) budget = 64ull << 20;
+    auto lz4_bound = [](uint64_t n) { return n + n / 255 + 16; }; // lib/lz4/ext/lz4.h:215
+    std::vector<uint64_t> src_off, dst_off, raw_off, out_off;
+    std::vector<uint32_t> len, raw_len;
+    uint32_t done_chunks = 0;
+    for (uint32_t b0 = 0; b0 < nblocks;)
+    {
+        uint64_t raw_bytes = 0, out_bytes = 0;
+        uint32_t b1 = b0;
+        raw_off.clear(); out_off.clear(); raw_len.clear(); src_off.clear(); dst_off.clear(); len.clear();
+        while (b1 < nblocks)
+        {
+            const Block& bl = blocks[b1];
+            const uint64_t r = ((uint64_t)bl.raw + 16 + 15) & ~15ull;
+            const uint64_t o = bl.tag ? ((8 + lz4_bound(bl.raw) + 15) & ~15ull) : 0;
+            if (b1 > b0 && raw_bytes + out_bytes + r + o > budget) break;
+            raw_off.push_back(raw_bytes);
+            out_off.push_back(out_bytes);
+            raw_len.push_back(bl.raw);
+            uint64_t w = raw_bytes;
+            for (uint32_t k = 0; k < bl.count; ++k)
+            {
+                src_off.push_back(chunk_arena_offsets[bl.first + k]);
+                dst_off.push_back(w);
+                len.push_back(chunk_sizes[bl.first + k]);
+                w += chunk_sizes[bl.first + k];
+            }
+            raw_bytes += r;
+            out_bytes += o;
+            ++b1;
+        }
+        const uint32_t nb = b1 - b0;
+        const uint32_t nc = (uint32_t)len.size();
+        TRY(ws_reserve(c, WS_BLK_RAW, raw_bytes + 64));
+        TRY(ws_reserve(c, WS_BLK_OUT, out_bytes + 64));
+        TRY(ws_reserve(c, WS_BLK_SRC_OFF, sizeof(uint64_t) * (size_t)nc));
+        TRY(ws_reserve(c, WS_BLK_DST_OFF, sizeof(uint64_t) * (size_t)nc));
+        TRY(ws_reserve(c, WS_BLK_LEN, sizeof(uint32_t) * (size_t)nc));
+        TRY(ws_reserve(c, WS_BLK_RAW_OFF, sizeof(uint64_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_RAW_LEN, sizeof(uint32_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_OUT_OFF, sizeof(uint64_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_SRC_OFF), src_off.data(), sizeof(uint64_t) * (size_t)nc, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_DST_OFF), dst_off.data(), sizeof(uint64_t) * (size_t)nc, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_LEN), len.data(), sizeof(uint32_t) * (size_t)nc, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_OFF), raw_off.data(), sizeof(uint64_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_LEN), raw_len.data(), sizeof(uint32_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_OUT_OFF), out_off.data(), sizeof(uint64_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream)); // the host vectors are reused by the next batch
+        {
+            ProfScope ps(c, LT_B200_KERNEL_GATHER, raw_bytes);
+            launch_gather_chunks(d_arena, ws<uint64_t>(c, WS_BLK_SRC_OFF), ws<uint64_t>(c, WS_BLK_DST_OFF), ws<uint32_t>(c, WS_BLK_LEN),
+                                 ws<uint8_t>(c, WS_BLK_RAW), nc, c->stream);
+        }
+        // LZ4 over the compressed-tag blocks of the batch: the kernel is launched over all blocks; raw ones are skipped by length 0
+        // in the launch table — simpler: launch over the whole batch and let tag-0 blocks be served straight from the raw buffer
+        std::vector<uint32_t> lz_idx;
+        for (uint32_t i = 0; i < nb; ++i) if (blocks[b0 + i].tag) lz_idx.push_back(i);
+        if (!lz_idx.empty())
+        {
+            // compact launch tables for the LZ4 blocks
+            std::vector<uint64_t> lro(lz_idx.size()), loo(lz_idx.size());
+            std::vector<uint32_t> lrl(lz_idx.size());
+            for (size_t i = 0; i < lz_idx.size(); ++i) { lro[i] = raw_off[lz_idx[i]]; loo[i] = out_off[lz_idx[i]]; lrl[i] = raw_len[lz_idx[i]]; }
+            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_OFF), lro.data(), sizeof(uint64_t) * lro.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_OUT_OFF), loo.data(), sizeof(uint64_t) * loo.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_LEN), lrl.data(), sizeof(uint32_t) * lrl.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            uint64_t lz_bytes = 0;
+            for (uint32_t v : lrl) lz_bytes += v;
+            ProfScope ps(c, LT_B200_KERNEL_LZ4, lz_bytes);
+            CU(launch_lz4_blocks(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
+                                 ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), (uint32_t)lz_idx.size(), c->stream));
+        }
+        c->launches += 2;
+        TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb + 16));
+        uint32_t* h_out_len = hs<uint32_t>(c, HS_BLK_OUT_LEN);
+        if (!lz_idx.empty())
+            CU(cudaMemcpyAsync(h_out_len, ws<void>(c, WS_BLK_OUT_LEN), sizeof(uint32_t) * lz_idx.size(), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        std::vector<uint32_t> payload_len(nb);
+        for (uint32_t i = 0; i < nb; ++i) payload_len[i] = blocks[b0 + i].raw;
+        for (size_t i = 0; i < lz_idx.size(); ++i) payload_len[lz_idx[i]] = h_out_len[i];
+
+        // ---- serialise (Longtail_WriteStoredBlockToBuffer, src/longtail.c:4111-4150) into pinned staging, a few blocks at a time
+        const uint64_t stage_cap = 256ull << 20;
+        uint32_t i = 0;
+        while (i < nb)
+        {
+            uint64_t used = 0;
+            uint32_t j = i;
+            std::vector<uint64_t> at;
+            while (j < nb)
+            {
+                const Block& bl = blocks[b0 + j];
+                const uint64_t need = ((20 + 12ull * bl.count + payload_len[j]) + 63) & ~63ull;
+                if (j > i && used + need > stage_cap) break;
+                at.push_back(used);
+                used += need;
+                ++j;
+            }
+            TRY(hs_reserve(c, HS_BLK_STAGE, used + 64));
+            uint8_t* stage = hs<uint8_t>(c, HS_BLK_STAGE);
+            for (uint32_t k = i; k < j; ++k)
+            {
+                const Block& bl = blocks[b0 + k];
+                uint8_t* p = stage + at[k - i];
+                memcpy(p, &h_blk_hash[b0 + k], 8);
+                memcpy(p + 8, &hash_type, 4);
+                memcpy(p + 12, &bl.count, 4);
+                memcpy(p + 16, &bl.tag, 4);
+                memcpy(p + 20, chunk_hashes + bl.first, 8ull * bl.count);
+                memcpy(p + 20 + 8ull * bl.count, chunk_sizes + bl.first, 4ull * bl.count);
+                const uint8_t* d_payload = bl.tag ? ws<uint8_t>(c, WS_BLK_OUT) + out_off[k] : ws<uint8_t>(c, WS_BLK_RAW) + raw_off[k];
+                CU(cudaMemcpyAsync(p + 20 + 12ull * bl.count, d_payload, payload_len[k], cudaMemcpyDeviceToHost, c->stream));
+            }
+            CU(cudaStreamSynchronize(c->stream));
+            for (uint32_t k = i; k < j; ++k)
+            {
+                const Block& bl = blocks[b0 + k];
+                lt_b200_stored_block_view v;
+                v.block_hash = h_blk_hash[b0 + k];
+                v.data = stage + at[k - i];
+                v.size = 20 + 12ull * bl.count + payload_len[k];
+                v.chunk_count = bl.count;
+                v.tag = bl.tag;
+                v.raw_payload_size = bl.raw;
+                v.first_chunk = bl.first;
+                int err = sink(user, &v);
+                if (err) return fail(c, err, "block sink failed with %d", err);
+            }
+            i = j;
+        }
+        done_chunks += nc;
+        b0 = b1;
+    }
+    (void)done_chunks;
+    return 0;
 }

@@ -27,6 +27,12 @@ void launch_blake3_leaves(const uint8_t* d_base, uint64_t base_size, const uint6
 void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, uint32_t count, uint32_t* d_cvs, uint64_t* d_hash_out,
                          cudaStream_t st);
 
+// ---- lz4.cu
+cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
+                              const uint64_t* d_out_off, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st);
+void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, const uint64_t* d_dst_off, const uint32_t* d_len,
+                          uint8_t* d_out, uint32_t count, cudaStream_t st);
+
 // ---- util.cu
 // exclusive prefix sum of count u32 values into out[0..count]; out[count] = total.  tmp: >= scan_tmp_words(count) u32.
 size_t scan_tmp_words(uint32_t count);
@@ -46,7 +52,7 @@ void launch_dedup_insert(const uint64_t* d_hash, uint32_t count, const DedupBuff
 void launch_dedup_lookup(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st);
 void launch_dedup_emit(const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, const DedupBuffers& b,
                        uint32_t* d_asset_chunk_index, uint64_t* d_unique_hash, uint32_t* d_unique_len, uint32_t* d_unique_tag,
-                       cudaStream_t st);
+                       const uint64_t* d_chunk_off, uint64_t* d_unique_off, cudaStream_t st);
 void launch_fill_u32(uint32_t* d, uint32_t value, size_t count, cudaStream_t st);
 
 // ---- synth.cu : deterministic synthetic asset bytes (include/lt_synth.h)

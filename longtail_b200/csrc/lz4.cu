@@ -1,0 +1,327 @@
+// lz4.cu — bit-exact LZ4 block encoder (LZ4_compress_fast, acceleration 1, notLimited / noDict) on sm_100a.
+//
+// Re-design of lib/lz4/ext/lz4.c:930-1338 (LZ4_compress_generic_validated as reached from
+// LZ4CompressionAPI_Compress, lib/lz4/longtail_lz4.c:52-77) for one WARP per stored block:
+//
+//  * the greedy parse is inherently sequential (the hash table's content depends on the parse), so a warp owns one block
+//    and its 16 KiB table in shared memory; parallelism across blocks comes from the grid;
+//  * inside the block the warp speculates the next 32 probe positions of the deterministic skip schedule
+//    (step = searchMatchNb++ >> 6, lz4.c:1023-1053): every lane hashes its position, intra-batch table conflicts are
+//    resolved with __match_any_sync (a lane's candidate is the closest lower lane with the same hash, else the table), the
+//    first matching lane wins (__ballot_sync) and only the table writes up to it are committed — exactly the state the
+//    sequential loop would have reached;
+//  * match extension (LZ4_count, lz4.c:1181), backward catch-up (:1104-1109), literal / length emission (:1112-1226) are
+//    lane-parallel.
+//
+// Output bytes are identical to the reference's for every input (tests/test_gpu_lz4.py).
+#include "lt_device.cuh"
+#include "lt_kernels.h"
+
+namespace ltb {
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t LZ4_TABLE_BYTES = 16384;
+constexpr uint32_t LZ4_64K_LIMIT = 65536 + 11; // LZ4_64Klimit, lz4.c:710
+constexpr uint32_t LZ4_MAX_DISTANCE = 65535;
+
+__device__ __forceinline__ uint32_t rd32(const uint8_t* __restrict__ s, uint32_t pos)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s + (pos & ~3u));
+    return __funnelshift_r(w[0], w[1], (pos & 3u) * 8u); // w[1] is only consumed when pos is unaligned (then it is in bounds)
+}
+__device__ __forceinline__ uint64_t rd64(const uint8_t* __restrict__ s, uint32_t pos)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s + (pos & ~3u));
+    const uint32_t sh = (pos & 3u) * 8u;
+    const uint32_t a = w[0], b = w[1], c = w[2];
+    return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
+}
+
+template <bool U16>
+__device__ __forceinline__ uint32_t lz4_hash(const uint8_t* __restrict__ s, uint32_t pos)
+{
+    if (U16) return (rd32(s, pos) * 2654435761u) >> 19;                   // LZ4_hash4, 13 bits (lz4.c:777-783)
+    return (uint32_t)(((rd64(s, pos) << 24) * 889523592379ull) >> 52);    // LZ4_hash5, 12 bits (lz4.c:785-795)
+}
+template <bool U16>
+__device__ __forceinline__ uint32_t tab_get(const uint32_t* t32, uint32_t h)
+{
+    return U16 ? (uint32_t)reinterpret_cast<const uint16_t*>(t32)[h] : t32[h];
+}
+template <bool U16>
+__device__ __forceinline__ void tab_put(uint32_t* t32, uint32_t h, uint32_t v)
+{
+    if (U16) reinterpret_cast<uint16_t*>(t32)[h] = (uint16_t)v; else t32[h] = v;
+}
+
+// position of the k-th probe of a search that started at S (k = 0, 1, ...): advances are 1 for k = 0 and (63+k)>>6 after
+__device__ __forceinline__ uint32_t probe_pos(uint32_t S, uint32_t k)
+{
+    if (k == 0) return S;
+    const uint32_t u = k - 1, q = u >> 6, r = u & 63u;
+    return S + 1u + 32u * q * (q + 1u) + r * (q + 1u);
+}
+__device__ __forceinline__ uint32_t probe_advance(uint32_t k) { return k == 0 ? 1u : (63u + k) >> 6; }
+
+// lane-parallel: dst[0..n) = 255 repeated, then the tail byte — the LZ4 length continuation (lz4.c:1126-1130, 1213-1224)
+__device__ __forceinline__ uint32_t put_length(uint8_t* __restrict__ dst, uint32_t op, uint32_t len, uint32_t lane)
+{
+    const uint32_t full = len / 255u;
+    for (uint32_t i = lane; i < full; i += 32) dst[op + i] = 255;
+    if (lane == 0) dst[op + full] = (uint8_t)(len - full * 255u);
+    return op + full + 1u;
+}
+
+__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane)
+{
+    // literal runs: short in compressible data, the whole block in incompressible data -> aligned word stores assembled
+    // from the (arbitrarily aligned) source with a funnel shift; head and tail by bytes
+    uint32_t i = 0;
+    if (n >= 128)
+    {
+        const uint32_t head = (4u - ((uintptr_t)dst & 3u)) & 3u;
+        if (lane < head) dst[lane] = src[lane];
+        const uint32_t words = (n - head - 4u) >> 2; // the funnel reads one word ahead: stay 4 bytes clear of the end
+        const uint8_t* s2 = src + head;
+        const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3u) * 8u;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - ((uintptr_t)s2 & 3u));
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
+        for (uint32_t w = lane; w < words; w += 32) d4[w] = __funnelshift_r(sw[w], sw[w + 1], sh);
+        i = head + words * 4u;
+    }
+    for (uint32_t j = i + lane; j < n; j += 32) dst[j] = src[j];
+}
+
+template <bool U16>
+__device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t* table, uint32_t lane)
+{
+    uint32_t op = 0;
+    uint32_t anchor = 0;
+    if (n >= 13) // LZ4_minLength (lz4.c:1001)
+    {
+        for (uint32_t i = lane; i < LZ4_TABLE_BYTES / 4; i += 32) table[i] = 0;
+        __syncwarp();
+        const uint32_t mflimit_plus_one = n - 11;
+        const uint32_t matchlimit = n - 5;
+        if (lane == 0) tab_put<U16>(table, lz4_hash<U16>(src, 0), 0); // lz4.c:1004-1010
+        __syncwarp();
+        uint32_t S = 1;   // start of the current search
+        uint32_t k0 = 0;  // probes of this search already committed
+        for (;;)
+        {
+            // ---------------- search: 32 probes per step (lz4.c:1043-1100)
+            uint32_t ip, match;
+            bool found = false, finished = false;
+            for (;;)
+            {
+                const uint32_t k = k0 + lane;
+                const uint32_t p = probe_pos(S, k);
+                const bool valid = p + probe_advance(k) <= mflimit_plus_one && p < n; // else: goto _last_literals before probing
+                const uint32_t h = valid ? lz4_hash<U16>(src, p) : 0xffffffffu - lane;
+                const uint32_t same = __match_any_sync(FULL, h);
+                const uint32_t lower = same & ((1u << lane) - 1u);
+                // candidate = what the sequential loop would find in the table: the closest lower lane of this batch with the
+                // same hash, else the committed table
+                const uint32_t from_lane = __shfl_sync(FULL, p, lower ? 31 - __clz(lower) : (int)lane);
+                const uint32_t cand = lower ? from_lane : (valid ? tab_get<U16>(table, h) : 0u);
+                bool hit = false;
+                if (valid && (U16 || cand + LZ4_MAX_DISTANCE >= p)) hit = rd32(src, cand) == rd32(src, p);
+                const uint32_t hits = __ballot_sync(FULL, hit);
+                const uint32_t valids = __ballot_sync(FULL, valid);
+                // lanes whose table write is committed: valid lanes up to and including the first hit
+                const uint32_t first_hit = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+                const uint32_t commit = valids & (first_hit >= 31u ? FULL : ((2u << first_hit) - 1u));
+                const uint32_t group = same & commit;
+                if ((commit >> lane) & 1u)
+                    if ((31 - __clz(group)) == (int)lane) tab_put<U16>(table, h, p); // the last writer of a hash value wins
+                __syncwarp();
+                if (hits)
+                {
+                    ip = __shfl_sync(FULL, p, first_hit);
+                    match = __shfl_sync(FULL, cand, first_hit);
+                    found = true;
+                    break;
+                }
+                if (valids != FULL)
+                {
+                    finished = true;
+                    break;
+                }
+                k0 += 32;
+            }
+            if (finished) break;
+
+            // ---------------- catch up (lz4.c:1104-1109)
+            for (;;)
+            {
+                bool eq = false;
+                if (ip > anchor + lane && match > lane) eq = src[ip - 1 - lane] == src[match - 1 - lane];
+                const uint32_t m = __ballot_sync(FULL, eq);
+                const uint32_t run = m == FULL ? 32u : (uint32_t)__ffs(~m) - 1u;
+                ip -= run;
+                match -= run;
+                if (run < 32) break;
+            }
+
+            bool literals_done = false;
+            for (;;) // _next_match (lz4.c:1140-1296)
+            {
+                // match length beyond MINMATCH: LZ4_count(ip+4, match+4, matchlimit)
+                uint32_t a = ip + 4, b = match + 4, code = 0;
+                for (;;)
+                {
+                    const uint32_t pa = a + 4 * lane;
+                    uint32_t eqb = 0; // equal bytes this lane contributes (0..4)
+                    bool stop = true;
+                    if (pa < matchlimit)
+                    {
+                        const uint32_t x = rd32(src, pa) ^ rd32(src, b + 4 * lane);
+                        eqb = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                        const uint32_t room = matchlimit - pa;
+                        if (eqb > room) eqb = room;
+                        stop = eqb < 4u;
+                    }
+                    const uint32_t stops = __ballot_sync(FULL, stop);
+                    if (stops)
+                    {
+                        const uint32_t f = (uint32_t)__ffs(stops) - 1u;
+                        code += 4u * f + __shfl_sync(FULL, eqb, f);
+                        break;
+                    }
+                    code += 128;
+                    a += 128;
+                    b += 128;
+                }
+                // token, literals (lz4.c:1112-1137) — skipped for the zero-literal sequences found by the post-match test
+                const uint32_t lit = literals_done ? 0u : ip - anchor;
+                const uint32_t token_pos = op++;
+                if (lit >= 15) op = put_length(dst, op, lit - 15, lane);
+                if (lit) copy_bytes(dst + op, src + anchor, lit, lane);
+                op += lit;
+                const uint32_t off = ip - match;
+                if (lane == 0)
+                {
+                    dst[op] = (uint8_t)off; // LZ4_writeLE16 (lz4.c:1157-1163)
+                    dst[op + 1] = (uint8_t)(off >> 8);
+                    dst[token_pos] = (uint8_t)((lit >= 15 ? 15u : lit) << 4 | (code >= 15 ? 15u : code));
+                }
+                op += 2;
+                if (code >= 15) op = put_length(dst, op, code - 15, lane);
+                ip += code + 4;
+                anchor = ip;
+                if (ip >= mflimit_plus_one) { finished = true; break; } // lz4.c:1233
+                // fill table with ip-2, then test ip itself (lz4.c:1236-1294)
+                const uint32_t h2 = lz4_hash<U16>(src, ip - 2);
+                const uint32_t h = lz4_hash<U16>(src, ip);
+                uint32_t cand = 0;
+                if (lane == 0)
+                {
+                    tab_put<U16>(table, h2, ip - 2);
+                    cand = tab_get<U16>(table, h);
+                    tab_put<U16>(table, h, ip);
+                }
+                cand = __shfl_sync(FULL, cand, 0);
+                __syncwarp();
+                if ((U16 || cand + LZ4_MAX_DISTANCE >= ip) && rd32(src, cand) == rd32(src, ip))
+                {
+                    match = cand;
+                    literals_done = true; // token = 0 literals, straight to the next match
+                    continue;
+                }
+                break;
+            }
+            if (finished) break;
+            S = ip + 1; // lz4.c:1298: forwardH = hash(++ip), a fresh search (step 1, searchMatchNb reset)
+            k0 = 0;
+            (void)found;
+        }
+    }
+    // last literals (lz4.c:1302-1329)
+    const uint32_t last = n - anchor;
+    const uint32_t token_pos = op++;
+    if (lane == 0) dst[token_pos] = (uint8_t)((last >= 15 ? 15u : last) << 4);
+    if (last >= 15) op = put_length(dst, op, last - 15, lane);
+    if (last) copy_bytes(dst + op, src + anchor, last, lane);
+    op += last;
+    return op;
+}
+
+} // namespace
+
+// one warp (= one CTA) per block.  dst layout per block: [u32 raw_size][u32 compressed_size][codec bytes]  — the payload
+// header compressblockstore writes (lib/compressblockstore/longtail_compressblockstore.c:103-137)
+__global__ void __launch_bounds__(32)
+k_lz4_blocks(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len,
+             uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t block_count)
+{
+    extern __shared__ __align__(16) uint32_t s_table[];
+    const uint32_t b = blockIdx.x;
+    if (b >= block_count) return;
+    const uint32_t lane = threadIdx.x;
+    const uint8_t* src = raw_base + raw_off[b];
+    const uint32_t n = raw_len[b];
+    uint8_t* dst = out_base + out_off[b];
+    uint32_t c = n < LZ4_64K_LIMIT ? lz4_encode_block<true>(src, n, dst + 8, s_table, lane)
+                                   : lz4_encode_block<false>(src, n, dst + 8, s_table, lane);
+    if (lane == 0)
+    {
+        reinterpret_cast<uint32_t*>(dst)[0] = n;
+        reinterpret_cast<uint32_t*>(dst)[1] = c;
+        out_len[b] = c + 8;
+    }
+}
+
+// payload gather (WriteContentBlockJob, src/longtail.c:4640-4721): block payload = its chunks' bytes, back to back.
+// One CTA per chunk copy job.
+__global__ void __launch_bounds__(256)
+k_gather_chunks(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ dst_off,
+                const uint32_t* __restrict__ len, uint8_t* __restrict__ out, uint32_t count)
+{
+    const uint32_t c = blockIdx.x;
+    if (c >= count) return;
+    const uint8_t* s = arena + src_off[c];
+    uint8_t* d = out + dst_off[c];
+    const uint32_t n = len[c];
+    // align the destination to 16 bytes, then move 16-byte vectors assembled from the (arbitrarily aligned) source
+    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
+    for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+    const uint8_t* s2 = s + head;
+    uint8_t* d2 = d + head;
+    const uint32_t vecs = n - head >= 20u ? (n - head - 4u) >> 4 : 0u; // the funnel reads one word ahead: stay clear of the end
+    const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - ((uintptr_t)s2 & 3u));
+    for (uint32_t v = threadIdx.x; v < vecs; v += blockDim.x)
+    {
+        const uint32_t* w = sw + 4 * v;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        uint4 o;
+        if (sh)
+        {
+            const uint32_t w4 = w[4];
+            o = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+        else
+            o = make_uint4(w0, w1, w2, w3);
+        reinterpret_cast<uint4*>(d2)[v] = o;
+    }
+    for (uint32_t i = head + vecs * 16u + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
+cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
+                              const uint64_t* d_out_off, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st)
+{
+    if (!block_count) return cudaSuccess;
+    k_lz4_blocks<<<block_count, 32, LZ4_TABLE_BYTES, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, block_count);
+    return cudaGetLastError();
+}
+
+void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, const uint64_t* d_dst_off, const uint32_t* d_len,
+                          uint8_t* d_out, uint32_t count, cudaStream_t st)
+{
+    if (!count) return;
+    k_gather_chunks<<<count, 256, 0, st>>>(d_arena, d_src_off, d_dst_off, d_len, d_out, count);
+}
+
+} // namespace ltb

@@ -182,7 +182,8 @@ __global__ void k_dedup_lookup(const uint64_t* __restrict__ hash, uint32_t count
 __global__ void k_dedup_emit(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ len, const uint32_t* __restrict__ tag,
                              uint32_t count, const uint32_t* __restrict__ first, const uint32_t* __restrict__ is_first,
                              const uint32_t* __restrict__ uidx, uint32_t* __restrict__ asset_chunk_index,
-                             uint64_t* __restrict__ unique_hash, uint32_t* __restrict__ unique_len, uint32_t* __restrict__ unique_tag)
+                             uint64_t* __restrict__ unique_hash, uint32_t* __restrict__ unique_len, uint32_t* __restrict__ unique_tag,
+                             const uint64_t* __restrict__ chunk_off, uint64_t* __restrict__ unique_off)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -193,6 +194,7 @@ __global__ void k_dedup_emit(const uint64_t* __restrict__ hash, const uint32_t* 
         unique_hash[u] = hash[i];
         unique_len[u] = len[i];
         unique_tag[u] = tag[i]; // tag of the first occurrence (src/longtail.c:2962)
+        if (chunk_off) unique_off[u] = chunk_off[i]; // where the first occurrence's bytes live (CreateAssetPartLookup, :4429-4500)
     }
 }
 
@@ -210,11 +212,11 @@ void launch_dedup_lookup(const uint64_t* d_hash, uint32_t count, const DedupBuff
 
 void launch_dedup_emit(const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, const DedupBuffers& b,
                        uint32_t* d_asset_chunk_index, uint64_t* d_unique_hash, uint32_t* d_unique_len, uint32_t* d_unique_tag,
-                       cudaStream_t st)
+                       const uint64_t* d_chunk_off, uint64_t* d_unique_off, cudaStream_t st)
 {
     if (!count) return;
     k_dedup_emit<<<(count + 255) / 256, 256, 0, st>>>(d_hash, d_len, d_tag, count, b.first, b.is_first, b.uidx, d_asset_chunk_index,
-                                                      d_unique_hash, d_unique_len, d_unique_tag);
+                                                      d_unique_hash, d_unique_len, d_unique_tag, d_chunk_off, d_unique_off);
 }
 
 // ---------------------------------------------------------------- synthetic assets (bench / test inputs only)
