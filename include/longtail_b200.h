@@ -209,6 +209,16 @@ LT_B200_EXPORT int lt_b200_write_blocks_device(lt_b200_context* context, const u
                                                const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
                                                uint32_t max_block_size, uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user);
 
+/* CompressionAPI.Compress / Decompress (src/longtail.h:266-272) for 'lz42' over `count` independent HOST buffers in one
+ * launch: LZ4_compress_fast(acceleration 1) / LZ4_decompress_safe semantics (lib/lz4/longtail_lz4.c:52-101), output bytes
+ * identical to the reference codec.  dst_capacity[i] must be at least lt_b200_lz4_bound(src_size[i]) for compression
+ * (the reference asserts the same through GetMaxCompressedSize).  Errors: ENOMEM capacity too small, EBADF malformed input. */
+LT_B200_EXPORT uint64_t lt_b200_lz4_bound(uint64_t size); /* LZ4_COMPRESSBOUND, lib/lz4/ext/lz4.h:215 */
+LT_B200_EXPORT int lt_b200_lz4_compress_host(lt_b200_context* context, uint32_t count, const void* const* src, const uint32_t* src_size,
+                                             void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
+LT_B200_EXPORT int lt_b200_lz4_decompress_host(lt_b200_context* context, uint32_t count, const void* const* src, const uint32_t* src_size,
+                                               void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
+
 /* Arena offsets of the unique chunks (first occurrences, VersionIndex order) found by the last lt_b200_index_device_assets
  * call on this context — the `chunk_arena_offsets` of a fresh-store lt_b200_write_blocks_device. */
 LT_B200_EXPORT int lt_b200_unique_chunk_offsets(lt_b200_context* context, uint64_t* out_offsets, uint32_t count);

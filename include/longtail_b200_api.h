@@ -60,6 +60,25 @@ LT_B200_EXPORT int Longtail_B200_CreateVersionIndex(
     int enable_file_map,
     struct Longtail_VersionIndex** out_version_index);
 
+/* CompressionAPI (src/longtail.h:266-272) for the 'lz42' type id: LZ4_compress_fast(acceleration 1) / LZ4_decompress_safe on the
+ * GPU, byte-identical to lib/lz4/longtail_lz4.c.  Compress returns ENOMEM when max_compressed_size is below
+ * GetMaxCompressedSize (the reference returns ENOMEM when LZ4 reports 0), Decompress returns EBADF on a malformed stream. */
+LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CreateB200LZ4CompressionAPI(void);
+/* Longtail_CompressionRegistry_CreateForTypeFunc (lib/compressionregistry/longtail_compression_registry.h:9): hand it to
+ * Longtail_CreateDefaultCompressionRegistry in place of Longtail_CompressionRegistry_CreateForLZ4 */
+LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CompressionRegistry_CreateForB200LZ4(uint32_t compression_type, uint32_t* out_settings);
+
+/* BlockStoreAPI decorator, replaces Longtail_CreateCompressBlockStoreAPI (lib/compressblockstore/longtail_compressblockstore.c:622):
+ * PutStoredBlock compresses on the GPU — concurrent calls from the JobAPI workers are gathered into one launch by a
+ * background thread, the caller's block stays alive until OnComplete as in the reference (:151-176) — and forwards the
+ * compressed block to the backing store; GetStoredBlock fetches from the backing store and decodes on the GPU;
+ * tag 0 passes through untouched; PruneBlocks returns ENOTSUP (:483-493); stats count what the reference counts (:199-201,
+ * :362-363).  Compression types without a device kernel make PutStoredBlock / GetStoredBlock fail with ENOTSUP.
+ * `compression_registry` is accepted for signature compatibility and not used. */
+LT_B200_EXPORT struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockStoreAPI(
+    struct Longtail_BlockStoreAPI* backing_block_store,
+    struct Longtail_CompressionRegistryAPI* compression_registry);
+
 #ifdef __cplusplus
 }
 #endif

@@ -329,8 +329,10 @@ class Context:
 
     # ---- layer 2
     def _result(self, buf, size, copy):
+        if copy:
+            return C.string_at(buf.value, size.value)
         raw = (C.c_uint8 * max(size.value, 1)).from_address(buf.value)
-        return bytes(raw[:size.value]) if copy else memoryview(raw)[:size.value]
+        return memoryview(raw)[:size.value]
 
     def build_version_index(self, assets, asset_chunk_counts, chunk_hashes=None, chunk_sizes=None, chunk_tags=None, chunk_count=None,
                             hash_type=HASH_BLAKE3, target_chunk_size=32768, copy=True):

@@ -30,7 +30,7 @@ enum WsSlot
     WS_DEDUP_KEYS, WS_DEDUP_VALS, WS_DEDUP_FIRST, WS_DEDUP_ISFIRST, WS_DEDUP_UIDX, WS_ACI, WS_UHASH, WS_ULEN, WS_UTAG,
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
-    WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN,
+    WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT,
     WS_COUNT
 };
 
@@ -1182,8 +1182,18 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
         {
             // compact launch tables for the LZ4 blocks
             std::vector<uint64_t> lro(lz_idx.size()), loo(lz_idx.size());
-            std::vector<uint32_t> lrl(lz_idx.size());
-            for (size_t i = 0; i < lz_idx.size(); ++i) { lro[i] = raw_off[lz_idx[i]]; loo[i] = out_off[lz_idx[i]]; lrl[i] = raw_len[lz_idx[i]]; }
+            std::vector<uint32_t> lrl(lz_idx.size()), ljs(lz_idx.size());
+            uint32_t job_cap = 0;
+            for (size_t i = 0; i < lz_idx.size(); ++i)
+            {
+                lro[i] = raw_off[lz_idx[i]]; loo[i] = out_off[lz_idx[i]]; lrl[i] = raw_len[lz_idx[i]];
+                ljs[i] = job_cap;
+                job_cap += lz4_copy_job_capacity(lrl[i]);
+            }
+            TRY(ws_reserve(c, WS_BLK_JOBS, sizeof(uint3) * (size_t)job_cap));
+            TRY(ws_reserve(c, WS_BLK_JOB_START, sizeof(uint32_t) * lz_idx.size()));
+            TRY(ws_reserve(c, WS_BLK_JOB_COUNT, sizeof(uint32_t) * lz_idx.size()));
+            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_JOB_START), ljs.data(), sizeof(uint32_t) * ljs.size(), cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_OFF), lro.data(), sizeof(uint64_t) * lro.size(), cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_OUT_OFF), loo.data(), sizeof(uint64_t) * loo.size(), cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_LEN), lrl.data(), sizeof(uint32_t) * lrl.size(), cudaMemcpyHostToDevice, c->stream));
@@ -1192,9 +1202,10 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
             for (uint32_t v : lrl) lz_bytes += v;
             ProfScope ps(c, LT_B200_KERNEL_LZ4, lz_bytes);
             CU(launch_lz4_blocks(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
-                                 ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), (uint32_t)lz_idx.size(), c->stream));
+                                 ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), ws<uint3>(c, WS_BLK_JOBS),
+                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), (uint32_t)lz_idx.size(), c->stream));
         }
-        c->launches += 2;
+        c->launches += 3;
         TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb + 16));
         uint32_t* h_out_len = hs<uint32_t>(c, HS_BLK_OUT_LEN);
         if (!lz_idx.empty())
@@ -1259,4 +1270,108 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
     }
     (void)done_chunks;
     return 0;
+}
+
+// ================================================================ CompressionAPI batch entry points (host buffers)
+
+extern "C" uint64_t lt_b200_lz4_bound(uint64_t size) { return size + size / 255 + 16; }
+
+namespace {
+
+// shared driver of the two directions: stage inputs at 16-byte aligned offsets, run `launch`, copy results out
+int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
+                     const uint64_t* dst_capacity, uint64_t* out_size, bool compress)
+{
+    if (!c || (count && (!src || !src_size || !dst || !dst_capacity || !out_size))) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = (uint64_t)(free_b * 0.4);
+    if (budget > (16ull << 30)) budget = 16ull << 30;
+    std::vector<uint64_t> in_off, out_off;
+    std::vector<uint32_t> in_len, out_cap, job_start;
+    for (uint32_t i0 = 0; i0 < count;)
+    {
+        uint64_t in_bytes = 0, out_bytes = 0;
+        uint32_t job_cap = 0;
+        uint32_t i1 = i0;
+        in_off.clear(); out_off.clear(); in_len.clear(); out_cap.clear(); job_start.clear();
+        while (i1 < count)
+        {
+            const uint64_t need_out = compress ? 8 + lt_b200_lz4_bound(src_size[i1]) : dst_capacity[i1];
+            if (compress && dst_capacity[i1] < lt_b200_lz4_bound(src_size[i1])) return fail(c, ENOMEM, "buffer %u: capacity below LZ4_COMPRESSBOUND", i1);
+            if (need_out >= 0xffffffffull) return fail(c, E2BIG, "buffer %u too large", i1);
+            const uint64_t a = ((uint64_t)src_size[i1] + 16 + 15) & ~15ull, b = (need_out + 16 + 15) & ~15ull;
+            if (i1 > i0 && in_bytes + out_bytes + a + b > budget) break;
+            in_off.push_back(in_bytes); out_off.push_back(out_bytes); in_len.push_back(src_size[i1]); out_cap.push_back((uint32_t)need_out);
+            job_start.push_back(job_cap);
+            job_cap += lz4_copy_job_capacity(src_size[i1]);
+            in_bytes += a; out_bytes += b;
+            ++i1;
+        }
+        const uint32_t nb = i1 - i0;
+        TRY(ws_reserve(c, WS_BLK_RAW, in_bytes + 64));
+        TRY(ws_reserve(c, WS_BLK_OUT, out_bytes + 64));
+        TRY(ws_reserve(c, WS_BLK_RAW_OFF, sizeof(uint64_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_RAW_LEN, sizeof(uint32_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_OUT_OFF, sizeof(uint64_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_LEN, sizeof(uint32_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_JOBS, sizeof(uint3) * (size_t)(job_cap + 1)));
+        TRY(ws_reserve(c, WS_BLK_JOB_START, sizeof(uint32_t) * (size_t)nb));
+        TRY(ws_reserve(c, WS_BLK_JOB_COUNT, sizeof(uint32_t) * (size_t)nb));
+        for (uint32_t i = 0; i < nb; ++i)
+            if (in_len[i]) CU(cudaMemcpyAsync(ws<uint8_t>(c, WS_BLK_RAW) + in_off[i], src[i0 + i], in_len[i], cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_OFF), in_off.data(), sizeof(uint64_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_LEN), in_len.data(), sizeof(uint32_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_OUT_OFF), out_off.data(), sizeof(uint64_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_LEN), out_cap.data(), sizeof(uint32_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_JOB_START), job_start.data(), sizeof(uint32_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+        if (compress)
+        {
+            ProfScope ps(c, LT_B200_KERNEL_LZ4, in_bytes);
+            CU(launch_lz4_blocks(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
+                                 ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), ws<uint3>(c, WS_BLK_JOBS),
+                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), nb, c->stream));
+            c->launches += 2;
+        }
+        else
+        {
+            CU(launch_lz4_decode(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
+                                 ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_LEN), ws<uint32_t>(c, WS_BLK_OUT_LEN), nb, c->stream));
+            c->launches += 1;
+        }
+        TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb + 16));
+        uint32_t* h_len = hs<uint32_t>(c, HS_BLK_OUT_LEN);
+        CU(cudaMemcpyAsync(h_len, ws<void>(c, WS_BLK_OUT_LEN), sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        for (uint32_t i = 0; i < nb; ++i)
+        {
+            if (h_len[i] == 0xffffffffu) return fail(c, EBADF, "buffer %u: malformed LZ4 stream", i0 + i);
+            const uint64_t n = compress ? h_len[i] - 8u : h_len[i];                       // the kernel writes the block-store header first
+            const uint8_t* d = ws<uint8_t>(c, WS_BLK_OUT) + out_off[i] + (compress ? 8 : 0);
+            if (n > dst_capacity[i0 + i]) return fail(c, ENOMEM, "buffer %u: output does not fit", i0 + i);
+            if (n) CU(cudaMemcpyAsync(dst[i0 + i], d, n, cudaMemcpyDeviceToHost, c->stream));
+            out_size[i0 + i] = n;
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        i0 = i1;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" int lt_b200_lz4_compress_host(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
+                                         const uint64_t* dst_capacity, uint64_t* out_size)
+{
+    return codec_host_batch(c, count, src, src_size, dst, dst_capacity, out_size, true);
+}
+
+extern "C" int lt_b200_lz4_decompress_host(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
+                                           const uint64_t* dst_capacity, uint64_t* out_size)
+{
+    return codec_host_batch(c, count, src, src_size, dst, dst_capacity, out_size, false);
 }

@@ -11,8 +11,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -408,7 +412,445 @@ struct Longtail_VersionIndex* wrap_version_index(const void* data, uint64_t size
     return v;
 }
 
+// ---------------------------------------------------------------- LZ4 CompressionAPI
+const uint32_t TYPE_LZ4 = LT_B200_COMPRESSION_LZ4;
+
+struct B200CompressionAPI
+{
+    struct Longtail_CompressionAPI api;
+};
+
+size_t lz4_max_size(struct Longtail_CompressionAPI*, uint32_t, size_t size) { return (size_t)lt_b200_lz4_bound(size); }
+
+int lz4_compress(struct Longtail_CompressionAPI*, uint32_t, const char* uncompressed, char* compressed, size_t uncompressed_size,
+                 size_t max_compressed_size, size_t* out_compressed_size)
+{
+    if (!compressed || !out_compressed_size || (!uncompressed && uncompressed_size) || uncompressed_size > 0x7E000000u) return EINVAL;
+    std::lock_guard<std::mutex> g(g_gpu);
+    int err = ensure_ctx();
+    if (err) return err;
+    const void* src = uncompressed;
+    void* dst = compressed;
+    uint32_t n = (uint32_t)uncompressed_size;
+    uint64_t cap = max_compressed_size, out = 0;
+    err = lt_b200_lz4_compress_host(g_ctx, 1, &src, &n, &dst, &cap, &out);
+    if (err) return err;
+    *out_compressed_size = (size_t)out;
+    return 0;
+}
+
+int lz4_decompress(struct Longtail_CompressionAPI*, const char* compressed, char* uncompressed, size_t compressed_size,
+                   size_t max_uncompressed_size, size_t* out_uncompressed_size)
+{
+    if (!compressed || !uncompressed || !out_uncompressed_size || compressed_size > 0x7fffffffu) return EINVAL;
+    std::lock_guard<std::mutex> g(g_gpu);
+    int err = ensure_ctx();
+    if (err) return err;
+    const void* src = compressed;
+    void* dst = uncompressed;
+    uint32_t n = (uint32_t)compressed_size;
+    uint64_t cap = max_uncompressed_size > 0xfffffff0u ? 0xfffffff0u : max_uncompressed_size, out = 0;
+    err = lt_b200_lz4_decompress_host(g_ctx, 1, &src, &n, &dst, &cap, &out);
+    if (err) return err;
+    *out_uncompressed_size = (size_t)out;
+    return 0;
+}
+
+void compression_api_dispose(struct Longtail_API* api) { lt_free(api); }
+
+// ---------------------------------------------------------------- compress block store
+size_t block_index_data_size(uint32_t chunk_count) { return 8 + 4 + 4 + 4 + 12 * (size_t)chunk_count; } // src/longtail.c:3585-3597
+
+// StoredBlock + BlockIndex + index data + payload in one allocation (the shape CompressBlock / DecompressBlock build,
+// lib/compressblockstore/longtail_compressblockstore.c:103-137, :300-312)
+int owned_block_dispose(struct Longtail_StoredBlock* b)
+{
+    lt_free(b);
+    return 0;
+}
+
+struct Longtail_StoredBlock* make_owned_block(const struct Longtail_BlockIndex* index, size_t payload_capacity)
+{
+    const uint32_t n = *index->m_ChunkCount;
+    const size_t ids = block_index_data_size(n);
+    uint8_t* mem = static_cast<uint8_t*>(lt_alloc("B200CompressBlockStore", sizeof(struct Longtail_StoredBlock) + sizeof(struct Longtail_BlockIndex) + ids + payload_capacity));
+    if (!mem) return nullptr;
+    struct Longtail_StoredBlock* b = reinterpret_cast<struct Longtail_StoredBlock*>(mem);
+    struct Longtail_BlockIndex* bi = reinterpret_cast<struct Longtail_BlockIndex*>(mem + sizeof(struct Longtail_StoredBlock));
+    uint8_t* p = reinterpret_cast<uint8_t*>(bi) + sizeof(struct Longtail_BlockIndex);
+    memcpy(p, index->m_BlockHash, ids); // the index data is contiguous from m_BlockHash on (Longtail_InitBlockIndex, src/longtail.c:3599-3627)
+    bi->m_BlockHash = reinterpret_cast<TLongtail_Hash*>(p);
+    bi->m_HashIdentifier = reinterpret_cast<uint32_t*>(p + 8);
+    bi->m_ChunkCount = reinterpret_cast<uint32_t*>(p + 12);
+    bi->m_Tag = reinterpret_cast<uint32_t*>(p + 16);
+    bi->m_ChunkHashes = reinterpret_cast<TLongtail_Hash*>(p + 20);
+    bi->m_ChunkSizes = reinterpret_cast<uint32_t*>(p + 20 + 8 * (size_t)n);
+    b->Dispose = owned_block_dispose;
+    b->m_BlockIndex = bi;
+    b->m_BlockData = p + ids;
+    b->m_BlockChunksDataSize = 0;
+    return b;
+}
+
+struct B200CompressStore;
+
+struct PutRequest
+{
+    struct Longtail_AsyncPutStoredBlockAPI api; // handed to the backing store; first member so the pointer converts back
+    B200CompressStore* store;
+    struct Longtail_StoredBlock* compressed;
+    struct Longtail_AsyncPutStoredBlockAPI* caller;
+};
+
+struct GetRequest
+{
+    struct Longtail_AsyncGetStoredBlockAPI api;
+    B200CompressStore* store;
+    struct Longtail_AsyncGetStoredBlockAPI* caller;
+};
+
+struct PendingPut
+{
+    struct Longtail_StoredBlock* block;
+    struct Longtail_AsyncPutStoredBlockAPI* caller;
+};
+
+struct B200CompressStore
+{
+    struct Longtail_BlockStoreAPI api;
+    struct Longtail_BlockStoreAPI* backing;
+    std::atomic<uint64_t> stats[Longtail_BlockStoreAPI_StatU64_Count];
+    std::mutex lock;
+    std::condition_variable wake;
+    std::vector<PendingPut> queue;
+    std::vector<struct Longtail_AsyncFlushAPI*> flushers;
+    int pending = 0; // requests not yet completed (guarded by lock)
+    bool stop = false;
+    std::thread worker;
+};
+
+void store_complete_request(B200CompressStore* s)
+{
+    std::vector<struct Longtail_AsyncFlushAPI*> fire;
+    {
+        std::lock_guard<std::mutex> g(s->lock);
+        if (--s->pending == 0) fire.swap(s->flushers);
+    }
+    for (auto* f : fire) f->OnComplete(f, 0); // longtail_compressblockstore.c:30-50
+}
+
+void put_backing_complete(struct Longtail_AsyncPutStoredBlockAPI* api, int err)
+{
+    PutRequest* r = reinterpret_cast<PutRequest*>(api);
+    B200CompressStore* s = r->store;
+    if (err) s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_FailCount]++;
+    if (r->compressed) r->compressed->Dispose(r->compressed);
+    r->caller->OnComplete(r->caller, err);
+    lt_free(r);
+    store_complete_request(s);
+}
+
+// forwards one (already compressed or pass-through) block to the backing store; on a synchronous error the caller's
+// completion is fired with it, because PutStoredBlock itself has long returned 0 for queued blocks
+void forward_put(B200CompressStore* s, struct Longtail_StoredBlock* to_store, struct Longtail_StoredBlock* owned,
+                 struct Longtail_AsyncPutStoredBlockAPI* caller)
+{
+    PutRequest* r = static_cast<PutRequest*>(lt_alloc("B200CompressBlockStore", sizeof(PutRequest)));
+    if (!r)
+    {
+        if (owned) owned->Dispose(owned);
+        s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_FailCount]++;
+        caller->OnComplete(caller, ENOMEM);
+        store_complete_request(s);
+        return;
+    }
+    r->api.m_API.Dispose = 0;
+    r->api.OnComplete = put_backing_complete;
+    r->store = s;
+    r->compressed = owned;
+    r->caller = caller;
+    int err = s->backing->PutStoredBlock(s->backing, to_store, &r->api);
+    if (err) put_backing_complete(&r->api, err);
+}
+
+void store_worker(B200CompressStore* s)
+{
+    for (;;)
+    {
+        std::vector<PendingPut> batch;
+        {
+            std::unique_lock<std::mutex> g(s->lock);
+            s->wake.wait(g, [&] { return s->stop || !s->queue.empty(); });
+            if (s->queue.empty() && s->stop) return;
+            // give concurrently running WriteContentBlockJobs a moment to queue their blocks too: one launch serves them all
+            g.unlock();
+            std::this_thread::sleep_for(std::chrono::microseconds(300));
+            g.lock();
+            batch.swap(s->queue);
+        }
+        const uint32_t n = (uint32_t)batch.size();
+        std::vector<struct Longtail_StoredBlock*> out(n, nullptr);
+        std::vector<const void*> src(n);
+        std::vector<void*> dst(n);
+        std::vector<uint32_t> src_size(n);
+        std::vector<uint64_t> cap(n), got(n, 0);
+        int err = 0;
+        for (uint32_t i = 0; i < n && !err; ++i)
+        {
+            const uint32_t raw = batch[i].block->m_BlockChunksDataSize;
+            cap[i] = lt_b200_lz4_bound(raw);
+            out[i] = make_owned_block(batch[i].block->m_BlockIndex, 8 + (size_t)cap[i]);
+            if (!out[i]) { err = ENOMEM; break; }
+            src[i] = batch[i].block->m_BlockData;
+            src_size[i] = raw;
+            dst[i] = static_cast<uint8_t*>(out[i]->m_BlockData) + 8;
+        }
+        if (!err)
+        {
+            std::lock_guard<std::mutex> g(g_gpu);
+            err = ensure_ctx();
+            if (!err) err = lt_b200_lz4_compress_host(g_ctx, n, src.data(), src_size.data(), dst.data(), cap.data(), got.data());
+        }
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            if (err)
+            {
+                if (out[i]) out[i]->Dispose(out[i]);
+                s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_FailCount]++;
+                batch[i].caller->OnComplete(batch[i].caller, err);
+                store_complete_request(s);
+                continue;
+            }
+            uint32_t* header = static_cast<uint32_t*>(out[i]->m_BlockData); // longtail_compressblockstore.c:135-137
+            header[0] = src_size[i];
+            header[1] = (uint32_t)got[i];
+            out[i]->m_BlockChunksDataSize = 8 + (uint32_t)got[i];
+            forward_put(s, out[i], out[i], batch[i].caller);
+        }
+    }
+}
+
+int store_put(struct Longtail_BlockStoreAPI* api, struct Longtail_StoredBlock* block, struct Longtail_AsyncPutStoredBlockAPI* async)
+{
+    B200CompressStore* s = reinterpret_cast<B200CompressStore*>(api);
+    if (!block || !async) return EINVAL;
+    const uint32_t n = *block->m_BlockIndex->m_ChunkCount;
+    s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Count]++;
+    s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Chunk_Count] += n;
+    s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Byte_Count] += block_index_data_size(n) + block->m_BlockChunksDataSize;
+    const uint32_t tag = *block->m_BlockIndex->m_Tag;
+    if (tag != 0 && tag != TYPE_LZ4)
+    {
+        s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_FailCount]++;
+        return ENOTSUP; // no device kernel for this codec yet; a non-zero return means OnComplete is not called (src/longtail.c:4747-4757)
+    }
+    {
+        std::lock_guard<std::mutex> g(s->lock);
+        ++s->pending;
+        if (tag != 0)
+        {
+            s->queue.push_back({block, async});
+            s->wake.notify_one();
+            return 0;
+        }
+    }
+    forward_put(s, block, nullptr, async); // tag 0: stored as is (longtail_compressblockstore.c:84-88)
+    return 0;
+}
+
+void get_backing_complete(struct Longtail_AsyncGetStoredBlockAPI* api, struct Longtail_StoredBlock* block, int err)
+{
+    GetRequest* r = reinterpret_cast<GetRequest*>(api);
+    B200CompressStore* s = r->store;
+    struct Longtail_AsyncGetStoredBlockAPI* caller = r->caller;
+    lt_free(r);
+    if (err)
+    {
+        if (err != ENOENT) s->stats[Longtail_BlockStoreAPI_StatU64_GetStoredBlock_FailCount]++;
+        caller->OnComplete(caller, block, err);
+        store_complete_request(s);
+        return;
+    }
+    const uint32_t n = *block->m_BlockIndex->m_ChunkCount;
+    s->stats[Longtail_BlockStoreAPI_StatU64_GetStoredBlock_Chunk_Count] += n;
+    s->stats[Longtail_BlockStoreAPI_StatU64_GetStoredBlock_Byte_Count] += block_index_data_size(n) + block->m_BlockChunksDataSize;
+    const uint32_t tag = *block->m_BlockIndex->m_Tag;
+    if (tag == 0)
+    {
+        caller->OnComplete(caller, block, 0);
+        store_complete_request(s);
+        return;
+    }
+    struct Longtail_StoredBlock* plain = nullptr;
+    if (tag != TYPE_LZ4 || block->m_BlockChunksDataSize < 8)
+        err = tag != TYPE_LZ4 ? ENOTSUP : EBADF;
+    else
+    {
+        const uint32_t* header = static_cast<const uint32_t*>(block->m_BlockData); // longtail_compressblockstore.c:292-296
+        const uint32_t raw = header[0], comp = header[1];
+        if ((uint64_t)comp + 8 > block->m_BlockChunksDataSize) err = EBADF;
+        if (!err)
+        {
+            plain = make_owned_block(block->m_BlockIndex, raw);
+            if (!plain) err = ENOMEM;
+        }
+        if (!err)
+        {
+            size_t got = 0;
+            err = lz4_decompress(nullptr, reinterpret_cast<const char*>(header + 2), static_cast<char*>(plain->m_BlockData), comp, raw, &got);
+            if (!err && got != raw) err = EBADF; // :323-327
+            plain->m_BlockChunksDataSize = raw;
+        }
+    }
+    if (err)
+    {
+        s->stats[Longtail_BlockStoreAPI_StatU64_GetStoredBlock_FailCount]++;
+        if (plain) plain->Dispose(plain);
+        if (block && block->Dispose) block->Dispose(block);
+        caller->OnComplete(caller, 0, err);
+    }
+    else
+    {
+        if (block->Dispose) block->Dispose(block);
+        caller->OnComplete(caller, plain, 0);
+    }
+    store_complete_request(s);
+}
+
+int store_get(struct Longtail_BlockStoreAPI* api, uint64_t block_hash, struct Longtail_AsyncGetStoredBlockAPI* async)
+{
+    B200CompressStore* s = reinterpret_cast<B200CompressStore*>(api);
+    if (!async) return EINVAL;
+    s->stats[Longtail_BlockStoreAPI_StatU64_GetStoredBlock_Count]++;
+    GetRequest* r = static_cast<GetRequest*>(lt_alloc("B200CompressBlockStore", sizeof(GetRequest)));
+    if (!r) return ENOMEM;
+    r->api.m_API.Dispose = 0;
+    r->api.OnComplete = get_backing_complete;
+    r->store = s;
+    r->caller = async;
+    {
+        std::lock_guard<std::mutex> g(s->lock);
+        ++s->pending;
+    }
+    int err = s->backing->GetStoredBlock(s->backing, block_hash, &r->api);
+    if (err)
+    {
+        if (err != ENOENT) s->stats[Longtail_BlockStoreAPI_StatU64_GetStoredBlock_FailCount]++;
+        lt_free(r);
+        store_complete_request(s);
+    }
+    return err;
+}
+
+int store_preflight(struct Longtail_BlockStoreAPI* api, uint32_t count, const TLongtail_Hash* hashes, struct Longtail_AsyncPreflightStartedAPI* async)
+{
+    B200CompressStore* s = reinterpret_cast<B200CompressStore*>(api);
+    s->stats[Longtail_BlockStoreAPI_StatU64_PreflightGet_Count]++;
+    int err = s->backing->PreflightGet(s->backing, count, hashes, async);
+    if (err) s->stats[Longtail_BlockStoreAPI_StatU64_PreflightGet_FailCount]++;
+    return err;
+}
+
+int store_existing(struct Longtail_BlockStoreAPI* api, uint32_t count, const TLongtail_Hash* hashes, uint32_t min_usage,
+                   struct Longtail_AsyncGetExistingContentAPI* async)
+{
+    B200CompressStore* s = reinterpret_cast<B200CompressStore*>(api);
+    s->stats[Longtail_BlockStoreAPI_StatU64_GetExistingContent_Count]++;
+    int err = s->backing->GetExistingContent(s->backing, count, hashes, min_usage, async);
+    if (err) s->stats[Longtail_BlockStoreAPI_StatU64_GetExistingContent_FailCount]++;
+    return err;
+}
+
+int store_prune(struct Longtail_BlockStoreAPI*, uint32_t, const TLongtail_Hash*, struct Longtail_AsyncPruneBlocksAPI*) { return ENOTSUP; }
+
+int store_stats(struct Longtail_BlockStoreAPI* api, struct Longtail_BlockStore_Stats* out)
+{
+    B200CompressStore* s = reinterpret_cast<B200CompressStore*>(api);
+    if (!out) return EINVAL;
+    s->stats[Longtail_BlockStoreAPI_StatU64_GetStats_Count]++;
+    for (int i = 0; i < Longtail_BlockStoreAPI_StatU64_Count; ++i) out->m_StatU64[i] = s->stats[i].load();
+    return 0;
+}
+
+int store_flush(struct Longtail_BlockStoreAPI* api, struct Longtail_AsyncFlushAPI* async)
+{
+    B200CompressStore* s = reinterpret_cast<B200CompressStore*>(api);
+    if (!async) return EINVAL;
+    s->stats[Longtail_BlockStoreAPI_StatU64_Flush_Count]++;
+    {
+        std::lock_guard<std::mutex> g(s->lock);
+        if (s->pending > 0)
+        {
+            s->flushers.push_back(async); // fired by the request that brings the count to zero
+            return 0;
+        }
+    }
+    async->OnComplete(async, 0);
+    return 0;
+}
+
+void store_dispose(struct Longtail_API* api)
+{
+    B200CompressStore* s = reinterpret_cast<B200CompressStore*>(api);
+    for (;;) // like the reference, wait for requests in flight (longtail_compressblockstore.c:564-571)
+    {
+        {
+            std::lock_guard<std::mutex> g(s->lock);
+            if (s->pending == 0) break;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+    {
+        std::lock_guard<std::mutex> g(s->lock);
+        s->stop = true;
+        s->wake.notify_all();
+    }
+    s->worker.join();
+    s->~B200CompressStore();
+    lt_free(s);
+}
+
 } // namespace
+
+extern "C" struct Longtail_CompressionAPI* Longtail_CreateB200LZ4CompressionAPI(void)
+{
+    B200CompressionAPI* a = static_cast<B200CompressionAPI*>(lt_alloc("Longtail_CreateB200LZ4CompressionAPI", sizeof(B200CompressionAPI)));
+    if (!a) return nullptr;
+    a->api.m_API.Dispose = compression_api_dispose;
+    a->api.GetMaxCompressedSize = lz4_max_size;
+    a->api.Compress = lz4_compress;
+    a->api.Decompress = lz4_decompress;
+    return &a->api;
+}
+
+extern "C" struct Longtail_CompressionAPI* Longtail_CompressionRegistry_CreateForB200LZ4(uint32_t compression_type, uint32_t* out_settings)
+{
+    if (compression_type != TYPE_LZ4) return nullptr; // lib/lz4/longtail_lz4.c:104-118
+    if (out_settings) *out_settings = TYPE_LZ4;
+    return Longtail_CreateB200LZ4CompressionAPI();
+}
+
+extern "C" struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockStoreAPI(struct Longtail_BlockStoreAPI* backing,
+                                                                                  struct Longtail_CompressionRegistryAPI* registry)
+{
+    (void)registry;
+    if (!backing) return nullptr;
+    void* mem = lt_alloc("Longtail_CreateB200CompressBlockStoreAPI", sizeof(B200CompressStore));
+    if (!mem) return nullptr;
+    B200CompressStore* s = new (mem) B200CompressStore();
+    s->api.m_API.Dispose = store_dispose;
+    s->api.PutStoredBlock = store_put;
+    s->api.PreflightGet = store_preflight;
+    s->api.GetStoredBlock = store_get;
+    s->api.GetExistingContent = store_existing;
+    s->api.PruneBlocks = store_prune;
+    s->api.GetStats = store_stats;
+    s->api.Flush = store_flush;
+    s->backing = backing;
+    for (auto& v : s->stats) v = 0;
+    s->worker = std::thread(store_worker, s);
+    return &s->api;
+}
 
 extern "C" int Longtail_B200_SetDevice(int device_ordinal)
 {

@@ -28,8 +28,12 @@ void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, u
                          cudaStream_t st);
 
 // ---- lz4.cu
+uint32_t lz4_copy_job_capacity(uint32_t raw_len);
+cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, uint8_t* d_out,
+                              const uint64_t* d_out_off, const uint32_t* d_out_cap, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st);
 cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
-                              const uint64_t* d_out_off, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st);
+                              const uint64_t* d_out_off, uint32_t* d_out_len, uint3* d_copy_jobs, const uint32_t* d_copy_job_start,
+                              uint32_t* d_copy_job_count, uint32_t block_count, cudaStream_t st);
 void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, const uint64_t* d_dst_off, const uint32_t* d_len,
                           uint8_t* d_out, uint32_t count, cudaStream_t st);
 

@@ -17,6 +17,8 @@
 #include "lt_device.cuh"
 #include "lt_kernels.h"
 
+#include <stdlib.h>
+
 namespace ltb {
 
 namespace {
@@ -44,6 +46,12 @@ __device__ __forceinline__ uint32_t lz4_hash(const uint8_t* __restrict__ s, uint
 {
     if (U16) return (rd32(s, pos) * 2654435761u) >> 19;                   // LZ4_hash4, 13 bits (lz4.c:777-783)
     return (uint32_t)(((rd64(s, pos) << 24) * 889523592379ull) >> 52);    // LZ4_hash5, 12 bits (lz4.c:785-795)
+}
+template <bool U16>
+__device__ __forceinline__ uint32_t lz4_hash_word(uint64_t w)
+{
+    if (U16) return ((uint32_t)w * 2654435761u) >> 19;
+    return (uint32_t)(((w << 24) * 889523592379ull) >> 52);
 }
 template <bool U16>
 __device__ __forceinline__ uint32_t tab_get(const uint32_t* t32, uint32_t h)
@@ -94,8 +102,32 @@ __device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint
     for (uint32_t j = i + lane; j < n; j += 32) dst[j] = src[j];
 }
 
+// Literal runs of LZ4_DEFER_MIN bytes or more are not copied by the (latency-bound) parsing warp: their position in the
+// output is fixed by the parse, so the warp only records {dst, src, len} and k_lz4_copy moves the bytes afterwards with the
+// whole GPU.  Incompressible blocks are one such run.
+constexpr uint32_t LZ4_DEFER_MIN = 2048;
+
+struct CopyJobs
+{
+    uint3* jobs; // {dst offset, src offset, length}
+    uint32_t count;
+};
+
+__device__ __forceinline__ void emit_literals(uint8_t* __restrict__ dst, uint32_t op, const uint8_t* __restrict__ src, uint32_t from, uint32_t lit,
+                                              uint32_t lane, CopyJobs& cj)
+{
+    if (lit >= LZ4_DEFER_MIN)
+    {
+        if (lane == 0) cj.jobs[cj.count] = make_uint3(op, from, lit);
+        ++cj.count;
+    }
+    else if (lit)
+        copy_bytes(dst + op, src + from, lit, lane);
+}
+
 template <bool U16>
-__device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t* table, uint32_t lane)
+__device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n, uint8_t* __restrict__ dst, uint32_t* table, uint32_t lane,
+                                     CopyJobs& cj)
 {
     uint32_t op = 0;
     uint32_t anchor = 0;
@@ -114,12 +146,23 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
             // ---------------- search: 32 probes per step (lz4.c:1043-1100)
             uint32_t ip, match;
             bool found = false, finished = false;
+            // the probe positions of a search are known in advance, so the 8 source bytes of the NEXT batch are requested
+            // before the current batch is resolved (wasted when a match ends the search, which is harmless)
+            uint32_t p_next = probe_pos(S, k0 + lane);
+            bool valid_next = p_next + probe_advance(k0 + lane) <= mflimit_plus_one && p_next < n;
+            uint64_t w_next = valid_next ? rd64(src, p_next) : 0ull;
             for (;;)
             {
-                const uint32_t k = k0 + lane;
-                const uint32_t p = probe_pos(S, k);
-                const bool valid = p + probe_advance(k) <= mflimit_plus_one && p < n; // else: goto _last_literals before probing
-                const uint32_t h = valid ? lz4_hash<U16>(src, p) : 0xffffffffu - lane;
+                const uint32_t p = p_next;
+                const bool valid = valid_next; // else: goto _last_literals before probing
+                const uint64_t w = w_next;
+                {
+                    const uint32_t kn = k0 + 32 + lane;
+                    p_next = probe_pos(S, kn);
+                    valid_next = p_next + probe_advance(kn) <= mflimit_plus_one && p_next < n;
+                    w_next = valid_next ? rd64(src, p_next) : 0ull;
+                }
+                const uint32_t h = valid ? lz4_hash_word<U16>(w) : 0xffffffffu - lane;
                 const uint32_t same = __match_any_sync(FULL, h);
                 const uint32_t lower = same & ((1u << lane) - 1u);
                 // candidate = what the sequential loop would find in the table: the closest lower lane of this batch with the
@@ -127,7 +170,7 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
                 const uint32_t from_lane = __shfl_sync(FULL, p, lower ? 31 - __clz(lower) : (int)lane);
                 const uint32_t cand = lower ? from_lane : (valid ? tab_get<U16>(table, h) : 0u);
                 bool hit = false;
-                if (valid && (U16 || cand + LZ4_MAX_DISTANCE >= p)) hit = rd32(src, cand) == rd32(src, p);
+                if (valid && (U16 || cand + LZ4_MAX_DISTANCE >= p)) hit = rd32(src, cand) == (uint32_t)w;
                 const uint32_t hits = __ballot_sync(FULL, hit);
                 const uint32_t valids = __ballot_sync(FULL, valid);
                 // lanes whose table write is committed: valid lanes up to and including the first hit
@@ -198,7 +241,7 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
                 const uint32_t lit = literals_done ? 0u : ip - anchor;
                 const uint32_t token_pos = op++;
                 if (lit >= 15) op = put_length(dst, op, lit - 15, lane);
-                if (lit) copy_bytes(dst + op, src + anchor, lit, lane);
+                emit_literals(dst, op, src, anchor, lit, lane, cj);
                 op += lit;
                 const uint32_t off = ip - match;
                 if (lane == 0)
@@ -243,7 +286,7 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
     const uint32_t token_pos = op++;
     if (lane == 0) dst[token_pos] = (uint8_t)((last >= 15 ? 15u : last) << 4);
     if (last >= 15) op = put_length(dst, op, last - 15, lane);
-    if (last) copy_bytes(dst + op, src + anchor, last, lane);
+    emit_literals(dst, op, src, anchor, last, lane, cj);
     op += last;
     return op;
 }
@@ -254,7 +297,9 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
 // header compressblockstore writes (lib/compressblockstore/longtail_compressblockstore.c:103-137)
 __global__ void __launch_bounds__(32)
 k_lz4_blocks(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len,
-             uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t block_count)
+             uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
+             uint3* __restrict__ copy_jobs, const uint32_t* __restrict__ copy_job_start, uint32_t* __restrict__ copy_job_count,
+             uint32_t block_count)
 {
     extern __shared__ __align__(16) uint32_t s_table[];
     const uint32_t b = blockIdx.x;
@@ -263,13 +308,54 @@ k_lz4_blocks(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ 
     const uint8_t* src = raw_base + raw_off[b];
     const uint32_t n = raw_len[b];
     uint8_t* dst = out_base + out_off[b];
-    uint32_t c = n < LZ4_64K_LIMIT ? lz4_encode_block<true>(src, n, dst + 8, s_table, lane)
-                                   : lz4_encode_block<false>(src, n, dst + 8, s_table, lane);
+    CopyJobs cj = {copy_jobs + copy_job_start[b], 0};
+    uint32_t c = n < LZ4_64K_LIMIT ? lz4_encode_block<true>(src, n, dst + 8, s_table, lane, cj)
+                                   : lz4_encode_block<false>(src, n, dst + 8, s_table, lane, cj);
     if (lane == 0)
     {
         reinterpret_cast<uint32_t*>(dst)[0] = n;
         reinterpret_cast<uint32_t*>(dst)[1] = c;
         out_len[b] = c + 8;
+        copy_job_count[b] = cj.count;
+    }
+}
+
+// the deferred literal runs of k_lz4_blocks: grid = (block, slice); every CTA copies its slice of every job of its block
+constexpr uint32_t LZ4_COPY_SLICES = 8;
+__global__ void __launch_bounds__(256)
+k_lz4_copy(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, uint8_t* __restrict__ out_base,
+           const uint64_t* __restrict__ out_off, const uint3* __restrict__ copy_jobs, const uint32_t* __restrict__ copy_job_start,
+           const uint32_t* __restrict__ copy_job_count)
+{
+    const uint32_t b = blockIdx.x;
+    const uint32_t njobs = copy_job_count[b];
+    const uint8_t* src = raw_base + raw_off[b];
+    uint8_t* dst = out_base + out_off[b] + 8;
+    for (uint32_t j = 0; j < njobs; ++j)
+    {
+        const uint3 job = copy_jobs[copy_job_start[b] + j];
+        // slice boundaries on 16-byte multiples of the job
+        const uint32_t per = ((job.z + LZ4_COPY_SLICES - 1) / LZ4_COPY_SLICES + 15u) & ~15u;
+        const uint32_t lo = min(job.z, per * blockIdx.y), hi = min(job.z, lo + per);
+        if (lo >= hi) continue;
+        uint8_t* d = dst + job.x + lo;
+        const uint8_t* s = src + job.y + lo;
+        const uint32_t n = hi - lo;
+        const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
+        for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+        const uint8_t* s2 = s + head;
+        uint4* d4 = reinterpret_cast<uint4*>(d + head);
+        const uint32_t vecs = n - head >= 20u ? (n - head - 4u) >> 4 : 0u;
+        const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3u) * 8u;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - ((uintptr_t)s2 & 3u));
+#pragma unroll 4
+        for (uint32_t v = threadIdx.x; v < vecs; v += blockDim.x)
+        {
+            const uint32_t* w = sw + 4 * v;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+            d4[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+        for (uint32_t i = head + vecs * 16u + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
     }
 }
 
@@ -309,11 +395,99 @@ k_gather_chunks(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ 
     for (uint32_t i = head + vecs * 16u + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
 }
 
-cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
-                              const uint64_t* d_out_off, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st)
+// LZ4 block decoder (LZ4_decompress_safe semantics, lib/lz4/longtail_lz4.c:79-101): one warp per block, the token stream is
+// walked by all lanes in lock step (uniform control flow), literal and match bytes are moved lane-parallel.  An overlapping
+// match (offset < length) repeats its first `offset` bytes, so byte i of the match is byte (i mod offset) of that period.
+// out_len[b] = decoded size, or 0xffffffff for a malformed / overflowing stream (the caller maps it to EBADF).
+__global__ void __launch_bounds__(32)
+k_lz4_decode(const uint8_t* __restrict__ in_base, const uint64_t* __restrict__ in_off, const uint32_t* __restrict__ in_len,
+             uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_cap,
+             uint32_t* __restrict__ out_len, uint32_t block_count)
+{
+    const uint32_t b = blockIdx.x;
+    if (b >= block_count) return;
+    const uint32_t lane = threadIdx.x;
+    const uint8_t* src = in_base + in_off[b];
+    const uint32_t n = in_len[b];
+    uint8_t* dst = out_base + out_off[b];
+    const uint32_t cap = out_cap[b];
+    uint32_t ip = 0, op = 0;
+    bool bad = n == 0;
+    while (!bad && ip < n)
+    {
+        const uint32_t token = src[ip++];
+        uint32_t lit = token >> 4;
+        if (lit == 15)
+        {
+            uint32_t v;
+            do
+            {
+                if (ip >= n) { bad = true; break; }
+                v = src[ip++];
+                lit += v;
+            } while (v == 255);
+            if (bad) break;
+        }
+        if (lit > n - ip || lit > cap - op) { bad = true; break; }
+        for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i];
+        ip += lit;
+        op += lit;
+        if (ip >= n) break; // the last sequence carries literals only
+        if (n - ip < 2) { bad = true; break; }
+        const uint32_t off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+        ip += 2;
+        uint32_t len = token & 15u;
+        if (len == 15)
+        {
+            uint32_t v;
+            do
+            {
+                if (ip >= n) { bad = true; break; }
+                v = src[ip++];
+                len += v;
+            } while (v == 255);
+            if (bad) break;
+        }
+        len += 4;
+        if (off == 0 || off > op || len > cap - op) { bad = true; break; }
+        __syncwarp(); // the literals just written may be the source of this match
+        const uint32_t from = op - off;
+        if (off >= len)
+            for (uint32_t i = lane; i < len; i += 32) dst[op + i] = dst[from + i];
+        else
+            for (uint32_t i = lane; i < len; i += 32) dst[op + i] = dst[from + i % off];
+        op += len;
+        __syncwarp();
+    }
+    if (lane == 0) out_len[b] = bad ? 0xffffffffu : op;
+}
+
+cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, uint8_t* d_out,
+                              const uint64_t* d_out_off, const uint32_t* d_out_cap, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st)
 {
     if (!block_count) return cudaSuccess;
-    k_lz4_blocks<<<block_count, 32, LZ4_TABLE_BYTES, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, block_count);
+    k_lz4_decode<<<block_count, 32, 0, st>>>(d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, block_count);
+    return cudaGetLastError();
+}
+
+uint32_t lz4_copy_job_capacity(uint32_t raw_len) { return raw_len / LZ4_DEFER_MIN + 2; }
+
+cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
+                              const uint64_t* d_out_off, uint32_t* d_out_len, uint3* d_copy_jobs, const uint32_t* d_copy_job_start,
+                              uint32_t* d_copy_job_count, uint32_t block_count, cudaStream_t st)
+{
+    if (!block_count) return cudaSuccess;
+    static int carveout = -2;
+    if (carveout == -2)
+    {
+        const char* e = getenv("LT_B200_LZ4_CARVEOUT"); // experiment knob: percent of the SM's L1/shared storage given to shared memory
+        carveout = e ? atoi(e) : -1;
+        if (carveout >= 0) cudaFuncSetAttribute(k_lz4_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    }
+    k_lz4_blocks<<<block_count, 32, LZ4_TABLE_BYTES, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs,
+                                                           d_copy_job_start, d_copy_job_count, block_count);
+    k_lz4_copy<<<dim3(block_count, LZ4_COPY_SLICES), 256, 0, st>>>(d_raw, d_raw_off, d_out, d_out_off, d_copy_jobs, d_copy_job_start,
+                                                                 d_copy_job_count);
     return cudaGetLastError();
 }
 

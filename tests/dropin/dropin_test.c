@@ -15,6 +15,11 @@
 #include "../lib/blake3/longtail_blake3.h"
 #include "../lib/hpcdcchunker/longtail_hpcdcchunker.h"
 #include "../lib/memstorage/longtail_memstorage.h"
+#include "../lib/compressblockstore/longtail_compressblockstore.h"
+#include "../lib/compressionregistry/longtail_compression_registry.h"
+#include "../lib/compressionregistry/longtail_full_compression_registry.h"
+#include "../lib/lz4/longtail_lz4.h"
+#include <pthread.h>
 
 #include <errno.h>
 #include <stdio.h>
@@ -73,6 +78,87 @@ static int feed_func(void* ctx, Longtail_ChunkerAPI_HChunker c, uint32_t request
     f->off += n;
     *out = (uint32_t)n;
     return 0;
+}
+
+/* ---- a backing block store that keeps every serialised block in memory (Put) and hands them back (Get) */
+struct kept_block { uint64_t hash; void* data; size_t size; };
+struct keep_store
+{
+    struct Longtail_BlockStoreAPI api;
+    pthread_mutex_t lock;
+    struct kept_block blocks[4096];
+    uint32_t count;
+};
+static int keep_put(struct Longtail_BlockStoreAPI* api, struct Longtail_StoredBlock* b, struct Longtail_AsyncPutStoredBlockAPI* async)
+{
+    struct keep_store* s = (struct keep_store*)api;
+    void* buf = 0; size_t size = 0;
+    int err = Longtail_WriteStoredBlockToBuffer(b, &buf, &size);
+    if (!err)
+    {
+        pthread_mutex_lock(&s->lock);
+        s->blocks[s->count].hash = *b->m_BlockIndex->m_BlockHash;
+        s->blocks[s->count].data = buf;
+        s->blocks[s->count].size = size;
+        ++s->count;
+        pthread_mutex_unlock(&s->lock);
+    }
+    async->OnComplete(async, err);
+    return 0;
+}
+static int keep_get(struct Longtail_BlockStoreAPI* api, uint64_t hash, struct Longtail_AsyncGetStoredBlockAPI* async)
+{
+    struct keep_store* s = (struct keep_store*)api;
+    for (uint32_t i = 0; i < s->count; ++i)
+        if (s->blocks[i].hash == hash)
+        {
+            struct Longtail_StoredBlock* b = 0;
+            int err = Longtail_ReadStoredBlockFromBuffer(s->blocks[i].data, s->blocks[i].size, &b);
+            async->OnComplete(async, b, err);
+            return 0;
+        }
+    return ENOENT;
+}
+static int keep_flush(struct Longtail_BlockStoreAPI* api, struct Longtail_AsyncFlushAPI* async) { (void)api; async->OnComplete(async, 0); return 0; }
+static void keep_dispose(struct Longtail_API* api)
+{
+    struct keep_store* s = (struct keep_store*)api;
+    for (uint32_t i = 0; i < s->count; ++i) Longtail_Free(s->blocks[i].data);
+    free(s);
+}
+static struct keep_store* make_keep_store(void)
+{
+    struct keep_store* s = (struct keep_store*)calloc(1, sizeof(*s));
+    s->api.m_API.Dispose = keep_dispose;
+    s->api.PutStoredBlock = keep_put;
+    s->api.GetStoredBlock = keep_get;
+    s->api.Flush = keep_flush;
+    pthread_mutex_init(&s->lock, 0);
+    return s;
+}
+static const struct kept_block* find_block(const struct keep_store* s, uint64_t hash)
+{
+    for (uint32_t i = 0; i < s->count; ++i) if (s->blocks[i].hash == hash) return &s->blocks[i];
+    return 0;
+}
+struct get_wait { struct Longtail_AsyncGetStoredBlockAPI api; struct Longtail_StoredBlock* block; int err; int done; };
+static void get_done(struct Longtail_AsyncGetStoredBlockAPI* a, struct Longtail_StoredBlock* b, int err)
+{
+    struct get_wait* w = (struct get_wait*)a;
+    w->block = b; w->err = err; w->done = 1;
+}
+
+/* upsync of a fresh store through `store`; the blocks land in whatever backing store it wraps */
+static int write_content(struct Longtail_StorageAPI* storage, struct Longtail_BlockStoreAPI* store, struct Longtail_JobAPI* jobs,
+                         struct Longtail_HashAPI* hash, struct Longtail_VersionIndex* vi, uint32_t block_size, uint32_t chunks_per_block,
+                         struct Longtail_StoreIndex** out_missing)
+{
+    struct Longtail_StoreIndex* empty = 0;
+    int err = Longtail_CreateStoreIndexFromBlocks(0, 0, &empty);
+    if (!err) err = Longtail_CreateMissingContent(hash, empty, vi, block_size, chunks_per_block, out_missing);
+    if (!err) err = Longtail_WriteContent(storage, store, jobs, 0, 0, 0, *out_missing, vi, "root");
+    Longtail_Free(empty);
+    return err;
 }
 
 int main(int argc, char** argv)
@@ -145,6 +231,69 @@ int main(int argc, char** argv)
         printf("Longtail_B200_CreateVersionIndex: %zu bytes %s\n", n, (n == n_ref && memcmp(b, b_ref, n) == 0) ? "identical" : "DIFFERENT");
         Longtail_Free(b);
         Longtail_Free(v_verb);
+    }
+
+    /* 5. the compress half inside the reference's Longtail_WriteContent: reference compressblockstore vs
+     *    (a) the B200 compress block store and (b) the reference compressblockstore with the B200 LZ4 CompressionAPI in its registry */
+    {
+        for (uint32_t i = 0; i < infos->m_Count; ++i) tags[i] = (i % 3) ? 0x6c7a3432u : 0u;
+        struct Longtail_VersionIndex* vi = 0;
+        CHECK(Longtail_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &vi) == 0, "index for upsync");
+        const uint32_t block_size = target * 16, per_block = 64;
+        struct Longtail_CompressionRegistryAPI* full = Longtail_CreateFullCompressionRegistry();
+        Longtail_CompressionRegistry_CreateForTypeFunc b200_funcs[1] = {Longtail_CompressionRegistry_CreateForB200LZ4};
+        struct Longtail_CompressionRegistryAPI* b200_registry = Longtail_CreateDefaultCompressionRegistry(1, b200_funcs);
+        struct keep_store* k_ref = make_keep_store();
+        struct keep_store* k_b200 = make_keep_store();
+        struct keep_store* k_codec = make_keep_store();
+        struct Longtail_BlockStoreAPI* s_ref = Longtail_CreateCompressBlockStoreAPI(&k_ref->api, full);
+        struct Longtail_BlockStoreAPI* s_b200 = Longtail_CreateB200CompressBlockStoreAPI(&k_b200->api, full);
+        struct Longtail_BlockStoreAPI* s_codec = Longtail_CreateCompressBlockStoreAPI(&k_codec->api, b200_registry);
+        struct Longtail_StoreIndex *m_ref = 0, *m_b200 = 0, *m_codec = 0;
+        CHECK(write_content(storage, s_ref, jobs, ref_hash, vi, block_size, per_block, &m_ref) == 0, "reference WriteContent");
+        int e1 = write_content(storage, s_b200, jobs, ref_hash, vi, block_size, per_block, &m_b200);
+        CHECK(e1 == 0, "WriteContent through Longtail_CreateB200CompressBlockStoreAPI: %d", e1);
+        int e2 = write_content(storage, s_codec, jobs, ref_hash, vi, block_size, per_block, &m_codec);
+        CHECK(e2 == 0, "WriteContent through the B200 LZ4 CompressionAPI: %d", e2);
+        CHECK(k_ref->count > 3 && k_ref->count == k_b200->count && k_ref->count == k_codec->count, "block counts %u %u %u", k_ref->count, k_b200->count, k_codec->count);
+        uint32_t same_a = 0, same_b = 0, lz4_blocks = 0;
+        for (uint32_t i = 0; i < k_ref->count; ++i)
+        {
+            const struct kept_block* a = find_block(k_b200, k_ref->blocks[i].hash);
+            const struct kept_block* b = find_block(k_codec, k_ref->blocks[i].hash);
+            if (a && a->size == k_ref->blocks[i].size && memcmp(a->data, k_ref->blocks[i].data, a->size) == 0) ++same_a;
+            if (b && b->size == k_ref->blocks[i].size && memcmp(b->data, k_ref->blocks[i].data, b->size) == 0) ++same_b;
+            if (((uint32_t*)k_ref->blocks[i].data)[4] != 0) ++lz4_blocks;
+        }
+        CHECK(same_a == k_ref->count, "B200 compress block store: %u of %u stored blocks identical", same_a, k_ref->count);
+        CHECK(same_b == k_ref->count, "B200 LZ4 CompressionAPI: %u of %u stored blocks identical", same_b, k_ref->count);
+        CHECK(lz4_blocks > 0 && lz4_blocks < k_ref->count, "mix of raw and lz4 blocks expected (%u of %u)", lz4_blocks, k_ref->count);
+        struct Longtail_BlockStore_Stats st_ref, st_b200;
+        s_ref->GetStats(s_ref, &st_ref);
+        s_b200->GetStats(s_b200, &st_b200);
+        for (int i = Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Count; i <= Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Byte_Count; ++i)
+            CHECK(st_ref.m_StatU64[i] == st_b200.m_StatU64[i], "stat %d: %llu vs %llu", i, (unsigned long long)st_ref.m_StatU64[i], (unsigned long long)st_b200.m_StatU64[i]);
+        /* read every block back through both stores: same uncompressed payloads */
+        uint32_t round_trips = 0;
+        for (uint32_t i = 0; i < k_ref->count; ++i)
+        {
+            struct get_wait w1, w2;
+            memset(&w1, 0, sizeof(w1)); memset(&w2, 0, sizeof(w2));
+            w1.api.OnComplete = get_done; w2.api.OnComplete = get_done;
+            CHECK(s_ref->GetStoredBlock(s_ref, k_ref->blocks[i].hash, &w1.api) == 0 && w1.done && w1.err == 0, "reference GetStoredBlock");
+            CHECK(s_b200->GetStoredBlock(s_b200, k_ref->blocks[i].hash, &w2.api) == 0 && w2.done && w2.err == 0, "B200 GetStoredBlock %d", w2.err);
+            if (w1.block && w2.block && w1.block->m_BlockChunksDataSize == w2.block->m_BlockChunksDataSize &&
+                memcmp(w1.block->m_BlockData, w2.block->m_BlockData, w1.block->m_BlockChunksDataSize) == 0) ++round_trips;
+            if (w1.block) w1.block->Dispose(w1.block);
+            if (w2.block) w2.block->Dispose(w2.block);
+        }
+        CHECK(round_trips == k_ref->count, "GetStoredBlock round trips: %u of %u", round_trips, k_ref->count);
+        printf("WriteContent: %u blocks (%u lz4), B200 block store %u identical, B200 codec %u identical, %u read back\n", k_ref->count, lz4_blocks, same_a, same_b, round_trips);
+        Longtail_Free(m_ref); Longtail_Free(m_b200); Longtail_Free(m_codec);
+        SAFE_DISPOSE_API(s_ref); SAFE_DISPOSE_API(s_b200); SAFE_DISPOSE_API(s_codec);
+        SAFE_DISPOSE_API(&k_ref->api); SAFE_DISPOSE_API(&k_b200->api); SAFE_DISPOSE_API(&k_codec->api);
+        SAFE_DISPOSE_API(full); SAFE_DISPOSE_API(b200_registry);
+        Longtail_Free(vi);
     }
 
     /* 4. golden chunker vector through the B200 ChunkerAPI */
