@@ -83,6 +83,7 @@ struct ChunkRec
 struct B200Chunker
 {
     uint32_t mn, av, mx;
+    uint32_t hash_type = LT_B200_HASH_BLAKE3; // which HashAPI the cached chunk hashes belong to
     uint8_t* buf = nullptr; // pinned host memory holding the whole part
     uint64_t cap = 0;
     uint64_t size = 0;
@@ -231,16 +232,38 @@ void chunker_api_dispose(struct Longtail_API* api) { lt_free(api); }
 struct B200HashAPI
 {
     struct Longtail_HashAPI api;
+    uint32_t type;
 };
+uint32_t hash_type_of(struct Longtail_HashAPI* api) { return reinterpret_cast<B200HashAPI*>(api)->type; }
 
 struct HashStream
 {
     std::vector<uint8_t> bytes;
 };
 
-uint32_t hash_identifier(struct Longtail_HashAPI*) { return HASH_BLK3; }
+uint32_t hash_identifier(struct Longtail_HashAPI* api) { return hash_type_of(api); }
 
-int hash_on_device(uint32_t length, const void* data, uint64_t* out)
+// the chunker hashed its chunks with BLAKE3 in its own pass; another HashAPI asking for them gets the whole part re-hashed
+// with its algorithm once (one upload, one launch), not chunk by chunk
+int rehash_chunker(B200Chunker* c, uint32_t type)
+{
+    std::lock_guard<std::mutex> g(g_gpu);
+    int err = ensure_ctx();
+    if (!err) err = ensure_arena(c->size + 64);
+    if (!err && c->size) err = lt_b200_copy_to_device(g_ctx, g_arena, c->buf, c->size);
+    if (err) return err;
+    const uint32_t n = (uint32_t)c->chunks.size();
+    std::vector<uint64_t> off(n), out(n);
+    std::vector<uint32_t> len(n);
+    for (uint32_t i = 0; i < n; ++i) { off[i] = c->chunks[i].offset; len[i] = c->chunks[i].len; }
+    err = lt_b200_hash_segments(g_ctx, type, static_cast<const uint8_t*>(g_arena), g_arena_cap, off.data(), len.data(), n, out.data());
+    if (err) return err;
+    for (uint32_t i = 0; i < n; ++i) c->chunks[i].hash = out[i];
+    c->hash_type = type;
+    return 0;
+}
+
+int hash_on_device(uint32_t type, uint32_t length, const void* data, uint64_t* out)
 {
     std::lock_guard<std::mutex> g(g_gpu);
     int err = ensure_ctx();
@@ -248,12 +271,13 @@ int hash_on_device(uint32_t length, const void* data, uint64_t* out)
     if (!err && length) err = lt_b200_copy_to_device(g_ctx, g_arena, data, length);
     if (err) return err;
     uint64_t off = 0;
-    return lt_b200_hash_segments(g_ctx, HASH_BLK3, static_cast<const uint8_t*>(g_arena), g_arena_cap, &off, &length, 1, out);
+    return lt_b200_hash_segments(g_ctx, type, static_cast<const uint8_t*>(g_arena), g_arena_cap, &off, &length, 1, out);
 }
 
-int hash_buffer(struct Longtail_HashAPI*, uint32_t length, const void* data, uint64_t* out)
+int hash_buffer(struct Longtail_HashAPI* api, uint32_t length, const void* data, uint64_t* out)
 {
     if (!out || (!data && length)) return EINVAL;
+    const uint32_t type = hash_type_of(api);
     const uint8_t* p = static_cast<const uint8_t*>(data);
     {
         // a range handed out by one of our chunkers: its hash was computed in the chunker's GPU pass
@@ -265,13 +289,14 @@ int hash_buffer(struct Longtail_HashAPI*, uint32_t length, const void* data, uin
             auto it = std::lower_bound(c->chunks.begin(), c->chunks.end(), off, [](const ChunkRec& r, uint64_t o) { return r.offset < o; });
             if (it != c->chunks.end() && it->offset == off && it->len == length)
             {
+                if (c->hash_type != type && rehash_chunker(c, type)) break; // one thread drives one chunker
                 *out = it->hash;
                 return 0;
             }
             break;
         }
     }
-    return hash_on_device(length, data, out);
+    return hash_on_device(type, length, data, out);
 }
 
 int hash_begin(struct Longtail_HashAPI*, Longtail_HashAPI_HContext* out)
@@ -290,11 +315,11 @@ void hash_update(struct Longtail_HashAPI*, Longtail_HashAPI_HContext h, uint32_t
     s->bytes.insert(s->bytes.end(), p, p + length);
 }
 
-uint64_t hash_end(struct Longtail_HashAPI*, Longtail_HashAPI_HContext h)
+uint64_t hash_end(struct Longtail_HashAPI* api, Longtail_HashAPI_HContext h)
 {
     HashStream* s = reinterpret_cast<HashStream*>(h);
     uint64_t out = 0;
-    hash_on_device((uint32_t)s->bytes.size(), s->bytes.data(), &out); // EndContext frees the context (lib/blake3/longtail_blake3.c:60-79)
+    hash_on_device(hash_type_of(api), (uint32_t)s->bytes.size(), s->bytes.data(), &out); // EndContext frees the context (lib/blake3/longtail_blake3.c:60-79)
     delete s;
     return out;
 }
@@ -873,10 +898,15 @@ extern "C" struct Longtail_ChunkerAPI* Longtail_CreateB200ChunkerAPI(void)
     return &a->api;
 }
 
-extern "C" struct Longtail_HashAPI* Longtail_CreateB200Blake3HashAPI(void)
+static struct Longtail_HashAPI* create_hash_api(uint32_t type);
+extern "C" struct Longtail_HashAPI* Longtail_CreateB200Blake3HashAPI(void) { return create_hash_api(LT_B200_HASH_BLAKE3); }
+extern "C" struct Longtail_HashAPI* Longtail_CreateB200Blake2HashAPI(void) { return create_hash_api(LT_B200_HASH_BLAKE2); }
+
+static struct Longtail_HashAPI* create_hash_api(uint32_t type)
 {
-    B200HashAPI* a = static_cast<B200HashAPI*>(lt_alloc("Longtail_CreateB200Blake3HashAPI", sizeof(B200HashAPI)));
+    B200HashAPI* a = static_cast<B200HashAPI*>(lt_alloc("Longtail_CreateB200HashAPI", sizeof(B200HashAPI)));
     if (!a) return nullptr;
+    a->type = type;
     a->api.m_API.Dispose = hash_api_dispose;
     a->api.GetIdentifier = hash_identifier;
     a->api.BeginContext = hash_begin;
@@ -897,7 +927,8 @@ extern "C" int Longtail_B200_CreateVersionIndex(struct Longtail_StorageAPI* stor
     // same argument validation as src/longtail.c:2826-2836
     if (!storage_api || !hash_api || !chunker_api || !root_path || !out_version_index || target_chunk_size == 0) return EINVAL;
     if (file_infos && file_infos->m_Count && !job_api) return EINVAL;
-    if (hash_api->GetIdentifier(hash_api) != HASH_BLK3) return ENOTSUP;
+    const uint32_t hash_type = hash_api->GetIdentifier(hash_api);
+    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2) return ENOTSUP;
     uint32_t min_chunk = 0;
     int err = chunker_api->GetMinChunkSize(chunker_api, &min_chunk);
     if (err) return err;
@@ -924,7 +955,7 @@ extern "C" int Longtail_B200_CreateVersionIndex(struct Longtail_StorageAPI* stor
     if (err) return err;
     const void* data = nullptr;
     uint64_t size = 0;
-    err = lt_b200_index_stream_assets(g_ctx, &assets, optional_asset_tags, HASH_BLK3, target_chunk_size, read_batch, &rc, &data, &size);
+    err = lt_b200_index_stream_assets(g_ctx, &assets, optional_asset_tags, hash_type, target_chunk_size, read_batch, &rc, &data, &size);
     if (err) return err;
     struct Longtail_VersionIndex* v = wrap_version_index(data, size);
     if (!v) return ENOMEM;

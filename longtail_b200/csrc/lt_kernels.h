@@ -27,6 +27,10 @@ void launch_blake3_leaves(const uint8_t* d_base, uint64_t base_size, const uint6
 void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, uint32_t count, uint32_t* d_cvs, uint64_t* d_hash_out,
                          cudaStream_t st);
 
+// ---- blake2s.cu : BLAKE2s-64 over segments; d_counter is one u32 of scratch (the work queue head)
+void launch_blake2s_segments(const uint8_t* d_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t count, uint32_t* d_counter,
+                             uint64_t* d_hash_out, int sm_count, cudaStream_t st);
+
 // ---- lz4.cu
 uint32_t lz4_copy_job_capacity(uint32_t raw_len);
 cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, uint8_t* d_out,

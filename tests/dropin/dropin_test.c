@@ -13,6 +13,7 @@
 #include "longtail_b200_api.h"
 #include "../lib/bikeshed/longtail_bikeshed.h"
 #include "../lib/blake3/longtail_blake3.h"
+#include "../lib/blake2/longtail_blake2.h"
 #include "../lib/hpcdcchunker/longtail_hpcdcchunker.h"
 #include "../lib/memstorage/longtail_memstorage.h"
 #include "../lib/compressblockstore/longtail_compressblockstore.h"
@@ -231,6 +232,28 @@ int main(int argc, char** argv)
         printf("Longtail_B200_CreateVersionIndex: %zu bytes %s\n", n, (n == n_ref && memcmp(b, b_ref, n) == 0) ? "identical" : "DIFFERENT");
         Longtail_Free(b);
         Longtail_Free(v_verb);
+    }
+
+    /* 3b. BLAKE2s: the reference core with the B200 chunker + B200 'blk2' HashAPI, and the batched verb selected by a 'blk2' HashAPI */
+    {
+        struct Longtail_HashAPI* ref_b2 = Longtail_CreateBlake2HashAPI();
+        struct Longtail_HashAPI* b200_b2 = Longtail_CreateB200Blake2HashAPI();
+        struct Longtail_VersionIndex *v0 = 0, *v1 = 0, *v2 = 0;
+        CHECK(Longtail_CreateVersionIndex(storage, ref_b2, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v0) == 0, "reference blk2 index");
+        int e1 = Longtail_CreateVersionIndex(storage, b200_b2, b200_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v1);
+        int e2 = Longtail_B200_CreateVersionIndex(storage, ref_b2, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v2);
+        CHECK(e1 == 0 && e2 == 0, "blk2 through B200: %d %d", e1, e2);
+        void *b0 = 0, *b1 = 0, *b2 = 0; size_t n0 = 0, n1 = 0, n2 = 0;
+        serialise(v0, &b0, &n0);
+        if (!e1) serialise(v1, &b1, &n1);
+        if (!e2) serialise(v2, &b2, &n2);
+        CHECK(n0 == n1 && b1 && memcmp(b0, b1, n0) == 0, "blk2 VersionIndex through the B200 API objects differs");
+        CHECK(n0 == n2 && b2 && memcmp(b0, b2, n0) == 0, "blk2 VersionIndex of Longtail_B200_CreateVersionIndex differs");
+        printf("BLAKE2s: %zu bytes, objects %s, verb %s\n", n0, (b1 && n0 == n1 && !memcmp(b0, b1, n0)) ? "identical" : "DIFFERENT",
+               (b2 && n0 == n2 && !memcmp(b0, b2, n0)) ? "identical" : "DIFFERENT");
+        Longtail_Free(b0); Longtail_Free(b1); Longtail_Free(b2);
+        Longtail_Free(v0); Longtail_Free(v1); Longtail_Free(v2);
+        SAFE_DISPOSE_API(ref_b2); SAFE_DISPOSE_API(b200_b2);
     }
 
     /* 5. the compress half inside the reference's Longtail_WriteContent: reference compressblockstore vs

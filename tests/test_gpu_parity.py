@@ -124,6 +124,64 @@ def test_hash_segments_sizes(ctx, oracle, n):
         assert "%016x" % got[0] == case[0]["blk3"]
 
 
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 127, 128, 129, 1023, 1024, 4097, 65536, 100000, (1 << 20) + 3])
+def test_blake2s_segments_sizes(ctx, oracle, n):
+    """BLAKE2s with digest length 8 (lib/blake2/longtail_blake2.c:95-112), every block-boundary case, unaligned starts"""
+    import longtail_b200
+    data = synth_bytes(100 + n, n + 64)
+    dev = DeviceBytes(ctx, data)
+    try:
+        offs = np.array([0, 1, 3, 16, 31, 7, 0], np.uint64)
+        lens = np.array([n, n, n, n, n, max(n - 5, 0), min(n, 64)], np.uint32)
+        got = ctx.hash_segments(dev.ptr, dev.size, offs, lens, hash_type=longtail_b200.HASH_BLAKE2)
+    finally:
+        dev.free()
+    exp = oracle.hash_segments(ol.HASH_BLAKE2, data, offs, lens)
+    assert got.tolist() == exp.tolist()
+    case = [c for c in GOLDEN["hash"] if c["n"] == n]
+    if case:
+        assert "%016x" % got[0] == case[0]["blk2"]
+
+
+def test_blake2s_many_ragged_segments(ctx, oracle):
+    """thousands of segments of very different lengths: the per-lane work queue must hand out every one exactly once"""
+    import longtail_b200
+    data = synth_bytes(9, 4 << 20)
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, 40000, 5000).astype(np.uint32)
+    lens[::97] = 0
+    offs = rng.integers(0, data.size - 40000, 5000).astype(np.uint64)
+    dev = DeviceBytes(ctx, data)
+    try:
+        got = ctx.hash_segments(dev.ptr, dev.size, offs, lens, hash_type=longtail_b200.HASH_BLAKE2)
+    finally:
+        dev.free()
+    assert got.tolist() == oracle.hash_segments(ol.HASH_BLAKE2, data, offs, lens).tolist()
+
+
+def test_hash_kats_both_algorithms(ctx):
+    import longtail_b200
+    s = np.frombuffer(b"This is the first test string which is fairly long and should - reconstructed properly, than you very much\0", dtype=np.uint8)
+    dev = DeviceBytes(ctx, s)
+    try:
+        assert ctx.hash_segments(dev.ptr, dev.size, [0], [s.size], hash_type=longtail_b200.HASH_BLAKE2)[0] == 0xD336E5AFA4FA1F4D  # test.cpp:460
+        assert ctx.hash_segments(dev.ptr, dev.size, [0], [s.size])[0] == 0xD38BBE79F1F03FDA  # test.cpp:472
+    finally:
+        dev.free()
+
+
+@pytest.mark.parametrize("case", [c for c in GOLDEN["version_index"] if c["hash"] == "blk2"], ids=lambda c: "t%d" % c["target"])
+def test_version_index_blake2(ctx, oracle, case):
+    import longtail_b200
+    target = case["target"]
+    assets, tags, perms = _tree(target)
+    al = longtail_b200.AssetList([p for p, _ in assets], [d.size for _, d in assets], perms)
+    v = ctx.index_host_assets(al, [d for _, d in assets], tags, hash_type=longtail_b200.HASH_BLAKE2, target_chunk_size=target)
+    assert len(v) == case["size"]
+    assert sha(v) == case["sha256"]
+    assert v == oracle.create_version_index(assets, target, hash_type=ol.HASH_BLAKE2, tags=tags, perms=perms)
+
+
 def test_hash_kat(ctx):
     s = np.frombuffer(b"This is the first test string which is fairly long and should - reconstructed properly, than you very much\0", dtype=np.uint8)
     dev = DeviceBytes(ctx, s)
