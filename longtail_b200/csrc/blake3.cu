@@ -75,7 +75,8 @@ __global__ void k_leaf_counts(const uint32_t* __restrict__ len, uint32_t count, 
 __global__ void __launch_bounds__(LEAF_THREADS, 3)
 k_blake3_leaves(const uint8_t* __restrict__ base, uint64_t base_size, const uint64_t* __restrict__ seg_off,
                 const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ leaf_prefix, uint32_t seg_count,
-                uint32_t total_leaves, uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out, uint32_t one)
+                uint32_t total_leaves, uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out, uint32_t one,
+                uint4* __restrict__ merge_items, uint32_t* __restrict__ merge_counts)
 {
     __shared__ __align__(16) uint8_t s_stage[LEAF_WARPS][2][LEAF_STAGE_BYTES];
     const uint32_t lane = threadIdx.x & 31u;
@@ -98,10 +99,12 @@ k_blake3_leaves(const uint8_t* __restrict__ base, uint64_t base_size, const uint
     uint64_t addr = 0;      // byte offset of my leaf inside base
     uint32_t len = 0;       // bytes in my leaf (0..1024)
     uint32_t leaf_in_seg = 0;
+    uint32_t seg_leaves = 0;
     bool single = false;
     if (live)
     {
         const uint32_t first = __ldg(&leaf_prefix[seg]);
+        seg_leaves = __ldg(&leaf_prefix[seg + 1]) - first;
         const uint32_t slen = __ldg(&seg_len[seg]);
         leaf_in_seg = leaf - first;
         addr = __ldg(&seg_off[seg]) + (uint64_t)leaf_in_seg * 1024u;
@@ -195,58 +198,61 @@ k_blake3_leaves(const uint8_t* __restrict__ base, uint64_t base_size, const uint
             dst[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
         }
     }
+    // level-0 work list of the tree merge: every even leaf that has a right sibling
+    const bool pair = live && !single && (leaf_in_seg & 1u) == 0 && leaf_in_seg + 1 < seg_leaves;
+    const uint32_t pairs = __ballot_sync(0xffffffffu, pair);
+    if (pairs)
+    {
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(&merge_counts[0], (uint32_t)__popc(pairs));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (pair) merge_items[at + __popc(pairs & ((1u << lane) - 1u))] = make_uint4(leaf, leaf_in_seg, seg_leaves, seg);
+    }
 }
 
+// Tree merge, one launch per level, one LANE per parent node (ext/blake3.c:161-166 restated bottom-up: nodes stay in the
+// slot of their first leaf; at level l the node at leaf k = 0 mod 2^(l+1) absorbs its sibling at k + 2^l when that exists,
+// an unpaired node simply stays — which is exactly "the left subtree takes the largest power of two").  The work list of a
+// level holds {slot, k, leaves, segment} of every left node that has a sibling; a lane that still has a sibling one level up
+// re-queues itself, so the lists stay dense and every warp is full at every level.
 constexpr int MERGE_THREADS = 128;
 
 __global__ void __launch_bounds__(MERGE_THREADS)
-k_blake3_merge(const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ leaf_prefix, uint32_t seg_count,
-               uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out, uint32_t one)
+k_blake3_merge_level(const uint4* __restrict__ items_in, uint4* __restrict__ items_out, uint32_t* __restrict__ counts, uint32_t level,
+                     uint32_t* __restrict__ cvs, uint64_t* __restrict__ hash_out, uint32_t one)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t seg = blockIdx.x * (MERGE_THREADS / 32) + (threadIdx.x >> 5);
-    if (seg >= seg_count) return;
-    if (seg_len[seg] <= 1024u) return; // single-leaf segments were finished by the leaf kernel
-    const uint32_t first = leaf_prefix[seg];
-    uint32_t n = leaf_prefix[seg + 1] - first;
-    uint4* node = reinterpret_cast<uint4*>(cvs + (size_t)first * 8u); // node i = node[2i], node[2i+1]
-    while (n > 1)
+    const uint32_t t = blockIdx.x * MERGE_THREADS + threadIdx.x;
+    const uint32_t count = counts[level];
+    bool again = false;
+    uint4 it = make_uint4(0, 0, 0, 0);
+    if (t < count)
     {
-        const uint32_t pairs = n >> 1;
-        const uint32_t flags = F_PARENT | (n == 2 ? F_ROOT : 0u);
-        for (uint32_t b = 0; b < pairs; b += 32)
+        it = items_in[t];
+        const uint32_t span = 1u << level;
+        uint4* left = reinterpret_cast<uint4*>(cvs + (size_t)it.x * 8u);
+        const uint4* right = reinterpret_cast<const uint4*>(cvs + (size_t)(it.x + span) * 8u);
+        const uint4 a0 = left[0], a1 = left[1], b0 = right[0], b1 = right[1];
+        uint32_t m[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t cv[8] = {IV0, IV1, IV2, IV3, IV4, IV5, IV6, IV7};
+        const bool root = it.y == 0 && 2u * span >= it.z;
+        b3_compress(cv, m, 0, 64, F_PARENT | (root ? F_ROOT : 0u), one); // parent node: key = IV, counter 0 (ext/blake3.c:89-116)
+        if (root)
+            hash_out[it.w] = (uint64_t)cv[0] | ((uint64_t)cv[1] << 32);
+        else
         {
-            const uint32_t i = b + lane;
-            uint32_t m[16];
-            uint32_t cv[8] = {IV0, IV1, IV2, IV3, IV4, IV5, IV6, IV7};
-            if (i < pairs)
-            {
-                uint4 a0 = node[4 * i], a1 = node[4 * i + 1], b0 = node[4 * i + 2], b1 = node[4 * i + 3];
-                m[0] = a0.x; m[1] = a0.y; m[2] = a0.z; m[3] = a0.w; m[4] = a1.x; m[5] = a1.y; m[6] = a1.z; m[7] = a1.w;
-                m[8] = b0.x; m[9] = b0.y; m[10] = b0.z; m[11] = b0.w; m[12] = b1.x; m[13] = b1.y; m[14] = b1.z; m[15] = b1.w;
-                b3_compress(cv, m, 0, 64, flags, one); // parent node: key = IV, counter 0 (ext/blake3.c:89-116)
-            }
-            __syncwarp(); // all loads of this batch happen before any store of it (in-place levels)
-            if (i < pairs)
-            {
-                node[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
-                node[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
-            }
-            __syncwarp();
+            left[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+            left[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+            again = (it.y & (4u * span - 1u)) == 0 && it.y + 2u * span < it.z;
         }
-        if (n & 1u)
-        {
-            // odd node out is promoted unchanged; slot `pairs` was read by no one in this level after batch order
-            if (lane < 2) { uint4 t = node[2 * (n - 1) + lane]; __syncwarp(0x3); node[2 * pairs + lane] = t; }
-        }
-        __syncwarp();
-        __threadfence_block();
-        n = (n + 1) >> 1;
     }
-    if (lane == 0)
+    const uint32_t m2 = __ballot_sync(0xffffffffu, again);
+    if (m2)
     {
-        uint4 r = node[0];
-        hash_out[seg] = (uint64_t)r.x | ((uint64_t)r.y << 32);
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(&counts[level + 1], (uint32_t)__popc(m2));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (again) items_out[at + __popc(m2 & ((1u << lane) - 1u))] = it;
     }
 }
 
@@ -258,20 +264,32 @@ void launch_leaf_counts(const uint32_t* d_len, uint32_t count, uint32_t* d_leaf_
 
 void launch_blake3_leaves(const uint8_t* d_base, uint64_t base_size, const uint64_t* d_off, const uint32_t* d_len,
                           const uint32_t* d_leaf_prefix, uint32_t count, uint32_t total_leaves, uint32_t* d_cvs,
-                          uint64_t* d_hash_out, cudaStream_t st)
+                          uint64_t* d_hash_out, uint4* d_merge_items, uint32_t* d_merge_counts, cudaStream_t st)
 {
     if (!count || !total_leaves) return;
+    cudaMemsetAsync(d_merge_counts, 0, sizeof(uint32_t) * BLAKE3_MAX_LEVELS, st);
     const uint32_t leaves_per_block = LEAF_WARPS * 32;
     k_blake3_leaves<<<(total_leaves + leaves_per_block - 1) / leaves_per_block, LEAF_THREADS, 0, st>>>(
-        d_base, base_size, d_off, d_len, d_leaf_prefix, count, total_leaves, d_cvs, d_hash_out, 1u);
+        d_base, base_size, d_off, d_len, d_leaf_prefix, count, total_leaves, d_cvs, d_hash_out, 1u, d_merge_items, d_merge_counts);
 }
 
-void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, uint32_t count, uint32_t* d_cvs, uint64_t* d_hash_out,
-                         cudaStream_t st)
+// levels = ceil(log2(largest leaf count of a segment)); items_a and items_b each hold total_leaves/2 + 2 entries
+uint32_t launch_blake3_merge(uint32_t total_leaves, uint32_t segment_count, uint32_t max_segment_leaves, uint32_t* d_cvs, uint64_t* d_hash_out,
+                             uint4* d_items_a, uint4* d_items_b, uint32_t* d_merge_counts, cudaStream_t st)
 {
-    if (!count) return;
-    const uint32_t segs_per_block = MERGE_THREADS / 32;
-    k_blake3_merge<<<(count + segs_per_block - 1) / segs_per_block, MERGE_THREADS, 0, st>>>(d_len, d_leaf_prefix, count, d_cvs, d_hash_out, 1u);
+    uint32_t launches = 0;
+    for (uint32_t level = 0; (1u << level) < max_segment_leaves && level + 1 < BLAKE3_MAX_LEVELS; ++level)
+    {
+        // a segment of n leaves has ceil((n - 2^l) / 2^(l+1)) < n / 2^(l+1) + 1/2 parents at level l, and never more than at level 0
+        uint64_t bound64 = ((uint64_t)total_leaves >> (level + 1)) + segment_count / 2 + 2;
+        if (bound64 > (uint64_t)total_leaves / 2 + 1) bound64 = (uint64_t)total_leaves / 2 + 1;
+        const uint32_t bound = (uint32_t)bound64;
+        const uint4* in = (level & 1u) ? d_items_b : d_items_a;
+        uint4* out = (level & 1u) ? d_items_a : d_items_b;
+        k_blake3_merge_level<<<(bound + MERGE_THREADS - 1) / MERGE_THREADS, MERGE_THREADS, 0, st>>>(in, out, d_merge_counts, level, d_cvs, d_hash_out, 1u);
+        ++launches;
+    }
+    return launches;
 }
 
 } // namespace ltb

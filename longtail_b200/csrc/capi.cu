@@ -30,7 +30,7 @@ enum WsSlot
     WS_DEDUP_KEYS, WS_DEDUP_VALS, WS_DEDUP_FIRST, WS_DEDUP_ISFIRST, WS_DEDUP_UIDX, WS_ACI, WS_UHASH, WS_ULEN, WS_UTAG,
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
-    WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD,
+    WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS,
     WS_COUNT
 };
 
@@ -228,7 +228,7 @@ int make_chunk_params(lt_b200_context* c, uint32_t mn, uint32_t av, uint32_t mx,
 // hash segments whose offsets / lengths already sit in device memory; result stays on the device
 int hash_segments_device(lt_b200_context* c, uint32_t hash_type, const uint8_t* d_base, uint64_t base_size, const uint64_t* d_off,
                          const uint32_t* d_len, uint32_t count, uint64_t upper_leaves, int slot_leaf_count, int slot_leaf_prefix,
-                         int slot_cvs, uint64_t* d_hash_out, uint64_t payload_bytes = 0)
+                         int slot_cvs, uint64_t* d_hash_out, uint64_t payload_bytes = 0, uint32_t max_segment_bytes = 0xffffffffu)
 {
     if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2)
         return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation yet", hash_type);
@@ -246,6 +246,9 @@ int hash_segments_device(lt_b200_context* c, uint32_t hash_type, const uint8_t* 
     TRY(ws_reserve(c, slot_leaf_prefix, sizeof(uint32_t) * ((size_t)count + 1)));
     TRY(ws_reserve(c, WS_SCAN_TMP, sizeof(uint32_t) * scan_tmp_words(count)));
     TRY(ws_reserve(c, slot_cvs, 32 * (size_t)upper_leaves));
+    TRY(ws_reserve(c, WS_MERGE_A, sizeof(uint4) * ((size_t)upper_leaves / 2 + 2)));
+    TRY(ws_reserve(c, WS_MERGE_B, sizeof(uint4) * ((size_t)upper_leaves / 2 + 2)));
+    TRY(ws_reserve(c, WS_MERGE_COUNTS, sizeof(uint32_t) * BLAKE3_MAX_LEVELS));
     launch_leaf_counts(d_len, count, ws<uint32_t>(c, slot_leaf_count), c->stream);
     launch_exclusive_scan(ws<uint32_t>(c, slot_leaf_count), count, ws<uint32_t>(c, slot_leaf_prefix), ws<uint32_t>(c, WS_SCAN_TMP), c->stream);
     c->launches += 4;
@@ -258,13 +261,15 @@ int hash_segments_device(lt_b200_context* c, uint32_t hash_type, const uint8_t* 
     {
         ProfScope ps(c, LT_B200_KERNEL_BLAKE3_LEAVES, seg_bytes);
         launch_blake3_leaves(d_base, base_size, d_off, d_len, ws<uint32_t>(c, slot_leaf_prefix), count, total_leaves,
-                             ws<uint32_t>(c, slot_cvs), d_hash_out, c->stream);
+                             ws<uint32_t>(c, slot_cvs), d_hash_out, ws<uint4>(c, WS_MERGE_A), ws<uint32_t>(c, WS_MERGE_COUNTS), c->stream);
     }
     {
         ProfScope ps(c, LT_B200_KERNEL_BLAKE3_MERGE, (uint64_t)total_leaves * 32);
-        launch_blake3_merge(d_len, ws<uint32_t>(c, slot_leaf_prefix), count, ws<uint32_t>(c, slot_cvs), d_hash_out, c->stream);
+        const uint32_t max_leaves = max_segment_bytes == 0xffffffffu ? 0x400000u : (max_segment_bytes + 1023u) / 1024u;
+        c->launches += launch_blake3_merge(total_leaves, count, max_leaves, ws<uint32_t>(c, slot_cvs), d_hash_out, ws<uint4>(c, WS_MERGE_A),
+                                           ws<uint4>(c, WS_MERGE_B), ws<uint32_t>(c, WS_MERGE_COUNTS), c->stream);
     }
-    c->launches += 2;
+    c->launches += 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -526,7 +531,7 @@ extern "C" int lt_b200_chunk_ranges(lt_b200_context* c, const uint8_t* d_arena, 
                           ws<uint32_t>(c, WS_CHUNK_LEN), ws<uint32_t>(c, WS_CHUNK_TAG), c->stream);
     c->launches += 1;
     TRY(hash_segments_device(c, hash_type, d_arena, arena_size, ws<uint64_t>(c, WS_CHUNK_OFF), ws<uint32_t>(c, WS_CHUNK_LEN), chunk_count,
-                             bytes / 1024 + chunk_count, WS_LEAF_COUNT, WS_LEAF_PREFIX, WS_CVS, ws<uint64_t>(c, WS_CHUNK_HASH), bytes));
+                             bytes / 1024 + chunk_count, WS_LEAF_COUNT, WS_LEAF_PREFIX, WS_CVS, ws<uint64_t>(c, WS_CHUNK_HASH), bytes, mx));
     c->table_chunks = chunk_count;
     if (want_host)
     {
@@ -556,10 +561,12 @@ extern "C" int lt_b200_hash_segments(lt_b200_context* c, uint32_t hash_type, con
     if (!count) return 0;
     if (((uintptr_t)d_base) & 15u) return fail(c, EINVAL, "device buffer must be 16-byte aligned");
     uint64_t upper = count;
+    uint32_t max_size = 0;
     for (uint32_t i = 0; i < count; ++i)
     {
         if (offsets[i] + sizes[i] > base_size) return fail(c, EINVAL, "segment %u outside the buffer", i);
         upper += sizes[i] / 1024;
+        if (sizes[i] > max_size) max_size = sizes[i];
     }
     TRY(ws_reserve(c, WS_SEG_OFF, sizeof(uint64_t) * (size_t)count));
     TRY(ws_reserve(c, WS_SEG_LEN, sizeof(uint32_t) * (size_t)count));
@@ -567,7 +574,7 @@ extern "C" int lt_b200_hash_segments(lt_b200_context* c, uint32_t hash_type, con
     CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_OFF), offsets, sizeof(uint64_t) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_LEN), sizes, sizeof(uint32_t) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
     TRY(hash_segments_device(c, hash_type, d_base, base_size, ws<uint64_t>(c, WS_SEG_OFF), ws<uint32_t>(c, WS_SEG_LEN), count, upper,
-                             WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, ws<uint64_t>(c, WS_SEG_HASH)));
+                             WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, ws<uint64_t>(c, WS_SEG_HASH), 0, max_size));
     CU(cudaMemcpyAsync(out_hashes, ws<void>(c, WS_SEG_HASH), sizeof(uint64_t) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -593,16 +600,19 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
     uint32_t* h_starts = h_len + 2 * (size_t)(A + 1);
     uint64_t run = 0;
     uint64_t upper = 2ull * A;
+    uint32_t max_content = 0, max_path = 0;
     for (uint32_t i = 0; i < A; ++i)
     {
         h_starts[i] = (uint32_t)run;
         h_off[i] = run * 8;
         h_len[i] = asset_chunk_counts[i] * 8u;
+        if (h_len[i] > max_content) max_content = h_len[i];
         upper += h_len[i] / 1024;
         run += asset_chunk_counts[i];
         const char* path = a->path_data + a->path_start_offsets[i];
         h_off[A + i] = a->path_start_offsets[i];
         h_len[A + i] = (uint32_t)strlen(path);
+        if (h_len[A + i] > max_path) max_path = h_len[A + i];
         upper += h_len[A + i] / 1024;
     }
     if (run != chunk_count) return fail(c, EINVAL, "asset chunk counts sum to %llu, table has %u", (unsigned long long)run, chunk_count);
@@ -621,9 +631,9 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
         // content hashes: base = the chunk-hash array itself (any valid pointer when there are no chunks at all)
         const uint8_t* hash_bytes = chunk_count ? reinterpret_cast<const uint8_t*>(d_hash) : ws<uint8_t>(c, WS_PATHS);
         TRY(hash_segments_device(c, hash_type, hash_bytes, 8ull * chunk_count, ws<uint64_t>(c, WS_SEG_OFF),
-                                 ws<uint32_t>(c, WS_SEG_LEN), A, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, d_seg_hash));
+                                 ws<uint32_t>(c, WS_SEG_LEN), A, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, d_seg_hash, 0, max_content));
         TRY(hash_segments_device(c, hash_type, ws<uint8_t>(c, WS_PATHS), a->path_data_size, ws<uint64_t>(c, WS_SEG_OFF) + A,
-                                 ws<uint32_t>(c, WS_SEG_LEN) + A, A, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, d_seg_hash + A));
+                                 ws<uint32_t>(c, WS_SEG_LEN) + A, A, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS, d_seg_hash + A, 0, max_path));
     }
 
     // ---- first-occurrence dedup (src/longtail.c:2952-2970)
@@ -1123,7 +1133,7 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
     CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_SEG_LEN), h_seg_len, sizeof(uint32_t) * (size_t)nblocks, cudaMemcpyHostToDevice, c->stream));
     TRY(hash_segments_device(c, hash_type, ws<uint8_t>(c, WS_BLK_HASHES), 8ull * chunk_count, ws<uint64_t>(c, WS_BLK_SEG_OFF),
                              ws<uint32_t>(c, WS_BLK_SEG_LEN), nblocks, upper, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_SEG_CVS,
-                             ws<uint64_t>(c, WS_BLK_HASH_OUT)));
+                             ws<uint64_t>(c, WS_BLK_HASH_OUT), 0, 8u * max_chunks_per_block));
     CU(cudaMemcpyAsync(h_blk_hash, ws<void>(c, WS_BLK_HASH_OUT), sizeof(uint64_t) * (size_t)nblocks, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
 

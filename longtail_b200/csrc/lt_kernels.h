@@ -21,11 +21,12 @@ void launch_compact_chunks(const PartDesc* d_parts, uint32_t part_count, const u
 // ---- blake3.cu : hash `count` byte segments [off, off+len) of `base` (device memory of `base_size` bytes)
 // leaf_prefix has count+1 entries: exclusive prefix of max(1, ceil(len/1024)); cvs holds 8 u32 per leaf.
 void launch_leaf_counts(const uint32_t* d_len, uint32_t count, uint32_t* d_leaf_count, cudaStream_t st);
+constexpr uint32_t BLAKE3_MAX_LEVELS = 24; // segments are < 4 GiB = 2^22 leaves
 void launch_blake3_leaves(const uint8_t* d_base, uint64_t base_size, const uint64_t* d_off, const uint32_t* d_len,
                           const uint32_t* d_leaf_prefix, uint32_t count, uint32_t total_leaves, uint32_t* d_cvs,
-                          uint64_t* d_hash_out, cudaStream_t st);
-void launch_blake3_merge(const uint32_t* d_len, const uint32_t* d_leaf_prefix, uint32_t count, uint32_t* d_cvs, uint64_t* d_hash_out,
-                         cudaStream_t st);
+                          uint64_t* d_hash_out, uint4* d_merge_items, uint32_t* d_merge_counts, cudaStream_t st);
+uint32_t launch_blake3_merge(uint32_t total_leaves, uint32_t segment_count, uint32_t max_segment_leaves, uint32_t* d_cvs, uint64_t* d_hash_out,
+                             uint4* d_items_a, uint4* d_items_b, uint32_t* d_merge_counts, cudaStream_t st);
 
 // ---- blake2s.cu : BLAKE2s-64 over segments; d_counter is one u32 of scratch (the work queue head)
 void launch_blake2s_segments(const uint8_t* d_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t count, uint32_t* d_counter,

@@ -313,3 +313,18 @@ def test_synth_matches_host_generator(ctx):
             finally:
                 ctx.device_free(ptr)
             assert (dev == host).all()
+
+
+def test_blake3_tree_shapes_many_small_segments(ctx, oracle):
+    """segments of 1..40 leaves (every tree shape incl. 3, 5, 6, 7 leaves) in bulk: the per-level work lists must cover every parent"""
+    data = synth_bytes(21, 8 << 20)
+    rng = np.random.default_rng(5)
+    leaves = np.concatenate([np.full(4000, 3), rng.integers(1, 41, 4000)])
+    lens = (leaves * 1024 - rng.integers(0, 1024, leaves.size)).astype(np.uint32)
+    offs = rng.integers(0, data.size - 41 * 1024, leaves.size).astype(np.uint64)
+    dev = DeviceBytes(ctx, data)
+    try:
+        got = ctx.hash_segments(dev.ptr, dev.size, offs, lens)
+    finally:
+        dev.free()
+    assert got.tolist() == oracle.hash_segments(ol.HASH_BLAKE3, data, offs, lens).tolist()
