@@ -63,7 +63,8 @@ enum
     LT_B200_KERNEL_GATHER = 4,
     LT_B200_KERNEL_LZ4 = 5,
     LT_B200_KERNEL_BLAKE2S = 6,
-    LT_B200_KERNEL_COUNT = 8
+    LT_B200_KERNEL_MEOW = 7,
+    LT_B200_KERNEL_COUNT = 16
 };
 LT_B200_EXPORT int lt_b200_profile_enable(lt_b200_context* context, int on);
 LT_B200_EXPORT int lt_b200_profile_reset(lt_b200_context* context);

@@ -40,11 +40,13 @@ LT_B200_EXPORT struct Longtail_ChunkerAPI* Longtail_CreateB200ChunkerAPI(void);
 LT_B200_EXPORT struct Longtail_HashAPI* Longtail_CreateB200Blake3HashAPI(void);
 /* identifier 'blk2': BLAKE2s with an 8-byte digest, replaces Longtail_CreateBlake2HashAPI() (lib/blake2/longtail_blake2.c:114) */
 LT_B200_EXPORT struct Longtail_HashAPI* Longtail_CreateB200Blake2HashAPI(void);
+/* identifier 'meow': Meow hash 0.5/calico, default seed, low 64 bits; replaces Longtail_CreateMeowHashAPI() (lib/meowhash/longtail_meowhash.c:73) */
+LT_B200_EXPORT struct Longtail_HashAPI* Longtail_CreateB200MeowHashAPI(void);
 
 /* Longtail_CreateVersionIndex with the reference's parameter list (src/longtail.h:1134-1147).  storage_api supplies the
  * bytes (ConcatPath / OpenReadFile / Read / CloseFile, exactly the calls DynamicChunking makes); job_api, when given, runs
  * the storage reads of one batch in parallel while the GPU works on the previous batch.  hash_api / chunker_api only select
- * the algorithms (GetIdentifier must be 'blk3' or 'blk2'; the chunker must report a minimum of 48): the work is done by
+ * the algorithms (GetIdentifier must be 'blk3', 'blk2' or 'meow'; the chunker must report a minimum of 48): the work is done by
  * lt_b200_index_host_assets' kernels, not by calling back into them.  enable_file_map is ignored, as in the reference.
  * *out_version_index is allocated with Longtail_Alloc (see above) and is released by the caller with Longtail_Free. */
 LT_B200_EXPORT int Longtail_B200_CreateVersionIndex(

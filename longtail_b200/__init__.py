@@ -102,7 +102,7 @@ def load_library():
     return lib
 
 
-KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks", 6: "k_blake2s_segments"}
+KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks", 6: "k_blake2s_segments", 7: "k_meow_segments"}
 
 
 def parse_version_index(buf):

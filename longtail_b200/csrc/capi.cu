@@ -30,7 +30,7 @@ enum WsSlot
     WS_DEDUP_KEYS, WS_DEDUP_VALS, WS_DEDUP_FIRST, WS_DEDUP_ISFIRST, WS_DEDUP_UIDX, WS_ACI, WS_UHASH, WS_ULEN, WS_UTAG,
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
-    WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS,
+    WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
     WS_COUNT
 };
 
@@ -230,8 +230,8 @@ int hash_segments_device(lt_b200_context* c, uint32_t hash_type, const uint8_t* 
                          const uint32_t* d_len, uint32_t count, uint64_t upper_leaves, int slot_leaf_count, int slot_leaf_prefix,
                          int slot_cvs, uint64_t* d_hash_out, uint64_t payload_bytes = 0, uint32_t max_segment_bytes = 0xffffffffu)
 {
-    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2)
-        return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation yet", hash_type);
+    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2 && hash_type != LT_B200_HASH_MEOW)
+        return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation", hash_type);
     if (!count) return 0;
     if (hash_type == LT_B200_HASH_BLAKE2)
     {
@@ -240,6 +240,22 @@ int hash_segments_device(lt_b200_context* c, uint32_t hash_type, const uint8_t* 
         launch_blake2s_segments(d_base, d_off, d_len, count, ws<uint32_t>(c, WS_QUEUE_HEAD), d_hash_out, c->sm_count, c->stream);
         c->launches += 1;
         CU(cudaGetLastError());
+        return 0;
+    }
+    if (hash_type == LT_B200_HASH_MEOW)
+    {
+        TRY(ws_reserve(c, WS_QUEUE_HEAD, 256));
+        if (!c->ws[WS_MEOW_TABLE].p)
+        {
+            uint32_t td0[256];
+            meow_build_table(td0);
+            TRY(ws_reserve(c, WS_MEOW_TABLE, sizeof(td0)));
+            CU(cudaMemcpyAsync(ws<void>(c, WS_MEOW_TABLE), td0, sizeof(td0), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream)); // td0 lives on this stack frame
+        }
+        ProfScope ps(c, LT_B200_KERNEL_MEOW, payload_bytes);
+        CU(launch_meow_segments(d_base, d_off, d_len, count, ws<uint32_t>(c, WS_QUEUE_HEAD), d_hash_out, ws<uint32_t>(c, WS_MEOW_TABLE), c->sm_count, c->stream));
+        c->launches += 1;
         return 0;
     }
     TRY(ws_reserve(c, slot_leaf_count, sizeof(uint32_t) * (size_t)count));
@@ -454,8 +470,8 @@ extern "C" int lt_b200_chunk_ranges(lt_b200_context* c, const uint8_t* d_arena, 
     c->table_chunks = 0;
     ChunkParams cp;
     TRY(make_chunk_params(c, mn, av, mx, &cp));
-    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2)
-        return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation yet", hash_type);
+    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2 && hash_type != LT_B200_HASH_MEOW)
+        return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation", hash_type);
     if (((uintptr_t)d_arena) & 15u) return fail(c, EINVAL, "device arena must be 16-byte aligned");
     out->range_count = range_count;
     if (!range_count) return 0;
@@ -1083,8 +1099,8 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
     if (max_chunks_per_block == 0) return EINVAL;
     CU(cudaSetDevice(c->device));
     c->err[0] = 0;
-    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2)
-        return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation yet", hash_type);
+    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2 && hash_type != LT_B200_HASH_MEOW)
+        return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation", hash_type);
     if (!chunk_count) return 0;
 
     // ---- Longtail_CreateStoreIndex's greedy packing (src/longtail.c:6796-6860): in order; a block closes on a tag change, at

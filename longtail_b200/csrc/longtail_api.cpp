@@ -901,6 +901,7 @@ extern "C" struct Longtail_ChunkerAPI* Longtail_CreateB200ChunkerAPI(void)
 static struct Longtail_HashAPI* create_hash_api(uint32_t type);
 extern "C" struct Longtail_HashAPI* Longtail_CreateB200Blake3HashAPI(void) { return create_hash_api(LT_B200_HASH_BLAKE3); }
 extern "C" struct Longtail_HashAPI* Longtail_CreateB200Blake2HashAPI(void) { return create_hash_api(LT_B200_HASH_BLAKE2); }
+extern "C" struct Longtail_HashAPI* Longtail_CreateB200MeowHashAPI(void) { return create_hash_api(LT_B200_HASH_MEOW); }
 
 static struct Longtail_HashAPI* create_hash_api(uint32_t type)
 {
@@ -928,7 +929,7 @@ extern "C" int Longtail_B200_CreateVersionIndex(struct Longtail_StorageAPI* stor
     if (!storage_api || !hash_api || !chunker_api || !root_path || !out_version_index || target_chunk_size == 0) return EINVAL;
     if (file_infos && file_infos->m_Count && !job_api) return EINVAL;
     const uint32_t hash_type = hash_api->GetIdentifier(hash_api);
-    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2) return ENOTSUP;
+    if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2 && hash_type != LT_B200_HASH_MEOW) return ENOTSUP;
     uint32_t min_chunk = 0;
     int err = chunker_api->GetMinChunkSize(chunker_api, &min_chunk);
     if (err) return err;

@@ -32,6 +32,11 @@ uint32_t launch_blake3_merge(uint32_t total_leaves, uint32_t segment_count, uint
 void launch_blake2s_segments(const uint8_t* d_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t count, uint32_t* d_counter,
                              uint64_t* d_hash_out, int sm_count, cudaStream_t st);
 
+// ---- meow.cu : Meow 0.5 (low 64 bits) over segments; d_td0 = the 256-entry inverse T-table of meow_build_table in device memory
+void meow_build_table(uint32_t out[256]);
+cudaError_t launch_meow_segments(const uint8_t* d_base, const uint64_t* d_off, const uint32_t* d_len, uint32_t count, uint32_t* d_counter,
+                                 uint64_t* d_hash_out, const uint32_t* d_td0, int sm_count, cudaStream_t st);
+
 // ---- lz4.cu
 uint32_t lz4_copy_job_capacity(uint32_t raw_len);
 cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, uint8_t* d_out,

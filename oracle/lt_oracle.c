@@ -228,10 +228,160 @@ uint64_t lto_blake2s_64(const void* data, uint64_t len)
     return (uint64_t)h[0] | ((uint64_t)h[1] << 32);
 }
 
+
+/* ================================================================ Meow hash 0.5/calico, low 64 bits
+ * (lib/meowhash/ext/meow_hash_x64_aesni.h:181-198 macros, :234 seed, :480-560 absorb, :583-700 MeowEnd;
+ *  lib/meowhash/longtail_meowhash.c:43-50).  The x86 AESDEC round is restated with one inverse T-table. */
+
+typedef struct { uint32_t w[4]; } m128; /* little-endian words of one xmm register */
+
+static uint32_t MEOW_TD0[256];
+static int meow_tables_ready;
+
+static uint8_t gf_mul(uint8_t a, uint8_t b)
+{
+    uint8_t r = 0;
+    while (b)
+    {
+        if (b & 1) r ^= a;
+        a = (uint8_t)((a << 1) ^ ((a & 0x80) ? 0x1b : 0));
+        b >>= 1;
+    }
+    return r;
+}
+
+static void meow_init_tables(void)
+{
+    if (meow_tables_ready) return;
+    uint8_t sbox[256], inv[256];
+    /* AES S-box: multiplicative inverse in GF(2^8) followed by the affine map (FIPS-197 5.1.1) */
+    for (int x = 0; x < 256; ++x)
+    {
+        uint8_t y = 0;
+        if (x) for (int c = 1; c < 256; ++c) if (gf_mul((uint8_t)x, (uint8_t)c) == 1) { y = (uint8_t)c; break; }
+        uint8_t z = y;
+        for (int k = 1; k <= 4; ++k) z ^= (uint8_t)((y << k) | (y >> (8 - k)));
+        sbox[x] = z ^ 0x63;
+    }
+    for (int x = 0; x < 256; ++x) inv[sbox[x]] = (uint8_t)x;
+    /* column of InvMixColumns hit by a row-0 byte: (0e, 09, 0d, 0b) (FIPS-197 5.3.3) */
+    for (int x = 0; x < 256; ++x)
+    {
+        uint8_t y = inv[x];
+        MEOW_TD0[x] = (uint32_t)gf_mul(y, 0x0e) | ((uint32_t)gf_mul(y, 0x09) << 8) | ((uint32_t)gf_mul(y, 0x0d) << 16) | ((uint32_t)gf_mul(y, 0x0b) << 24);
+    }
+    meow_tables_ready = 1;
+}
+
+/* _mm_aesdec_si128(a, k) = InvMixColumns(InvSubBytes(InvShiftRows(a))) ^ k; byte 4c+r of the register is state[r][c] */
+static m128 meow_aesdec(m128 a, m128 k)
+{
+    m128 o;
+    for (int c = 0; c < 4; ++c)
+    {
+        uint32_t b0 = a.w[c] & 0xff, b1 = (a.w[(c + 3) & 3] >> 8) & 0xff, b2 = (a.w[(c + 2) & 3] >> 16) & 0xff, b3 = a.w[(c + 1) & 3] >> 24;
+        o.w[c] = MEOW_TD0[b0] ^ rotl32(MEOW_TD0[b1], 8) ^ rotl32(MEOW_TD0[b2], 16) ^ rotl32(MEOW_TD0[b3], 24) ^ k.w[c];
+    }
+    return o;
+}
+static m128 meow_paddq(m128 a, m128 b)
+{
+    uint64_t a0 = a.w[0] | ((uint64_t)a.w[1] << 32), a1 = a.w[2] | ((uint64_t)a.w[3] << 32);
+    uint64_t b0 = b.w[0] | ((uint64_t)b.w[1] << 32), b1 = b.w[2] | ((uint64_t)b.w[3] << 32);
+    a0 += b0; a1 += b1;
+    m128 o = {{(uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32)}};
+    return o;
+}
+static m128 meow_pxor(m128 a, m128 b) { m128 o = {{a.w[0] ^ b.w[0], a.w[1] ^ b.w[1], a.w[2] ^ b.w[2], a.w[3] ^ b.w[3]}}; return o; }
+static m128 meow_load(const uint8_t* p) { m128 o = {{load32(p), load32(p + 4), load32(p + 8), load32(p + 12)}}; return o; }
+
+/* MEOW_MIX_REG (:181-189) on state lanes (r1..r5) with the four 16-byte inputs */
+static void meow_mix_reg(m128* x, int r1, int r2, int r3, int r4, int r5, m128 i1, m128 i2, m128 i3, m128 i4)
+{
+    x[r1] = meow_aesdec(x[r1], x[r2]);
+    x[r3] = meow_paddq(x[r3], i1);
+    x[r2] = meow_pxor(x[r2], i2);
+    x[r2] = meow_aesdec(x[r2], x[r4]);
+    x[r5] = meow_paddq(x[r5], i3);
+    x[r4] = meow_pxor(x[r4], i4);
+}
+/* MEOW_MIX (:191-192): inputs are the loads at +15, +0, +1, +16 of a 32-byte lane */
+static void meow_mix(m128* x, int s, const uint8_t* p)
+{
+    /* lane roles rotate by one register per 32 bytes (:494-501): (0,4,6,1,2), (1,5,7,2,3), ... */
+    meow_mix_reg(x, s & 7, (s + 4) & 7, (s + 6) & 7, (s + 1) & 7, (s + 2) & 7, meow_load(p + 15), meow_load(p), meow_load(p + 1), meow_load(p + 16));
+}
+/* MEOW_SHUFFLE (:194-200) */
+static void meow_shuffle(m128* x, int r1, int r2, int r3, int r4, int r5, int r6)
+{
+    x[r1] = meow_aesdec(x[r1], x[r4]);
+    x[r2] = meow_paddq(x[r2], x[r5]);
+    x[r4] = meow_pxor(x[r4], x[r6]);
+    x[r4] = meow_aesdec(x[r4], x[r2]);
+    x[r5] = meow_paddq(x[r5], x[r6]);
+    x[r2] = meow_pxor(x[r2], x[r3]);
+}
+
+static const uint8_t MEOW_SEED[128] = { /* :234-252, "an encoding of Pi" */
+    0x32, 0x43, 0xF6, 0xA8, 0x88, 0x5A, 0x30, 0x8D, 0x31, 0x31, 0x98, 0xA2, 0xE0, 0x37, 0x07, 0x34, 0x4A, 0x40, 0x93, 0x82, 0x22, 0x99, 0xF3, 0x1D,
+    0x00, 0x82, 0xEF, 0xA9, 0x8E, 0xC4, 0xE6, 0xC8, 0x94, 0x52, 0x82, 0x1E, 0x63, 0x8D, 0x01, 0x37, 0x7B, 0xE5, 0x46, 0x6C, 0xF3, 0x4E, 0x90, 0xC6,
+    0xCC, 0x0A, 0xC2, 0x9B, 0x7C, 0x97, 0xC5, 0x0D, 0xD3, 0xF8, 0x4D, 0x5B, 0x5B, 0x54, 0x70, 0x91, 0x79, 0x21, 0x6D, 0x5D, 0x98, 0x97, 0x9F, 0xB1,
+    0xBD, 0x13, 0x10, 0xBA, 0x69, 0x8D, 0xFB, 0x5A, 0xC2, 0xFF, 0xD7, 0x2D, 0xBD, 0x01, 0xAD, 0xFB, 0x7B, 0x8E, 0x1A, 0xFE, 0xD6, 0xA2, 0x67, 0xE9,
+    0x6B, 0xA7, 0xC9, 0x04, 0x5F, 0x12, 0xC7, 0xF9, 0x92, 0x4A, 0x19, 0x94, 0x7B, 0x39, 0x16, 0xCF, 0x70, 0x80, 0x1F, 0x2E, 0x28, 0x58, 0xEF, 0xC1,
+    0x66, 0x36, 0x92, 0x0D, 0x87, 0x15, 0x74, 0xE6};
+
+uint64_t lto_meow_64(const void* data, uint64_t len)
+{
+    meow_init_tables();
+    const uint8_t* p = (const uint8_t*)data;
+    m128 x[8];
+    for (int i = 0; i < 8; ++i) x[i] = meow_load(MEOW_SEED + 16 * i);
+    /* full 256-byte blocks (MeowAbsorbBlocks :480-540) */
+    uint64_t blocks = len >> 8;
+    for (uint64_t b = 0; b < blocks; ++b, p += 256)
+        for (int s = 0; s < 8; ++s) meow_mix(x, s, p + 32 * s);
+    /* MeowEnd (:583-700): the residual (< 256 bytes) sits in a zero-padded buffer */
+    uint8_t buf[256 + 32];
+    memset(buf, 0, sizeof(buf));
+    uint32_t rest = (uint32_t)(len & 255u);
+    if (rest) memcpy(buf, p, rest);
+    uint8_t tail[32]; /* xmm11 (bytes 0..15) then xmm9 (bytes 16..31) */
+    memset(tail, 0, sizeof(tail));
+    const uint8_t* last = buf + (len & 0xf0);
+    uint32_t len8 = (uint32_t)(len & 0xf);
+    memcpy(tail + 16, last, len8); /* masked load of the ragged 16 bytes */
+    if (len & 0x10)
+    {
+        memcpy(tail, tail + 16, 16);      /* xmm11 = xmm9 */
+        memcpy(tail + 16, last - 16, 16); /* xmm9 = the full 16 bytes before */
+    }
+    /* xmm8 = palignr(xmm9, xmm11, 15), xmm10 = palignr(xmm9, xmm11, 1): byte windows +15 and +1 of the pair xmm11:xmm9 */
+    m128 xmm8 = meow_load(tail + 15), xmm9 = meow_load(tail + 16), xmm10 = meow_load(tail + 1), xmm11 = meow_load(tail);
+    /* length lanes: xmm15 = (len, 0), xmm12 = palignr(0, xmm15, 15), xmm14 = palignr(0, xmm15, 1), xmm13 = 0 */
+    uint8_t l15[32];
+    memset(l15, 0, sizeof(l15));
+    for (int i = 0; i < 8; ++i) l15[i] = (uint8_t)(len >> (8 * i));
+    m128 xmm15 = meow_load(l15), xmm12 = meow_load(l15 + 15), xmm14 = meow_load(l15 + 1), xmm13 = {{0, 0, 0, 0}};
+    meow_mix_reg(x, 0, 4, 6, 1, 2, xmm8, xmm9, xmm10, xmm11);
+    meow_mix_reg(x, 1, 5, 7, 2, 3, xmm12, xmm13, xmm14, xmm15);
+    uint32_t lanes = (uint32_t)((len >> 5) & 7);
+    for (uint32_t s = 0; s < lanes; ++s) meow_mix(x, 2 + (int)s, buf + 32 * s);
+    for (int s = 0; s < 12; ++s) meow_shuffle(x, s & 7, (s + 1) & 7, (s + 2) & 7, (s + 4) & 7, (s + 5) & 7, (s + 6) & 7);
+    x[0] = meow_paddq(x[0], x[2]);
+    x[1] = meow_paddq(x[1], x[3]);
+    x[4] = meow_paddq(x[4], x[6]);
+    x[5] = meow_paddq(x[5], x[7]);
+    x[0] = meow_pxor(x[0], x[1]);
+    x[4] = meow_pxor(x[4], x[5]);
+    x[0] = meow_paddq(x[0], x[4]);
+    return x[0].w[0] | ((uint64_t)x[0].w[1] << 32);
+}
+
 int lto_hash_buffer(uint32_t hash_type, const void* data, uint64_t len, uint64_t* out_hash)
 {
     if (hash_type == LTO_HASH_BLAKE3) { *out_hash = lto_blake3_64(data, len); return 0; }
     if (hash_type == LTO_HASH_BLAKE2) { *out_hash = lto_blake2s_64(data, len); return 0; }
+    if (hash_type == LTO_HASH_MEOW) { *out_hash = lto_meow_64(data, len); return 0; }
     return EINVAL;
 }
 

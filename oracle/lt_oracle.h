@@ -41,6 +41,8 @@ int lto_hpcdc_chunk(const uint8_t* data, uint64_t size, uint32_t min, uint32_t a
 uint64_t lto_blake3_64(const void* data, uint64_t len);
 /* lib/blake2/longtail_blake2.c:95-112: blake2s with outlen 8 */
 uint64_t lto_blake2s_64(const void* data, uint64_t len);
+/* lib/meowhash/longtail_meowhash.c:43-50: Meow 0.5/calico with the default seed, low 64 bits of the 128-bit hash */
+uint64_t lto_meow_64(const void* data, uint64_t len);
 /* HashAPI.HashBuffer by type id; returns 0 or EINVAL */
 int lto_hash_buffer(uint32_t hash_type, const void* data, uint64_t len, uint64_t* out_hash);
 int lto_hash_segments(uint32_t hash_type, const uint8_t* base, uint64_t count,

@@ -14,6 +14,7 @@
 #include "../lib/bikeshed/longtail_bikeshed.h"
 #include "../lib/blake3/longtail_blake3.h"
 #include "../lib/blake2/longtail_blake2.h"
+#include "../lib/meowhash/longtail_meowhash.h"
 #include "../lib/hpcdcchunker/longtail_hpcdcchunker.h"
 #include "../lib/memstorage/longtail_memstorage.h"
 #include "../lib/compressblockstore/longtail_compressblockstore.h"
@@ -234,26 +235,30 @@ int main(int argc, char** argv)
         Longtail_Free(v_verb);
     }
 
-    /* 3b. BLAKE2s: the reference core with the B200 chunker + B200 'blk2' HashAPI, and the batched verb selected by a 'blk2' HashAPI */
+    /* 3b. BLAKE2s and Meow: the reference core with the B200 chunker + the B200 'blk2' / 'meow' HashAPI, and the batched verb
+     *     selected by the reference's own HashAPI of that identifier */
+    for (int alg = 0; alg < 2; ++alg)
     {
-        struct Longtail_HashAPI* ref_b2 = Longtail_CreateBlake2HashAPI();
-        struct Longtail_HashAPI* b200_b2 = Longtail_CreateB200Blake2HashAPI();
+        const char* name = alg ? "Meow" : "BLAKE2s";
+        struct Longtail_HashAPI* ref_h = alg ? Longtail_CreateMeowHashAPI() : Longtail_CreateBlake2HashAPI();
+        struct Longtail_HashAPI* b200_h = alg ? Longtail_CreateB200MeowHashAPI() : Longtail_CreateB200Blake2HashAPI();
         struct Longtail_VersionIndex *v0 = 0, *v1 = 0, *v2 = 0;
-        CHECK(Longtail_CreateVersionIndex(storage, ref_b2, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v0) == 0, "reference blk2 index");
-        int e1 = Longtail_CreateVersionIndex(storage, b200_b2, b200_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v1);
-        int e2 = Longtail_B200_CreateVersionIndex(storage, ref_b2, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v2);
-        CHECK(e1 == 0 && e2 == 0, "blk2 through B200: %d %d", e1, e2);
+        CHECK(ref_h && b200_h && ref_h->GetIdentifier(ref_h) == b200_h->GetIdentifier(b200_h), "%s identifiers differ", name);
+        CHECK(Longtail_CreateVersionIndex(storage, ref_h, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v0) == 0, "reference %s index", name);
+        int e1 = Longtail_CreateVersionIndex(storage, b200_h, b200_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v1);
+        int e2 = Longtail_B200_CreateVersionIndex(storage, ref_h, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v2);
+        CHECK(e1 == 0 && e2 == 0, "%s through B200: %d %d", name, e1, e2);
         void *b0 = 0, *b1 = 0, *b2 = 0; size_t n0 = 0, n1 = 0, n2 = 0;
         serialise(v0, &b0, &n0);
         if (!e1) serialise(v1, &b1, &n1);
         if (!e2) serialise(v2, &b2, &n2);
-        CHECK(n0 == n1 && b1 && memcmp(b0, b1, n0) == 0, "blk2 VersionIndex through the B200 API objects differs");
-        CHECK(n0 == n2 && b2 && memcmp(b0, b2, n0) == 0, "blk2 VersionIndex of Longtail_B200_CreateVersionIndex differs");
-        printf("BLAKE2s: %zu bytes, objects %s, verb %s\n", n0, (b1 && n0 == n1 && !memcmp(b0, b1, n0)) ? "identical" : "DIFFERENT",
+        CHECK(n0 == n1 && b1 && memcmp(b0, b1, n0) == 0, "%s VersionIndex through the B200 API objects differs", name);
+        CHECK(n0 == n2 && b2 && memcmp(b0, b2, n0) == 0, "%s VersionIndex of Longtail_B200_CreateVersionIndex differs", name);
+        printf("%s: %zu bytes, objects %s, verb %s\n", name, n0, (b1 && n0 == n1 && !memcmp(b0, b1, n0)) ? "identical" : "DIFFERENT",
                (b2 && n0 == n2 && !memcmp(b0, b2, n0)) ? "identical" : "DIFFERENT");
         Longtail_Free(b0); Longtail_Free(b1); Longtail_Free(b2);
         Longtail_Free(v0); Longtail_Free(v1); Longtail_Free(v2);
-        SAFE_DISPOSE_API(ref_b2); SAFE_DISPOSE_API(b200_b2);
+        SAFE_DISPOSE_API(ref_h); SAFE_DISPOSE_API(b200_h);
     }
 
     /* 5. the compress half inside the reference's Longtail_WriteContent: reference compressblockstore vs

@@ -159,6 +159,52 @@ def test_blake2s_many_ragged_segments(ctx, oracle):
     assert got.tolist() == oracle.hash_segments(ol.HASH_BLAKE2, data, offs, lens).tolist()
 
 
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 255, 256, 257, 287, 288, 511, 512, 513, 1023, 4097, 65536, 100000, (1 << 20) + 19])
+def test_meow_segments_sizes(ctx, oracle, n):
+    """Meow 0.5 low 64 bits (lib/meowhash/longtail_meowhash.c:43-50): every residual / lane-count / 16-byte case of MeowEnd
+    (meow_hash_x64_aesni.h:583-700), unaligned starts"""
+    import longtail_b200
+    data = synth_bytes(300 + n, n + 64)
+    dev = DeviceBytes(ctx, data)
+    try:
+        offs = np.array([0, 1, 3, 16, 31, 7, 0, 13], np.uint64)
+        lens = np.array([n, n, n, n, n, max(n - 5, 0), min(n, 64), max(n - 17, 0)], np.uint32)
+        got = ctx.hash_segments(dev.ptr, dev.size, offs, lens, hash_type=longtail_b200.HASH_MEOW)
+    finally:
+        dev.free()
+    exp = oracle.hash_segments(ol.HASH_MEOW, data, offs, lens)
+    assert got.tolist() == exp.tolist()
+
+
+def test_meow_many_ragged_segments(ctx, oracle):
+    """thousands of segments of very different lengths (work queue + deferred finalisation), all lengths 0..600 included"""
+    import longtail_b200
+    data = synth_bytes(19, 4 << 20)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 40000, 6000).astype(np.uint32)
+    lens[:601] = np.arange(601)
+    lens[601::97] = 0
+    offs = rng.integers(0, data.size - 40000, 6000).astype(np.uint64)
+    dev = DeviceBytes(ctx, data)
+    try:
+        got = ctx.hash_segments(dev.ptr, dev.size, offs, lens, hash_type=longtail_b200.HASH_MEOW)
+    finally:
+        dev.free()
+    assert got.tolist() == oracle.hash_segments(ol.HASH_MEOW, data, offs, lens).tolist()
+
+
+def test_version_index_meow(ctx, oracle):
+    """whole CreateVersionIndex with the 'meow' identifier == the oracle (which is pinned to the reference in test_oracle.py)"""
+    import longtail_b200
+    target = 4096
+    assets = [("a/one.bin", synth_bytes(1, 3 * target * 1024 + 777)), ("a/two.bin", synth_bytes(2, 500000, "nib")),
+              ("b/", synth_bytes(3, 0)), ("b/dup.bin", synth_bytes(2, 500000, "nib")), ("c.txt", synth_bytes(4, 123456, "text")), ("e", synth_bytes(5, 0))]
+    tags = [0, ol.COMP_LZ4, 0, ol.COMP_LZ4, 0, 0]
+    al = longtail_b200.AssetList([p for p, _ in assets], [d.size for _, d in assets])
+    v = ctx.index_host_assets(al, [d for _, d in assets], tags, hash_type=longtail_b200.HASH_MEOW, target_chunk_size=target)
+    assert v == oracle.create_version_index(assets, target, hash_type=ol.HASH_MEOW, tags=tags)
+
+
 def test_hash_kats_both_algorithms(ctx):
     import longtail_b200
     s = np.frombuffer(b"This is the first test string which is fairly long and should - reconstructed properly, than you very much\0", dtype=np.uint8)
@@ -166,6 +212,7 @@ def test_hash_kats_both_algorithms(ctx):
     try:
         assert ctx.hash_segments(dev.ptr, dev.size, [0], [s.size], hash_type=longtail_b200.HASH_BLAKE2)[0] == 0xD336E5AFA4FA1F4D  # test.cpp:460
         assert ctx.hash_segments(dev.ptr, dev.size, [0], [s.size])[0] == 0xD38BBE79F1F03FDA  # test.cpp:472
+        assert ctx.hash_segments(dev.ptr, dev.size, [0], [s.size], hash_type=longtail_b200.HASH_MEOW)[0] == 0x4EDC68DAC105C4EE  # test.cpp:484
     finally:
         dev.free()
 

@@ -33,6 +33,7 @@ def test_chunker_golden_vector(oracle):
 def test_hash_kats(oracle):
     assert oracle.hash(ol.HASH_BLAKE3, KAT_STRING) == 0xD38BBE79F1F03FDA  # test.cpp:472
     assert oracle.hash(ol.HASH_BLAKE2, KAT_STRING) == 0xD336E5AFA4FA1F4D  # test.cpp:460
+    assert oracle.hash(ol.HASH_MEOW, KAT_STRING) == 0x4EDC68DAC105C4EE  # test.cpp:484
 
 
 def test_discriminator(oracle):
@@ -63,6 +64,7 @@ def test_hash_fixtures(oracle, case):
     x = synth_bytes(100 + case["n"], case["n"])
     assert "%016x" % oracle.hash(ol.HASH_BLAKE3, x) == case["blk3"]
     assert "%016x" % oracle.hash(ol.HASH_BLAKE2, x) == case["blk2"]
+    assert "%016x" % oracle.hash(ol.HASH_MEOW, x) == case["meow"]
 
 
 @pytest.mark.parametrize("case", GOLDEN["lz4"], ids=lambda c: "%s-%d" % (c["kind"], c["n"]))
@@ -121,6 +123,15 @@ def test_chunker_vs_reference(oracle, reference, seed, n, target, kind):
     x = synth_bytes(seed, n, kind)
     mn, av, mx = chunker_params(target)
     assert oracle.chunk(x, mn, av, mx).tolist() == reference.chunk(x, mn, av, mx).tolist()
+
+
+def test_meow_vs_reference_every_small_length(oracle, reference):
+    """MeowEnd's residual / lane / 16-byte branches (meow_hash_x64_aesni.h:583-700): all lengths 0..1100 and a few large ones"""
+    if reference is None:
+        pytest.skip("reference not built")
+    x = synth_bytes(77, 300000)
+    for n in list(range(0, 1101)) + [4096, 65535, 65536, 131072, 299999]:
+        assert oracle.hash(ol.HASH_MEOW, x[3:3 + n]) == reference.hash(ol.HASH_MEOW, x[3:3 + n]), n
 
 
 @pytest.mark.parametrize("n,kind", [(70000, "text"), (65546, "nib"), (65547, "nib"), (2 << 20, "text"), (9 << 20, "nib"), (1 << 20, "rand")])
