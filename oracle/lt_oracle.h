@@ -54,6 +54,13 @@ uint64_t lto_lz4_bound(uint64_t size);
 int lto_lz4_compress(const uint8_t* src, uint64_t size, uint8_t* dst, uint64_t cap, uint64_t* out_size);
 int lto_lz4_decompress(const uint8_t* src, uint64_t size, uint8_t* dst, uint64_t cap, uint64_t* out_size);
 
+/* lib/zstd/longtail_zstd.c:107-140 with 'ztd1' / 'ztd2' (both ZStd level 3): one frame per call, content size in the header, no
+ * checksum; restated in lt_zstd.c from lib/zstd/ext (zstd 1.5.6).  cap must be >= lto_zstd_bound(size) (zstd.h:232). */
+#define LTO_COMPRESSION_ZSTD_DEFAULT 0x7a746432u /* 'ztd2' lib/zstd/longtail_zstd.c:20 */
+#define LTO_COMPRESSION_ZSTD_MIN 0x7a746431u     /* 'ztd1' -> level 0 == default == 3, lib/zstd/longtail_zstd.c:19,47 */
+uint64_t lto_zstd_bound(uint64_t size);
+int lto_zstd_compress(const uint8_t* src, uint64_t size, uint8_t* dst, uint64_t cap, uint64_t* out_size);
+
 /* src/longtail.c:2808-3017 (Longtail_CreateVersionIndex) + :3415-3439 (serialise).
  * Assets are in-memory; paths are relative, directories end with '/'.  *out_buf is malloc'd. */
 int lto_create_version_index(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,

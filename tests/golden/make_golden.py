@@ -21,6 +21,13 @@ LZ4_CASES = [(0, "rand"), (5, "rand"), (12, "zero"), (13, "zero"), (41, "text"),
              (200000, "rand"), (300000, "zero"), (500000, "nib"), (720000, "text"), (1 << 20, "p3"), (3 << 20, "nib")]
 
 
+# ZStd level 3 ('ztd2'): every parameter row of clevels.h (<=16 KiB, <=128 KiB, <=256 KiB, above), block-size edges, inputs larger
+# than the 2 MiB window, incompressible / RLE / tiny inputs
+ZSTD_CASES = [(0, "rand"), (1, "rand"), (6, "zero"), (7, "zero"), (40, "text"), (63, "rec"), (64, "rec"), (300, "rec"), (1024, "rec"), (1025, "text"),
+              (16384, "rec"), (16385, "rec"), (65536, "nib"), (131072, "rec"), (131073, "rec"), (200000, "zero"), (262144, "rec"),
+              (262145, "rec"), (300000, "p7"), (500000, "text"), (1 << 20, "rand"), (1 << 20, "rec"), (2500000, "nib"), (7 << 20, "rec")]
+
+
 def sha(b):
     return hashlib.sha256(bytes(b)).hexdigest()
 
@@ -28,7 +35,10 @@ def sha(b):
 def main():
     r = ol.Reference()
     assert r.available, "build the reference first: make -C oracle ref"
-    g = {"chunker": [], "hash": [], "lz4": [], "version_index": [], "upsync": []}
+    g = {"chunker": [], "hash": [], "lz4": [], "zstd": [], "version_index": [], "upsync": []}
+    for n, kind in ZSTD_CASES:
+        c = r.compress(ol.COMP_ZSTD_DEFAULT, synth_bytes(500 + n, n, kind))
+        g["zstd"].append({"n": n, "kind": kind, "size": len(c), "sha256": sha(c)})
     for seed, n, target, kind in CHUNK_CASES:
         mn, av, mx = chunker_params(target)
         lens = r.chunk(synth_bytes(seed, n, kind), mn, av, mx)

@@ -21,6 +21,7 @@ HASH_BLAKE2 = 0x626C6B32
 HASH_MEOW = 0x6D656F77
 COMP_LZ4 = 0x6C7A3432
 COMP_ZSTD_DEFAULT = 0x7A746432  # 'ztd2'
+COMP_ZSTD_MIN = 0x7A746431  # 'ztd1' (level 0 -> default level 3)
 
 _u8p = C.POINTER(C.c_uint8)
 
@@ -90,6 +91,10 @@ class Oracle:
         lib.lto_lz4_bound.restype = C.c_uint64
         lib.lto_lz4_bound.argtypes = [C.c_uint64]
         lib.lto_free.argtypes = [C.c_void_p]
+        lib.lto_zstd_bound.restype = C.c_uint64
+        lib.lto_zstd_bound.argtypes = [C.c_uint64]
+        lib.lto_meow_64.restype = C.c_uint64
+        lib.lto_meow_64.argtypes = [C.c_void_p, C.c_uint64]
 
     def discriminator(self, avg):
         return self.lib.lto_hpcdc_discriminator(C.c_uint32(avg))
@@ -120,6 +125,17 @@ class Oracle:
                                          _ptr(lens, C.c_uint32), _ptr(out, C.c_uint64))
         assert err == 0, err
         return out
+
+    def zstd_compress(self, data):
+        """'ztd2' / 'ztd1' (ZStd level 3), one frame"""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        cap = self.lib.lto_zstd_bound(data.size)
+        dst = np.zeros(cap + 8, dtype=np.uint8)
+        n = C.c_uint64(0)
+        dummy = np.zeros(1, dtype=np.uint8)
+        err = self.lib.lto_zstd_compress(_ptr(data) if data.size else _ptr(dummy), C.c_uint64(data.size), _ptr(dst), C.c_uint64(cap), C.byref(n))
+        assert err == 0, err
+        return dst[:n.value].tobytes()
 
     def lz4_compress(self, data):
         data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)

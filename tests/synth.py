@@ -13,9 +13,11 @@ def _mix(z):
 
 
 def synth_bytes(seed, n, kind="rand"):
-    """n bytes: rand | nib (4-bit entropy) | bit | zero | text | p<k> (period k of random bytes)"""
+    """n bytes: rand | nib (4-bit entropy) | bit | zero | text | p<k> (period k of random bytes) | rec (LZ-compressible records)"""
     if kind == "zero":
         return np.zeros(n, dtype=np.uint8)
+    if kind == "rec":
+        return synth_records(seed, n)
     if kind.startswith("p") and kind[1:].isdigit():
         k = int(kind[1:])
         unit = synth_bytes(seed, k, "rand")
@@ -35,6 +37,36 @@ def synth_bytes(seed, n, kind="rand"):
         alphabet = np.frombuffer(b"eeeeeeee tttttt aaaaa ooooo iiii nnnn ssss hhh rrr dd ll cu\nmwfgyp", dtype=np.uint8)
         return alphabet[b & np.uint8(63)]
     raise ValueError(kind)
+
+
+def synth_records(seed, n):
+    """LZ-compressible bytes: phrases drawn from a 4 KiB text vocabulary, sprinkled with random bytes, long byte runs and
+    (every ~3 MiB) a 300 KiB copy of data from more than 2 MiB back — exercises matches, repcodes, long lengths, RLE blocks
+    and the window limit of the block codecs"""
+    vocab = synth_bytes(seed + 1, 4096, "text").tobytes()
+    noise = synth_bytes(seed + 2, 65536, "rand").tobytes()
+    out = bytearray()
+    i = 0
+    next_far = 3 << 20
+    mask = (1 << 64) - 1
+    while len(out) < n:
+        z = (seed * 0x9E3779B97F4A7C15 + (i + 1) * 0xD1B54A32D192ED03) & mask
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+        z ^= z >> 31
+        a = z % 4000
+        out += vocab[a:a + 4 + ((z >> 12) % 60)]
+        if (z >> 20) % 4 == 0:
+            b = (z >> 24) % 65000
+            out += noise[b:b + (z >> 44) % 24]
+        if (z >> 30) % 512 == 0:
+            out += bytes([(z >> 40) & 255]) * ((z >> 48) % 200000)
+        if len(out) >= next_far:
+            src = len(out) - (2 << 20) - 400000
+            out += out[src:src + 300000]
+            next_far += 3 << 20
+        i += 1
+    return np.frombuffer(bytes(out[:n]), dtype=np.uint8).copy()
 
 
 def chunker_params(target):

@@ -102,6 +102,14 @@ def test_upsync_fixtures(oracle, case):
     assert sha(b"".join(h.to_bytes(8, "little") + b for h, b in blocks)) == case["blocks_sha256"]
 
 
+@pytest.mark.parametrize("case", GOLDEN["zstd"], ids=lambda c: "%s-%d" % (c["kind"], c["n"]))
+def test_zstd_fixtures(oracle, case):
+    """ZStd level 3 frames ('ztd2', lib/zstd/longtail_zstd.c:107-140) == the fixtures generated from the reference"""
+    c = oracle.zstd_compress(synth_bytes(500 + case["n"], case["n"], case["kind"]))
+    assert len(c) == case["size"]
+    assert sha(c) == case["sha256"]
+
+
 # ---------------------------------------------------------------- live differential vs the unmodified reference
 
 
@@ -140,6 +148,30 @@ def test_lz4_vs_reference(oracle, reference, n, kind):
         pytest.skip("reference not built")
     x = synth_bytes(300 + n, n, kind)
     assert oracle.lz4_compress(x) == reference.compress(ol.COMP_LZ4, x)
+
+
+@pytest.mark.parametrize("n,kind", [(100, "rec"), (5000, "rec"), (70000, "rec"), (140000, "text"), (270000, "rec"), (3 << 20, "rec"), (1 << 20, "nib"),
+                                    (600000, "zero"), (9 << 20, "rec")])
+def test_zstd_vs_reference(oracle, reference, n, kind):
+    if reference is None:
+        pytest.skip("reference not built")
+    x = synth_bytes(900 + n, n, kind)
+    c = oracle.zstd_compress(x)
+    assert c == reference.compress(ol.COMP_ZSTD_DEFAULT, x)
+    assert c == reference.compress(ol.COMP_ZSTD_MIN, x)  # 'ztd1' -> level 0 == level 3
+    assert len(c) < n or kind == "rand"
+
+
+def test_zstd_vs_reference_real_files(oracle, reference):
+    """source text and machine code of the reference tree itself: real match / literal / sequence statistics"""
+    if reference is None or not os.path.isdir("/root/reference"):
+        pytest.skip("reference not available")
+    import glob
+    files = sorted(glob.glob("/root/reference/src/*.c") + glob.glob("/root/reference/lib/zstd/ext/compress/*.c"))[:12]
+    files.append(os.path.join(HERE, "..", "oracle", "_ref", "libref_shim.so"))
+    for f in files:
+        x = np.fromfile(f, dtype=np.uint8)[:6 << 20]
+        assert oracle.zstd_compress(x) == reference.compress(ol.COMP_ZSTD_DEFAULT, x), f
 
 
 def test_upsync_vs_reference_default_params(oracle, reference):
