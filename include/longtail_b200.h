@@ -37,6 +37,8 @@ extern "C" {
 #define LT_B200_HASH_BLAKE2 0x626c6b32u /* 'blk2', lib/blake2/longtail_blake2.c:9 */
 #define LT_B200_HASH_MEOW 0x6d656f77u   /* 'meow', lib/meowhash/longtail_meowhash.c:7 */
 #define LT_B200_COMPRESSION_LZ4 0x6c7a3432u /* 'lz42', lib/lz4/longtail_lz4.c:10 */
+#define LT_B200_COMPRESSION_ZSTD_MIN 0x7a746431u     /* 'ztd1' -> ZStd level 0 == default == 3, lib/zstd/longtail_zstd.c:19,47 */
+#define LT_B200_COMPRESSION_ZSTD_DEFAULT 0x7a746432u /* 'ztd2' -> ZStd level 3, lib/zstd/longtail_zstd.c:20,49 */
 
 typedef struct lt_b200_context lt_b200_context;
 
@@ -64,6 +66,7 @@ enum
     LT_B200_KERNEL_LZ4 = 5,
     LT_B200_KERNEL_BLAKE2S = 6,
     LT_B200_KERNEL_MEOW = 7,
+    LT_B200_KERNEL_ZSTD = 8,
     LT_B200_KERNEL_COUNT = 16
 };
 LT_B200_EXPORT int lt_b200_profile_enable(lt_b200_context* context, int on);
@@ -220,6 +223,15 @@ LT_B200_EXPORT int lt_b200_lz4_compress_host(lt_b200_context* context, uint32_t 
                                              void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
 LT_B200_EXPORT int lt_b200_lz4_decompress_host(lt_b200_context* context, uint32_t count, const void* const* src, const uint32_t* src_size,
                                                void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
+
+/* CompressionAPI.Compress (src/longtail.h:266-272) for 'ztd1' / 'ztd2' over `count` independent HOST buffers in one launch:
+ * ZSTD_compressCCtx(level 3) semantics (lib/zstd/longtail_zstd.c:107-140), one frame per buffer, output bytes identical to the
+ * reference codec (vendored zstd 1.5.6).  dst_capacity[i] must be at least lt_b200_zstd_bound(src_size[i]) (EINVAL otherwise,
+ * the reference's answer to a ZStd error).  The other ZStd quality ids ('ztd3' / 'ztd4' / 'ztd5': levels 22 / 8 / 22) have no
+ * device encoder: ENOTSUP. */
+LT_B200_EXPORT uint64_t lt_b200_zstd_bound(uint64_t size); /* ZSTD_COMPRESSBOUND, lib/zstd/ext/zstd.h:232 */
+LT_B200_EXPORT int lt_b200_zstd_compress_host(lt_b200_context* context, uint32_t compression_type, uint32_t count, const void* const* src,
+                                              const uint32_t* src_size, void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
 
 /* Arena offsets of the unique chunks (first occurrences, VersionIndex order) found by the last lt_b200_index_device_assets
  * call on this context — the `chunk_arena_offsets` of a fresh-store lt_b200_write_blocks_device. */

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "_lib", "liblongtail_b200.so")
 HASH_BLAKE3 = 0x626C6B33  # 'blk3'
 HASH_BLAKE2 = 0x626C6B32  # 'blk2'
 HASH_MEOW = 0x6D656F77  # 'meow'
+COMPRESSION_ZSTD_MIN = 0x7A746431  # 'ztd1' (level 0 -> 3)
+COMPRESSION_ZSTD_DEFAULT = 0x7A746432  # 'ztd2' (level 3)
 COMPRESSION_LZ4 = 0x6C7A3432  # 'lz42'
 
 _lib = None
@@ -102,7 +104,7 @@ def load_library():
     return lib
 
 
-KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks", 6: "k_blake2s_segments", 7: "k_meow_segments"}
+KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks", 6: "k_blake2s_segments", 7: "k_meow_segments", 8: "k_zstd_frames"}
 
 
 def parse_version_index(buf):
@@ -326,6 +328,23 @@ class Context:
                                                          s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
                                                          int(hash_type), int(max_block_size), int(max_chunks_per_block), cb, None), "write_blocks_device")
         return blocks
+
+    def zstd_compress_host(self, buffers, compression_type=None):
+        """CompressionAPI.Compress for 'ztd2' / 'ztd1' over a list of host buffers in one launch -> list of frames (bytes)"""
+        ctype = COMPRESSION_ZSTD_DEFAULT if compression_type is None else compression_type
+        keep = [np.ascontiguousarray(b, dtype=np.uint8) for b in buffers]
+        n = len(keep)
+        self.lib.lt_b200_zstd_bound.restype = C.c_uint64
+        self.lib.lt_b200_zstd_bound.argtypes = [C.c_uint64]
+        caps = [int(self.lib.lt_b200_zstd_bound(b.size)) for b in keep]
+        outs = [np.empty(max(c, 1), dtype=np.uint8) for c in caps]
+        src = (C.c_void_p * max(n, 1))(*[b.ctypes.data if b.size else None for b in keep])
+        dst = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+        sizes = (C.c_uint32 * max(n, 1))(*[b.size for b in keep])
+        cap = (C.c_uint64 * max(n, 1))(*caps)
+        got = (C.c_uint64 * max(n, 1))()
+        self._check(self.lib.lt_b200_zstd_compress_host(self.handle, C.c_uint32(ctype), C.c_uint32(n), src, sizes, dst, cap, got), "zstd_compress_host")
+        return [outs[i][:got[i]].tobytes() for i in range(n)]
 
     # ---- layer 2
     def _result(self, buf, size, copy):

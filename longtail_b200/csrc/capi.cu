@@ -31,6 +31,7 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
+    WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN,
     WS_COUNT
 };
 
@@ -1090,6 +1091,37 @@ extern "C" int lt_b200_unique_chunk_offsets(lt_b200_context* c, uint64_t* out_of
     return 0;
 }
 
+extern "C" uint64_t lt_b200_zstd_bound(uint64_t n) { return n + (n >> 8) + (n < (128u << 10) ? ((128u << 10) - n) >> 11 : 0); }
+
+namespace {
+
+bool is_zstd_level3(uint32_t tag) { return tag == LT_B200_COMPRESSION_ZSTD_DEFAULT || tag == LT_B200_COMPRESSION_ZSTD_MIN; }
+
+// launch the ZStd frame encoder over frames laid out in device buffers; results land in WS_ZSTD_OUT_LEN (device)
+int zstd_launch(lt_b200_context* c, const uint8_t* d_raw, const std::vector<uint64_t>& raw_off, const std::vector<uint32_t>& raw_len, uint8_t* d_out,
+                const std::vector<uint64_t>& out_off, uint64_t payload_bytes)
+{
+    const uint32_t n = (uint32_t)raw_len.size();
+    const uint32_t workers = zstd_worker_count(n, c->sm_count);
+    TRY(ws_reserve(c, WS_ZSTD_WORKERS, zstd_worker_bytes() * (size_t)workers));
+    TRY(ws_reserve(c, WS_ZSTD_RAW_OFF, sizeof(uint64_t) * (size_t)n));
+    TRY(ws_reserve(c, WS_ZSTD_OUT_OFF, sizeof(uint64_t) * (size_t)n));
+    TRY(ws_reserve(c, WS_ZSTD_RAW_LEN, sizeof(uint32_t) * (size_t)n));
+    TRY(ws_reserve(c, WS_ZSTD_OUT_LEN, sizeof(uint32_t) * (size_t)n));
+    TRY(ws_reserve(c, WS_QUEUE_HEAD, 256));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_ZSTD_RAW_OFF), raw_off.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_ZSTD_OUT_OFF), out_off.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_ZSTD_RAW_LEN), raw_len.data(), sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream)); // the host vectors belong to the caller's scope
+    ProfScope ps(c, LT_B200_KERNEL_ZSTD, payload_bytes);
+    CU(launch_zstd_frames(d_raw, ws<uint64_t>(c, WS_ZSTD_RAW_OFF), ws<uint32_t>(c, WS_ZSTD_RAW_LEN), d_out, ws<uint64_t>(c, WS_ZSTD_OUT_OFF),
+                          ws<uint32_t>(c, WS_ZSTD_OUT_LEN), n, ws<void>(c, WS_ZSTD_WORKERS), workers, ws<uint32_t>(c, WS_QUEUE_HEAD), c->stream));
+    c->launches += 1;
+    return 0;
+}
+
+} // namespace
+
 extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
                                            const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
                                            const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
@@ -1111,7 +1143,8 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
     for (uint32_t i = 0; i < chunk_count;)
     {
         Block b = {i, 1, chunk_sizes[i], chunk_tags ? chunk_tags[i] : 0u};
-        if (b.tag != 0 && b.tag != LT_B200_COMPRESSION_LZ4) return fail(c, ENOTSUP, "compression type 0x%08x has no device implementation yet", b.tag);
+        if (b.tag != 0 && b.tag != LT_B200_COMPRESSION_LZ4 && !is_zstd_level3(b.tag))
+            return fail(c, ENOTSUP, "compression type 0x%08x has no device implementation", b.tag);
         if (chunk_arena_offsets[i] + chunk_sizes[i] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", i);
         while (i + b.count < chunk_count)
         {
@@ -1172,7 +1205,7 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
         {
             const Block& bl = blocks[b1];
             const uint64_t r = ((uint64_t)bl.raw + 16 + 15) & ~15ull;
-            const uint64_t o = bl.tag ? ((8 + lz4_bound(bl.raw) + 15) & ~15ull) : 0;
+            const uint64_t o = bl.tag ? ((8 + (is_zstd_level3(bl.tag) ? lt_b200_zstd_bound(bl.raw) : lz4_bound(bl.raw)) + 15) & ~15ull) : 0;
             if (b1 > b0 && raw_bytes + out_bytes + r + o > budget) break;
             raw_off.push_back(raw_bytes);
             out_off.push_back(out_bytes);
@@ -1215,7 +1248,12 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
         // LZ4 over the compressed-tag blocks of the batch: the kernel is launched over all blocks; raw ones are skipped by length 0
         // in the launch table — simpler: launch over the whole batch and let tag-0 blocks be served straight from the raw buffer
         std::vector<uint32_t> lz_idx;
-        for (uint32_t i = 0; i < nb; ++i) if (blocks[b0 + i].tag) lz_idx.push_back(i);
+        std::vector<uint32_t> zs_idx;
+        for (uint32_t i = 0; i < nb; ++i)
+        {
+            if (blocks[b0 + i].tag == LT_B200_COMPRESSION_LZ4) lz_idx.push_back(i);
+            else if (blocks[b0 + i].tag) zs_idx.push_back(i);
+        }
         if (!lz_idx.empty())
         {
             // compact launch tables for the LZ4 blocks
@@ -1243,16 +1281,37 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
                                  ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), ws<uint3>(c, WS_BLK_JOBS),
                                  ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), (uint32_t)lz_idx.size(), c->stream));
         }
+        // ZStd level 3 over the 'ztd1' / 'ztd2' blocks of the batch: one frame per block
+        if (!zs_idx.empty())
+        {
+            std::vector<uint64_t> zro(zs_idx.size()), zoo(zs_idx.size());
+            std::vector<uint32_t> zrl(zs_idx.size());
+            uint64_t zs_bytes = 0;
+            for (size_t i = 0; i < zs_idx.size(); ++i)
+            {
+                zro[i] = raw_off[zs_idx[i]]; zoo[i] = out_off[zs_idx[i]]; zrl[i] = raw_len[zs_idx[i]];
+                zs_bytes += zrl[i];
+            }
+            TRY(zstd_launch(c, ws<uint8_t>(c, WS_BLK_RAW), zro, zrl, ws<uint8_t>(c, WS_BLK_OUT), zoo, zs_bytes));
+        }
         c->launches += 3;
-        TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb + 16));
+        TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * 2 * (size_t)nb + 16));
         uint32_t* h_out_len = hs<uint32_t>(c, HS_BLK_OUT_LEN);
+        uint32_t* h_zs_len = h_out_len + nb;
         if (!lz_idx.empty())
             CU(cudaMemcpyAsync(h_out_len, ws<void>(c, WS_BLK_OUT_LEN), sizeof(uint32_t) * lz_idx.size(), cudaMemcpyDeviceToHost, c->stream));
+        if (!zs_idx.empty())
+            CU(cudaMemcpyAsync(h_zs_len, ws<void>(c, WS_ZSTD_OUT_LEN), sizeof(uint32_t) * zs_idx.size(), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaGetLastError());
         std::vector<uint32_t> payload_len(nb);
         for (uint32_t i = 0; i < nb; ++i) payload_len[i] = blocks[b0 + i].raw;
         for (size_t i = 0; i < lz_idx.size(); ++i) payload_len[lz_idx[i]] = h_out_len[i];
+        for (size_t i = 0; i < zs_idx.size(); ++i)
+        {
+            if (h_zs_len[i] == 0xffffffffu) return fail(c, EINVAL, "ZStd encoder failed on block %u", b0 + zs_idx[i]);
+            payload_len[zs_idx[i]] = h_zs_len[i];
+        }
 
         // ---- serialise (Longtail_WriteStoredBlockToBuffer, src/longtail.c:4111-4150) into pinned staging, a few blocks at a time
         const uint64_t stage_cap = 256ull << 20;
@@ -1401,6 +1460,62 @@ int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src,
 }
 
 } // namespace
+
+extern "C" int lt_b200_zstd_compress_host(lt_b200_context* c, uint32_t compression_type, uint32_t count, const void* const* src, const uint32_t* src_size,
+                                          void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size)
+{
+    if (!c || (count && (!src || !src_size || !dst || !dst_capacity || !out_size))) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    if (!is_zstd_level3(compression_type)) return fail(c, ENOTSUP, "compression type 0x%08x has no device encoder (only 'ztd1' / 'ztd2' = level 3)", compression_type);
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = (uint64_t)(free_b * 0.3);
+    if (budget > (16ull << 30)) budget = 16ull << 30;
+    std::vector<uint64_t> in_off, out_off;
+    std::vector<uint32_t> in_len;
+    for (uint32_t i0 = 0; i0 < count;)
+    {
+        uint64_t in_bytes = 0, out_bytes = 0;
+        uint32_t i1 = i0;
+        in_off.clear(); out_off.clear(); in_len.clear();
+        while (i1 < count)
+        {
+            if (src_size[i1] >= 0x7E000000u) return fail(c, E2BIG, "buffer %u too large", i1);
+            if (dst_capacity[i1] < lt_b200_zstd_bound(src_size[i1])) return fail(c, EINVAL, "buffer %u: capacity below ZSTD_COMPRESSBOUND", i1);
+            const uint64_t a = ((uint64_t)src_size[i1] + 16 + 15) & ~15ull, b = (8 + lt_b200_zstd_bound(src_size[i1]) + 16 + 15) & ~15ull;
+            if (i1 > i0 && in_bytes + out_bytes + a + b > budget) break;
+            in_off.push_back(in_bytes); out_off.push_back(out_bytes); in_len.push_back(src_size[i1]);
+            in_bytes += a; out_bytes += b;
+            ++i1;
+        }
+        const uint32_t nb = i1 - i0;
+        TRY(ws_reserve(c, WS_BLK_RAW, in_bytes + 64));
+        TRY(ws_reserve(c, WS_BLK_OUT, out_bytes + 64));
+        uint64_t payload = 0;
+        for (uint32_t i = 0; i < nb; ++i)
+        {
+            payload += in_len[i];
+            if (in_len[i]) CU(cudaMemcpyAsync(ws<uint8_t>(c, WS_BLK_RAW) + in_off[i], src[i0 + i], in_len[i], cudaMemcpyHostToDevice, c->stream));
+        }
+        TRY(zstd_launch(c, ws<uint8_t>(c, WS_BLK_RAW), in_off, in_len, ws<uint8_t>(c, WS_BLK_OUT), out_off, payload));
+        TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb + 16));
+        uint32_t* h_len = hs<uint32_t>(c, HS_BLK_OUT_LEN);
+        CU(cudaMemcpyAsync(h_len, ws<void>(c, WS_ZSTD_OUT_LEN), sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        for (uint32_t i = 0; i < nb; ++i)
+        {
+            if (h_len[i] == 0xffffffffu) return fail(c, EINVAL, "buffer %u: ZStd encoder error", i0 + i);
+            const uint64_t n = h_len[i] - 8u; // the kernel writes the block-store header first
+            CU(cudaMemcpyAsync(dst[i0 + i], ws<uint8_t>(c, WS_BLK_OUT) + out_off[i] + 8, n, cudaMemcpyDeviceToHost, c->stream));
+            out_size[i0 + i] = n;
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        i0 = i1;
+    }
+    return 0;
+}
 
 extern "C" int lt_b200_lz4_compress_host(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
                                          const uint64_t* dst_capacity, uint64_t* out_size)

@@ -231,6 +231,14 @@ class Reference:
         assert err == 0, err
         return dst[:n.value].tobytes()
 
+    def decompress(self, comp_type, data, raw_size):
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        dst = np.zeros(max(raw_size, 1), dtype=np.uint8)
+        n = C.c_uint64(0)
+        err = self.lib.ref_decompress(C.c_uint32(comp_type), _ptr(data), C.c_uint64(data.size), _ptr(dst), C.c_uint64(raw_size), C.byref(n))
+        assert err == 0, err
+        return dst[:n.value].tobytes()
+
     def create_version_index(self, assets, target_chunk_size, hash_type=HASH_BLAKE3, tags=None, perms=None, workers=0, want_seconds=False):
         a = _AssetArgs(assets, tags, perms)
         buf = C.c_void_p()

@@ -1,0 +1,114 @@
+"""GPU parity (-m gpu) of the ZStd level 3 frame encoder ('ztd1' / 'ztd2'): frames byte-identical to the CPU oracle (itself pinned
+to the unmodified reference in test_oracle.py) and to the fixtures generated from the reference."""
+import hashlib
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from synth import small_tree, synth_bytes
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import longtail_b200
+    c = longtail_b200.Context(0)
+    yield c
+    c.close()
+
+
+def test_zstd_golden_fixtures(ctx):
+    """all reference fixtures in ONE launch (one warp per frame): every parameter row of clevels.h, block edges, > window inputs"""
+    cases = GOLDEN["zstd"]
+    frames = ctx.zstd_compress_host([synth_bytes(500 + c["n"], c["n"], c["kind"]) for c in cases])
+    for c, f in zip(cases, frames):
+        assert len(f) == c["size"], (c, len(f))
+        assert sha(f) == c["sha256"], c
+
+
+@pytest.mark.parametrize("kind", ["rec", "text", "nib", "rand", "zero", "p7", "bit"])
+def test_zstd_vs_oracle_sizes(ctx, oracle, kind):
+    sizes = [0, 1, 2, 6, 7, 8, 9, 63, 64, 65, 255, 256, 257, 1023, 1024, 1025, 4095, 4096, 16384, 16385, 40960, 65535, 65536, 65792, 131071,
+             131072, 131073, 262144, 262145, 300000, 700001, (1 << 20) + 3, 3 << 20]
+    bufs = [synth_bytes(700 + n, n, kind) for n in sizes]
+    frames = ctx.zstd_compress_host(bufs)
+    for n, b, f in zip(sizes, bufs, frames):
+        want = oracle.zstd_compress(b)
+        assert len(f) == len(want), (kind, n, len(f), len(want))
+        assert f == want, (kind, n)
+
+
+def test_zstd_large_blocks_vs_oracle(ctx, oracle):
+    """stored-block sized frames (> the 2 MiB window: the lowest valid match index moves, zstd_compress_internal.h:1305-1316)"""
+    import longtail_b200
+    bufs = [synth_bytes(800, 9 << 20, "rec"), synth_bytes(801, (8 << 20) + 12345, "nib"), synth_bytes(802, 5 << 20, "text"),
+            np.concatenate([synth_bytes(803, 3 << 20, "rec"), synth_bytes(804, 1 << 20, "rand"), synth_bytes(803, 3 << 20, "rec")])]
+    frames = ctx.zstd_compress_host(bufs, longtail_b200.COMPRESSION_ZSTD_MIN)  # 'ztd1' == level 3 as well
+    for b, f in zip(bufs, frames):
+        assert f == oracle.zstd_compress(b)
+
+
+def test_zstd_decodes_with_the_reference(ctx, reference):
+    """the frames are valid ZStd: the unmodified reference decoder returns the input"""
+    if reference is None:
+        pytest.skip("reference not built")
+    x = synth_bytes(810, 2500000, "rec")
+    (f,) = ctx.zstd_compress_host([x])
+    assert reference.decompress(ol.COMP_ZSTD_DEFAULT, f, x.size) == x.tobytes()
+    assert len(f) < x.size // 4
+
+
+def test_zstd_unsupported_levels_fail_loudly(ctx):
+    import longtail_b200
+    for t in (0x7A746433, 0x7A746434, 0x7A746435):  # 'ztd3' level 22, 'ztd4' level 8, 'ztd5' -> 22 (reference bug kept): no device encoder
+        with pytest.raises(longtail_b200.LongtailB200Error) as e:
+            ctx.zstd_compress_host([synth_bytes(1, 1000)], t)
+        assert e.value.errno == 95  # ENOTSUP
+
+
+def test_stored_blocks_zstd_vs_reference(ctx, oracle, reference):
+    """WriteContent with tag 'ztd2': serialised StoredBlocks (index + {raw, comp} header + frame) == the reference's upsync"""
+    if reference is None:
+        pytest.skip("reference not built")
+    import longtail_b200
+    target = 256
+    assets = small_tree(target)
+    assets.append(("r/rec.bin", synth_bytes(820, 1500000, "rec")))
+    assets.sort(key=lambda a: a[0].encode())
+    tags = [ol.COMP_ZSTD_DEFAULT if i % 3 else 0 for i in range(len(assets))]
+    want_blocks, want_index = reference.upsync(assets, target, max_block_size=262144, max_chunks_per_block=64, tags=tags, workers=3)
+    offs, off = [], 0
+    for _, d in assets:
+        offs.append(off)
+        off = (off + d.size + 255) & ~255
+    arena = np.zeros(off + 256, np.uint8)
+    for o, (_, d) in zip(offs, assets):
+        arena[o:o + d.size] = d
+    ptr = ctx.device_alloc(arena.size)
+    try:
+        ctx.to_device(ptr, arena)
+        al = longtail_b200.AssetList([p for p, _ in assets], [d.size for _, d in assets])
+        v = ctx.index_device_assets(ptr, arena.size, al, offs, tags, target_chunk_size=target)
+        assert v == want_index
+        vi = longtail_b200.parse_version_index(v)
+        uoff = ctx.unique_chunk_offsets(vi["chunk_count"])
+        blocks = ctx.write_blocks_device(ptr, arena.size, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"], uoff, max_block_size=262144,
+                                         max_chunks_per_block=64)
+    finally:
+        ctx.device_free(ptr)
+    assert len(blocks) == len(want_blocks)
+    assert [h for h, _ in blocks] == [h for h, _ in want_blocks]
+    for (h, got), (_, want) in zip(blocks, want_blocks):
+        assert got == want, "block %016x differs" % h
