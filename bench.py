@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--gib", type=float, default=64.0, help="size of the synthetic file per GPU (GiB)")
     ap.add_argument("--e2e-gib", type=float, default=None, help="size of the host-resident file for the e2e leg (default: --gib, bounded by host RAM)")
     ap.add_argument("--cpu-gib", type=float, default=8.0, help="bounded sample for the CPU baseline / the reference arm")
+    ap.add_argument("--compress-gib", type=float, default=16.0, help="size of the configs[2]-shaped asset set of the LZ4 leg (0 = skip; 128 = the full config)")
+    ap.add_argument("--zstd-gib", type=float, default=4.0, help="size of the asset set of the ZStd leg (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", action="store_true", help="small sizes only: compare the final VersionIndex with the CPU checker, byte for byte")
@@ -107,6 +109,95 @@ def host_sample(nbytes, threads, asset_id=0):
     spec = longtail_b200.SynthSpec(SEED, 0, 1, 0, 0)
     lib.synth_fill_mt(C.byref(spec), C.c_uint64(asset_id), C.c_uint64(0), buf.ctypes.data_as(C.c_void_p), C.c_uint64(nbytes), C.c_uint32(threads))
     return buf
+
+
+def config3_asset_sizes(total_bytes, count):
+    """sizes log-uniform in [64 KiB, 256 MiB], rescaled to the total, 256-byte granules"""
+    import math
+    x, sizes = 12345, []
+    for _ in range(count):
+        x = (x * 6364136223846793005 + 1442695040888963407) & ((1 << 64) - 1)
+        u = (x >> 11) / float(1 << 53)
+        sizes.append(math.exp(math.log(65536.0) + u * (math.log(268435456.0) - math.log(65536.0))))
+    scale = total_bytes / sum(sizes)
+    return [max(4096, int(v * scale) // 256 * 256) for v in sizes]
+
+
+def compress_leg(ctx, torch, stream, codec, gib, cpu_sample_gib, want_cpu):
+    """configs[2] shape (10 000 assets per 128 GiB, 50 % byte redundancy, random / 4-bit / text-like segments) through
+    CreateVersionIndex + WriteContent with the codec tag on every asset: gather + compress on the device, every StoredBlock
+    copied to a host sink (memory is the sink: SURVEY.md section 8d)."""
+    import numpy as np
+
+    import longtail_b200
+    tag = longtail_b200.COMPRESSION_LZ4 if codec == "lz4" else longtail_b200.COMPRESSION_ZSTD_DEFAULT
+    kernel = "k_lz4_blocks" if codec == "lz4" else "k_zstd_frames"
+    total = int(gib * GIB)
+    count = max(8, int(round(10000 * gib / 128.0)))
+    sizes = config3_asset_sizes(total, count)
+    offs, off = [], 0
+    for sz in sizes:
+        offs.append(off)
+        off += (sz + 255) & ~255
+    arena_bytes = off + 4096
+    arena = ctx.device_alloc(arena_bytes)
+    pool = max(8, int(8192 * gib / 128.0))  # the shared pool is 8 GiB at full size (1 MiB segments)
+    for i, (o, sz) in enumerate(zip(offs, sizes)):
+        ctx.synth_fill(arena + o, sz, seed=2, asset_id=i, class_mode=1, shared_permille=500, pool_segments=pool)
+    ctx.synchronize()
+    al = longtail_b200.AssetList(["a/%05d.bin" % i for i in range(count)], sizes)
+    tags = [tag] * count
+    nbytes = sum(sizes)
+    out = {"codec": codec, "assets": count, "bytes": nbytes}
+    res = None
+    for it in range(2):  # pass 0 warms up (workspace growth, pinned staging), pass 1 is reported
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        v = ctx.index_device_assets(arena, arena_bytes, al, offs, tags, target_chunk_size=TARGET_CHUNK_SIZE)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        vi = longtail_b200.parse_version_index(v)
+        uoff = ctx.unique_chunk_offsets(vi["chunk_count"])
+        t2 = time.perf_counter()
+        blocks = ctx.write_blocks_device(arena, arena_bytes, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"], uoff, keep_bytes=False)
+        t3 = time.perf_counter()
+        ctx.profile_enable(False)
+        prof = ctx.profile_read()
+        unique = int(vi["chunk_sizes"].astype(np.uint64).sum())
+        stored = sum(sz for _, sz in blocks)
+        index_ms = e0.elapsed_time(e1)
+        dev_ms = index_ms + prof["k_gather_chunks"][0] + prof[kernel][0]
+        res = {"unique_bytes": unique, "unique_frac": round(unique / nbytes, 4), "blocks": len(blocks), "stored_bytes": stored,
+               "ratio": round(stored / max(unique, 1), 4), "index_ms": round(index_ms, 2), "gather_ms": round(prof["k_gather_chunks"][0], 2),
+               "codec_kernel_ms": round(prof[kernel][0], 2), "codec_kernel_GBps": round(unique / max(prof[kernel][0], 1e-9) / 1e6, 2),
+               "value_GiBps": round(nbytes / (dev_ms / 1e3) / GIB, 3),
+               "e2e_GiBps": round(nbytes / ((t1 - t0) + (t3 - t2)) / GIB, 3), "write_wall_ms": round(1e3 * (t3 - t2), 1),
+               "d2h_bytes": stored, "note": "value = asset bytes / (index + gather + codec kernel device time); e2e adds the block-store "
+                                            "hand-over: every StoredBlock copied to pinned host memory and passed to the sink"}
+    out.update(res)
+    if want_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        ref = ol.Reference()
+        if ref.available:
+            assets, acc = [], 0
+            for i, (o, sz) in enumerate(zip(offs, sizes)):
+                if acc + sz > cpu_sample_gib * GIB and assets:
+                    break
+                assets.append(("a/%05d.bin" % i, ctx.to_host(arena + o, sz)))
+                acc += sz
+            cores = ref.cpu_count()
+            secs, _stored = ref.upsync(assets, TARGET_CHUNK_SIZE, tags=[tag] * len(assets), workers=cores, keep_bytes=False)
+            out["cpu_baseline"] = {"value": round(acc / sum(secs) / GIB, 4), "unit": "GiB/s", "cores": cores, "kind": "reference",
+                                   "sample": "first %d assets (%.2f GiB): CreateVersionIndex + CreateMissingContent + WriteContent through "
+                                             "compressblockstore, bikeshed %d workers" % (len(assets), acc / GIB, cores),
+                                   "seconds_index_missing_write": [round(x, 3) for x in secs]}
+    ctx.device_free(arena)
+    return out
 
 
 def reference_pass(ref, data, workers):
@@ -320,6 +411,20 @@ def run_b200(args):
             cpu = {"value": round(small.size / secs / GIB, 4), "unit": "GiB/s", "cores": 1, "kind": "port",
                    "sample": "first %.1f GiB of the file, oracle/lt_oracle.c single thread" % (small.size / GIB)}
 
+    # ---- the compress half on a configs[2]-shaped asset set (rank 0, N == 1): LZ4 and ZStd level 3
+    compress = None
+    if rank == 0 and world == 1 and (args.compress_gib > 0 or args.zstd_gib > 0):
+        ctx.device_free(arena)
+        arena = None
+        if host_buf is not None:
+            ctx.pinned_free(host_buf)
+            host_buf = None
+        compress = {}
+        if args.compress_gib > 0:
+            compress["lz4"] = compress_leg(ctx, torch, stream, "lz4", args.compress_gib, 2.0, not args.no_cpu)
+        if args.zstd_gib > 0:
+            compress["zstd"] = compress_leg(ctx, torch, stream, "zstd", args.zstd_gib, 1.0, not args.no_cpu)
+
     if rank == 0:
         peak, peak_src = peaks()
         # dominant kernel = the one with the largest share of device time
@@ -342,11 +447,13 @@ def run_b200(args):
                          "share_of_step": shares, "per_kernel": per_kernel,
                          "note": "algorithmic bytes = 1 B read per asset byte (SURVEY.md §8d); both hot kernels are integer-issue bound, see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "write_content": compress,
         }
         print(json.dumps(line))
     if host_buf is not None:
         ctx.pinned_free(host_buf)
-    ctx.device_free(arena)
+    if arena is not None:
+        ctx.device_free(arena)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -72,12 +72,21 @@ LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CreateB200LZ4Compression
  * Longtail_CreateDefaultCompressionRegistry in place of Longtail_CompressionRegistry_CreateForLZ4 */
 LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CompressionRegistry_CreateForB200LZ4(uint32_t compression_type, uint32_t* out_settings);
 
+/* CompressionAPI for the ZStd type ids (lib/zstd/longtail_zstd.c:31-42, :107-140): Compress with settings 'ztd1' / 'ztd2' is
+ * ZSTD_compressCCtx(level 3) on the GPU, one frame per call, byte-identical to the reference (vendored zstd 1.5.6);
+ * GetMaxCompressedSize is ZSTD_COMPRESSBOUND.  The other quality ids ('ztd3' level 22, 'ztd4' level 8, 'ztd5') and Decompress
+ * return ENOTSUP: there is no device kernel for them and no CPU fallback. */
+LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CreateB200ZStdCompressionAPI(void);
+/* replaces Longtail_CompressionRegistry_CreateForZstd (lib/zstd/longtail_zstd.c:31) in Longtail_CreateDefaultCompressionRegistry */
+LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CompressionRegistry_CreateForB200ZStd(uint32_t compression_type, uint32_t* out_settings);
+
 /* BlockStoreAPI decorator, replaces Longtail_CreateCompressBlockStoreAPI (lib/compressblockstore/longtail_compressblockstore.c:622):
  * PutStoredBlock compresses on the GPU — concurrent calls from the JobAPI workers are gathered into one launch by a
  * background thread, the caller's block stays alive until OnComplete as in the reference (:151-176) — and forwards the
  * compressed block to the backing store; GetStoredBlock fetches from the backing store and decodes on the GPU;
  * tag 0 passes through untouched; PruneBlocks returns ENOTSUP (:483-493); stats count what the reference counts (:199-201,
- * :362-363).  Compression types without a device kernel make PutStoredBlock / GetStoredBlock fail with ENOTSUP.
+ * :362-363).  PutStoredBlock handles 'lz42', 'ztd1' and 'ztd2' (ZStd level 3); GetStoredBlock decodes 'lz42'.  Compression types without a
+ * device kernel make PutStoredBlock / GetStoredBlock fail with ENOTSUP.
  * `compression_registry` is accepted for signature compatibility and not used. */
 LT_B200_EXPORT struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockStoreAPI(
     struct Longtail_BlockStoreAPI* backing_block_store,

@@ -483,6 +483,33 @@ int lz4_decompress(struct Longtail_CompressionAPI*, const char* compressed, char
 
 void compression_api_dispose(struct Longtail_API* api) { lt_free(api); }
 
+// ---------------------------------------------------------------- ZStd CompressionAPI ('ztd1' / 'ztd2' = level 3; lib/zstd/longtail_zstd.c)
+bool is_zstd_level3(uint32_t type) { return type == LT_B200_COMPRESSION_ZSTD_DEFAULT || type == LT_B200_COMPRESSION_ZSTD_MIN; }
+bool is_zstd_type(uint32_t type) { return (type & 0xffffff00u) == 0x7a746400u; } // lib/zstd/longtail_zstd.c:33
+
+size_t zstd_max_size(struct Longtail_CompressionAPI*, uint32_t, size_t size) { return (size_t)lt_b200_zstd_bound(size); } // :83-86
+
+int zstd_compress(struct Longtail_CompressionAPI*, uint32_t settings_id, const char* uncompressed, char* compressed, size_t uncompressed_size,
+                  size_t max_compressed_size, size_t* out_compressed_size)
+{
+    if (!compressed || !out_compressed_size || (!uncompressed && uncompressed_size) || uncompressed_size > 0x7E000000u) return EINVAL;
+    if (!is_zstd_level3(settings_id)) return ENOTSUP; // levels 8 / 22 ('ztd3', 'ztd4', 'ztd5') have no device encoder
+    std::lock_guard<std::mutex> g(g_gpu);
+    int err = ensure_ctx();
+    if (err) return err;
+    const void* src = uncompressed;
+    void* dst = compressed;
+    uint32_t n = (uint32_t)uncompressed_size;
+    uint64_t cap = max_compressed_size, out = 0;
+    err = lt_b200_zstd_compress_host(g_ctx, settings_id, 1, &src, &n, &dst, &cap, &out);
+    if (err) return err;
+    *out_compressed_size = (size_t)out;
+    return 0;
+}
+
+// No device ZStd decoder exists yet (the downsync direction is SURVEY.md section 8f row 3); failing loudly beats a CPU fallback.
+int zstd_decompress(struct Longtail_CompressionAPI*, const char*, char*, size_t, size_t, size_t*) { return ENOTSUP; }
+
 // ---------------------------------------------------------------- compress block store
 size_t block_index_data_size(uint32_t chunk_count) { return 8 + 4 + 4 + 4 + 12 * (size_t)chunk_count; } // src/longtail.c:3585-3597
 
@@ -623,7 +650,7 @@ void store_worker(B200CompressStore* s)
         for (uint32_t i = 0; i < n && !err; ++i)
         {
             const uint32_t raw = batch[i].block->m_BlockChunksDataSize;
-            cap[i] = lt_b200_lz4_bound(raw);
+            cap[i] = *batch[i].block->m_BlockIndex->m_Tag == TYPE_LZ4 ? lt_b200_lz4_bound(raw) : lt_b200_zstd_bound(raw);
             out[i] = make_owned_block(batch[i].block->m_BlockIndex, 8 + (size_t)cap[i]);
             if (!out[i]) { err = ENOMEM; break; }
             src[i] = batch[i].block->m_BlockData;
@@ -634,7 +661,23 @@ void store_worker(B200CompressStore* s)
         {
             std::lock_guard<std::mutex> g(g_gpu);
             err = ensure_ctx();
-            if (!err) err = lt_b200_lz4_compress_host(g_ctx, n, src.data(), src_size.data(), dst.data(), cap.data(), got.data());
+            // one launch per codec present in the batch
+            for (int codec = 0; codec < 2 && !err; ++codec)
+            {
+                std::vector<uint32_t> idx;
+                for (uint32_t i = 0; i < n; ++i)
+                    if ((*batch[i].block->m_BlockIndex->m_Tag == TYPE_LZ4) == (codec == 0)) idx.push_back(i);
+                if (idx.empty()) continue;
+                const uint32_t m = (uint32_t)idx.size();
+                std::vector<const void*> s2(m);
+                std::vector<void*> d2(m);
+                std::vector<uint32_t> z2(m);
+                std::vector<uint64_t> c2(m), g2(m, 0);
+                for (uint32_t k = 0; k < m; ++k) { s2[k] = src[idx[k]]; d2[k] = dst[idx[k]]; z2[k] = src_size[idx[k]]; c2[k] = cap[idx[k]]; }
+                err = codec == 0 ? lt_b200_lz4_compress_host(g_ctx, m, s2.data(), z2.data(), d2.data(), c2.data(), g2.data())
+                                 : lt_b200_zstd_compress_host(g_ctx, LT_B200_COMPRESSION_ZSTD_DEFAULT, m, s2.data(), z2.data(), d2.data(), c2.data(), g2.data());
+                for (uint32_t k = 0; k < m; ++k) got[idx[k]] = g2[k];
+            }
         }
         for (uint32_t i = 0; i < n; ++i)
         {
@@ -664,10 +707,10 @@ int store_put(struct Longtail_BlockStoreAPI* api, struct Longtail_StoredBlock* b
     s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Chunk_Count] += n;
     s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Byte_Count] += block_index_data_size(n) + block->m_BlockChunksDataSize;
     const uint32_t tag = *block->m_BlockIndex->m_Tag;
-    if (tag != 0 && tag != TYPE_LZ4)
+    if (tag != 0 && tag != TYPE_LZ4 && !is_zstd_level3(tag))
     {
         s->stats[Longtail_BlockStoreAPI_StatU64_PutStoredBlock_FailCount]++;
-        return ENOTSUP; // no device kernel for this codec yet; a non-zero return means OnComplete is not called (src/longtail.c:4747-4757)
+        return ENOTSUP; // no device kernel for this codec; a non-zero return means OnComplete is not called (src/longtail.c:4747-4757)
     }
     {
         std::lock_guard<std::mutex> g(s->lock);
@@ -853,6 +896,24 @@ extern "C" struct Longtail_CompressionAPI* Longtail_CompressionRegistry_CreateFo
     if (compression_type != TYPE_LZ4) return nullptr; // lib/lz4/longtail_lz4.c:104-118
     if (out_settings) *out_settings = TYPE_LZ4;
     return Longtail_CreateB200LZ4CompressionAPI();
+}
+
+extern "C" struct Longtail_CompressionAPI* Longtail_CreateB200ZStdCompressionAPI(void)
+{
+    B200CompressionAPI* a = static_cast<B200CompressionAPI*>(lt_alloc("Longtail_CreateB200ZStdCompressionAPI", sizeof(B200CompressionAPI)));
+    if (!a) return nullptr;
+    a->api.m_API.Dispose = compression_api_dispose;
+    a->api.GetMaxCompressedSize = zstd_max_size;
+    a->api.Compress = zstd_compress;
+    a->api.Decompress = zstd_decompress;
+    return &a->api;
+}
+
+extern "C" struct Longtail_CompressionAPI* Longtail_CompressionRegistry_CreateForB200ZStd(uint32_t compression_type, uint32_t* out_settings)
+{
+    if (!is_zstd_type(compression_type)) return nullptr; // lib/zstd/longtail_zstd.c:31-42: every 'ztd?' id maps to the one ZStd API
+    if (out_settings) *out_settings = compression_type;
+    return Longtail_CreateB200ZStdCompressionAPI();
 }
 
 extern "C" struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockStoreAPI(struct Longtail_BlockStoreAPI* backing,

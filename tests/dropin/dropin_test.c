@@ -262,14 +262,18 @@ int main(int argc, char** argv)
     }
 
     /* 5. the compress half inside the reference's Longtail_WriteContent: reference compressblockstore vs
-     *    (a) the B200 compress block store and (b) the reference compressblockstore with the B200 LZ4 CompressionAPI in its registry */
+     *    (a) the B200 compress block store and (b) the reference compressblockstore with the B200 CompressionAPI in its registry;
+     *    pass 0 = LZ4 ('lz42'), pass 1 = ZStd level 3 ('ztd2' and 'ztd1') */
+    for (int pass = 0; pass < 2; ++pass)
     {
-        for (uint32_t i = 0; i < infos->m_Count; ++i) tags[i] = (i % 3) ? 0x6c7a3432u : 0u;
+        const char* codec_name = pass ? "zstd" : "lz4";
+        for (uint32_t i = 0; i < infos->m_Count; ++i)
+            tags[i] = pass == 0 ? ((i % 3) ? 0x6c7a3432u : 0u) : ((i % 3) == 1 ? 0x7a746432u : (i % 3) == 2 ? 0x7a746431u : 0u);
         struct Longtail_VersionIndex* vi = 0;
         CHECK(Longtail_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &vi) == 0, "index for upsync");
         const uint32_t block_size = target * 16, per_block = 64;
         struct Longtail_CompressionRegistryAPI* full = Longtail_CreateFullCompressionRegistry();
-        Longtail_CompressionRegistry_CreateForTypeFunc b200_funcs[1] = {Longtail_CompressionRegistry_CreateForB200LZ4};
+        Longtail_CompressionRegistry_CreateForTypeFunc b200_funcs[1] = {pass ? Longtail_CompressionRegistry_CreateForB200ZStd : Longtail_CompressionRegistry_CreateForB200LZ4};
         struct Longtail_CompressionRegistryAPI* b200_registry = Longtail_CreateDefaultCompressionRegistry(1, b200_funcs);
         struct keep_store* k_ref = make_keep_store();
         struct keep_store* k_b200 = make_keep_store();
@@ -282,7 +286,7 @@ int main(int argc, char** argv)
         int e1 = write_content(storage, s_b200, jobs, ref_hash, vi, block_size, per_block, &m_b200);
         CHECK(e1 == 0, "WriteContent through Longtail_CreateB200CompressBlockStoreAPI: %d", e1);
         int e2 = write_content(storage, s_codec, jobs, ref_hash, vi, block_size, per_block, &m_codec);
-        CHECK(e2 == 0, "WriteContent through the B200 LZ4 CompressionAPI: %d", e2);
+        CHECK(e2 == 0, "WriteContent through the B200 %s CompressionAPI: %d", codec_name, e2);
         CHECK(k_ref->count > 3 && k_ref->count == k_b200->count && k_ref->count == k_codec->count, "block counts %u %u %u", k_ref->count, k_b200->count, k_codec->count);
         uint32_t same_a = 0, same_b = 0, lz4_blocks = 0;
         for (uint32_t i = 0; i < k_ref->count; ++i)
@@ -294,16 +298,17 @@ int main(int argc, char** argv)
             if (((uint32_t*)k_ref->blocks[i].data)[4] != 0) ++lz4_blocks;
         }
         CHECK(same_a == k_ref->count, "B200 compress block store: %u of %u stored blocks identical", same_a, k_ref->count);
-        CHECK(same_b == k_ref->count, "B200 LZ4 CompressionAPI: %u of %u stored blocks identical", same_b, k_ref->count);
-        CHECK(lz4_blocks > 0 && lz4_blocks < k_ref->count, "mix of raw and lz4 blocks expected (%u of %u)", lz4_blocks, k_ref->count);
+        CHECK(same_b == k_ref->count, "B200 %s CompressionAPI: %u of %u stored blocks identical", codec_name, same_b, k_ref->count);
+        CHECK(lz4_blocks > 0 && lz4_blocks < k_ref->count, "mix of raw and compressed blocks expected (%u of %u)", lz4_blocks, k_ref->count);
         struct Longtail_BlockStore_Stats st_ref, st_b200;
         s_ref->GetStats(s_ref, &st_ref);
         s_b200->GetStats(s_b200, &st_b200);
         for (int i = Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Count; i <= Longtail_BlockStoreAPI_StatU64_PutStoredBlock_Byte_Count; ++i)
             CHECK(st_ref.m_StatU64[i] == st_b200.m_StatU64[i], "stat %d: %llu vs %llu", i, (unsigned long long)st_ref.m_StatU64[i], (unsigned long long)st_b200.m_StatU64[i]);
-        /* read every block back through both stores: same uncompressed payloads */
+        /* read every block back through both stores: same uncompressed payloads (LZ4 only: there is no device ZStd decoder, the
+         * B200 store answers ENOTSUP for those blocks) */
         uint32_t round_trips = 0;
-        for (uint32_t i = 0; i < k_ref->count; ++i)
+        for (uint32_t i = 0; i < k_ref->count && pass == 0; ++i)
         {
             struct get_wait w1, w2;
             memset(&w1, 0, sizeof(w1)); memset(&w2, 0, sizeof(w2));
@@ -315,8 +320,8 @@ int main(int argc, char** argv)
             if (w1.block) w1.block->Dispose(w1.block);
             if (w2.block) w2.block->Dispose(w2.block);
         }
-        CHECK(round_trips == k_ref->count, "GetStoredBlock round trips: %u of %u", round_trips, k_ref->count);
-        printf("WriteContent: %u blocks (%u lz4), B200 block store %u identical, B200 codec %u identical, %u read back\n", k_ref->count, lz4_blocks, same_a, same_b, round_trips);
+        CHECK(pass || round_trips == k_ref->count, "GetStoredBlock round trips: %u of %u", round_trips, k_ref->count);
+        printf("WriteContent: %u blocks (%u %s), B200 block store %u identical, B200 codec %u identical, %u read back\n", k_ref->count, lz4_blocks, codec_name, same_a, same_b, round_trips);
         Longtail_Free(m_ref); Longtail_Free(m_b200); Longtail_Free(m_codec);
         SAFE_DISPOSE_API(s_ref); SAFE_DISPOSE_API(s_b200); SAFE_DISPOSE_API(s_codec);
         SAFE_DISPOSE_API(&k_ref->api); SAFE_DISPOSE_API(&k_b200->api); SAFE_DISPOSE_API(&k_codec->api);
