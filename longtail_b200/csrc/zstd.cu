@@ -624,15 +624,82 @@ __device__ bool huf_validate(const HufTable* t, const uint32_t* count, uint32_t 
     return !bad;
 }
 
-// one Huffman stream: symbols last to first, codes LSB first, closed by a 1 bit (:984-1110)
-__device__ uint32_t huf_encode_1x(uint8_t* dst, const uint8_t* src, uint32_t n, const HufTable* t)
+// ---- warp-level pieces of the literal stage.  WarpShared = this warp's slice of shared memory.
+struct WarpShared
 {
-    BitW w;
-    bw_init(w, dst);
-    for (uint32_t i = n; i-- > 0;) bw_add(w, t->code[src[i]], t->nb_bits[src[i]]);
-    return bw_close(w);
+    uint32_t hist[256]; // byte histogram
+    uint32_t tab[256];  // Huffman table of the block being encoded: code | nb_bits << 16
+};
+
+// HIST_count (hist.c:29-56) with all lanes: shared-memory atomics, then the counts go to `count` (global) for the serial stages
+__device__ uint32_t hist_w(WarpShared* sh, uint32_t* count, uint32_t* max_symbol, const uint8_t* src, uint32_t n, uint32_t lane)
+{
+    for (uint32_t i = lane; i < 256; i += 32) sh->hist[i] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) atomicAdd(&sh->hist[src[i]], 1u);
+    __syncwarp();
+    uint32_t largest = 0, top = 0;
+    for (uint32_t i = lane; i < 256; i += 32)
+    {
+        const uint32_t c = sh->hist[i];
+        count[i] = c;
+        if (c > largest) largest = c;
+        if (c) top = i;
+    }
+    for (int d = 16; d; d >>= 1)
+    {
+        largest = max(largest, __shfl_xor_sync(FULL, largest, d));
+        top = max(top, __shfl_xor_sync(FULL, top, d));
+    }
+    __syncwarp();
+    *max_symbol = n ? top : 0;
+    return largest;
 }
-__device__ uint32_t huf_encode_4x(uint8_t* dst, const uint8_t* src, uint32_t n, const HufTable* t) // :1168-1213
+
+__device__ void load_tab_w(WarpShared* sh, const HufTable* t, uint32_t lane)
+{
+    for (uint32_t i = lane; i < 256; i += 32) sh->tab[i] = (uint32_t)t->code[i] | ((uint32_t)t->nb_bits[i] << 16);
+    __syncwarp();
+}
+
+// One Huffman stream (huf_compress.c:984-1110: symbols last to first, codes LSB first, closed by a 1 bit) with all lanes: the
+// input is cut into 32 contiguous pieces, a first pass sizes every piece, a suffix scan gives each piece its bit offset (the
+// LAST piece comes first in the stream), and every lane ORs its bits into the zeroed output words.
+__device__ uint32_t huf_encode_1x_w(const WarpShared* sh, uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
+{
+    const uint32_t piece = (n + 31) / 32;
+    const uint32_t lo = min(n, lane * piece), hi = min(n, lo + piece);
+    uint32_t bits = 0;
+    for (uint32_t i = lo; i < hi; ++i) bits += sh->tab[src[i]] >> 16;
+    // suffix sum over lanes: offset = bits of all higher lanes
+    uint32_t incl = bits;
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_down_sync(FULL, incl, d);
+        if (lane + d < 32) incl += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 0);
+    const uint32_t size = (total + 8) >> 3; // + the end mark, rounded up to bytes
+    for (uint32_t i = lane; i < size; i += 32) dst[i] = 0;
+    __syncwarp();
+    uint32_t* const words = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(dst) & ~(uintptr_t)3);
+    uint32_t cur = (incl - bits) + (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u) * 8u;
+    uint32_t widx = cur >> 5, fill = cur & 31u;
+    uint64_t acc = 0;
+    for (uint32_t i = hi; i-- > lo;)
+    {
+        const uint32_t e = sh->tab[src[i]];
+        acc |= (uint64_t)(e & 0xffffu) << fill;
+        fill += e >> 16;
+        if (fill >= 32) { atomicOr(&words[widx++], (uint32_t)acc); acc >>= 32; fill -= 32; }
+    }
+    if (lane == 0) { acc |= 1ull << fill; fill += 1; } // the end mark follows the first symbol, which lane 0 holds
+    if (fill) atomicOr(&words[widx], (uint32_t)acc);
+    if (fill > 32) atomicOr(&words[widx + 1], (uint32_t)(acc >> 32));
+    __syncwarp();
+    return size;
+}
+__device__ uint32_t huf_encode_4x_w(const WarpShared* sh, uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) // :1168-1213
 {
     const uint32_t seg = (n + 3) / 4;
     uint32_t pos = 6;
@@ -640,59 +707,86 @@ __device__ uint32_t huf_encode_4x(uint8_t* dst, const uint8_t* src, uint32_t n, 
     for (int i = 0; i < 4; ++i)
     {
         const uint32_t len = i < 3 ? seg : n - 3 * seg;
-        const uint32_t c = huf_encode_1x(dst + pos, src + (uint32_t)i * seg, len, t);
+        const uint32_t c = huf_encode_1x_w(sh, dst + pos, src + (uint32_t)i * seg, len, lane);
         if (c == 0 || c > 65535) return 0;
-        if (i < 3) { dst[2 * i] = (uint8_t)c; dst[2 * i + 1] = (uint8_t)(c >> 8); }
+        if (i < 3 && lane == 0) { dst[2 * i] = (uint8_t)c; dst[2 * i + 1] = (uint8_t)(c >> 8); }
         pos += c;
     }
+    __syncwarp();
     return pos;
 }
-__device__ uint32_t huf_encode_with(uint8_t* dst, uint32_t head, const uint8_t* src, uint32_t n, bool four, const HufTable* t) // :1223-1239
+__device__ uint32_t huf_encode_with_w(WarpShared* sh, uint8_t* dst, uint32_t head, const uint8_t* src, uint32_t n, bool four, const HufTable* t,
+                                      uint32_t lane) // :1223-1239
 {
-    const uint32_t c = four ? huf_encode_4x(dst + head, src, n, t) : huf_encode_1x(dst + head, src, n, t);
+    load_tab_w(sh, t, lane);
+    const uint32_t c = four ? huf_encode_4x_w(sh, dst + head, src, n, lane) : huf_encode_1x_w(sh, dst + head, src, n, lane);
     if (c == 0) return 0;
     if (head + c >= n - 1) return 0;
     return head + c;
 }
 
-// HUF_compress_internal (:1334-1431).  `t` enters as the previous block's table and leaves as the table the next block may
-// reuse; *repeat enters as that table's status.  Returns 0 = not compressible, 1 = single symbol, ZS_ERR.
-__device__ uint32_t huf_compress(ZstdWorker* W, uint8_t* dst, const uint8_t* src, uint32_t n, bool four, HufTable* t, int* repeat, bool prefer_repeat,
-                                 bool suspect)
+// HUF_compress_internal (:1334-1431), warp-level: histogram and bit packing use all lanes, the table construction and its
+// description (a few thousand dependent steps over <= 256 symbols) run on lane 0.  `t` enters as the previous block's table
+// and leaves as the table the next block may reuse; *repeat enters as that table's status (all lanes hold the same value).
+// Returns 0 = not compressible, 1 = single symbol, ZS_ERR.
+__device__ uint32_t huf_compress_w(ZstdWorker* W, WarpShared* sh, uint8_t* dst, const uint8_t* src, uint32_t n, bool four, HufTable* t, int* repeat,
+                                   bool prefer_repeat, bool suspect, uint32_t lane)
 {
     uint32_t* count = W->count;
     uint32_t max_symbol = 255;
     if (!n) return 0;
-    if (prefer_repeat && *repeat == 2) return huf_encode_with(dst, 0, src, n, four, t);
+    if (prefer_repeat && *repeat == 2) return huf_encode_with_w(sh, dst, 0, src, n, four, t, lane);
     if (suspect && n >= 4096 * 10)
     {
         uint32_t m = 255;
-        uint32_t total = hist(count, &m, src, 4096);
+        uint32_t total = hist_w(sh, count, &m, src, 4096, lane);
         m = 255;
-        total += hist(count, &m, src + n - 4096, 4096);
+        total += hist_w(sh, count, &m, src + n - 4096, 4096, lane);
         if (total <= ((2 * 4096) >> 7) + 4) return 0;
     }
     {
-        const uint32_t largest = hist(count, &max_symbol, src, n);
-        if (largest == n) { dst[0] = src[0]; return 1; }
+        const uint32_t largest = hist_w(sh, count, &max_symbol, src, n, lane);
+        if (largest == n) { if (lane == 0) dst[0] = src[0]; return 1; }
         if (largest <= (n >> 7) + 4) return 0;
     }
-    if (*repeat == 1 && !huf_validate(t, count, max_symbol)) *repeat = 0;
-    if (prefer_repeat && *repeat != 0) return huf_encode_with(dst, 0, src, n, four, t);
-    HufTable* fresh = &W->huf_fresh;
-    huf_build_table(W, fresh, count, max_symbol, fse_optimal_table_log(11, n, max_symbol, 1)); // HUF_optimalTableLog w/o depth search
-    const uint32_t h = huf_write_table(W, dst, fresh);
-    if (h == ZS_ERR) return ZS_ERR;
-    if (*repeat != 0)
+    // lane 0: table decisions.  verdict: 0 = return `h` as the result, 1 = encode with the old table, 2 = encode with the new one
+    uint32_t verdict = 0, h = 0;
+    int rep_now = *repeat;
+    if (lane == 0)
     {
-        const uint32_t old_size = huf_estimate(t, count, max_symbol), new_size = huf_estimate(fresh, count, max_symbol);
-        if (old_size <= h + new_size || h + 12 >= n) return huf_encode_with(dst, 0, src, n, four, t);
+        if (rep_now == 1 && !huf_validate(t, count, max_symbol)) rep_now = 0;
+        if (prefer_repeat && rep_now != 0) verdict = 1;
+        else
+        {
+            HufTable* fresh = &W->huf_fresh;
+            huf_build_table(W, fresh, count, max_symbol, fse_optimal_table_log(11, n, max_symbol, 1)); // HUF_optimalTableLog w/o depth search
+            h = huf_write_table(W, dst, fresh);
+            if (h != ZS_ERR)
+            {
+                bool use_old = false;
+                if (rep_now != 0)
+                {
+                    const uint32_t old_size = huf_estimate(t, count, max_symbol), new_size = huf_estimate(fresh, count, max_symbol);
+                    use_old = old_size <= h + new_size || h + 12 >= n;
+                }
+                if (use_old) verdict = 1;
+                else if (h + 12 >= n) { verdict = 0; h = 0; }
+                else
+                {
+                    verdict = 2;
+                    rep_now = 0;
+                    fresh->repeat = t->repeat;
+                    *t = *fresh;
+                }
+            }
+        }
     }
-    if (h + 12 >= n) return 0;
-    *repeat = 0;
-    fresh->repeat = t->repeat;
-    *t = *fresh;
-    return huf_encode_with(dst, h, src, n, four, t);
+    verdict = __shfl_sync(FULL, verdict, 0);
+    h = __shfl_sync(FULL, h, 0);
+    *repeat = __shfl_sync(FULL, rep_now, 0);
+    __syncwarp();
+    if (verdict == 0) return h; // 0 or ZS_ERR
+    return huf_encode_with_w(sh, dst, verdict == 2 ? h : 0, src, n, four, t, lane);
 }
 
 __device__ uint32_t lit_header_plain(uint8_t* dst, uint32_t type, uint32_t n) // zstd_compress_literals.c:39-63, :78-104
@@ -703,45 +797,60 @@ __device__ uint32_t lit_header_plain(uint8_t* dst, uint32_t type, uint32_t n) //
     else { const uint32_t v = type + (3u << 2) + (n << 4); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); }
     return fl;
 }
-__device__ uint32_t lit_raw(uint8_t* dst, const uint8_t* src, uint32_t n)
+__device__ uint32_t lit_raw_w(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
 {
-    const uint32_t fl = lit_header_plain(dst, 0, n);
-    for (uint32_t i = 0; i < n; ++i) dst[fl + i] = src[i];
+    const uint32_t fl = 1 + (n > 31) + (n > 4095);
+    if (lane == 0) lit_header_plain(dst, 0, n);
+    for (uint32_t i = lane; i < n; i += 32) dst[fl + i] = src[i];
+    __syncwarp();
     return n + fl;
 }
-__device__ uint32_t lit_rle(uint8_t* dst, const uint8_t* src, uint32_t n)
+__device__ uint32_t lit_rle_w(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
 {
-    const uint32_t fl = lit_header_plain(dst, 1, n);
-    dst[fl] = src[0];
+    const uint32_t fl = 1 + (n > 31) + (n > 4095);
+    if (lane == 0) { lit_header_plain(dst, 1, n); dst[fl] = src[0]; }
+    __syncwarp();
     return fl + 1;
 }
+__device__ void copy_huf_table_w(HufTable* dst, const HufTable* src, uint32_t lane)
+{
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* b = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t i = lane; i < sizeof(HufTable) / 4; i += 32) b[i] = a[i];
+    __syncwarp();
+}
 
-// ZSTD_compressLiterals at strategy dfast (zstd_compress_literals.c:129-235)
-__device__ uint32_t compress_literals(ZstdWorker* W, uint8_t* dst, const uint8_t* src, uint32_t n, const HufTable* prev, HufTable* next, bool suspect)
+// ZSTD_compressLiterals at strategy dfast (zstd_compress_literals.c:129-235), warp-level
+__device__ uint32_t compress_literals_w(ZstdWorker* W, WarpShared* sh, uint8_t* dst, const uint8_t* src, uint32_t n, const HufTable* prev, HufTable* next,
+                                        bool suspect, uint32_t lane)
 {
     const uint32_t lh = 3 + (n >= 1024) + (n >= 16384);
     bool single = n < 256;
     uint32_t type = 2; // set_compressed
-    *next = *prev;
-    if (n < (prev->repeat == 2 ? 6u : 64u)) return lit_raw(dst, src, n);
+    copy_huf_table_w(next, prev, lane);
     int repeat = prev->repeat;
+    if (n < (repeat == 2 ? 6u : 64u)) return lit_raw_w(dst, src, n, lane);
     if (repeat == 2 && lh == 3) single = true;
-    const uint32_t c = huf_compress(W, dst + lh, src, n, !single, next, &repeat, n <= 1024, suspect);
+    const uint32_t c = huf_compress_w(W, sh, dst + lh, src, n, !single, next, &repeat, n <= 1024, suspect, lane);
     if (repeat != 0) type = 3; // set_repeat
     {
         const uint32_t min_gain = (n >> 6) + 2;
-        if (c == 0 || c == ZS_ERR || c >= n - min_gain) { *next = *prev; return lit_raw(dst, src, n); }
+        if (c == 0 || c == ZS_ERR || c >= n - min_gain) { copy_huf_table_w(next, prev, lane); return lit_raw_w(dst, src, n, lane); }
     }
     if (c == 1)
     {
         bool same = true;
         if (n < 8) for (uint32_t i = 1; i < n; ++i) if (src[i] != src[0]) same = false;
-        if (n >= 8 || same) { *next = *prev; return lit_rle(dst, src, n); }
+        if (n >= 8 || same) { copy_huf_table_w(next, prev, lane); return lit_rle_w(dst, src, n, lane); }
     }
-    if (type == 2) next->repeat = 1; // HUF_repeat_check
-    if (lh == 3) { const uint32_t v = type + ((uint32_t)(!single) << 2) + (n << 4) + (c << 14); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); }
-    else if (lh == 4) { const uint32_t v = type + (2u << 2) + (n << 4) + (c << 18); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); }
-    else { const uint32_t v = type + (3u << 2) + (n << 4) + (c << 22); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); dst[4] = (uint8_t)(c >> 10); }
+    if (lane == 0)
+    {
+        if (type == 2) next->repeat = 1; // HUF_repeat_check
+        if (lh == 3) { const uint32_t v = type + ((uint32_t)(!single) << 2) + (n << 4) + (c << 14); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); }
+        else if (lh == 4) { const uint32_t v = type + (2u << 2) + (n << 4) + (c << 18); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); }
+        else { const uint32_t v = type + (3u << 2) + (n << 4) + (c << 22); dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24); dst[4] = (uint8_t)(c >> 10); }
+    }
+    __syncwarp();
     return lh + c;
 }
 
@@ -811,11 +920,9 @@ __device__ uint32_t build_seq_table(ZstdWorker* W, uint8_t* dst, FseTable* ct, u
     return h;
 }
 
-// literals + sequences of one block (zstd_compress.c:2876-2990); 0 = emit the block raw, ZS_ERR on error
-__device__ uint32_t entropy_compress(ZstdWorker* W, uint8_t* dst, uint32_t lit_size, uint32_t nb_seq)
+// the sequence section of one block on lane 0 (zstd_compress.c:2930-2990); `op` follows the literal section
+__device__ uint32_t sequences_compress(ZstdWorker* W, uint8_t* dst, uint8_t* op, uint32_t nb_seq)
 {
-    uint8_t* op = dst;
-    op += compress_literals(W, op, W->lits, lit_size, &W->huf_prev, &W->huf_next, (nb_seq == 0) || (lit_size / nb_seq >= 20));
     if (nb_seq < 128) *op++ = (uint8_t)nb_seq;
     else if (nb_seq < 0x7F00) { op[0] = (uint8_t)((nb_seq >> 8) + 0x80); op[1] = (uint8_t)nb_seq; op += 2; }
     else { op[0] = 0xFF; const uint32_t v = nb_seq - 0x7F00; op[1] = (uint8_t)v; op[2] = (uint8_t)(v >> 8); op += 3; }
@@ -824,12 +931,6 @@ __device__ uint32_t entropy_compress(ZstdWorker* W, uint8_t* dst, uint32_t lit_s
     uint8_t* ll_code = W->ll_code;
     uint8_t* of_code = W->of_code;
     uint8_t* ml_code = W->ml_code;
-    for (uint32_t i = 0; i < nb_seq; ++i)
-    {
-        ll_code[i] = (uint8_t)ll_code_of(W->seq_lit[i]);
-        of_code[i] = (uint8_t)hibit(W->seq_off[i]);
-        ml_code[i] = (uint8_t)ml_code_of(W->seq_len[i] - 3);
-    }
     uint8_t* seq_head = op++;
     uint32_t* count = W->count;
     uint32_t last_count_size = 0;
@@ -893,6 +994,25 @@ __device__ uint32_t entropy_compress(ZstdWorker* W, uint8_t* dst, uint32_t lit_s
     return (uint32_t)(op - dst);
 }
 
+// literals + sequences of one block (zstd_compress.c:2876-2990), warp-level; 0 = emit the block raw, ZS_ERR on error
+__device__ uint32_t entropy_compress_w(ZstdWorker* W, WarpShared* sh, uint8_t* dst, uint32_t lit_size, uint32_t nb_seq, uint32_t lane)
+{
+    const uint32_t lit_bytes = compress_literals_w(W, sh, dst, W->lits, lit_size, &W->huf_prev, &W->huf_next, (nb_seq == 0) || (lit_size / nb_seq >= 20), lane);
+    // sequence codes with all lanes (ZSTD_seqToCodes, zstd_compress.c:2681-2705)
+    for (uint32_t i = lane; i < nb_seq; i += 32)
+    {
+        W->ll_code[i] = (uint8_t)ll_code_of(W->seq_lit[i]);
+        W->of_code[i] = (uint8_t)hibit(W->seq_off[i]);
+        W->ml_code[i] = (uint8_t)ml_code_of(W->seq_len[i] - 3);
+    }
+    __syncwarp();
+    uint32_t c = 0;
+    if (lane == 0) c = sequences_compress(W, dst, dst + lit_bytes, nb_seq);
+    c = __shfl_sync(FULL, c, 0);
+    __syncwarp();
+    return c;
+}
+
 // ================================================================== double-fast matcher
 
 __device__ __forceinline__ uint32_t hash_long(uint64_t v, uint32_t bits) { return (uint32_t)((v * 0xCF1BBCDCB7A56463ull) >> (64 - bits)); }
@@ -901,34 +1021,74 @@ __device__ __forceinline__ uint32_t hash_short(const uint8_t* s, uint32_t pos, u
     if (mls == 5) return (uint32_t)(((rd64(s, pos) << 24) * 889523592379ull) >> (64 - bits));
     return (rd32(s, pos) * 2654435761u) >> (32 - bits);
 }
-// ZSTD_count: common bytes of s[a..) and s[b..), a > b, a bounded by end (zstd_compress_internal.h:744-767)
-__device__ uint32_t count_equal(const uint8_t* __restrict__ s, uint32_t a, uint32_t b, uint32_t end)
+// ZSTD_count (zstd_compress_internal.h:744-767) with all lanes: common bytes of s[a..) and s[b..), a > b, a bounded by end
+__device__ uint32_t count_equal_w(const uint8_t* __restrict__ s, uint32_t a, uint32_t b, uint32_t end, uint32_t lane)
 {
-    const uint32_t start = a;
-    while (a + 4 <= end)
+    uint32_t total = 0;
+    for (;;)
     {
-        const uint32_t x = rd32(s, a) ^ rd32(s, b);
-        if (x) return a - start + ((uint32_t)(__ffs(x) - 1) >> 3);
-        a += 4;
-        b += 4;
+        const uint32_t pa = a + 4 * lane;
+        uint32_t eq = 0;
+        bool stop = true;
+        if (pa < end)
+        {
+            const uint32_t x = rd32(s, pa) ^ rd32(s, b + 4 * lane);
+            eq = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+            const uint32_t room = end - pa;
+            if (eq > room) eq = room;
+            stop = eq < 4u;
+        }
+        const uint32_t stops = __ballot_sync(FULL, stop);
+        if (stops)
+        {
+            const uint32_t f = (uint32_t)__ffs(stops) - 1u;
+            return total + 4u * f + __shfl_sync(FULL, eq, f);
+        }
+        total += 128;
+        a += 128;
+        b += 128;
     }
-    while (a < end && s[a] == s[b]) { a++; b++; }
-    return a - start;
+}
+// backward catch-up (zstd_double_fast.c:192, :256, :265) with all lanes: how many bytes before ip / m are equal
+__device__ uint32_t catch_up_w(const uint8_t* __restrict__ s, uint32_t ip, uint32_t m, uint32_t anchor, uint32_t lowest, uint32_t lane)
+{
+    uint32_t back = 0;
+    for (;;)
+    {
+        bool eq = false;
+        if (ip > anchor + lane && m > lowest + lane) eq = s[ip - 1 - lane] == s[m - 1 - lane];
+        const uint32_t mask = __ballot_sync(FULL, eq);
+        const uint32_t run = mask == FULL ? 32u : (uint32_t)__ffs(~mask) - 1u;
+        back += run;
+        if (run < 32) return back;
+        ip -= 32;
+        m -= 32;
+    }
 }
 
-// ZSTD_compressBlock_doubleFast_noDict_generic (zstd_double_fast.c:105-311).  Positions are frame offsets; the match index of
-// frame byte p is p + 2 (ZSTD_WINDOW_START_INDEX, zstd_compress_internal.h:211), 0 in a table = empty.  Literals are
-// appended to W->lits as sequences are stored; returns the sequence count, *lit_total = all literals incl. the last run.
-__device__ uint32_t dfast_block(ZstdWorker* W, const uint8_t* __restrict__ s, uint32_t block_start, uint32_t block_size, uint32_t rep[3], uint32_t* lit_total)
+// ZSTD_compressBlock_doubleFast_noDict_generic (zstd_double_fast.c:105-311) by one warp.  Positions are frame offsets; the
+// match index of frame byte p is p + 2 (ZSTD_WINDOW_START_INDEX, zstd_compress_internal.h:211), 0 in a table = empty.
+//
+// The parse is sequential, but between two matches it only walks a deterministic stride schedule (step grows by one every
+// 256 bytes, :253-258) and every probe does the same thing: read both tables, write both tables, test repcode / long / short
+// candidates.  The warp therefore SPECULATES the next 32 probes at once: lane k takes the k-th position of the schedule; a
+// table read that an earlier lane of the same batch would have overwritten is resolved inside the warp (__match_any_sync:
+// the candidate is the closest lower lane with the same hash, else the table); the first lane whose probe matches wins
+// (__ballot_sync) and only the table writes up to that lane are committed — exactly the state the sequential loop would have
+// reached.  Match extension, catch-up and literal copies are lane-parallel; the few table insertions after a match and the
+// immediate-repcode loop are warp-uniform.
+__device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, uint32_t block_start, uint32_t block_size, uint32_t rep[3],
+                                  uint32_t* lit_total, uint32_t lane)
 {
     const uint32_t hl_bits = W->hash_log, hs_bits = W->chain_log, mls = W->min_match;
     uint32_t* const hash_l = W->hash_long;
     uint32_t* const hash_s = W->hash_small;
     uint8_t* const lits = W->lits;
     const uint32_t max_dist = 1u << W->window_log;
+    const uint32_t dict_limit = W->dict_limit;
     const uint32_t end_index = block_start + 2 + block_size;
-    const uint32_t prefix_lowest_index = (end_index - W->dict_limit > max_dist) ? end_index - max_dist : W->dict_limit;
-    const uint32_t prefix_lowest = prefix_lowest_index - 2; // as a position
+    const uint32_t lowest_index = (end_index - dict_limit > max_dist) ? end_index - max_dist : dict_limit;
+    const uint32_t lowest = lowest_index - 2; // as a position
     const uint32_t iend = block_start + block_size;
     const int32_t ilimit = (int32_t)iend - 8; // may be negative for a 7-byte frame: positions are < 2^31, compare signed
     uint32_t offset_1 = rep[0], offset_2 = rep[1], saved_1 = 0, saved_2 = 0;
@@ -936,112 +1096,184 @@ __device__ uint32_t dfast_block(ZstdWorker* W, const uint8_t* __restrict__ s, ui
     uint32_t anchor = block_start;
     uint32_t ip = block_start;
 
-    ip += (ip == prefix_lowest);
+    ip += (ip == lowest);
     {
         const uint32_t current = ip + 2;
-        const uint32_t window_low = (current - W->dict_limit > max_dist) ? current - max_dist : W->dict_limit;
+        const uint32_t window_low = (current - dict_limit > max_dist) ? current - max_dist : dict_limit;
         const uint32_t max_rep = current - window_low;
         if (offset_2 > max_rep) { saved_2 = offset_2; offset_2 = 0; }
         if (offset_1 > max_rep) { saved_1 = offset_1; offset_1 = 0; }
     }
-    for (;;)
+    for (;;) // one iteration per stored match (the reference's outer loop)
     {
-        uint32_t step = 1;
-        uint32_t next_step = ip + 256; // kSearchStrength = 8 (zstd_double_fast.c:35)
-        uint32_t ip1 = ip + 1;
-        uint32_t m_len = 0, offset = 0, curr = 0, hl1 = 0;
-        int found = 0; // 1 = repcode sequence stored, 2 = match to store
-        if ((int32_t)ip1 > ilimit) break;
-        uint64_t w0 = rd64(s, ip);
-        uint32_t hl0 = hash_long(w0, hl_bits);
-        uint32_t idxl0 = hash_l[hl0];
-        do
+        // schedule state at the start of the next unprobed iteration
+        uint32_t q_ip = ip, q_ip1 = ip + 1, q_step = 1, q_next = ip + 256; // kSearchStrength = 8 (:35)
+        bool found = false, finished = false;
+        uint32_t P = 0, P1 = 0, f_step = 0, f_type = 0, f_cand = 0, hl1 = 0, idxl1 = 0;
+        uint64_t w_f = 0, w1 = 0;
+        for (;;) // batches of 32 speculative probes
         {
-            const uint32_t hs0 = hash_short(s, ip, hs_bits, mls);
-            const uint32_t idxs0 = hash_s[hs0];
-            curr = ip + 2;
-            hash_l[hl0] = curr;
-            hash_s[hs0] = curr;
-            if (offset_1 > 0 && rd32(s, ip + 1 - offset_1) == rd32(s, ip + 1))
+            // lane k's iteration: position cp, next position cp1, stride in force cs
+            uint32_t cp, cp1, cs = q_step, cn = q_next;
+            if (q_ip1 + 32u * q_step < q_next) // no stride change inside this batch (the common case)
             {
-                m_len = count_equal(s, ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
-                ip++;
-                const uint32_t ll = ip - anchor;
-                for (uint32_t i = 0; i < ll; ++i) lits[nlit + i] = s[anchor + i];
-                nlit += ll;
-                W->seq_lit[nb] = ll; W->seq_len[nb] = m_len; W->seq_off[nb] = 1; nb++;
-                found = 1;
-                break;
+                cp = lane ? q_ip1 + (lane - 1) * q_step : q_ip;
+                cp1 = q_ip1 + lane * q_step;
             }
-            const uint64_t w1 = rd64(s, ip1);
-            hl1 = hash_long(w1, hl_bits);
-            if (idxl0 > prefix_lowest_index && rd64(s, idxl0 - 2) == w0)
+            else
             {
-                uint32_t m = idxl0 - 2;
-                m_len = count_equal(s, ip + 8, m + 8, iend) + 8;
-                offset = ip - m;
-                while (ip > anchor && m > prefix_lowest && s[ip - 1] == s[m - 1]) { ip--; m--; m_len++; }
-                found = 2;
-                break;
-            }
-            const uint32_t idxl1 = hash_l[hl1];
-            if (idxs0 > prefix_lowest_index && rd32(s, idxs0 - 2) == (uint32_t)w0)
-            {
-                if (idxl1 > prefix_lowest_index && rd64(s, idxl1 - 2) == w1)
+                cp = q_ip; cp1 = q_ip1;
+                for (uint32_t j = 0; j < lane; ++j)
                 {
-                    uint32_t m = idxl1 - 2;
-                    ip = ip1;
-                    m_len = count_equal(s, ip + 8, m + 8, iend) + 8;
-                    offset = ip - m;
-                    while (ip > anchor && m > prefix_lowest && s[ip - 1] == s[m - 1]) { ip--; m--; m_len++; }
+                    if (cp1 >= cn) { cs++; cn += 256; }
+                    cp = cp1;
+                    cp1 += cs;
+                }
+            }
+            const bool readable = (int32_t)cp <= ilimit;  // 8 bytes can be hashed here
+            const bool valid = (int32_t)cp1 <= ilimit;    // the sequential loop executes this iteration
+            const uint64_t w = readable ? rd64(s, cp) : 0ull;
+            const uint32_t hl = readable ? hash_long(w, hl_bits) : 0xffffffffu - lane;
+            const uint32_t hs = readable ? (mls == 5 ? (uint32_t)(((w << 24) * 889523592379ull) >> (64 - hs_bits)) : ((uint32_t)w * 2654435761u) >> (32 - hs_bits))
+                                         : 0xffffffffu - lane;
+            const uint32_t valids = __ballot_sync(FULL, valid);
+            const uint32_t below = (1u << lane) - 1u;
+            const uint32_t same_l = __match_any_sync(FULL, hl);
+            const uint32_t same_s = __match_any_sync(FULL, hs);
+            const uint32_t low_l = same_l & valids & below, low_s = same_s & valids & below;
+            const uint32_t from_l = __shfl_sync(FULL, cp, low_l ? 31 - __clz(low_l) : (int)lane);
+            const uint32_t from_s = __shfl_sync(FULL, cp, low_s ? 31 - __clz(low_s) : (int)lane);
+            const uint32_t cand_l = low_l ? from_l + 2 : (readable ? hash_l[hl] : 0u);
+            const uint32_t cand_s = low_s ? from_s + 2 : (readable ? hash_s[hs] : 0u);
+            uint32_t type = 0; // 1 repcode at ip+1, 2 long match at ip, 3 short match at ip (then the long match at ip1 is preferred)
+            if (valid)
+            {
+                if (offset_1 > 0 && rd32(s, cp + 1 - offset_1) == (uint32_t)(w >> 8)) type = 1;
+                else if (cand_l > lowest_index && rd64(s, cand_l - 2) == w) type = 2;
+                else if (cand_s > lowest_index && rd32(s, cand_s - 2) == (uint32_t)w) type = 3;
+            }
+            const uint32_t hits = __ballot_sync(FULL, type != 0);
+            const uint32_t first = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+            const uint32_t commit = valids & (first >= 31u ? FULL : ((2u << first) - 1u));
+            __syncwarp(); // every table read of the batch precedes every table write
+            if ((commit >> lane) & 1u)
+            {
+                if ((31 - __clz(same_l & commit)) == (int)lane) hash_l[hl] = cp + 2; // the last writer of a slot wins
+                if ((31 - __clz(same_s & commit)) == (int)lane) hash_s[hs] = cp + 2;
+            }
+            __syncwarp();
+            if (hits)
+            {
+                P = __shfl_sync(FULL, cp, first);
+                P1 = __shfl_sync(FULL, cp1, first);
+                f_step = __shfl_sync(FULL, cs, first);
+                f_type = __shfl_sync(FULL, type, first);
+                f_cand = __shfl_sync(FULL, f_type == 2 ? cand_l : cand_s, first);
+                w_f = __shfl_sync(FULL, w, first);
+                if (first < 31)
+                {
+                    // the next lane probed ip1: its hash and its (batch-resolved) long candidate are hl1 / idxl1 of :175, :199
+                    hl1 = __shfl_sync(FULL, hl, first + 1);
+                    idxl1 = __shfl_sync(FULL, cand_l, first + 1);
+                    w1 = __shfl_sync(FULL, w, first + 1);
                 }
                 else
                 {
-                    uint32_t m = idxs0 - 2;
-                    m_len = count_equal(s, ip + 4, m + 4, iend) + 4;
-                    offset = ip - m;
-                    while (ip > anchor && m > prefix_lowest && s[ip - 1] == s[m - 1]) { ip--; m--; m_len++; }
+                    w1 = rd64(s, P1);
+                    hl1 = hash_long(w1, hl_bits);
+                    idxl1 = hash_l[hl1];
                 }
-                found = 2;
+                found = true;
                 break;
             }
-            if (ip1 >= next_step) { step++; next_step += 256; }
-            ip = ip1;
-            ip1 += step;
-            hl0 = hl1;
-            idxl0 = idxl1;
-            w0 = w1;
-        } while ((int32_t)ip1 <= ilimit);
-        if (!found) break;
-        if (found == 2)
+            if (valids != FULL) { finished = true; break; }
+            // all 32 iterations ran without a match: advance the schedule by the state lane 31 ended in
+            {
+                uint32_t n_cs = cs, n_cn = cn;
+                if (cp1 >= n_cn) { n_cs++; n_cn += 256; }
+                q_ip = __shfl_sync(FULL, cp1, 31);
+                q_ip1 = __shfl_sync(FULL, cp1 + n_cs, 31);
+                q_step = __shfl_sync(FULL, n_cs, 31);
+                q_next = __shfl_sync(FULL, n_cn, 31);
+            }
+        }
+        if (finished || !found) break;
+
+        uint32_t m_len, offset = 0;
+        const uint32_t curr = P + 2;
+        ip = P;
+        if (f_type == 1)
         {
+            m_len = count_equal_w(s, ip + 1 + 4, ip + 1 + 4 - offset_1, iend, lane) + 4;
+            ip++;
+        }
+        else
+        {
+            uint32_t m;
+            if (f_type == 2)
+            {
+                m = f_cand - 2;
+                m_len = count_equal_w(s, ip + 8, m + 8, iend, lane) + 8;
+            }
+            else if (idxl1 > lowest_index && rd64(s, idxl1 - 2) == w1) // _search_next_long (:238-259)
+            {
+                ip = P1;
+                m = idxl1 - 2;
+                m_len = count_equal_w(s, ip + 8, m + 8, iend, lane) + 8;
+            }
+            else
+            {
+                m = f_cand - 2;
+                m_len = count_equal_w(s, ip + 4, m + 4, iend, lane) + 4;
+            }
+            offset = ip - m;
+            const uint32_t back = catch_up_w(s, ip, m, anchor, lowest, lane);
+            ip -= back;
+            m_len += back;
             offset_2 = offset_1;
             offset_1 = offset;
-            if (step < 4) hash_l[hl1] = ip1 + 2;
+            if (f_step < 4 && lane == 0) hash_l[hl1] = P1 + 2; // :261-273
+        }
+        {
             const uint32_t ll = ip - anchor;
-            for (uint32_t i = 0; i < ll; ++i) lits[nlit + i] = s[anchor + i];
+            for (uint32_t i = lane; i < ll; i += 32) lits[nlit + i] = s[anchor + i];
+            if (lane == 0) { W->seq_lit[nb] = ll; W->seq_len[nb] = m_len; W->seq_off[nb] = f_type == 1 ? 1u : offset + 3u; }
             nlit += ll;
-            W->seq_lit[nb] = ll; W->seq_len[nb] = m_len; W->seq_off[nb] = offset + 3; nb++;
+            nb++;
         }
         ip += m_len;
         anchor = ip;
+        __syncwarp();
         if ((int32_t)ip <= ilimit)
         {
+            // complementary insertions (:286-291), in the reference's order; all lanes compute, lane 0 stores
             const uint32_t insert = curr + 2; // an index; its position is curr
-            hash_l[hash_long(rd64(s, insert - 2), hl_bits)] = insert;
-            hash_l[hash_long(rd64(s, ip - 2), hl_bits)] = ip;        // index of position ip - 2
-            hash_s[hash_short(s, insert - 2, hs_bits, mls)] = insert;
-            hash_s[hash_short(s, ip - 1, hs_bits, mls)] = ip + 1;    // index of position ip - 1
+            const uint32_t h_a = hash_long(rd64(s, insert - 2), hl_bits), h_b = hash_long(rd64(s, ip - 2), hl_bits);
+            const uint32_t h_c = hash_short(s, insert - 2, hs_bits, mls), h_d = hash_short(s, ip - 1, hs_bits, mls);
+            if (lane == 0)
+            {
+                hash_l[h_a] = insert;
+                hash_l[h_b] = ip;     // index of position ip - 2
+                hash_s[h_c] = insert;
+                hash_s[h_d] = ip + 1; // index of position ip - 1
+            }
+            // immediate repcodes (:294-308)
             while ((int32_t)ip <= ilimit && offset_2 > 0 && rd32(s, ip) == rd32(s, ip - offset_2))
             {
-                const uint32_t r_len = count_equal(s, ip + 4, ip + 4 - offset_2, iend) + 4;
+                const uint32_t r_len = count_equal_w(s, ip + 4, ip + 4 - offset_2, iend, lane) + 4;
                 const uint32_t t = offset_2; offset_2 = offset_1; offset_1 = t;
-                hash_s[hash_short(s, ip, hs_bits, mls)] = ip + 2;
-                hash_l[hash_long(rd64(s, ip), hl_bits)] = ip + 2;
-                W->seq_lit[nb] = 0; W->seq_len[nb] = r_len; W->seq_off[nb] = 1; nb++;
+                const uint64_t wi = rd64(s, ip);
+                if (lane == 0)
+                {
+                    hash_s[hash_short(s, ip, hs_bits, mls)] = ip + 2;
+                    hash_l[hash_long(wi, hl_bits)] = ip + 2;
+                    W->seq_lit[nb] = 0; W->seq_len[nb] = r_len; W->seq_off[nb] = 1;
+                }
+                nb++;
                 ip += r_len;
                 anchor = ip;
             }
+            __syncwarp();
         }
     }
     saved_2 = (saved_1 != 0 && offset_1 != 0) ? saved_1 : saved_2;
@@ -1049,9 +1281,10 @@ __device__ uint32_t dfast_block(ZstdWorker* W, const uint8_t* __restrict__ s, ui
     rep[1] = offset_2 ? offset_2 : saved_2;
     {
         const uint32_t ll = iend - anchor;
-        for (uint32_t i = 0; i < ll; ++i) lits[nlit + i] = s[anchor + i];
+        for (uint32_t i = lane; i < ll; i += 32) lits[nlit + i] = s[anchor + i];
         nlit += ll;
     }
+    __syncwarp();
     *lit_total = nlit;
     return nb;
 }
@@ -1073,7 +1306,7 @@ __device__ void zs_set_params(ZstdWorker* W, uint32_t n)
 }
 
 // one frame by one warp; returns the frame size (warp-uniform)
-__device__ uint32_t zstd_compress_frame(ZstdWorker* W, const uint8_t* __restrict__ src, uint32_t size, uint8_t* __restrict__ dst, uint32_t lane)
+__device__ uint32_t zstd_compress_frame(ZstdWorker* W, WarpShared* sh, const uint8_t* __restrict__ src, uint32_t size, uint8_t* __restrict__ dst, uint32_t lane)
 {
     if (lane == 0)
     {
@@ -1120,41 +1353,41 @@ __device__ uint32_t zstd_compress_frame(ZstdWorker* W, const uint8_t* __restrict
         const uint32_t bs = (size - pos) < block_max ? (size - pos) : block_max;
         const uint32_t last = (pos + bs == size);
         uint32_t c = 0;
-        if (lane == 0)
+        // ZSTD_window_enforceMaxDist, called with the block START (zstd_compress.c:4525)
+        if (lane == 0 && pos + 2 > max_dist)
         {
-            // ZSTD_window_enforceMaxDist, called with the block START (zstd_compress.c:4525)
-            if (pos + 2 > max_dist)
+            const uint32_t low = pos + 2 - max_dist;
+            if (W->dict_limit < low) W->dict_limit = low;
+        }
+        __syncwarp();
+        if (bs >= 7) // MIN_CBLOCK_SIZE + block header + 2 (zstd_compress.c:3212)
+        {
+            uint32_t next_rep[3] = {W->rep[0], W->rep[1], W->rep[2]};
+            uint32_t lit_size = 0;
+            const uint32_t nb = dfast_block_w(W, src, pos, bs, next_rep, &lit_size, lane);
+            c = entropy_compress_w(W, sh, W->scratch, lit_size, nb, lane);
+            if (c != ZS_ERR)
             {
-                const uint32_t low = pos + 2 - max_dist;
-                if (W->dict_limit < low) W->dict_limit = low;
-            }
-            if (bs >= 7) // MIN_CBLOCK_SIZE + block header + 2 (zstd_compress.c:3212)
-            {
-                uint32_t next_rep[3] = {W->rep[0], W->rep[1], W->rep[2]};
-                uint32_t lit_size = 0;
-                const uint32_t nb = dfast_block(W, src, pos, bs, next_rep, &lit_size);
-                c = entropy_compress(W, W->scratch, lit_size, nb);
-                if (c != ZS_ERR)
+                if (c && c >= bs - ((bs >> 6) + 2)) c = 0; // ZSTD_minGain gate, zstd_compress.c:3021-3024
+                if (!first_block && c < 25)                 // RLE block, zstd_compress.c:4359-4370
                 {
-                    if (c && c >= bs - ((bs >> 6) + 2)) c = 0; // ZSTD_minGain gate, zstd_compress.c:3021-3024
-                    if (!first_block && c < 25)                 // RLE block, zstd_compress.c:4359-4370
-                    {
-                        bool rle = true;
-                        const uint8_t v = src[pos];
-                        for (uint32_t i = 1; i < bs; ++i) if (src[pos + i] != v) { rle = false; break; }
-                        if (rle) { c = 1; W->scratch[0] = v; }
-                    }
-                    if (c > 1) // ZSTD_blockState_confirmRepcodesAndEntropyTables
-                    {
-                        W->huf_prev = W->huf_next;
-                        W->rep[0] = next_rep[0]; W->rep[1] = next_rep[1]; W->rep[2] = next_rep[2];
-                    }
+                    const uint8_t v = src[pos];
+                    bool differs = false;
+                    for (uint32_t i = 1 + lane; i < bs && !differs; i += 32) differs = src[pos + i] != v;
+                    if (!__any_sync(FULL, differs)) { c = 1; if (lane == 0) W->scratch[0] = v; }
+                }
+                if (c > 1) // ZSTD_blockState_confirmRepcodesAndEntropyTables
+                {
+                    copy_huf_table_w(&W->huf_prev, &W->huf_next, lane);
+                    if (lane == 0) { W->rep[0] = next_rep[0]; W->rep[1] = next_rep[1]; W->rep[2] = next_rep[2]; }
                 }
             }
+        }
+        if (lane == 0)
+        {
             const uint32_t h = c == 0 || c == ZS_ERR ? last + (0u << 1) + (bs << 3) : c == 1 ? last + (1u << 1) + (bs << 3) : last + (2u << 1) + (c << 3);
             dst[op] = (uint8_t)h; dst[op + 1] = (uint8_t)(h >> 8); dst[op + 2] = (uint8_t)(h >> 16);
         }
-        c = __shfl_sync(FULL, c, 0);
         if (c == ZS_ERR) return ZS_ERR;
         __syncwarp();
         op += 3;
@@ -1166,7 +1399,7 @@ __device__ uint32_t zstd_compress_frame(ZstdWorker* W, const uint8_t* __restrict
         else
         {
             const uint8_t* sc = W->scratch;
-            for (uint32_t i = lane; i < c; i += 32) dst[op + i] = sc[i];
+            for (uint32_t i = lane; i < c; i += 32) dst[op + i] = __ldcg(sc + i); // the bit packers wrote through L2 atomics
             op += c;
         }
         __syncwarp();
@@ -1184,9 +1417,11 @@ __global__ void __launch_bounds__(128)
 k_zstd_frames(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len, uint8_t* __restrict__ out,
               const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t frame_count, ZstdWorker* workers, uint32_t* queue)
 {
+    __shared__ WarpShared s_warp[4];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     ZstdWorker* W = workers + warp;
+    WarpShared* sh = &s_warp[threadIdx.x >> 5];
     for (;;)
     {
         uint32_t f = 0;
@@ -1195,7 +1430,7 @@ k_zstd_frames(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_
         if (f >= frame_count) break;
         const uint32_t n = raw_len[f];
         uint8_t* dst = out + out_off[f];
-        const uint32_t c = zstd_compress_frame(W, raw + raw_off[f], n, dst + 8, lane);
+        const uint32_t c = zstd_compress_frame(W, sh, raw + raw_off[f], n, dst + 8, lane);
         if (lane == 0)
         {
             if (c == ZS_ERR) out_len[f] = 0xffffffffu;
