@@ -229,6 +229,8 @@ LT_B200_EXPORT int lt_b200_lz4_decompress_host(lt_b200_context* context, uint32_
  * reference codec (vendored zstd 1.5.6).  dst_capacity[i] must be at least lt_b200_zstd_bound(src_size[i]) (EINVAL otherwise,
  * the reference's answer to a ZStd error).  The other ZStd quality ids ('ztd3' / 'ztd4' / 'ztd5': levels 22 / 8 / 22) have no
  * device encoder: ENOTSUP. */
+/* diagnostic: GPU cycles the ZStd workers have spent in {matcher, literal stage, sequence stage, copy-out}, summed over workers */
+LT_B200_EXPORT int lt_b200_zstd_phase_cycles(lt_b200_context* context, uint64_t out_cycles[4]);
 LT_B200_EXPORT uint64_t lt_b200_zstd_bound(uint64_t size); /* ZSTD_COMPRESSBOUND, lib/zstd/ext/zstd.h:232 */
 LT_B200_EXPORT int lt_b200_zstd_compress_host(lt_b200_context* context, uint32_t compression_type, uint32_t count, const void* const* src,
                                               const uint32_t* src_size, void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);

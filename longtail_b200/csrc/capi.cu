@@ -1461,6 +1461,23 @@ int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src,
 
 } // namespace
 
+// diagnostic: cycles the ZStd workers spent per phase since the worker slabs were (re)allocated
+extern "C" int lt_b200_zstd_phase_cycles(lt_b200_context* c, uint64_t out_cycles[4])
+{
+    if (!c || !out_cycles) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < 4; ++i) out_cycles[i] = 0;
+    const size_t slab = zstd_worker_bytes();
+    const size_t n = c->ws[WS_ZSTD_WORKERS].cap / slab;
+    for (size_t w = 0; w < n; ++w)
+    {
+        unsigned long long t[4];
+        CU(cudaMemcpy(t, ws<uint8_t>(c, WS_ZSTD_WORKERS) + w * slab + zstd_worker_phase_offset(), sizeof(t), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 4; ++i) out_cycles[i] += t[i];
+    }
+    return 0;
+}
+
 extern "C" int lt_b200_zstd_compress_host(lt_b200_context* c, uint32_t compression_type, uint32_t count, const void* const* src, const uint32_t* src_size,
                                           void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size)
 {

@@ -50,6 +50,7 @@ void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, con
 // ---- zstd.cu : ZStd level 3 frames ('ztd1' / 'ztd2'), one warp per frame from a queue; output = {u32 raw, u32 comp} + frame.
 // d_workers = zstd_worker_count() slabs of zstd_worker_bytes(); d_out_len[i] = 8 + frame size, 0xffffffff on an encoder error
 size_t zstd_worker_bytes();
+size_t zstd_worker_phase_offset(); // 4 x u64 cycle counters inside a worker slab (matcher, literals, sequences, copy-out)
 uint32_t zstd_worker_count(uint32_t frame_count, int sm_count);
 cudaError_t launch_zstd_frames(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out, const uint64_t* d_out_off,
                                uint32_t* d_out_len, uint32_t frame_count, void* d_workers, uint32_t worker_count, uint32_t* d_queue, cudaStream_t st);

@@ -19,6 +19,8 @@
 #include "lt_device.cuh"
 #include "lt_kernels.h"
 
+#include <stddef.h>
+
 namespace ltb {
 
 namespace {
@@ -56,6 +58,7 @@ struct alignas(16) ZstdWorker
     uint32_t seq_lit[ZS_MAX_SEQ], seq_len[ZS_MAX_SEQ], seq_off[ZS_MAX_SEQ];
     uint8_t lits[ZS_BLOCK_MAX + 64];
     uint8_t ll_code[ZS_MAX_SEQ + 6], of_code[ZS_MAX_SEQ + 6], ml_code[ZS_MAX_SEQ + 6];
+    uint16_t enc_of[ZS_MAX_SEQ + 6], enc_ml[ZS_MAX_SEQ + 6], enc_ll[ZS_MAX_SEQ + 6]; // per sequence: FSE state bits | count << 12
     uint8_t scratch[3 * ZS_BLOCK_MAX + 4096]; // a block that expands is discarded afterwards, so it needs room
     HufTable huf_prev, huf_next, huf_fresh;
     FseTable ct_ll, ct_of, ct_ml, ct_w;
@@ -70,6 +73,7 @@ struct alignas(16) ZstdWorker
     uint32_t rep[3];
     uint32_t dict_limit;
     uint32_t window_log, chain_log, hash_log, min_match;
+    unsigned long long t_phase[4]; // diagnostic: cycles spent in the matcher, the literal stage, the sequence stage, copy-out
 };
 
 // ------------------------------------------------------------------ unaligned little-endian loads from a 4-byte aligned base
@@ -86,6 +90,31 @@ __device__ __forceinline__ uint64_t rd64(const uint8_t* __restrict__ s, uint32_t
     return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
 }
 __device__ __forceinline__ uint32_t hibit(uint32_t v) { return 31u - (uint32_t)__clz(v); }
+
+// warp-wide byte copy, any alignment: aligned 4-byte stores assembled from the source with a funnel shift.  The source must
+// be readable up to 4 bytes past its end (every source on this path is).  CG = read through L2 (data written by atomics).
+template <bool CG>
+__device__ void copy_w(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane)
+{
+    uint32_t done = 0;
+    if (n >= 64)
+    {
+        const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+        if (lane < head) dst[lane] = CG ? __ldcg(src + lane) : src[lane];
+        const uint32_t words = (n - head) >> 2;
+        const uint8_t* s2 = src + head;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s2) & 3u) * 8u;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - (reinterpret_cast<uintptr_t>(s2) & 3u));
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
+        for (uint32_t w = lane; w < words; w += 32)
+        {
+            const uint32_t a = CG ? __ldcg(sw + w) : sw[w], b = CG ? __ldcg(sw + w + 1) : sw[w + 1];
+            d4[w] = __funnelshift_r(a, b, sh);
+        }
+        done = head + words * 4u;
+    }
+    for (uint32_t i = done + lane; i < n; i += 32) dst[i] = CG ? __ldcg(src + i) : src[i];
+}
 
 // ------------------------------------------------------------------ forward bit writer (common/bitstream.h:150-241)
 struct BitW
@@ -801,7 +830,7 @@ __device__ uint32_t lit_raw_w(uint8_t* dst, const uint8_t* src, uint32_t n, uint
 {
     const uint32_t fl = 1 + (n > 31) + (n > 4095);
     if (lane == 0) lit_header_plain(dst, 0, n);
-    for (uint32_t i = lane; i < n; i += 32) dst[fl + i] = src[i];
+    copy_w<false>(dst + fl, src, n, lane);
     __syncwarp();
     return n + fl;
 }
@@ -920,84 +949,149 @@ __device__ uint32_t build_seq_table(ZstdWorker* W, uint8_t* dst, FseTable* ct, u
     return h;
 }
 
-// the sequence section of one block on lane 0 (zstd_compress.c:2930-2990); `op` follows the literal section
-__device__ uint32_t sequences_compress(ZstdWorker* W, uint8_t* dst, uint8_t* op, uint32_t nb_seq)
+// the sequence section of one block (zstd_compress.c:2930-2990), warp-level; `op` follows the literal section.
+//   * code histograms with all lanes, table construction (normalise, NCount, state table: a few hundred dependent steps) on lane 0;
+//   * the three FSE state chains (offset, match length, literal length) are independent of each other and of the extra bits, so
+//     lanes 0-2 walk one chain each and record, per sequence, the bits that transition emits;
+//   * the bitstream (ZSTD_encodeSequences, zstd_compress_sequences.c:293-385: last sequence first) is then packed by all lanes:
+//     pieces of the sequence range are sized, suffix-scanned and ORed into the zeroed output, like the Huffman streams.
+__device__ uint32_t sequences_compress_w(ZstdWorker* W, WarpShared* sh, uint8_t* dst, uint8_t* op, uint32_t nb_seq, uint32_t lane)
 {
-    if (nb_seq < 128) *op++ = (uint8_t)nb_seq;
-    else if (nb_seq < 0x7F00) { op[0] = (uint8_t)((nb_seq >> 8) + 0x80); op[1] = (uint8_t)nb_seq; op += 2; }
-    else { op[0] = 0xFF; const uint32_t v = nb_seq - 0x7F00; op[1] = (uint8_t)v; op[2] = (uint8_t)(v >> 8); op += 3; }
+    if (lane == 0)
+    {
+        if (nb_seq < 128) op[0] = (uint8_t)nb_seq;
+        else if (nb_seq < 0x7F00) { op[0] = (uint8_t)((nb_seq >> 8) + 0x80); op[1] = (uint8_t)nb_seq; }
+        else { op[0] = 0xFF; const uint32_t v = nb_seq - 0x7F00; op[1] = (uint8_t)v; op[2] = (uint8_t)(v >> 8); }
+    }
+    op += nb_seq < 128 ? 1 : nb_seq < 0x7F00 ? 2 : 3;
     if (nb_seq == 0) return (uint32_t)(op - dst);
 
-    uint8_t* ll_code = W->ll_code;
-    uint8_t* of_code = W->of_code;
-    uint8_t* ml_code = W->ml_code;
+    const uint8_t* ll_code = W->ll_code;
+    const uint8_t* of_code = W->of_code;
+    const uint8_t* ml_code = W->ml_code;
     uint8_t* seq_head = op++;
     uint32_t* count = W->count;
     uint32_t last_count_size = 0;
-    int ll_type, of_type, ml_type;
+    uint32_t types[3];
+    for (int k = 0; k < 3; ++k) // 0 literal lengths, 1 offsets, 2 match lengths: the order of the table descriptions
     {
-        uint32_t max = 35;
-        const uint32_t most = hist(count, &max, ll_code, nb_seq);
-        ll_type = select_encoding(most, nb_seq, 6, true);
-        const uint32_t h = build_seq_table(W, op, &W->ct_ll, 9, ll_type, count, max, ll_code, nb_seq, c_ll_default, 6, 35);
+        const uint8_t* codes = k == 0 ? ll_code : k == 1 ? of_code : ml_code;
+        uint32_t max = k == 0 ? 35 : k == 1 ? 31 : 52;
+        const uint32_t most = hist_w(sh, count, &max, codes, nb_seq, lane);
+        uint32_t type = 0, h = 0;
+        if (lane == 0)
+        {
+            if (k == 0) { type = select_encoding(most, nb_seq, 6, true); h = build_seq_table(W, op, &W->ct_ll, 9, type, count, max, codes, nb_seq, c_ll_default, 6, 35); }
+            else if (k == 1) { type = select_encoding(most, nb_seq, 5, max <= 28); h = build_seq_table(W, op, &W->ct_of, 8, type, count, max, codes, nb_seq, c_of_default, 5, 28); }
+            else { type = select_encoding(most, nb_seq, 6, true); h = build_seq_table(W, op, &W->ct_ml, 9, type, count, max, codes, nb_seq, c_ml_default, 6, 52); }
+        }
+        type = __shfl_sync(FULL, type, 0);
+        h = __shfl_sync(FULL, h, 0);
+        __syncwarp();
         if (h == ZS_ERR) return ZS_ERR;
-        if (ll_type == 2) last_count_size = h;
+        if (type == 2) last_count_size = h;
+        types[k] = type;
         op += h;
     }
+    if (lane == 0) *seq_head = (uint8_t)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
+
+    // ---- state chains: lane 0 offsets, lane 1 match lengths, lane 2 literal lengths (fse.h:452-470)
+    uint32_t final_state = 0, final_log = 0;
+    if (lane < 3)
     {
-        uint32_t max = 31;
-        const uint32_t most = hist(count, &max, of_code, nb_seq);
-        of_type = select_encoding(most, nb_seq, 5, max <= 28);
-        const uint32_t h = build_seq_table(W, op, &W->ct_of, 8, of_type, count, max, of_code, nb_seq, c_of_default, 5, 28);
-        if (h == ZS_ERR) return ZS_ERR;
-        if (of_type == 2) last_count_size = h;
-        op += h;
-    }
-    {
-        uint32_t max = 52;
-        const uint32_t most = hist(count, &max, ml_code, nb_seq);
-        ml_type = select_encoding(most, nb_seq, 6, true);
-        const uint32_t h = build_seq_table(W, op, &W->ct_ml, 9, ml_type, count, max, ml_code, nb_seq, c_ml_default, 6, 52);
-        if (h == ZS_ERR) return ZS_ERR;
-        if (ml_type == 2) last_count_size = h;
-        op += h;
-    }
-    *seq_head = (uint8_t)((ll_type << 6) + (of_type << 4) + (ml_type << 2));
-    {
-        // ZSTD_encodeSequences (zstd_compress_sequences.c:293-385): last sequence first, three interleaved FSE states
-        BitW w;
-        FseState st_ml, st_of, st_ll;
-        bw_init(w, op);
+        const FseTable* ct = lane == 0 ? &W->ct_of : lane == 1 ? &W->ct_ml : &W->ct_ll;
+        const uint8_t* codes = lane == 0 ? of_code : lane == 1 ? ml_code : ll_code;
+        uint16_t* enc = lane == 0 ? W->enc_of : lane == 1 ? W->enc_ml : W->enc_ll;
         uint32_t n = nb_seq - 1;
-        fse_init_state(st_ml, &W->ct_ml, ml_code[n]);
-        fse_init_state(st_of, &W->ct_of, of_code[n]);
-        fse_init_state(st_ll, &W->ct_ll, ll_code[n]);
-        bw_add(w, W->seq_lit[n], c_ll_bits[ll_code[n]]);
-        bw_add(w, W->seq_len[n] - 3, c_ml_bits[ml_code[n]]);
-        bw_add(w, W->seq_off[n], of_code[n]);
+        uint32_t value;
+        {
+            const uint32_t sym = codes[n];
+            const uint32_t nbi = (ct->delta_nb_bits[sym] + (1u << 15)) >> 16;
+            const uint32_t v = (nbi << 16) - ct->delta_nb_bits[sym];
+            value = ct->next_state[(int32_t)(v >> nbi) + ct->delta_find_state[sym]];
+        }
         while (n-- > 0)
         {
-            fse_encode(w, st_of, of_code[n]);
-            fse_encode(w, st_ml, ml_code[n]);
-            fse_encode(w, st_ll, ll_code[n]);
-            bw_add(w, W->seq_lit[n], c_ll_bits[ll_code[n]]);
-            bw_add(w, W->seq_len[n] - 3, c_ml_bits[ml_code[n]]);
-            bw_add(w, W->seq_off[n], of_code[n]);
+            const uint32_t sym = codes[n];
+            const uint32_t nbo = (value + ct->delta_nb_bits[sym]) >> 16;
+            enc[n] = (uint16_t)((value & ((1u << nbo) - 1u)) | (nbo << 12));
+            value = ct->next_state[(int32_t)(value >> nbo) + ct->delta_find_state[sym]];
         }
-        fse_flush_state(w, st_ml);
-        fse_flush_state(w, st_of);
-        fse_flush_state(w, st_ll);
-        const uint32_t stream = bw_close(w);
-        op += stream;
-        if (last_count_size && last_count_size + stream < 4) return 0; // zstd <= 1.3.4 decoder quirk, zstd_compress.c:2982-2988
+        final_state = value;
+        final_log = ct->table_log;
     }
+    __syncwarp();
+    const uint32_t fs_of = __shfl_sync(FULL, final_state, 0), fl_of = __shfl_sync(FULL, final_log, 0);
+    const uint32_t fs_ml = __shfl_sync(FULL, final_state, 1), fl_ml = __shfl_sync(FULL, final_log, 1);
+    const uint32_t fs_ll = __shfl_sync(FULL, final_state, 2), fl_ll = __shfl_sync(FULL, final_log, 2);
+
+    // ---- pack
+    const uint32_t piece = (nb_seq + 31) / 32;
+    const uint32_t lo = min(nb_seq, lane * piece), hi = min(nb_seq, lo + piece);
+    uint32_t bits = 0;
+    for (uint32_t n = lo; n < hi; ++n)
+    {
+        bits += c_ll_bits[ll_code[n]] + c_ml_bits[ml_code[n]] + of_code[n];
+        if (n + 1 < nb_seq) bits += (W->enc_of[n] >> 12) + (W->enc_ml[n] >> 12) + (W->enc_ll[n] >> 12);
+    }
+    if (lane == 0) bits += fl_ml + fl_of + fl_ll;
+    uint32_t incl = bits;
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_down_sync(FULL, incl, d);
+        if (lane + d < 32) incl += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 0);
+    const uint32_t stream = (total + 8) >> 3;
+    for (uint32_t i = lane; i < stream; i += 32) op[i] = 0;
+    __syncwarp();
+    {
+        uint32_t* const words = reinterpret_cast<uint32_t*>(reinterpret_cast<uintptr_t>(op) & ~(uintptr_t)3);
+        const uint32_t cur = (incl - bits) + (uint32_t)(reinterpret_cast<uintptr_t>(op) & 3u) * 8u;
+        uint32_t widx = cur >> 5, fill = cur & 31u;
+        uint64_t acc = 0;
+#define ZS_PUT(value, count_)                                                                                   \
+    {                                                                                                           \
+        const uint32_t nb_ = (count_);                                                                          \
+        acc |= (uint64_t)((value) & ((1u << nb_) - 1u)) << fill;                                                \
+        fill += nb_;                                                                                            \
+        if (fill >= 32) { atomicOr(&words[widx++], (uint32_t)acc); acc >>= 32; fill -= 32; }                    \
+    }
+        for (uint32_t n = hi; n-- > lo;)
+        {
+            if (n + 1 < nb_seq)
+            {
+                const uint32_t eo = W->enc_of[n], em = W->enc_ml[n], el = W->enc_ll[n];
+                ZS_PUT(eo, eo >> 12);
+                ZS_PUT(em, em >> 12);
+                ZS_PUT(el, el >> 12);
+            }
+            ZS_PUT(W->seq_lit[n], c_ll_bits[ll_code[n]]);
+            ZS_PUT(W->seq_len[n] - 3, c_ml_bits[ml_code[n]]);
+            ZS_PUT(W->seq_off[n], of_code[n]);
+        }
+        if (lane == 0)
+        {
+            ZS_PUT(fs_ml, fl_ml);
+            ZS_PUT(fs_of, fl_of);
+            ZS_PUT(fs_ll, fl_ll);
+            ZS_PUT(1u, 1u); // end mark
+        }
+#undef ZS_PUT
+        if (fill) atomicOr(&words[widx], (uint32_t)acc);
+    }
+    __syncwarp();
+    op += stream;
+    if (last_count_size && last_count_size + stream < 4) return 0; // zstd <= 1.3.4 decoder quirk, zstd_compress.c:2982-2988
     return (uint32_t)(op - dst);
 }
 
 // literals + sequences of one block (zstd_compress.c:2876-2990), warp-level; 0 = emit the block raw, ZS_ERR on error
 __device__ uint32_t entropy_compress_w(ZstdWorker* W, WarpShared* sh, uint8_t* dst, uint32_t lit_size, uint32_t nb_seq, uint32_t lane)
 {
+    const long long t0 = clock64();
     const uint32_t lit_bytes = compress_literals_w(W, sh, dst, W->lits, lit_size, &W->huf_prev, &W->huf_next, (nb_seq == 0) || (lit_size / nb_seq >= 20), lane);
+    const long long t1 = clock64();
     // sequence codes with all lanes (ZSTD_seqToCodes, zstd_compress.c:2681-2705)
     for (uint32_t i = lane; i < nb_seq; i += 32)
     {
@@ -1006,10 +1100,8 @@ __device__ uint32_t entropy_compress_w(ZstdWorker* W, WarpShared* sh, uint8_t* d
         W->ml_code[i] = (uint8_t)ml_code_of(W->seq_len[i] - 3);
     }
     __syncwarp();
-    uint32_t c = 0;
-    if (lane == 0) c = sequences_compress(W, dst, dst + lit_bytes, nb_seq);
-    c = __shfl_sync(FULL, c, 0);
-    __syncwarp();
+    const uint32_t c = sequences_compress_w(W, sh, dst, dst + lit_bytes, nb_seq, lane);
+    if (lane == 0) { W->t_phase[1] += (unsigned long long)(t1 - t0); W->t_phase[2] += (unsigned long long)(clock64() - t1); }
     return c;
 }
 
@@ -1236,7 +1328,7 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
         }
         {
             const uint32_t ll = ip - anchor;
-            for (uint32_t i = lane; i < ll; i += 32) lits[nlit + i] = s[anchor + i];
+            copy_w<false>(lits + nlit, s + anchor, ll, lane);
             if (lane == 0) { W->seq_lit[nb] = ll; W->seq_len[nb] = m_len; W->seq_off[nb] = f_type == 1 ? 1u : offset + 3u; }
             nlit += ll;
             nb++;
@@ -1281,7 +1373,7 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
     rep[1] = offset_2 ? offset_2 : saved_2;
     {
         const uint32_t ll = iend - anchor;
-        for (uint32_t i = lane; i < ll; i += 32) lits[nlit + i] = s[anchor + i];
+        copy_w<false>(lits + nlit, s + anchor, ll, lane);
         nlit += ll;
     }
     __syncwarp();
@@ -1364,7 +1456,9 @@ __device__ uint32_t zstd_compress_frame(ZstdWorker* W, WarpShared* sh, const uin
         {
             uint32_t next_rep[3] = {W->rep[0], W->rep[1], W->rep[2]};
             uint32_t lit_size = 0;
+            const long long tm = clock64();
             const uint32_t nb = dfast_block_w(W, src, pos, bs, next_rep, &lit_size, lane);
+            if (lane == 0) W->t_phase[0] += (unsigned long long)(clock64() - tm);
             c = entropy_compress_w(W, sh, W->scratch, lit_size, nb, lane);
             if (c != ZS_ERR)
             {
@@ -1390,19 +1484,20 @@ __device__ uint32_t zstd_compress_frame(ZstdWorker* W, WarpShared* sh, const uin
         }
         if (c == ZS_ERR) return ZS_ERR;
         __syncwarp();
+        const long long tc = clock64();
         op += 3;
         if (c == 0)
         {
-            for (uint32_t i = lane; i < bs; i += 32) dst[op + i] = src[pos + i];
+            copy_w<false>(dst + op, src + pos, bs, lane);
             op += bs;
         }
         else
         {
-            const uint8_t* sc = W->scratch;
-            for (uint32_t i = lane; i < c; i += 32) dst[op + i] = __ldcg(sc + i); // the bit packers wrote through L2 atomics
+            copy_w<true>(dst + op, W->scratch, c, lane); // the bit packers wrote through L2 atomics
             op += c;
         }
         __syncwarp();
+        if (lane == 0) W->t_phase[3] += (unsigned long long)(clock64() - tc);
         pos += bs;
         first_block = false;
     }
@@ -1413,7 +1508,7 @@ __device__ uint32_t zstd_compress_frame(ZstdWorker* W, WarpShared* sh, const uin
 
 // one warp per frame from a global queue; output = the compress block store's {u32 raw size, u32 compressed size} header
 // (lib/compressblockstore/longtail_compressblockstore.c:127-131) followed by the frame
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_zstd_frames(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len, uint8_t* __restrict__ out,
               const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t frame_count, ZstdWorker* workers, uint32_t* queue)
 {
@@ -1422,6 +1517,8 @@ k_zstd_frames(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     ZstdWorker* W = workers + warp;
     WarpShared* sh = &s_warp[threadIdx.x >> 5];
+    if (lane == 0) { W->t_phase[0] = 0; W->t_phase[1] = 0; W->t_phase[2] = 0; W->t_phase[3] = 0; }
+    __syncwarp();
     for (;;)
     {
         uint32_t f = 0;
@@ -1446,10 +1543,11 @@ k_zstd_frames(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_
 }
 
 size_t zstd_worker_bytes() { return sizeof(ZstdWorker); }
+size_t zstd_worker_phase_offset() { return offsetof(ZstdWorker, t_phase); }
 
 uint32_t zstd_worker_count(uint32_t frame_count, int sm_count)
 {
-    const uint32_t resident = (uint32_t)sm_count * 32u; // 8 CTAs of 4 warps per SM
+    const uint32_t resident = (uint32_t)sm_count * 20u; // 5 CTAs of 4 warps per SM (register bound)
     return frame_count < resident ? (frame_count + 3u) & ~3u : resident;
 }
 

@@ -39,3 +39,10 @@ for it in range(2):
     print("iter %d: index %.1f ms (%.1f GiB/s); write %d blocks %.1f ms (%.2f GiB/s of unique %.2f GiB, ratio %.3f); codec kernel %.1f ms (%.2f GB/s), gather %.1f ms" % (
         it, 1e3 * (t1 - t0), n / (t1 - t0) / 2**30, len(blocks), 1e3 * (t3 - t2), uniq / (t3 - t2) / 2**30, uniq / 2**30, stored / max(uniq, 1),
         prof[KERNEL][0], prof[KERNEL][2] / max(prof[KERNEL][0], 1e-9) / 1e6, prof["k_gather_chunks"][0]))
+
+if codec == "zstd":
+    import ctypes as C
+    t = (C.c_uint64 * 4)()
+    ctx.lib.lt_b200_zstd_phase_cycles(ctx.handle, t)
+    tot = float(sum(t)) or 1.0
+    print("zstd phase cycles: matcher %.1f%%, literals %.1f%%, sequences %.1f%%, copy-out %.1f%%" % tuple(100.0 * x / tot for x in t))
