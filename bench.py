@@ -40,8 +40,8 @@ def parse_args():
     ap.add_argument("--gib", type=float, default=64.0, help="size of the synthetic file per GPU (GiB)")
     ap.add_argument("--e2e-gib", type=float, default=None, help="size of the host-resident file for the e2e leg (default: --gib, bounded by host RAM)")
     ap.add_argument("--cpu-gib", type=float, default=8.0, help="bounded sample for the CPU baseline / the reference arm")
-    ap.add_argument("--compress-gib", type=float, default=16.0, help="size of the configs[2]-shaped asset set of the LZ4 leg (0 = skip; 128 = the full config)")
-    ap.add_argument("--zstd-gib", type=float, default=4.0, help="size of the asset set of the ZStd leg (0 = skip)")
+    ap.add_argument("--compress-gib", type=float, default=32.0, help="size of the configs[2]-shaped asset set of the LZ4 leg (0 = skip; 128 = the full config)")
+    ap.add_argument("--zstd-gib", type=float, default=32.0, help="size of the asset set of the ZStd leg (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", action="store_true", help="small sizes only: compare the final VersionIndex with the CPU checker, byte for byte")

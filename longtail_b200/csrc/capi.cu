@@ -1189,8 +1189,10 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
     // ---- batches of blocks bounded by a device-memory budget: gather -> LZ4 -> copy out -> sink, in store order
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t budget = (uint64_t)(free_b * 0.4);
-    if (budget > (24ull << 30)) budget = 24ull << 30;
+    // a batch should hold enough blocks to occupy every resident codec warp (~3000 ZStd frames, ~2000 LZ4 blocks of ~9 MiB, twice
+    // that in bytes for input + output), memory permitting
+    uint64_t budget = (uint64_t)(free_b * 0.45);
+    if (budget > (64ull << 30)) budget = 64ull << 30;
     if (budget < (64ull << 20)) budget = 64ull << 20;
     auto lz4_bound = [](uint64_t n) { return n + n / 255 + 16; }; // lib/lz4/ext/lz4.h:215
     std::vector<uint64_t> src_off, dst_off, raw_off, out_off;
