@@ -192,6 +192,17 @@ def compress_leg(ctx, torch, stream, codec, gib, cpu_sample_gib, want_cpu):
                 acc += sz
             cores = ref.cpu_count()
             secs, _stored = ref.upsync(assets, TARGET_CHUNK_SIZE, tags=[tag] * len(assets), workers=cores, keep_bytes=False)
+            # parity on the same sample: the GPU path over exactly these assets must store exactly as many bytes as the reference
+            k = len(assets)
+            sub = longtail_b200.AssetList(["a/%05d.bin" % i for i in range(k)], sizes[:k])
+            v = ctx.index_device_assets(arena, arena_bytes, sub, offs[:k], [tag] * k, target_chunk_size=TARGET_CHUNK_SIZE)
+            vi = longtail_b200.parse_version_index(v)
+            blocks = ctx.write_blocks_device(arena, arena_bytes, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"],
+                                             ctx.unique_chunk_offsets(vi["chunk_count"]), keep_bytes=False)
+            gpu_stored = sum(sz for _, sz in blocks)
+            if gpu_stored != _stored:
+                raise SystemExit("%s parity check failed: %d stored bytes on the GPU, %d in the reference" % (codec, gpu_stored, _stored))
+            out["parity"] = "sample of %d assets: %d blocks, %d stored bytes, identical to the reference's upsync" % (k, len(blocks), gpu_stored)
             out["cpu_baseline"] = {"value": round(acc / sum(secs) / GIB, 4), "unit": "GiB/s", "cores": cores, "kind": "reference",
                                    "sample": "first %d assets (%.2f GiB): CreateVersionIndex + CreateMissingContent + WriteContent through "
                                              "compressblockstore, bikeshed %d workers" % (len(assets), acc / GIB, cores),
@@ -309,22 +320,43 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- parity spot check before anything is timed: first 2 parts against the CPU checker
+    # ---- parity before anything is timed: 8 parts spread over the whole file (first, last, 6 pseudo-random) against the CPU checker,
+    # chunk sizes and chunk hashes bit for bit; then size-independent properties of the full-size VersionIndex
     parity = "skipped"
     if rank == 0:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as ol
-        check_n = min(nbytes, 2 * part)
-        got = ctx.chunk_ranges(arena, nbytes + 4096, [(o, min(part, check_n - o), 0) for o in range(0, check_n, part)], mn, av, mx)
-        host = ctx.to_host(arena, check_n)
+        nparts = (nbytes + part - 1) // part
+        picks = sorted({0, nparts - 1} | {(k * 2654435761 + 12345) % nparts for k in range(6)})
+        ranges_chk = [(pi * part, min(part, nbytes - pi * part), 0) for pi in picks]
+        got = ctx.chunk_ranges(arena, nbytes + 4096, ranges_chk, mn, av, mx)
         ref = ol.Reference()
         checker = ref if ref.available else ol.Oracle()
-        exp = np.concatenate([checker.chunk(host[o:o + part], mn, av, mx) for o in range(0, check_n, part)])
-        offs = np.concatenate([[0], np.cumsum(exp.astype(np.uint64))[:-1]]).astype(np.uint64)
-        ok = got["sizes"].tolist() == exp.tolist() and got["hashes"].tolist() == checker.hash_segments(ol.HASH_BLAKE3, host, offs, exp).tolist()
-        parity = ("bit-exact vs %s on the first %d MiB" % ("reference" if ref.available else "oracle", check_n >> 20)) if ok else "MISMATCH"
+        exp_sizes, exp_hashes = [], []
+        for o, sz, _ in ranges_chk:
+            host = ctx.to_host(arena + o, sz)
+            e = checker.chunk(host, mn, av, mx)
+            offs = np.concatenate([[0], np.cumsum(e.astype(np.uint64))[:-1]]).astype(np.uint64)
+            exp_sizes.append(e)
+            exp_hashes.append(checker.hash_segments(ol.HASH_BLAKE3, host, offs, e))
+        ok = got["sizes"].tolist() == np.concatenate(exp_sizes).tolist() and got["hashes"].tolist() == np.concatenate(exp_hashes).tolist()
         if not ok:
             raise SystemExit("parity check failed: the CUDA path differs from the CPU checker")
+        # full-size properties: chunk sizes tile every part exactly, lie in [min, max] except a part's last chunk, the index is
+        # deterministic (two passes give identical bytes) and its asset content hash is the hash of the chunk-hash array
+        v1 = bytes(step_resident()) if world == 1 else None
+        if v1 is not None:
+            vi = longtail_b200.parse_version_index(v1)
+            v2 = bytes(step_resident())
+            sizes_all = vi["chunk_sizes"][vi["asset_chunk_indexes"]].astype(np.uint64)
+            props = (v1 == v2 and int(sizes_all.sum()) == nbytes and int(vi["chunk_sizes"].max()) <= mx
+                     and int((vi["chunk_sizes"] < mn).sum()) <= nparts
+                     and int(vi["content_hashes"][0]) == checker.hash(ol.HASH_BLAKE3, vi["chunk_hashes"][vi["asset_chunk_indexes"]].astype("<u8").tobytes()))
+            if not props:
+                raise SystemExit("full-size property check failed")
+        parity = "bit-exact vs %s on %d parts (%d MiB) spread over the file%s" % (
+            "reference" if ref.available else "oracle", len(picks), sum(r[1] for r in ranges_chk) >> 20,
+            "; full-size properties hold (sizes tile the file, [min,max], deterministic, content hash)" if v1 is not None else "")
 
     if args.verify:
         v = step_resident()

@@ -214,6 +214,13 @@ LT_B200_EXPORT int lt_b200_write_blocks_device(lt_b200_context* context, const u
                                                const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
                                                uint32_t max_block_size, uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user);
 
+/* Host helper (no GPU needed): Longtail_CreateStoreIndex's greedy block packing (src/longtail.c:6796-6860) over chunks in store
+ * order — a block closes on a tag change, at max_chunks_per_block chunks, or when the next chunk would exceed
+ * max_block_size + max_block_size/10.  out_block_first / out_block_count need room for chunk_count entries.  Used by planners
+ * that shard WriteContent by block across GPUs (longtail_b200/distributed.py). */
+LT_B200_EXPORT int lt_b200_pack_blocks(uint32_t chunk_count, const uint32_t* chunk_sizes, const uint32_t* chunk_tags, uint32_t max_block_size,
+                                       uint32_t max_chunks_per_block, uint32_t* out_block_first, uint32_t* out_block_count, uint32_t* out_blocks);
+
 /* CompressionAPI.Compress / Decompress (src/longtail.h:266-272) for 'lz42' over `count` independent HOST buffers in one
  * launch: LZ4_compress_fast(acceleration 1) / LZ4_decompress_safe semantics (lib/lz4/longtail_lz4.c:52-101), output bytes
  * identical to the reference codec.  dst_capacity[i] must be at least lt_b200_lz4_bound(src_size[i]) for compression

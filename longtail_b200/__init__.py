@@ -329,6 +329,22 @@ class Context:
                                                          int(hash_type), int(max_block_size), int(max_chunks_per_block), cb, None), "write_blocks_device")
         return blocks
 
+    def lz4_compress_host(self, buffers):
+        """CompressionAPI.Compress for 'lz42' over a list of host buffers in one launch -> list of LZ4 blocks (bytes)"""
+        keep = [np.ascontiguousarray(b, dtype=np.uint8) for b in buffers]
+        n = len(keep)
+        self.lib.lt_b200_lz4_bound.restype = C.c_uint64
+        self.lib.lt_b200_lz4_bound.argtypes = [C.c_uint64]
+        caps = [int(self.lib.lt_b200_lz4_bound(b.size)) for b in keep]
+        outs = [np.empty(max(c, 1), dtype=np.uint8) for c in caps]
+        src = (C.c_void_p * max(n, 1))(*[b.ctypes.data if b.size else None for b in keep])
+        dst = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+        sizes = (C.c_uint32 * max(n, 1))(*[b.size for b in keep])
+        cap = (C.c_uint64 * max(n, 1))(*caps)
+        got = (C.c_uint64 * max(n, 1))()
+        self._check(self.lib.lt_b200_lz4_compress_host(self.handle, C.c_uint32(n), src, sizes, dst, cap, got), "lz4_compress_host")
+        return [outs[i][:got[i]].tobytes() for i in range(n)]
+
     def zstd_compress_host(self, buffers, compression_type=None):
         """CompressionAPI.Compress for 'ztd2' / 'ztd1' over a list of host buffers in one launch -> list of frames (bytes)"""
         ctype = COMPRESSION_ZSTD_DEFAULT if compression_type is None else compression_type

@@ -31,7 +31,7 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
-    WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN,
+    WS_LZ4_TABLES, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN,
     WS_COUNT
 };
 
@@ -1122,6 +1122,34 @@ int zstd_launch(lt_b200_context* c, const uint8_t* d_raw, const std::vector<uint
 
 } // namespace
 
+// Longtail_CreateStoreIndex's greedy packing (src/longtail.c:6796-6860) as a host helper for planners (multi-GPU sharding by block)
+extern "C" int lt_b200_pack_blocks(uint32_t chunk_count, const uint32_t* chunk_sizes, const uint32_t* chunk_tags, uint32_t max_block_size,
+                                   uint32_t max_chunks_per_block, uint32_t* out_block_first, uint32_t* out_block_count, uint32_t* out_blocks)
+{
+    if ((chunk_count && (!chunk_sizes || !out_block_first || !out_block_count)) || !out_blocks || max_chunks_per_block == 0) return EINVAL;
+    const uint64_t limit = (uint64_t)max_block_size + max_block_size / 10;
+    uint32_t nb = 0;
+    for (uint32_t i = 0; i < chunk_count;)
+    {
+        uint32_t count = 1;
+        uint64_t raw = chunk_sizes[i];
+        const uint32_t tag = chunk_tags ? chunk_tags[i] : 0u;
+        while (i + count < chunk_count)
+        {
+            const uint32_t j = i + count;
+            if ((chunk_tags ? chunk_tags[j] : 0u) != tag || count == max_chunks_per_block || raw + chunk_sizes[j] > limit) break;
+            raw += chunk_sizes[j];
+            ++count;
+        }
+        out_block_first[nb] = i;
+        out_block_count[nb] = count;
+        ++nb;
+        i += count;
+    }
+    *out_blocks = nb;
+    return 0;
+}
+
 extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
                                            const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
                                            const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
@@ -1278,10 +1306,12 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
             CU(cudaStreamSynchronize(c->stream));
             uint64_t lz_bytes = 0;
             for (uint32_t v : lrl) lz_bytes += v;
+            TRY(ws_reserve(c, WS_LZ4_TABLES, LZ4_TABLE_BYTES_PER_BLOCK * lz_idx.size()));
             ProfScope ps(c, LT_B200_KERNEL_LZ4, lz_bytes);
             CU(launch_lz4_blocks(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
                                  ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), ws<uint3>(c, WS_BLK_JOBS),
-                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), (uint32_t)lz_idx.size(), c->stream));
+                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), (uint32_t)lz_idx.size(),
+                                 ws<uint32_t>(c, WS_LZ4_TABLES), c->stream));
         }
         // ZStd level 3 over the 'ztd1' / 'ztd2' blocks of the batch: one frame per block
         if (!zs_idx.empty())
@@ -1429,10 +1459,11 @@ int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src,
         CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_JOB_START), job_start.data(), sizeof(uint32_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
         if (compress)
         {
+            TRY(ws_reserve(c, WS_LZ4_TABLES, LZ4_TABLE_BYTES_PER_BLOCK * (size_t)nb));
             ProfScope ps(c, LT_B200_KERNEL_LZ4, in_bytes);
             CU(launch_lz4_blocks(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
                                  ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), ws<uint3>(c, WS_BLK_JOBS),
-                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), nb, c->stream));
+                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), nb, ws<uint32_t>(c, WS_LZ4_TABLES), c->stream));
             c->launches += 2;
         }
         else

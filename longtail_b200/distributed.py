@@ -86,3 +86,95 @@ class DeviceArray:
 
     def __init__(self, ptr, count, typestr):
         self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# WriteContent across GPUs: stored blocks are independent, so they shard by block.  Block composition
+# needs the merged unique-chunk order, which every rank derives from the allgathered chunk table (no extra collective); a
+# block goes to the rank that holds the first occurrence of its first chunk.  Ranks own contiguous ordinal ranges and unique
+# chunks are ordered by first occurrence, so a block's chunks live on a contiguous run of ranks: at most world-1 blocks
+# straddle a rank boundary, and only their foreign chunks (a few MiB) cross NVLink, point to point.
+
+
+def first_occurrences(hashes):
+    """global ordinals of the first occurrence of every distinct chunk hash, ascending = the VersionIndex's unique-chunk order
+    (first-occurrence dedup, src/longtail.c:2952-2970)"""
+    _, idx = np.unique(np.asarray(hashes, dtype=np.uint64), return_index=True)
+    return np.sort(idx).astype(np.int64)
+
+
+def pack_blocks(sizes, tags, max_block_size=8388608, max_chunks_per_block=1024):
+    """Longtail_CreateStoreIndex's greedy packing over the unique chunks in order (src/longtail.c:6796-6860): a block closes on a tag
+    change, at max_chunks_per_block chunks, or when the next chunk would exceed max_block_size + max_block_size/10.
+    -> list of (first_unique_chunk, chunk_count).  Runs in the C library (lt_b200_pack_blocks, a host-only helper)."""
+    import ctypes as C
+
+    from . import load_library
+    lib = load_library()
+    sz = np.ascontiguousarray(sizes, dtype=np.uint32)
+    tg = np.ascontiguousarray(tags, dtype=np.uint32)
+    first = np.zeros(max(sz.size, 1), dtype=np.uint32)
+    count = np.zeros(max(sz.size, 1), dtype=np.uint32)
+    nb = C.c_uint32(0)
+    err = lib.lt_b200_pack_blocks(C.c_uint32(sz.size), sz.ctypes.data_as(C.c_void_p), tg.ctypes.data_as(C.c_void_p), C.c_uint32(int(max_block_size)),
+                                  C.c_uint32(int(max_chunks_per_block)), first.ctypes.data_as(C.c_void_p), count.ctypes.data_as(C.c_void_p), C.byref(nb))
+    if err:
+        raise RuntimeError("lt_b200_pack_blocks failed with %d" % err)
+    return list(zip(first[:nb.value].tolist(), count[:nb.value].tolist()))
+
+
+def plan_write(hashes, sizes, tags, rank_chunk_counts, max_block_size=8388608, max_chunks_per_block=1024):
+    """Every rank calls this with the same allgathered table and gets the same plan.
+
+    -> dict(first=ordinals of the unique chunks, blocks=[(first_unique, count)], owner=rank per block,
+            chunk_owner=rank holding each unique chunk's first occurrence,
+            fetch={(needer, holder): [unique chunk indices]} for the chunks of straddling blocks)"""
+    first = first_occurrences(hashes)
+    sizes_u = np.asarray(sizes)[first]
+    tags_u = np.asarray(tags)[first]
+    blocks = pack_blocks(sizes_u, tags_u, max_block_size, max_chunks_per_block)
+    starts = np.concatenate([[0], np.cumsum(np.asarray(rank_chunk_counts, dtype=np.int64))])
+    chunk_owner = (np.searchsorted(starts, first, side="right") - 1).astype(np.int64)
+    bf = np.array([b[0] for b in blocks], dtype=np.int64)
+    bl = np.array([b[0] + b[1] - 1 for b in blocks], dtype=np.int64)
+    owner = chunk_owner[bf] if blocks else np.zeros(0, np.int64)
+    fetch = {}
+    # owners are non-decreasing along the unique-chunk order, so a block straddles iff its last chunk lives elsewhere
+    for b in np.nonzero(chunk_owner[bl] != owner)[0] if blocks else []:
+        f, c = blocks[int(b)]
+        o = int(owner[b])
+        for u in range(f, f + c):
+            if chunk_owner[u] != o:
+                fetch.setdefault((o, int(chunk_owner[u])), []).append(u)
+    return {"first": first, "sizes": sizes_u, "tags": tags_u, "blocks": blocks, "owner": owner, "chunk_owner": chunk_owner,
+            "fetch": fetch, "rank_starts": starts}
+
+
+def exchange_chunks(plan, rank, read_local, device, group=None):
+    """Move the foreign chunks of straddling blocks to the ranks that need them (torch.distributed point to point: NCCL over
+    NVLink for device tensors, gloo on CPU).  read_local(unique_chunk_index) -> 1-D uint8 torch tensor on `device` holding that
+    chunk's bytes (only called for chunks this rank owns).  -> {unique chunk index: uint8 tensor} for the chunks this rank needs."""
+    import torch
+    import torch.distributed as dist
+
+    ops, recv_bufs = [], []
+    for (needer, holder), chunks in sorted(plan["fetch"].items()):
+        total = int(sum(int(plan["sizes"][u]) for u in chunks))
+        if holder == rank:
+            buf = torch.cat([read_local(u) for u in chunks]) if chunks else torch.zeros(0, dtype=torch.uint8, device=device)
+            ops.append(dist.P2POp(dist.isend, buf.contiguous(), needer, group=group))
+        elif needer == rank:
+            buf = torch.empty(total, dtype=torch.uint8, device=device)
+            recv_bufs.append((chunks, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, holder, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    got = {}
+    for chunks, buf in recv_bufs:
+        off = 0
+        for u in chunks:
+            n = int(plan["sizes"][u])
+            got[u] = buf[off:off + n]
+            off += n
+    return got

@@ -60,6 +60,28 @@ def test_zstd_large_blocks_vs_oracle(ctx, oracle):
         assert f == oracle.zstd_compress(b)
 
 
+def test_zstd_adversarial_structures(ctx, oracle):
+    """inputs built to hit the rare paths: long runs (RLE blocks, long-length escapes), repcode chains (period-k data), matches
+    that straddle 128 KiB block edges and the 2 MiB window edge, a frame whose blocks alternate compressible / incompressible
+    (repcodes and Huffman tables confirmed or not, zstd_compress.c:4372-4375), tiny literal sections (raw / RLE literals)"""
+    rec = synth_bytes(830, 1 << 20, "rec")
+    rnd = synth_bytes(831, 1 << 20, "rand")
+    bufs = [
+        np.concatenate([np.zeros(200000, np.uint8), rec[:70000], np.full(131072 * 2, 7, np.uint8), rec[:1000]]),
+        np.tile(rec[:131072 - 5], 9),                                      # every block repeats the previous one, shifted by 5
+        np.concatenate([rec[:131072], rnd[:131072]] * 6),                  # alternate: compressed block, raw block, ...
+        np.concatenate([rec[:300000], np.zeros(2200000, np.uint8), rec[:300000]]),  # match source just outside the window
+        np.concatenate([rec[:300000], np.zeros(1700000, np.uint8), rec[:300000]]),  # ... and just inside
+        np.tile(np.arange(256, dtype=np.uint8), 3000),                     # period 256: offsets repeat, literals vanish
+        np.concatenate([synth_bytes(832 + i, 37 + 11 * i, "text") for i in range(400)] * 3),
+        synth_bytes(833, 131072 * 3 + 6, "rec"),                           # last block of 6 bytes: below the 7-byte compress threshold
+        synth_bytes(834, 131072 * 3 + 7, "rec"),
+    ]
+    frames = ctx.zstd_compress_host(bufs)
+    for i, (b, f) in enumerate(zip(bufs, frames)):
+        assert f == oracle.zstd_compress(b), "case %d (%d bytes)" % (i, b.size)
+
+
 def test_zstd_decodes_with_the_reference(ctx, reference):
     """the frames are valid ZStd: the unmodified reference decoder returns the input"""
     if reference is None:

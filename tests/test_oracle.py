@@ -162,6 +162,27 @@ def test_zstd_vs_reference(oracle, reference, n, kind):
     assert len(c) < n or kind == "rand"
 
 
+def test_zstd_vs_reference_adversarial(oracle, reference):
+    """the same rare-path inputs the GPU test uses, oracle vs the unmodified reference"""
+    if reference is None:
+        pytest.skip("reference not built")
+    rec = synth_bytes(830, 1 << 20, "rec")
+    rnd = synth_bytes(831, 1 << 20, "rand")
+    bufs = [
+        np.concatenate([np.zeros(200000, np.uint8), rec[:70000], np.full(131072 * 2, 7, np.uint8), rec[:1000]]),
+        np.tile(rec[:131072 - 5], 9),
+        np.concatenate([rec[:131072], rnd[:131072]] * 6),
+        np.concatenate([rec[:300000], np.zeros(2200000, np.uint8), rec[:300000]]),
+        np.concatenate([rec[:300000], np.zeros(1700000, np.uint8), rec[:300000]]),
+        np.tile(np.arange(256, dtype=np.uint8), 3000),
+        np.concatenate([synth_bytes(832 + i, 37 + 11 * i, "text") for i in range(400)] * 3),
+        synth_bytes(833, 131072 * 3 + 6, "rec"),
+        synth_bytes(834, 131072 * 3 + 7, "rec"),
+    ]
+    for i, b in enumerate(bufs):
+        assert oracle.zstd_compress(b) == reference.compress(ol.COMP_ZSTD_DEFAULT, b), "case %d" % i
+
+
 def test_zstd_vs_reference_real_files(oracle, reference):
     """source text and machine code of the reference tree itself: real match / literal / sequence statistics"""
     if reference is None or not os.path.isdir("/root/reference"):
