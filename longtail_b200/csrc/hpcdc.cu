@@ -188,6 +188,9 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
         for (int w = 0; w < SCAN_SEG / 32; ++w)
         {
             uint32_t v = s_bits[w];
+            // always clear: a candidate bit beyond the end of the part (zero-filled tail of a ragged last tile) is masked out below
+            // and must not survive into the next tile this warp scans
+            s_bits[w] = 0;
             // a cut after byte q is position q+1; keep it only inside the part
             uint32_t first = seg_first + 32 * w + 1;
             if (first > pd.size) v = 0;
@@ -215,7 +218,6 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
                 for (int w = 0; w < SCAN_SEG / 32; ++w)
                 {
                     uint32_t v = words[w];
-                    s_bits[w] = 0;
                     while (v)
                     {
                         uint32_t b = __ffs(v) - 1;

@@ -375,3 +375,17 @@ def test_blake3_tree_shapes_many_small_segments(ctx, oracle):
     finally:
         dev.free()
     assert got.tolist() == oracle.hash_segments(ol.HASH_BLAKE3, data, offs, lens).tolist()
+
+
+@pytest.mark.parametrize("target", [64, 2048])
+def test_many_ragged_parts_in_one_batch(ctx, oracle, target):
+    """hundreds of assets whose parts end in the middle of a scan tile, all in ONE batch: candidate bits that a ragged tail leaves
+    beyond the end of a part (zero-filled staging) must not leak into the next tile the same warp scans (regression: they did,
+    found by bench.py's stored-bytes check against the reference on the configs[2] sample)"""
+    import longtail_b200
+    part = target * 1024
+    sizes = [(int(x) % (3 * part + 5000)) + 1 for x in (np.arange(1, 401, dtype=np.uint64) * np.uint64(2654435761)) % np.uint64(1 << 31)]
+    assets = [("r/%04d.bin" % i, synth_bytes(3000 + i, n, "rand" if i % 3 else "nib")) for i, n in enumerate(sizes)]
+    al = longtail_b200.AssetList([p for p, _ in assets], [d.size for _, d in assets])
+    v = ctx.index_host_assets(al, [d for _, d in assets], None, target_chunk_size=target)
+    assert v == oracle.create_version_index(assets, target)
