@@ -453,9 +453,9 @@ def run_b200(args):
             host_buf = None
         compress = {}
         if args.compress_gib > 0:
-            compress["lz4"] = compress_leg(ctx, torch, stream, "lz4", args.compress_gib, 2.0, not args.no_cpu)
+            compress["lz4"] = compress_leg(ctx, torch, stream, "lz4", args.compress_gib, 4.0, not args.no_cpu)
         if args.zstd_gib > 0:
-            compress["zstd"] = compress_leg(ctx, torch, stream, "zstd", args.zstd_gib, 1.0, not args.no_cpu)
+            compress["zstd"] = compress_leg(ctx, torch, stream, "zstd", args.zstd_gib, 2.0, not args.no_cpu)
 
     if rank == 0:
         peak, peak_src = peaks()
