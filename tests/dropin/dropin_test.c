@@ -88,8 +88,8 @@ struct keep_store
 {
     struct Longtail_BlockStoreAPI api;
     pthread_mutex_t lock;
-    struct kept_block blocks[4096];
-    uint32_t count;
+    struct kept_block* blocks;
+    uint32_t count, capacity;
 };
 static int keep_put(struct Longtail_BlockStoreAPI* api, struct Longtail_StoredBlock* b, struct Longtail_AsyncPutStoredBlockAPI* async)
 {
@@ -99,6 +99,11 @@ static int keep_put(struct Longtail_BlockStoreAPI* api, struct Longtail_StoredBl
     if (!err)
     {
         pthread_mutex_lock(&s->lock);
+        if (s->count == s->capacity)
+        {
+            s->capacity = s->capacity ? s->capacity * 2 : 4096;
+            s->blocks = (struct kept_block*)realloc(s->blocks, sizeof(struct kept_block) * s->capacity);
+        }
         s->blocks[s->count].hash = *b->m_BlockIndex->m_BlockHash;
         s->blocks[s->count].data = buf;
         s->blocks[s->count].size = size;
@@ -126,6 +131,7 @@ static void keep_dispose(struct Longtail_API* api)
 {
     struct keep_store* s = (struct keep_store*)api;
     for (uint32_t i = 0; i < s->count; ++i) Longtail_Free(s->blocks[i].data);
+    free(s->blocks);
     free(s);
 }
 static struct keep_store* make_keep_store(void)
@@ -188,6 +194,17 @@ int main(int argc, char** argv)
         uint8_t* d = (uint8_t*)malloc(files[i].size ? files[i].size : 1);
         fill(d, files[i].size, strstr(files[i].path, "dup") ? 99 : 7 + i, files[i].low);
         CHECK(write_file(storage, files[i].path, d, files[i].size) == 0, "write %s", files[i].path);
+        free(d);
+    }
+    /* many assets whose parts end in the middle of a scan tile, so that one GPU batch holds dozens of ragged part tails */
+    for (uint32_t i = 0; i < (target < 256 ? 24u : 120u); ++i) /* tiny targets mean one GPU round trip per ~50-byte block in section 5 */
+    {
+        char path[64];
+        snprintf(path, sizeof(path), "root/r%u/f%03u.bin", i % 5, i);
+        const size_t size = 1 + (size_t)(((uint64_t)(i + 1) * 2654435761u) % (part + 100000));
+        uint8_t* d = (uint8_t*)malloc(size);
+        fill(d, size, 1000 + i, (int)(i % 3 == 0));
+        CHECK(write_file(storage, path, d, size) == 0, "write %s", path);
         free(d);
     }
     struct Longtail_FileInfos* infos = 0;
