@@ -214,6 +214,12 @@ LT_B200_EXPORT int lt_b200_write_blocks_device(lt_b200_context* context, const u
                                                const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
                                                uint32_t max_block_size, uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user);
 
+/* DiffHashes of Longtail_CreateMissingContent (src/longtail.c:6620-6743, :6882-6998) on the device: out_missing[i] = 1 when
+ * chunk_hashes[i] (the version's unique chunks, HOST array) is absent from existing_hashes (the chunk hashes of the store index, HOST
+ * array).  The chunks to write are the flagged ones in their given order; pass them to lt_b200_write_blocks_device. */
+LT_B200_EXPORT int lt_b200_missing_chunks(lt_b200_context* context, uint32_t chunk_count, const uint64_t* chunk_hashes,
+                                          uint32_t existing_count, const uint64_t* existing_hashes, uint8_t* out_missing);
+
 /* Host helper (no GPU needed): Longtail_CreateStoreIndex's greedy block packing (src/longtail.c:6796-6860) over chunks in store
  * order — a block closes on a tag change, at max_chunks_per_block chunks, or when the next chunk would exceed
  * max_block_size + max_block_size/10.  out_block_first / out_block_count need room for chunk_count entries.  Used by planners

@@ -309,6 +309,15 @@ class Context:
         self._check(self.lib.lt_b200_unique_chunk_offsets(self.handle, out.ctypes.data_as(C.c_void_p), int(count)), "unique_chunk_offsets")
         return out
 
+    def missing_chunks(self, chunk_hashes, existing_hashes):
+        """-> bool mask over chunk_hashes: True where the store (existing_hashes) does not hold the chunk yet (DiffHashes)"""
+        h = np.ascontiguousarray(chunk_hashes, dtype=np.uint64)
+        e = np.ascontiguousarray(existing_hashes, dtype=np.uint64)
+        out = np.zeros(max(h.size, 1), dtype=np.uint8)
+        self._check(self.lib.lt_b200_missing_chunks(self.handle, C.c_uint32(h.size), h.ctypes.data_as(C.c_void_p), C.c_uint32(e.size),
+                                                    e.ctypes.data_as(C.c_void_p) if e.size else None, out.ctypes.data_as(C.c_void_p)), "missing_chunks")
+        return out[:h.size].astype(bool)
+
     def write_blocks_device(self, dptr, arena_size, chunk_hashes, chunk_sizes, chunk_tags, chunk_offsets, max_block_size=8388608,
                             max_chunks_per_block=1024, hash_type=HASH_BLAKE3, keep_bytes=True):
         """-> list of (block_hash, serialised stored block bytes | size) in store order"""

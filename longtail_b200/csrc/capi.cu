@@ -1122,6 +1122,43 @@ int zstd_launch(lt_b200_context* c, const uint8_t* d_raw, const std::vector<uint
 
 } // namespace
 
+// DiffHashes of Longtail_CreateMissingContent (src/longtail.c:6620-6743, :6882-6998) on the device: which of the version's unique chunks
+// does the store NOT hold yet.  The reference sorts both hash lists and merges them; here the store's hashes go into the dedup hash
+// table and every version chunk probes it.  out_missing[i] = 1 when chunk_hashes[i] is absent from existing_hashes; the caller keeps the
+// flagged chunks in their (version) order, which is the order the reference restores after its sort (:6719-6739).
+extern "C" int lt_b200_missing_chunks(lt_b200_context* c, uint32_t chunk_count, const uint64_t* chunk_hashes, uint32_t existing_count,
+                                      const uint64_t* existing_hashes, uint8_t* out_missing)
+{
+    if (!c || (chunk_count && (!chunk_hashes || !out_missing)) || (existing_count && !existing_hashes)) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    if (!chunk_count) return 0;
+    if (!existing_count) { memset(out_missing, 1, chunk_count); return 0; }
+    uint32_t cap = 1024;
+    while (cap < 2ull * existing_count && cap < 0x80000000u) cap <<= 1;
+    TRY(ws_reserve(c, WS_DEDUP_KEYS, sizeof(uint64_t) * (size_t)cap));
+    TRY(ws_reserve(c, WS_DEDUP_VALS, sizeof(uint32_t) * ((size_t)cap + 1)));
+    TRY(ws_reserve(c, WS_SEG_OFF, sizeof(uint64_t) * (size_t)(chunk_count > existing_count ? chunk_count : existing_count)));
+    TRY(ws_reserve(c, WS_DEDUP_FIRST, (size_t)chunk_count + 16));
+    DedupBuffers db;
+    db.keys = ws<uint64_t>(c, WS_DEDUP_KEYS);
+    db.vals = ws<uint32_t>(c, WS_DEDUP_VALS);
+    db.capacity = cap;
+    db.first = nullptr; db.is_first = nullptr; db.uidx = nullptr;
+    CU(cudaMemsetAsync(db.keys, 0xff, sizeof(uint64_t) * (size_t)cap, c->stream));
+    CU(cudaMemsetAsync(db.vals, 0xff, sizeof(uint32_t) * ((size_t)cap + 1), c->stream));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_OFF), existing_hashes, sizeof(uint64_t) * (size_t)existing_count, cudaMemcpyHostToDevice, c->stream));
+    launch_dedup_insert(ws<uint64_t>(c, WS_SEG_OFF), existing_count, db, c->stream);
+    CU(cudaMemcpyAsync(ws<void>(c, WS_SEG_OFF), chunk_hashes, sizeof(uint64_t) * (size_t)chunk_count, cudaMemcpyHostToDevice, c->stream));
+    launch_set_contains(ws<uint64_t>(c, WS_SEG_OFF), chunk_count, db, ws<uint8_t>(c, WS_DEDUP_FIRST), c->stream);
+    c->launches += 2;
+    CU(cudaMemcpyAsync(out_missing, ws<void>(c, WS_DEDUP_FIRST), chunk_count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    for (uint32_t i = 0; i < chunk_count; ++i) out_missing[i] = out_missing[i] ? 0 : 1; // present -> missing
+    return 0;
+}
+
 // Longtail_CreateStoreIndex's greedy packing (src/longtail.c:6796-6860) as a host helper for planners (multi-GPU sharding by block)
 extern "C" int lt_b200_pack_blocks(uint32_t chunk_count, const uint32_t* chunk_sizes, const uint32_t* chunk_tags, uint32_t max_block_size,
                                    uint32_t max_chunks_per_block, uint32_t* out_block_first, uint32_t* out_block_count, uint32_t* out_blocks)

@@ -73,6 +73,8 @@ struct DedupBuffers
 };
 void launch_dedup_insert(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st);
 void launch_dedup_lookup(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st);
+// present[i] = 1 when d_hash[i] was inserted into b (launch_dedup_insert) before
+void launch_set_contains(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, uint8_t* d_present, cudaStream_t st);
 void launch_dedup_emit(const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, const DedupBuffers& b,
                        uint32_t* d_asset_chunk_index, uint64_t* d_unique_hash, uint32_t* d_unique_len, uint32_t* d_unique_tag,
                        const uint64_t* d_chunk_off, uint64_t* d_unique_off, cudaStream_t st);

@@ -198,6 +198,33 @@ __global__ void k_dedup_emit(const uint64_t* __restrict__ hash, const uint32_t* 
     }
 }
 
+// membership of every hash in the set previously inserted with k_dedup_insert (DiffHashes, src/longtail.c:6620-6743: which of the
+// version's chunks does the store already hold): 1 = present
+__global__ void k_set_contains(const uint64_t* __restrict__ hash, uint32_t count, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                               uint32_t capacity, uint8_t* __restrict__ present)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t key = hash[i];
+    bool found;
+    if (key == DEDUP_EMPTY)
+        found = vals[capacity] != 0xffffffffu;
+    else
+    {
+        const uint32_t mask = capacity - 1;
+        uint32_t s = dedup_slot(key, mask);
+        while (keys[s] != key && keys[s] != DEDUP_EMPTY) s = (s + 1) & mask;
+        found = keys[s] == key;
+    }
+    present[i] = found ? 1 : 0;
+}
+
+void launch_set_contains(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, uint8_t* d_present, cudaStream_t st)
+{
+    if (!count) return;
+    k_set_contains<<<(count + 255) / 256, 256, 0, st>>>(d_hash, count, b.keys, b.vals, b.capacity, d_present);
+}
+
 void launch_dedup_insert(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, cudaStream_t st)
 {
     if (!count) return;

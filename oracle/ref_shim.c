@@ -443,11 +443,12 @@ static struct capture_store* make_capture_store(int keep_bytes)
  * { u64 block_hash, u64 size, u8 serialised_stored_block[size] } (Longtail_WriteStoredBlockToBuffer),
  * followed by the serialised VersionIndex { u64 size, bytes }.  With keep_bytes == 0 only sizes are
  * recorded (timing runs).  seconds[0..2] = CreateVersionIndex, CreateMissingContent, WriteContent. */
-REF_EXPORT int ref_upsync(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
+static int upsync_impl(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
                           const uint16_t* perms, const uint32_t* tags, uint32_t hash_type,
                           uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block,
                           uint32_t workers, int keep_bytes,
-                          void** out_buf, uint64_t* out_size, double* seconds, uint64_t* out_stored_bytes)
+                          void** out_buf, uint64_t* out_size, double* seconds, uint64_t* out_stored_bytes,
+                       uint32_t existing_count, const uint64_t* existing_hashes)
 {
     struct Longtail_HashAPI* hash = make_hash(hash_type);
     if (!hash) return EINVAL;
@@ -465,7 +466,24 @@ REF_EXPORT int ref_upsync(uint32_t count, const char** paths, const uint8_t** da
     double t0 = now_s();
     int err = Longtail_CreateVersionIndex(storage, hash, chunker, job, 0, 0, 0, "root", fi, tags, target_chunk_size, 0, &vi);
     double t1 = now_s();
-    if (!err) err = Longtail_CreateStoreIndexFromBlocks(0, 0, &empty);
+    if (!err && existing_count == 0) err = Longtail_CreateStoreIndexFromBlocks(0, 0, &empty);
+    if (!err && existing_count)
+    {
+        /* a store that already holds `existing_count` chunks: one synthetic block lists them (sizes are irrelevant to DiffHashes) */
+        uint32_t* idx = (uint32_t*)malloc(sizeof(uint32_t) * existing_count);
+        uint32_t* szs = (uint32_t*)malloc(sizeof(uint32_t) * existing_count);
+        for (uint32_t i = 0; i < existing_count; ++i) { idx[i] = i; szs[i] = 1; }
+        struct Longtail_BlockIndex* bi = 0;
+        err = Longtail_CreateBlockIndex(hash, 0, existing_count, idx, existing_hashes, szs, &bi);
+        if (!err)
+        {
+            const struct Longtail_BlockIndex* list[1] = {bi};
+            err = Longtail_CreateStoreIndexFromBlocks(1, list, &empty);
+        }
+        Longtail_Free(bi);
+        free(idx);
+        free(szs);
+    }
     double t2 = now_s();
     if (!err) err = Longtail_CreateMissingContent(hash, empty, vi, max_block_size, max_chunks_per_block, &missing);
     double t3 = now_s();
@@ -519,3 +537,27 @@ REF_EXPORT int ref_upsync(uint32_t count, const char** paths, const uint8_t** da
     SAFE_DISPOSE_API(hash);
     return err;
 }
+
+REF_EXPORT int ref_upsync(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
+                          const uint16_t* perms, const uint32_t* tags, uint32_t hash_type,
+                          uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block,
+                          uint32_t workers, int keep_bytes,
+                          void** out_buf, uint64_t* out_size, double* seconds, uint64_t* out_stored_bytes)
+{
+    return upsync_impl(count, paths, datas, sizes, perms, tags, hash_type, target_chunk_size, max_block_size, max_chunks_per_block, workers,
+                       keep_bytes, out_buf, out_size, seconds, out_stored_bytes, 0, 0);
+}
+
+/* upsync into a store that already holds the chunks `existing_hashes`: Longtail_CreateMissingContent (src/longtail.c:6882-6998) keeps
+ * only the version's chunks the store lacks, in version order (DiffHashes, :6620-6743), and packs those */
+REF_EXPORT int ref_upsync_existing(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
+                                   const uint16_t* perms, const uint32_t* tags, uint32_t hash_type,
+                                   uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block,
+                                   uint32_t workers, int keep_bytes,
+                                   void** out_buf, uint64_t* out_size, double* seconds, uint64_t* out_stored_bytes,
+                                   uint32_t existing_count, const uint64_t* existing_hashes)
+{
+    return upsync_impl(count, paths, datas, sizes, perms, tags, hash_type, target_chunk_size, max_block_size, max_chunks_per_block, workers,
+                       keep_bytes, out_buf, out_size, seconds, out_stored_bytes, existing_count, existing_hashes);
+}
+

@@ -252,15 +252,23 @@ class Reference:
         return (out, secs.value) if want_seconds else out
 
     def upsync(self, assets, target_chunk_size, max_block_size=8388608, max_chunks_per_block=1024, hash_type=HASH_BLAKE3,
-               tags=None, perms=None, workers=0, keep_bytes=True, want_seconds=False):
+               tags=None, perms=None, workers=0, keep_bytes=True, want_seconds=False, existing_hashes=None):
+        """existing_hashes: chunk hashes a (non-empty) store already holds -> only the missing chunks are packed and written"""
         a = _AssetArgs(assets, tags, perms)
         buf = C.c_void_p()
         size = C.c_uint64(0)
         secs = (C.c_double * 3)()
         stored = C.c_uint64(0)
-        err = self.lib.ref_upsync(C.c_uint32(a.n), a.paths, a.datas, a.sizes, a.perms, a.tags, C.c_uint32(hash_type),
-                                  C.c_uint32(target_chunk_size), C.c_uint32(max_block_size), C.c_uint32(max_chunks_per_block),
-                                  C.c_uint32(workers), C.c_int(1 if keep_bytes else 0), C.byref(buf), C.byref(size), secs, C.byref(stored))
+        if existing_hashes is not None and len(existing_hashes):
+            eh = np.ascontiguousarray(existing_hashes, dtype=np.uint64)
+            err = self.lib.ref_upsync_existing(C.c_uint32(a.n), a.paths, a.datas, a.sizes, a.perms, a.tags, C.c_uint32(hash_type),
+                                               C.c_uint32(target_chunk_size), C.c_uint32(max_block_size), C.c_uint32(max_chunks_per_block),
+                                               C.c_uint32(workers), C.c_int(1 if keep_bytes else 0), C.byref(buf), C.byref(size), secs, C.byref(stored),
+                                               C.c_uint32(eh.size), eh.ctypes.data_as(C.c_void_p))
+        else:
+            err = self.lib.ref_upsync(C.c_uint32(a.n), a.paths, a.datas, a.sizes, a.perms, a.tags, C.c_uint32(hash_type),
+                                      C.c_uint32(target_chunk_size), C.c_uint32(max_block_size), C.c_uint32(max_chunks_per_block),
+                                      C.c_uint32(workers), C.c_int(1 if keep_bytes else 0), C.byref(buf), C.byref(size), secs, C.byref(stored))
         assert err == 0, err
         out = C.string_at(buf, size.value)
         self.lib.ref_free(buf)

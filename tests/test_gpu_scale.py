@@ -93,3 +93,28 @@ def test_other_hashes_at_scale(workload, hash_type):
     v = w["ctx"].index_device_assets(w["arena"], w["arena_bytes"], al, w["offs"][:n], w["tags"][:n], hash_type=ht_b, target_chunk_size=TARGET)
     ref = ol.Reference()
     assert v == ref.create_version_index(w["assets"][:n], TARGET, hash_type=ht_o, tags=w["tags"][:n], workers=8)
+
+
+def test_incremental_upsync_missing_chunks(workload):
+    """upsync into a store that already holds part of the content (CreateMissingContent's DiffHashes on
+    the device): the store knows every third unique chunk plus some foreign hashes; only the missing chunks are packed and written,
+    in version order — blocks byte-identical to the reference's CreateMissingContent + WriteContent against the same store index"""
+    import longtail_b200
+    w = workload
+    ctx = w["ctx"]
+    al = longtail_b200.AssetList([p for p, _ in w["assets"]], w["sizes"])
+    v = ctx.index_device_assets(w["arena"], w["arena_bytes"], al, w["offs"], w["tags"], target_chunk_size=TARGET)
+    vi = longtail_b200.parse_version_index(v)
+    uoff = ctx.unique_chunk_offsets(vi["chunk_count"])
+    existing = np.concatenate([vi["chunk_hashes"][::3], np.arange(1, 5000, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)])
+    missing = ctx.missing_chunks(vi["chunk_hashes"], existing)
+    assert missing.tolist() == (~np.isin(vi["chunk_hashes"], existing)).tolist()
+    assert 0 < missing.sum() < missing.size
+    blocks = ctx.write_blocks_device(w["arena"], w["arena_bytes"], vi["chunk_hashes"][missing], vi["chunk_sizes"][missing], vi["chunk_tags"][missing],
+                                     uoff[missing])
+    ref = ol.Reference()
+    want_blocks, want_index = ref.upsync(w["assets"], TARGET, tags=w["tags"], workers=8, existing_hashes=existing)
+    assert want_index == v
+    assert len(blocks) == len(want_blocks) and len(blocks) > 30
+    for (h, got), (hw, want) in zip(blocks, want_blocks):
+        assert h == hw and got == want, "block %016x differs" % hw
