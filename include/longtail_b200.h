@@ -67,6 +67,8 @@ enum
     LT_B200_KERNEL_BLAKE2S = 6,
     LT_B200_KERNEL_MEOW = 7,
     LT_B200_KERNEL_ZSTD = 8,
+    LT_B200_KERNEL_LZ4_DECODE = 9,
+    LT_B200_KERNEL_ZSTD_DECODE = 10,
     LT_B200_KERNEL_COUNT = 16
 };
 LT_B200_EXPORT int lt_b200_profile_enable(lt_b200_context* context, int on);
@@ -247,6 +249,14 @@ LT_B200_EXPORT int lt_b200_zstd_phase_cycles(lt_b200_context* context, uint64_t 
 LT_B200_EXPORT uint64_t lt_b200_zstd_bound(uint64_t size); /* ZSTD_COMPRESSBOUND, lib/zstd/ext/zstd.h:232 */
 LT_B200_EXPORT int lt_b200_zstd_compress_host(lt_b200_context* context, uint32_t compression_type, uint32_t count, const void* const* src,
                                               const uint32_t* src_size, void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
+
+/* CompressionAPI.Decompress (src/longtail.h:266-272) for every ZStd type id ('ztd1' .. 'ztd5'; lib/zstd/longtail_zstd.c:143-176 ->
+ * ZSTD_decompressDCtx) over `count` independent HOST buffers in one launch, one warp per frame.  A frame written by any level
+ * decodes (raw / RLE / compressed blocks, raw / RLE / Huffman / treeless literals, predefined / RLE / FSE / repeat sequence
+ * tables); dictionaries are not supported (longtail uses none).  out_size[i] = the decoded size; EBADF on a malformed frame or
+ * a frame whose content does not fit dst_capacity[i]. */
+LT_B200_EXPORT int lt_b200_zstd_decompress_host(lt_b200_context* context, uint32_t count, const void* const* src, const uint32_t* src_size,
+                                                void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
 
 /* Arena offsets of the unique chunks (first occurrences, VersionIndex order) found by the last lt_b200_index_device_assets
  * call on this context — the `chunk_arena_offsets` of a fresh-store lt_b200_write_blocks_device. */

@@ -104,7 +104,7 @@ def load_library():
     return lib
 
 
-KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks", 6: "k_blake2s_segments", 7: "k_meow_segments", 8: "k_zstd_frames"}
+KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks", 6: "k_blake2s_segments", 7: "k_meow_segments", 8: "k_zstd_frames", 9: "k_lz4_decode", 10: "k_zstd_decode"}
 
 
 def parse_version_index(buf):
@@ -370,6 +370,26 @@ class Context:
         got = (C.c_uint64 * max(n, 1))()
         self._check(self.lib.lt_b200_zstd_compress_host(self.handle, C.c_uint32(ctype), C.c_uint32(n), src, sizes, dst, cap, got), "zstd_compress_host")
         return [outs[i][:got[i]].tobytes() for i in range(n)]
+
+    def _decompress_host(self, fn, name, buffers, raw_sizes):
+        keep = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b, dtype=np.uint8) for b in buffers]
+        n = len(keep)
+        outs = [np.empty(max(int(c), 1), dtype=np.uint8) for c in raw_sizes]
+        src = (C.c_void_p * max(n, 1))(*[b.ctypes.data if b.size else None for b in keep])
+        dst = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+        sizes = (C.c_uint32 * max(n, 1))(*[b.size for b in keep])
+        cap = (C.c_uint64 * max(n, 1))(*[int(c) for c in raw_sizes])
+        got = (C.c_uint64 * max(n, 1))()
+        self._check(fn(self.handle, C.c_uint32(n), src, sizes, dst, cap, got), name)
+        return [outs[i][:got[i]].tobytes() for i in range(n)]
+
+    def lz4_decompress_host(self, buffers, raw_sizes):
+        """CompressionAPI.Decompress for 'lz42' over a list of LZ4 blocks in one launch; raw_sizes = capacities of the outputs"""
+        return self._decompress_host(self.lib.lt_b200_lz4_decompress_host, "lz4_decompress_host", buffers, raw_sizes)
+
+    def zstd_decompress_host(self, buffers, raw_sizes):
+        """CompressionAPI.Decompress for 'ztd1'..'ztd5' over a list of frames in one launch (one warp per frame)"""
+        return self._decompress_host(self.lib.lt_b200_zstd_decompress_host, "zstd_decompress_host", buffers, raw_sizes)
 
     # ---- layer 2
     def _result(self, buf, size, copy):

@@ -31,7 +31,7 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
-    WS_LZ4_TABLES, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN,
+    WS_LZ4_TABLES, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
     WS_COUNT
 };
 
@@ -1444,10 +1444,13 @@ extern "C" uint64_t lt_b200_lz4_bound(uint64_t size) { return size + size / 255 
 
 namespace {
 
-// shared driver of the two directions: stage inputs at 16-byte aligned offsets, run `launch`, copy results out
+enum CodecMode { CODEC_LZ4_ENCODE, CODEC_LZ4_DECODE, CODEC_ZSTD_DECODE };
+
+// shared driver of LZ4 encode and the two decoders: stage inputs at 16-byte aligned offsets, run the kernel, copy results out
 int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
-                     const uint64_t* dst_capacity, uint64_t* out_size, bool compress)
+                     const uint64_t* dst_capacity, uint64_t* out_size, CodecMode mode)
 {
+    const bool compress = mode == CODEC_LZ4_ENCODE;
     if (!c || (count && (!src || !src_size || !dst || !dst_capacity || !out_size))) return EINVAL;
     CU(cudaSetDevice(c->device));
     c->err[0] = 0;
@@ -1503,10 +1506,22 @@ int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src,
                                  ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), nb, ws<uint32_t>(c, WS_LZ4_TABLES), c->stream));
             c->launches += 2;
         }
-        else
+        else if (mode == CODEC_LZ4_DECODE)
         {
+            ProfScope ps(c, LT_B200_KERNEL_LZ4_DECODE, out_bytes);
             CU(launch_lz4_decode(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
                                  ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_LEN), ws<uint32_t>(c, WS_BLK_OUT_LEN), nb, c->stream));
+            c->launches += 1;
+        }
+        else
+        {
+            const uint32_t workers = zstd_dec_worker_count(nb, c->sm_count);
+            TRY(ws_reserve(c, WS_ZSTD_DEC_WORKERS, zstd_dec_worker_bytes() * (size_t)workers));
+            TRY(ws_reserve(c, WS_QUEUE_HEAD, 64));
+            ProfScope ps(c, LT_B200_KERNEL_ZSTD_DECODE, out_bytes);
+            CU(launch_zstd_decode(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
+                                  ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_LEN), ws<uint32_t>(c, WS_BLK_OUT_LEN), nb,
+                                  ws<void>(c, WS_ZSTD_DEC_WORKERS), workers, ws<uint32_t>(c, WS_QUEUE_HEAD), c->stream));
             c->launches += 1;
         }
         TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb + 16));
@@ -1516,7 +1531,7 @@ int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src,
         CU(cudaGetLastError());
         for (uint32_t i = 0; i < nb; ++i)
         {
-            if (h_len[i] == 0xffffffffu) return fail(c, EBADF, "buffer %u: malformed LZ4 stream", i0 + i);
+            if (h_len[i] == 0xffffffffu) return fail(c, EBADF, "buffer %u: malformed %s", i0 + i, mode == CODEC_ZSTD_DECODE ? "ZStd frame" : "LZ4 stream");
             const uint64_t n = compress ? h_len[i] - 8u : h_len[i];                       // the kernel writes the block-store header first
             const uint8_t* d = ws<uint8_t>(c, WS_BLK_OUT) + out_off[i] + (compress ? 8 : 0);
             if (n > dst_capacity[i0 + i]) return fail(c, ENOMEM, "buffer %u: output does not fit", i0 + i);
@@ -1607,11 +1622,17 @@ extern "C" int lt_b200_zstd_compress_host(lt_b200_context* c, uint32_t compressi
 extern "C" int lt_b200_lz4_compress_host(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
                                          const uint64_t* dst_capacity, uint64_t* out_size)
 {
-    return codec_host_batch(c, count, src, src_size, dst, dst_capacity, out_size, true);
+    return codec_host_batch(c, count, src, src_size, dst, dst_capacity, out_size, CODEC_LZ4_ENCODE);
 }
 
 extern "C" int lt_b200_lz4_decompress_host(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
                                            const uint64_t* dst_capacity, uint64_t* out_size)
 {
-    return codec_host_batch(c, count, src, src_size, dst, dst_capacity, out_size, false);
+    return codec_host_batch(c, count, src, src_size, dst, dst_capacity, out_size, CODEC_LZ4_DECODE);
+}
+
+extern "C" int lt_b200_zstd_decompress_host(lt_b200_context* c, uint32_t count, const void* const* src, const uint32_t* src_size, void* const* dst,
+                                            const uint64_t* dst_capacity, uint64_t* out_size)
+{
+    return codec_host_batch(c, count, src, src_size, dst, dst_capacity, out_size, CODEC_ZSTD_DECODE);
 }

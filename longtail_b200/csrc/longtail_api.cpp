@@ -507,8 +507,23 @@ int zstd_compress(struct Longtail_CompressionAPI*, uint32_t settings_id, const c
     return 0;
 }
 
-// No device ZStd decoder exists yet (the downsync direction is SURVEY.md section 8f row 3); failing loudly beats a CPU fallback.
-int zstd_decompress(struct Longtail_CompressionAPI*, const char*, char*, size_t, size_t, size_t*) { return ENOTSUP; }
+// ZStdCompressionAPI_Decompress (lib/zstd/longtail_zstd.c:143-176): frames of every level decode on the device (zstd_dec.cu)
+int zstd_decompress(struct Longtail_CompressionAPI*, const char* compressed, char* uncompressed, size_t compressed_size,
+                    size_t max_uncompressed_size, size_t* out_uncompressed_size)
+{
+    if (!compressed || !uncompressed || !out_uncompressed_size || compressed_size > 0x7fffffffu) return EINVAL;
+    std::lock_guard<std::mutex> g(g_gpu);
+    int err = ensure_ctx();
+    if (err) return err;
+    const void* src = compressed;
+    void* dst = uncompressed;
+    uint32_t n = (uint32_t)compressed_size;
+    uint64_t cap = max_uncompressed_size > 0xfffffff0u ? 0xfffffff0u : max_uncompressed_size, out = 0;
+    err = lt_b200_zstd_decompress_host(g_ctx, 1, &src, &n, &dst, &cap, &out);
+    if (err) return err == EBADF ? EINVAL : err; // the reference maps every ZSTD error to EINVAL (:168-172)
+    *out_uncompressed_size = (size_t)out;
+    return 0;
+}
 
 // ---------------------------------------------------------------- compress block store
 size_t block_index_data_size(uint32_t chunk_count) { return 8 + 4 + 4 + 4 + 12 * (size_t)chunk_count; } // src/longtail.c:3585-3597
@@ -750,8 +765,9 @@ void get_backing_complete(struct Longtail_AsyncGetStoredBlockAPI* api, struct Lo
         return;
     }
     struct Longtail_StoredBlock* plain = nullptr;
-    if (tag != TYPE_LZ4 || block->m_BlockChunksDataSize < 8)
-        err = tag != TYPE_LZ4 ? ENOTSUP : EBADF;
+    const bool known = tag == TYPE_LZ4 || is_zstd_type(tag);
+    if (!known || block->m_BlockChunksDataSize < 8)
+        err = !known ? ENOTSUP : EBADF;
     else
     {
         const uint32_t* header = static_cast<const uint32_t*>(block->m_BlockData); // longtail_compressblockstore.c:292-296
@@ -765,7 +781,8 @@ void get_backing_complete(struct Longtail_AsyncGetStoredBlockAPI* api, struct Lo
         if (!err)
         {
             size_t got = 0;
-            err = lz4_decompress(nullptr, reinterpret_cast<const char*>(header + 2), static_cast<char*>(plain->m_BlockData), comp, raw, &got);
+            err = (tag == TYPE_LZ4 ? lz4_decompress : zstd_decompress)(nullptr, reinterpret_cast<const char*>(header + 2),
+                                                                       static_cast<char*>(plain->m_BlockData), comp, raw, &got);
             if (!err && got != raw) err = EBADF; // :323-327
             plain->m_BlockChunksDataSize = raw;
         }

@@ -56,6 +56,13 @@ uint32_t zstd_worker_count(uint32_t frame_count, int sm_count);
 cudaError_t launch_zstd_frames(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out, const uint64_t* d_out_off,
                                uint32_t* d_out_len, uint32_t frame_count, void* d_workers, uint32_t worker_count, uint32_t* d_queue, cudaStream_t st);
 
+// ---- zstd_dec.cu : ZStd frame decoder (any level's frames), one warp per frame from a queue; d_out_len[i] = 0xffffffff on a malformed frame
+size_t zstd_dec_worker_bytes();
+uint32_t zstd_dec_worker_count(uint32_t frame_count, int sm_count);
+cudaError_t launch_zstd_decode(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, uint8_t* d_out, const uint64_t* d_out_off,
+                               const uint32_t* d_out_cap, uint32_t* d_out_len, uint32_t frame_count, void* d_workers, uint32_t worker_count,
+                               uint32_t* d_queue, cudaStream_t st);
+
 // ---- util.cu
 // exclusive prefix sum of count u32 values into out[0..count]; out[count] = total.  tmp: >= scan_tmp_words(count) u32.
 size_t scan_tmp_words(uint32_t count);
