@@ -34,9 +34,10 @@ __global__ void k_tile_part(const PartDesc* __restrict__ parts, uint32_t part_co
 }
 
 // Re-evaluation of one 8-byte group after the group-level divisibility filter fired (about one group in 400 at the
-// default parameters).  Runs divergent, so it is kept short: same table lookups as the main loop, the filter again per byte
-// and the true `%` only where the filter passes.
-__device__ __noinline__ void scan_group_exact(uint32_t in_addr, uint32_t out_addr, uint32_t h, uint32_t d, uint32_t d_odd_inv,
+// default parameters): same table lookups as the main loop, the filter again per byte and the true `%` only where the filter
+// passes.  The main loop only RECORDS such groups (start hash + position, two per lane in registers); they are re-walked after
+// the tile's main loop, when the 48 ring registers are dead and every lane with a recorded group works at the same time.
+__device__ __forceinline__ void scan_group_exact(uint32_t in_addr, uint32_t out_addr, uint32_t h, uint32_t d, uint32_t d_odd_inv,
                                               uint32_t d_odd_thr, uint32_t tab_lane, uint32_t bitmap_row, uint32_t first_bit)
 {
 #pragma unroll 4
@@ -56,10 +57,120 @@ __device__ __noinline__ void scan_group_exact(uint32_t in_addr, uint32_t out_add
     }
 }
 
+// third and later recorded group of one lane in one tile (dense candidates: tiny discriminators, degenerate data): resolved on the spot
+__device__ __noinline__ void scan_group_exact_now(uint32_t in_addr, uint32_t out_addr, uint32_t h, uint32_t d, uint32_t d_odd_inv,
+                                                  uint32_t d_odd_thr, uint32_t tab_lane, uint32_t bitmap_row, uint32_t first_bit)
+{
+    scan_group_exact(in_addr, out_addr, h, d, d_odd_inv, d_odd_thr, tab_lane, bitmap_row, first_bit);
+}
+
+// Recorded groups live in the 16 padding bytes behind the lane's own row: three start hashes (12 B) and three group indices
+// (1 B each).  A fourth recorded group in one lane-tile (probability ~1e-6 at the default parameters) marks the tile as
+// overflowed, which k_hpcdc_walk resolves exactly.
+constexpr uint32_t SCAN_PEND_MAX = 3;
+
+// Sixteen positions of the rolling hash.  ring[] holds the table ADDRESS of each of the last 48 bytes (one register each, slots
+// are compile-time constants): the PRMT that extracts a byte and forms its table address runs once per byte, when the byte
+// enters the window; when it leaves, 48 positions later, its rotl(T,16) is read from the same address + 128
+// (longtail_hpcdcchunker.c:295-297).
+template <int SLOT, bool SPARSE>
+__device__ __forceinline__ void scan_step16(uint32_t (&ring)[SCAN_WINDOW], uint32_t& h, uint32_t& npend, uint32_t pad_addr, uint32_t in_addr,
+                                            uint32_t out_addr, uint32_t first_bit, const ChunkParams& cp, uint32_t tab_lane, uint32_t bits_addr)
+{
+    const uint4 cin = lds128(in_addr);
+    const uint32_t wi[4] = {cin.x, cin.y, cin.z, cin.w};
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+    {
+        const uint32_t h0 = h;
+        uint32_t best = 0xffffffffu;
+#pragma unroll
+        for (int k = 8 * g; k < 8 * g + 8; ++k)
+        {
+            const uint32_t a = __byte_perm(wi[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4));
+            h = rotl32(h, 1) ^ lds32_off128(ring[SLOT + k]) ^ lds32(a);
+            ring[SLOT + k] = a;
+            best = min(best, h * cp.d_odd_inv + cp.d_odd_inv); // (h+1)/odd(d) exact-division test, superset of :298
+        }
+        if (best <= cp.d_odd_thr)
+        {
+            if (SPARSE)
+            {
+                if (npend < SCAN_PEND_MAX)
+                {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(pad_addr + 4u * npend), "r"(h0) : "memory");
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(pad_addr + 12u + npend), "r"((first_bit >> 3) + g) : "memory");
+                }
+                ++npend;
+            }
+            else
+                scan_group_exact_now(in_addr + 8 * g, out_addr + 8 * g, h0, cp.d, cp.d_odd_inv, cp.d_odd_thr, tab_lane, bits_addr, first_bit + 8 * g);
+        }
+    }
+}
+
+// One lane's 256-byte segment of a staged tile: seed, rolling hash with the group filter, re-walk of the recorded groups.
+// Deliberately NOT inlined: the 48 ring registers plus the lookups in flight need the whole register file, and a call boundary
+// makes the compiler park the tile loop's state once per tile (outside) instead of spilling ring slots inside the hot loop.
+// Returns the number of groups this lane recorded (SPARSE) — more than SCAN_PEND_MAX means the tile must be flagged as overflowed.
+template <bool SPARSE>
+__device__ __noinline__ uint32_t scan_segment(uint32_t my, uint32_t prev, uint32_t tab_lane, uint32_t bits_addr, const ChunkParams cp)
+{
+    // seed: hash of the 48 bytes in front of my segment (longtail_hpcdcchunker.c:273-279); their table addresses fill the ring
+    uint32_t h = 0;
+    uint32_t ring[SCAN_WINDOW];
+    uint32_t npend = 0;
+    const uint32_t pad = my + SCAN_SEG;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+    {
+        uint4 w = lds128(prev + 16 * j);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            const uint32_t a = __byte_perm(ws[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4));
+            h ^= rotl32(lds32(a), (47 - (16 * j + k)) & 31);
+            ring[16 * j + k] = a;
+        }
+    }
+
+    // 256 = 5 * 48 + 16 positions; the byte leaving the window at position q sits in ring slot q % 48
+    scan_step16<0, SPARSE>(ring, h, npend, pad, my, prev, 0, cp, tab_lane, bits_addr);
+    scan_step16<16, SPARSE>(ring, h, npend, pad, my + 16, prev + 16, 16, cp, tab_lane, bits_addr);
+    scan_step16<32, SPARSE>(ring, h, npend, pad, my + 32, prev + 32, 32, cp, tab_lane, bits_addr);
+#pragma unroll 1
+    for (uint32_t q = 48; q < SCAN_SEG - 16; q += 48)
+    {
+        scan_step16<0, SPARSE>(ring, h, npend, pad, my + q, my + q - 48, q, cp, tab_lane, bits_addr);
+        scan_step16<16, SPARSE>(ring, h, npend, pad, my + q + 16, my + q - 32, q + 16, cp, tab_lane, bits_addr);
+        scan_step16<32, SPARSE>(ring, h, npend, pad, my + q + 32, my + q - 16, q + 32, cp, tab_lane, bits_addr);
+    }
+    scan_step16<0, SPARSE>(ring, h, npend, pad, my + (SCAN_SEG - 16), my + (SCAN_SEG - 64), SCAN_SEG - 16, cp, tab_lane, bits_addr);
+    // the recorded groups, every lane its own (about one lane-group per tile at the default parameters)
+    if (SPARSE)
+    {
+        const uint32_t np = min(npend, SCAN_PEND_MAX);
+#pragma unroll 1
+        for (uint32_t e = 0; e < np; ++e)
+        {
+            uint32_t fb;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(fb) : "r"(pad + 12u + e));
+            fb *= 8u;
+            scan_group_exact(my + fb, fb < (uint32_t)SCAN_WINDOW ? prev + fb : my + fb - SCAN_WINDOW, lds32(pad + 4u * e), cp.d, cp.d_odd_inv,
+                             cp.d_odd_thr, tab_lane, bits_addr, fb);
+        }
+    }
+    return npend;
+}
+
 // Shared-memory layout (ScanLayout, computed on the host from the probed base of the dynamic window): the 64 KiB table is
 // placed at a shared address that is a multiple of 64 KiB, so that "table base + byte * 256 + lane * 4" is produced by the
 // single PRMT that extracts the byte — no address add per lookup.  `warps_before` per-warp buffers sit in front of the
 // table, the rest behind it.
+// SPARSE: groups that pass the filter are recorded and re-walked after the main loop (the common case, odd(d) >= 1024);
+// otherwise (tiny discriminators: most groups pass) they are re-walked on the spot.
+template <bool SPARSE>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ parts, const uint32_t* __restrict__ tile_part,
              uint32_t num_tiles, ChunkParams cp, const uint32_t* __restrict__ g_table,
@@ -71,7 +182,6 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
-    const uint32_t lane4 = lane * 4u;
 
     // bank-replicated substitution table: entry v occupies 256 B = 32 lanes x T[v] then 32 lanes x rotl(T[v],16),
     // so lane l always reads bank l and a lookup is conflict free for any byte values
@@ -88,7 +198,7 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
     __syncthreads(); // the only block-wide barrier: the table is ready
 
     const uint32_t tab = smem_u32(s_table);   // multiple of 65536 by construction
-    const uint32_t tab_lane = tab | lane4;     // bytes 2..3: table base, byte 1: free for the data byte, byte 0: lane * 4
+    const uint32_t tab_lane = tab | (lane * 4u); // bytes 2..3: table base, byte 1: free for the data byte, byte 0: lane * 4
     const uint32_t rows = smem_u32(s_mine);
     const uint32_t my = rows + (lane + 1u) * SCAN_ROW;
     const uint32_t prev = my - SCAN_ROW + (SCAN_SEG - SCAN_WINDOW);
@@ -105,12 +215,23 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
         const uint8_t* src = arena + pd.data_off + tile_off;
         // stage the tile: 512 sixteen-byte pieces, consecutive lanes fetch consecutive pieces (coalesced); bytes past the
         // end of the part are zero-filled
-#pragma unroll 4
-        for (uint32_t i = lane; i < SCAN_TILE / 16; i += 32)
+        if (tile_off + (uint32_t)SCAN_TILE <= pd.size)
         {
-            uint32_t off = tile_off + i * 16u;
-            uint32_t nb = pd.size > off ? min(16u, pd.size - off) : 0u;
-            cp_async16(rows + ((i >> 4) + 1u) * SCAN_ROW + (i & 15u) * 16u, nb ? src + i * 16u : arena, nb);
+            // interior tile (all but the last tile of a part): two base registers, sixteen copies with immediate offsets
+            const uint32_t dst0 = rows + ((lane >> 4) + 1u) * SCAN_ROW + (lane & 15u) * 16u;
+            const uint8_t* src0 = src + lane * 16u;
+#pragma unroll
+            for (uint32_t it = 0; it < SCAN_TILE / 512; ++it) cp_async16_full(dst0 + it * 2u * SCAN_ROW, src0 + it * 512u);
+        }
+        else
+        {
+#pragma unroll 4
+            for (uint32_t i = lane; i < SCAN_TILE / 16; i += 32)
+            {
+                uint32_t off = tile_off + i * 16u;
+                uint32_t nb = pd.size > off ? min(16u, pd.size - off) : 0u;
+                cp_async16(rows + ((i >> 4) + 1u) * SCAN_ROW + (i & 15u) * 16u, nb ? src + i * 16u : arena, nb);
+            }
         }
         if (lane < 3)
         {
@@ -136,47 +257,10 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
         cp_async_wait<0>();
         __syncwarp();
 
-        // seed: hash of the 48 bytes in front of my segment (longtail_hpcdcchunker.c:273-279)
-        uint32_t h = 0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
+        bool overflow = false;
         {
-            uint4 w = lds128(prev + 16 * j);
-            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-            {
-                uint32_t idx = __byte_perm(ws[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4));
-                h ^= rotl32(lds32(idx), (47 - (16 * j + k)) & 31);
-            }
-        }
-
-#pragma unroll 2
-        for (int j = 0; j < SCAN_SEG / 16; ++j)
-        {
-            const uint32_t in_addr = my + 16 * j;
-            const uint32_t out_addr = j < 3 ? prev + 16 * j : my + 16 * (j - 3);
-            const uint4 cin = lds128(in_addr);
-            const uint4 cout = lds128(out_addr);
-            const uint32_t wi[4] = {cin.x, cin.y, cin.z, cin.w};
-            const uint32_t wo[4] = {cout.x, cout.y, cout.z, cout.w};
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-            {
-                const uint32_t h0 = h;
-                uint32_t best = 0xffffffffu;
-#pragma unroll
-                for (int k = 8 * g; k < 8 * g + 8; ++k)
-                {
-                    const uint32_t sel = 0x7604 | ((k & 3) << 4);
-                    uint32_t tin = lds32(__byte_perm(wi[k >> 2], tab_lane, sel));
-                    uint32_t tout = lds32_off128(__byte_perm(wo[k >> 2], tab_lane, sel));
-                    h = rotl32(h, 1) ^ tout ^ tin;              // :295-297 with rotl(T[out],48&31) pre-rotated in the table
-                    best = min(best, h * cp.d_odd_inv + cp.d_odd_inv); // (h+1)/odd(d) exact-division test, superset of :298
-                }
-                if (best <= cp.d_odd_thr)
-                    scan_group_exact(in_addr + 8 * g, out_addr + 8 * g, h0, cp.d, cp.d_odd_inv, cp.d_odd_thr, tab_lane, bits_addr, 16 * j + 8 * g);
-            }
+            const uint32_t npend = scan_segment<SPARSE>(my, prev, tab_lane, bits_addr, cp);
+            overflow = __any_sync(0xffffffffu, npend > SCAN_PEND_MAX);
         }
         __syncwarp(); // every lane is done with the rows: the next iteration may overwrite them
 
@@ -228,7 +312,7 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
                 }
             }
         }
-        if (lane == 0) tile_count[tile] = total;
+        if (lane == 0) tile_count[tile] = overflow ? cp.slots + 1u : total; // > slots: k_hpcdc_walk hashes the queried interval itself
         part_idx = next_part;
     }
 }
@@ -431,7 +515,9 @@ cudaError_t make_scan_layout(ScanLayout* lay, cudaStream_t st)
         }
     }
     if (best_total > (uint32_t)max_optin) return cudaErrorInvalidConfiguration;
-    return cudaFuncSetAttribute(k_hpcdc_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay->total_bytes);
+    e = cudaFuncSetAttribute(k_hpcdc_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay->total_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_hpcdc_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay->total_bytes);
 }
 
 cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, const uint32_t* d_tile_part, uint32_t num_tiles,
@@ -441,7 +527,12 @@ cudaError_t launch_hpcdc_scan(const uint8_t* d_arena, const PartDesc* d_parts, c
     if (!num_tiles) return cudaSuccess;
     uint32_t grid = (num_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
     if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-    k_hpcdc_scan<<<grid, SCAN_THREADS, lay.total_bytes, st>>>(d_arena, d_parts, d_tile_part, num_tiles, cp, d_table, d_tile_count, d_tile_slots, lay);
+    uint32_t d_odd = cp.d;
+    while (d_odd && !(d_odd & 1u)) d_odd >>= 1;
+    if (d_odd >= 1024u) // expected recorded groups per lane-tile = 256 / odd(d) <= 0.25
+        k_hpcdc_scan<true><<<grid, SCAN_THREADS, lay.total_bytes, st>>>(d_arena, d_parts, d_tile_part, num_tiles, cp, d_table, d_tile_count, d_tile_slots, lay);
+    else
+        k_hpcdc_scan<false><<<grid, SCAN_THREADS, lay.total_bytes, st>>>(d_arena, d_parts, d_tile_part, num_tiles, cp, d_table, d_tile_count, d_tile_slots, lay);
     return cudaGetLastError();
 }
 
