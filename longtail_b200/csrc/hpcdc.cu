@@ -40,20 +40,23 @@ __global__ void k_tile_part(const PartDesc* __restrict__ parts, uint32_t part_co
 __device__ __forceinline__ void scan_group_exact(uint32_t in_addr, uint32_t out_addr, uint32_t h, uint32_t d, uint32_t d_odd_inv,
                                               uint32_t d_odd_thr, uint32_t tab_lane, uint32_t bitmap_row, uint32_t first_bit)
 {
-#pragma unroll 4
-    for (uint32_t k = 0; k < 8; ++k)
+    // both groups are 8-byte aligned in their rows: two 8-byte loads, then the same PRMT-formed table addresses as the main loop
+    uint32_t wi[2], wo[2];
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wi[0]), "=r"(wi[1]) : "r"(in_addr));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wo[0]), "=r"(wo[1]) : "r"(out_addr));
+    uint32_t found = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
     {
-        uint32_t in, out;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(in) : "r"(in_addr + k));
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(out) : "r"(out_addr + k));
-        h = rotl32(h, 1) ^ lds32(tab_lane + 128u + (out << 8)) ^ lds32(tab_lane + (in << 8)); // longtail_hpcdcchunker.c:295-297
-        if (h * d_odd_inv + d_odd_inv <= d_odd_thr && h % d == d - 1)                          // :298
-        {
-            uint32_t bit = first_bit + k;
-            uint32_t a = bitmap_row + (bit >> 5) * 4u;
-            uint32_t v = lds32(a) | (1u << (bit & 31));
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-        }
+        const uint32_t sel = 0x7604 | ((k & 3) << 4);
+        h = rotl32(h, 1) ^ lds32_off128(__byte_perm(wo[k >> 2], tab_lane, sel)) ^ lds32(__byte_perm(wi[k >> 2], tab_lane, sel)); // :295-297
+        if (h * d_odd_inv + d_odd_inv <= d_odd_thr && h % d == d - 1) found |= 1u << k;                                           // :298
+    }
+    if (found)
+    {
+        const uint32_t a = bitmap_row + (first_bit >> 5) * 4u; // the group lies inside one bitmap word (first_bit is a multiple of 8)
+        const uint32_t v = lds32(a) | (found << (first_bit & 31u));
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
     }
 }
 
