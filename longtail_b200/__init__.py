@@ -62,10 +62,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("LT_B200_LIB", LIB_PATH)  # development: A/B a differently built library
+    if not os.path.exists(path):
         raise LongtailB200Error(errno.ENOENT, "liblongtail_b200.so is not built: run `python -m longtail_b200.build` "
                                               "(or __graft_entry__.build()); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.lt_b200_last_error.restype = C.c_char_p
     lib.lt_b200_last_error.argtypes = [C.c_void_p]
     lib.lt_b200_launch_count.restype = C.c_uint64

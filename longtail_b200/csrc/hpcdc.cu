@@ -271,19 +271,30 @@ k_hpcdc_scan(const uint8_t* __restrict__ arena, const PartDesc* __restrict__ par
         const uint32_t seg_first = tile_off + lane * SCAN_SEG; // part-relative position of my first byte
         uint32_t words[SCAN_SEG / 32];
         uint32_t cnt = 0;
-#pragma unroll
-        for (int w = 0; w < SCAN_SEG / 32; ++w)
         {
-            uint32_t v = s_bits[w];
-            // always clear: a candidate bit beyond the end of the part (zero-filled tail of a ragged last tile) is masked out below
-            // and must not survive into the next tile this warp scans
-            s_bits[w] = 0;
-            // a cut after byte q is position q+1; keep it only inside the part
-            uint32_t first = seg_first + 32 * w + 1;
-            if (first > pd.size) v = 0;
-            else if (first + 31 > pd.size) v &= (1u << (pd.size - first + 1)) - 1u;
-            words[w] = v;
-            cnt += __popc(v);
+            // most tiles hold no candidate at all (0.33 expected per tile at the default parameters): one vote decides
+            static_assert(SCAN_SEG / 32 == 8, "two 16-byte loads cover a lane's bitmap row");
+            const uint4 b0 = lds128(bits_addr), b1 = lds128(bits_addr + 16u);
+            words[0] = b0.x; words[1] = b0.y; words[2] = b0.z; words[3] = b0.w;
+            words[4] = b1.x; words[5] = b1.y; words[6] = b1.z; words[7] = b1.w;
+            const uint32_t orv = (b0.x | b0.y) | (b0.z | b0.w) | (b1.x | b1.y) | (b1.z | b1.w);
+            if (orv)
+            {
+#pragma unroll
+                for (int w = 0; w < SCAN_SEG / 32; ++w)
+                {
+                    uint32_t v = words[w];
+                    // always clear: a candidate bit beyond the end of the part (zero-filled tail of a ragged last tile) is masked out
+                    // below and must not survive into the next tile this warp scans
+                    s_bits[w] = 0;
+                    // a cut after byte q is position q+1; keep it only inside the part
+                    uint32_t first = seg_first + 32 * w + 1;
+                    if (first > pd.size) v = 0;
+                    else if (first + 31 > pd.size) v &= (1u << (pd.size - first + 1)) - 1u;
+                    words[w] = v;
+                    cnt += __popc(v);
+                }
+            }
         }
         const uint32_t any = __ballot_sync(0xffffffffu, cnt != 0);
         uint32_t total = 0;
