@@ -467,8 +467,8 @@ def run_b200(args):
         per_kernel = {k: {"ms_per_launch": round(v[0] / max(v[1], 1), 4), "launches": v[1],
                           "GBps": round((v[2] / max(v[1], 1)) / ((v[0] / max(v[1], 1)) / 1e3) / 1e9, 1) if v[0] > 0 else None} for k, v in prof.items()}
         # DRAM traffic per launch of the dominant kernel: (dram__bytes_read + dram__bytes_write) / algorithmic bytes as captured by
-        # `ncu --set full` on an 8 GiB launch (profiles/r01f_*_ncu.txt), applied to this run's algorithmic bytes per launch
-        ncu_traffic_ratio = {"k_blake3_leaves": (8.977670e9 + 0.338740e9) / 8.589934592e9, "k_hpcdc_scan": (8.617261e9 + 0.017702e9) / 8.589934592e9}
+        # `ncu --set full` on an 8 GiB launch (profiles/r01p_*_ncu.txt), applied to this run's algorithmic bytes per launch
+        ncu_traffic_ratio = {"k_blake3_leaves": (8.963703e9 + 0.340567e9) / 8.589934592e9, "k_hpcdc_scan": (8.609740e9 + 0.019096e9) / 8.589934592e9}
         traffic = round(kbytes / max(kn, 1) * ncu_traffic_ratio[name]) if name in ncu_traffic_ratio else None
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "GiB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -480,8 +480,8 @@ def run_b200(args):
             "hbm_roofline_frac_whole_step": round(value * GIB / 1e9 / world / peak, 4),
             "roofline": {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
-                         "traffic_source": "ncu --set full on an 8 GiB launch (profiles/r01f_leaves_ncu.txt, r01f_scan_ncu.txt): DRAM read+write / algorithmic bytes = "
-                                           "1.085 (leaves: chaining values written) and 1.005 (scan), scaled to this launch", "peak_source": peak_src,
+                         "traffic_source": "ncu --set full on an 8 GiB launch (profiles/r01p_leaves_ncu.txt, r01p_scan_ncu.txt): DRAM read+write / algorithmic bytes = "
+                                           "1.083 (leaves: chaining values written) and 1.005 (scan), scaled to this launch", "peak_source": peak_src,
                          "share_of_step": shares, "per_kernel": per_kernel,
                          "note": "algorithmic bytes = 1 B read per asset byte (SURVEY.md §8d); both hot kernels are integer-issue bound, see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
