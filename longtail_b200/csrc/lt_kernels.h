@@ -44,7 +44,7 @@ cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, con
 cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
                               const uint64_t* d_out_off, uint32_t* d_out_len, uint3* d_copy_jobs, const uint32_t* d_copy_job_start,
                               uint32_t* d_copy_job_count, uint32_t block_count, uint32_t* d_tables, cudaStream_t st);
-constexpr size_t LZ4_TABLE_BYTES_PER_BLOCK = 16384; // d_tables: one hash table per block (nullptr = shared memory, 14 warps per SM)
+constexpr size_t LZ4_TABLE_BYTES_PER_BLOCK = 32768; // d_tables: one hash table per block (nullptr = shared memory, 7 warps per SM)
 void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, const uint64_t* d_dst_off, const uint32_t* d_len,
                           uint8_t* d_out, uint32_t count, cudaStream_t st);
 

@@ -24,7 +24,7 @@ namespace ltb {
 namespace {
 
 constexpr uint32_t FULL = 0xffffffffu;
-constexpr uint32_t LZ4_TABLE_BYTES = 16384;
+constexpr uint32_t LZ4_TABLE_BYTES = 32768; // byU32: 4096 x {position, the 4 bytes at that position}; byU16: 8192 x u16 in the first half
 constexpr uint32_t LZ4_64K_LIMIT = 65536 + 11; // LZ4_64Klimit, lz4.c:710
 constexpr uint32_t LZ4_MAX_DISTANCE = 65535;
 
@@ -53,15 +53,32 @@ __device__ __forceinline__ uint32_t lz4_hash_word(uint64_t w)
     if (U16) return ((uint32_t)w * 2654435761u) >> 19;
     return (uint32_t)(((w << 24) * 889523592379ull) >> 52);
 }
-template <bool U16>
-__device__ __forceinline__ uint32_t tab_get(const uint32_t* t32, uint32_t h)
+// A byU32 entry carries the 4 bytes found at its position next to the position, so the match test of a candidate
+// (LZ4_read32(match) == LZ4_read32(ip), lz4.c:1092, :1262) needs no second dependent load from the source: table -> compare instead
+// of table -> source -> compare.  The table is this encoder's private state; what it answers is unchanged.  byU16 blocks
+// (< 64 KiB) keep plain 16-bit positions and read the source.
+struct TabEntry
 {
-    return U16 ? (uint32_t)reinterpret_cast<const uint16_t*>(t32)[h] : t32[h];
+    uint32_t pos, tag;
+};
+template <bool U16>
+__device__ __forceinline__ TabEntry tab_get(const uint32_t* t32, uint32_t h)
+{
+    TabEntry e;
+    if (U16) { e.pos = (uint32_t)reinterpret_cast<const uint16_t*>(t32)[h]; e.tag = 0; }
+    else { const uint2 v = reinterpret_cast<const uint2*>(t32)[h]; e.pos = v.x; e.tag = v.y; }
+    return e;
 }
 template <bool U16>
-__device__ __forceinline__ void tab_put(uint32_t* t32, uint32_t h, uint32_t v)
+__device__ __forceinline__ void tab_put(uint32_t* t32, uint32_t h, uint32_t v, uint32_t tag)
 {
-    if (U16) reinterpret_cast<uint16_t*>(t32)[h] = (uint16_t)v; else t32[h] = v;
+    if (U16) reinterpret_cast<uint16_t*>(t32)[h] = (uint16_t)v; else reinterpret_cast<uint2*>(t32)[h] = make_uint2(v, tag);
+}
+// does the candidate start with the 4 bytes `word`?
+template <bool U16>
+__device__ __forceinline__ bool cand_matches(const uint8_t* __restrict__ s, uint32_t cand, uint32_t tag, uint32_t word)
+{
+    return U16 ? rd32(s, cand) == word : tag == word;
 }
 
 // position of the k-th probe of a search that started at S (k = 0, 1, ...): advances are 1 for k = 0 and (63+k)>>6 after
@@ -133,11 +150,15 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
     uint32_t anchor = 0;
     if (n >= 13) // LZ4_minLength (lz4.c:1001)
     {
-        for (uint32_t i = lane; i < LZ4_TABLE_BYTES / 4; i += 32) table[i] = 0;
+        {
+            // zeroed table = every slot points at position 0 (a legal candidate, lz4.c:1004-1010), so the tags start as its 4 bytes
+            const uint32_t first4 = U16 ? 0u : rd32(src, 0);
+            for (uint32_t i = lane; i < LZ4_TABLE_BYTES / 4; i += 32) table[i] = (i & 1u) ? first4 : 0u;
+        }
         __syncwarp();
         const uint32_t mflimit_plus_one = n - 11;
         const uint32_t matchlimit = n - 5;
-        if (lane == 0) tab_put<U16>(table, lz4_hash<U16>(src, 0), 0); // lz4.c:1004-1010
+        if (lane == 0) tab_put<U16>(table, lz4_hash<U16>(src, 0), 0, rd32(src, 0)); // lz4.c:1004-1010
         __syncwarp();
         uint32_t S = 1;   // start of the current search
         uint32_t k0 = 0;  // probes of this search already committed
@@ -167,10 +188,15 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
                 const uint32_t lower = same & ((1u << lane) - 1u);
                 // candidate = what the sequential loop would find in the table: the closest lower lane of this batch with the
                 // same hash, else the committed table
-                const uint32_t from_lane = __shfl_sync(FULL, p, lower ? 31 - __clz(lower) : (int)lane);
-                const uint32_t cand = lower ? from_lane : (valid ? tab_get<U16>(table, h) : 0u);
+                const int from = lower ? 31 - __clz(lower) : (int)lane;
+                const uint32_t from_lane = __shfl_sync(FULL, p, from);
+                const uint32_t from_tag = __shfl_sync(FULL, (uint32_t)w, from);
+                TabEntry e = {0u, 0u};
+                if (!lower && valid) e = tab_get<U16>(table, h);
+                const uint32_t cand = lower ? from_lane : e.pos;
+                const uint32_t tag = lower ? from_tag : e.tag;
                 bool hit = false;
-                if (valid && (U16 || cand + LZ4_MAX_DISTANCE >= p)) hit = rd32(src, cand) == (uint32_t)w;
+                if (valid && (U16 || cand + LZ4_MAX_DISTANCE >= p)) hit = cand_matches<U16>(src, cand, tag, (uint32_t)w);
                 const uint32_t hits = __ballot_sync(FULL, hit);
                 const uint32_t valids = __ballot_sync(FULL, valid);
                 // lanes whose table write is committed: valid lanes up to and including the first hit
@@ -178,7 +204,7 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
                 const uint32_t commit = valids & (first_hit >= 31u ? FULL : ((2u << first_hit) - 1u));
                 const uint32_t group = same & commit;
                 if ((commit >> lane) & 1u)
-                    if ((31 - __clz(group)) == (int)lane) tab_put<U16>(table, h, p); // the last writer of a hash value wins
+                    if ((31 - __clz(group)) == (int)lane) tab_put<U16>(table, h, p, (uint32_t)w); // the last writer of a hash value wins
                 __syncwarp();
                 if (hits)
                 {
@@ -256,18 +282,22 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
                 anchor = ip;
                 if (ip >= mflimit_plus_one) { finished = true; break; } // lz4.c:1233
                 // fill table with ip-2, then test ip itself (lz4.c:1236-1294)
-                const uint32_t h2 = lz4_hash<U16>(src, ip - 2);
-                const uint32_t h = lz4_hash<U16>(src, ip);
-                uint32_t cand = 0;
+                const uint64_t w2 = rd64(src, ip - 2), w0 = rd64(src, ip);
+                const uint32_t h2 = lz4_hash_word<U16>(w2);
+                const uint32_t h = lz4_hash_word<U16>(w0);
+                uint32_t cand = 0, tag = 0;
                 if (lane == 0)
                 {
-                    tab_put<U16>(table, h2, ip - 2);
-                    cand = tab_get<U16>(table, h);
-                    tab_put<U16>(table, h, ip);
+                    tab_put<U16>(table, h2, ip - 2, (uint32_t)w2);
+                    const TabEntry e = tab_get<U16>(table, h);
+                    cand = e.pos;
+                    tag = e.tag;
+                    tab_put<U16>(table, h, ip, (uint32_t)w0);
                 }
                 cand = __shfl_sync(FULL, cand, 0);
+                tag = __shfl_sync(FULL, tag, 0);
                 __syncwarp();
-                if ((U16 || cand + LZ4_MAX_DISTANCE >= ip) && rd32(src, cand) == rd32(src, ip))
+                if ((U16 || cand + LZ4_MAX_DISTANCE >= ip) && cand_matches<U16>(src, cand, tag, (uint32_t)w0))
                 {
                     match = cand;
                     literals_done = true; // token = 0 literals, straight to the next match
