@@ -53,8 +53,12 @@ struct HufNode
 
 struct alignas(16) ZstdWorker
 {
-    uint32_t hash_long[1u << 17];
-    uint32_t hash_small[1u << 16];
+    // Table entries carry the bytes found at their position next to the index ({index, 8 bytes} / {index, 4 bytes}), so the match test
+    // of a candidate (MEM_read64(matchl0) == MEM_read64(ip), zstd_double_fast.c:186; MEM_read32(matchs0) == MEM_read32(ip), :207) needs
+    // no second dependent load from the source: table -> compare instead of table -> source -> compare.  The tables are this encoder's
+    // private state; what they answer is unchanged.
+    uint4 hash_long[1u << 17];  // {index, bytes 0..3, bytes 4..7, 0}
+    uint2 hash_small[1u << 16]; // {index, bytes 0..3}
     uint32_t seq_lit[ZS_MAX_SEQ], seq_len[ZS_MAX_SEQ], seq_off[ZS_MAX_SEQ];
     uint8_t lits[ZS_BLOCK_MAX + 64];
     uint8_t ll_code[ZS_MAX_SEQ + 6], of_code[ZS_MAX_SEQ + 6], ml_code[ZS_MAX_SEQ + 6];
@@ -1108,11 +1112,13 @@ __device__ uint32_t entropy_compress_w(ZstdWorker* W, WarpShared* sh, uint8_t* d
 // ================================================================== double-fast matcher
 
 __device__ __forceinline__ uint32_t hash_long(uint64_t v, uint32_t bits) { return (uint32_t)((v * 0xCF1BBCDCB7A56463ull) >> (64 - bits)); }
-__device__ __forceinline__ uint32_t hash_short(const uint8_t* s, uint32_t pos, uint32_t bits, uint32_t mls) // zstd_compress_internal.h:803-841
+__device__ __forceinline__ uint32_t hash_short_w(uint64_t w, uint32_t bits, uint32_t mls) // zstd_compress_internal.h:803-841, from the 8 bytes at the position
 {
-    if (mls == 5) return (uint32_t)(((rd64(s, pos) << 24) * 889523592379ull) >> (64 - bits));
-    return (rd32(s, pos) * 2654435761u) >> (32 - bits);
+    if (mls == 5) return (uint32_t)(((w << 24) * 889523592379ull) >> (64 - bits));
+    return ((uint32_t)w * 2654435761u) >> (32 - bits);
 }
+__device__ __forceinline__ uint4 entry_long(uint32_t index, uint64_t w) { return make_uint4(index, (uint32_t)w, (uint32_t)(w >> 32), 0u); }
+__device__ __forceinline__ uint2 entry_short(uint32_t index, uint64_t w) { return make_uint2(index, (uint32_t)w); }
 // ZSTD_count (zstd_compress_internal.h:744-767) with all lanes: common bytes of s[a..) and s[b..), a > b, a bounded by end
 __device__ uint32_t count_equal_w(const uint8_t* __restrict__ s, uint32_t a, uint32_t b, uint32_t end, uint32_t lane)
 {
@@ -1173,8 +1179,8 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
                                   uint32_t* lit_total, uint32_t lane)
 {
     const uint32_t hl_bits = W->hash_log, hs_bits = W->chain_log, mls = W->min_match;
-    uint32_t* const hash_l = W->hash_long;
-    uint32_t* const hash_s = W->hash_small;
+    uint4* const hash_l = W->hash_long;
+    uint2* const hash_s = W->hash_small;
     uint8_t* const lits = W->lits;
     const uint32_t max_dist = 1u << W->window_log;
     const uint32_t dict_limit = W->dict_limit;
@@ -1202,7 +1208,7 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
         uint32_t q_ip = ip, q_ip1 = ip + 1, q_step = 1, q_next = ip + 256; // kSearchStrength = 8 (:35)
         bool found = false, finished = false;
         uint32_t P = 0, P1 = 0, f_step = 0, f_type = 0, f_cand = 0, hl1 = 0, idxl1 = 0;
-        uint64_t w_f = 0, w1 = 0;
+        uint64_t w_f = 0, w1 = 0, tagl1 = 0;
         for (;;) // batches of 32 speculative probes
         {
             // lane k's iteration: position cp, next position cp1, stride in force cs
@@ -1226,23 +1232,31 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
             const bool valid = (int32_t)cp1 <= ilimit;    // the sequential loop executes this iteration
             const uint64_t w = readable ? rd64(s, cp) : 0ull;
             const uint32_t hl = readable ? hash_long(w, hl_bits) : 0xffffffffu - lane;
-            const uint32_t hs = readable ? (mls == 5 ? (uint32_t)(((w << 24) * 889523592379ull) >> (64 - hs_bits)) : ((uint32_t)w * 2654435761u) >> (32 - hs_bits))
-                                         : 0xffffffffu - lane;
+            const uint32_t hs = readable ? hash_short_w(w, hs_bits, mls) : 0xffffffffu - lane;
             const uint32_t valids = __ballot_sync(FULL, valid);
             const uint32_t below = (1u << lane) - 1u;
             const uint32_t same_l = __match_any_sync(FULL, hl);
             const uint32_t same_s = __match_any_sync(FULL, hs);
             const uint32_t low_l = same_l & valids & below, low_s = same_s & valids & below;
-            const uint32_t from_l = __shfl_sync(FULL, cp, low_l ? 31 - __clz(low_l) : (int)lane);
-            const uint32_t from_s = __shfl_sync(FULL, cp, low_s ? 31 - __clz(low_s) : (int)lane);
-            const uint32_t cand_l = low_l ? from_l + 2 : (readable ? hash_l[hl] : 0u);
-            const uint32_t cand_s = low_s ? from_s + 2 : (readable ? hash_s[hs] : 0u);
+            const int src_l = low_l ? 31 - __clz(low_l) : (int)lane, src_s = low_s ? 31 - __clz(low_s) : (int)lane;
+            const uint32_t from_l = __shfl_sync(FULL, cp, src_l);
+            const uint32_t from_s = __shfl_sync(FULL, cp, src_s);
+            const uint64_t from_wl = __shfl_sync(FULL, w, src_l);
+            const uint32_t from_ws = __shfl_sync(FULL, (uint32_t)w, src_s);
+            uint4 el = make_uint4(0u, 0u, 0u, 0u);
+            uint2 es = make_uint2(0u, 0u);
+            if (!low_l && readable) el = hash_l[hl];
+            if (!low_s && readable) es = hash_s[hs];
+            const uint32_t cand_l = low_l ? from_l + 2 : el.x;
+            const uint32_t cand_s = low_s ? from_s + 2 : es.x;
+            const uint64_t tag_l = low_l ? from_wl : ((uint64_t)el.y | ((uint64_t)el.z << 32)); // the 8 bytes at the long candidate
+            const uint32_t tag_s = low_s ? from_ws : es.y;                                       // the 4 bytes at the short candidate
             uint32_t type = 0; // 1 repcode at ip+1, 2 long match at ip, 3 short match at ip (then the long match at ip1 is preferred)
             if (valid)
             {
                 if (offset_1 > 0 && rd32(s, cp + 1 - offset_1) == (uint32_t)(w >> 8)) type = 1;
-                else if (cand_l > lowest_index && rd64(s, cand_l - 2) == w) type = 2;
-                else if (cand_s > lowest_index && rd32(s, cand_s - 2) == (uint32_t)w) type = 3;
+                else if (cand_l > lowest_index && tag_l == w) type = 2;
+                else if (cand_s > lowest_index && tag_s == (uint32_t)w) type = 3;
             }
             const uint32_t hits = __ballot_sync(FULL, type != 0);
             const uint32_t first = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
@@ -1250,8 +1264,8 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
             __syncwarp(); // every table read of the batch precedes every table write
             if ((commit >> lane) & 1u)
             {
-                if ((31 - __clz(same_l & commit)) == (int)lane) hash_l[hl] = cp + 2; // the last writer of a slot wins
-                if ((31 - __clz(same_s & commit)) == (int)lane) hash_s[hs] = cp + 2;
+                if ((31 - __clz(same_l & commit)) == (int)lane) hash_l[hl] = entry_long(cp + 2, w); // the last writer of a slot wins
+                if ((31 - __clz(same_s & commit)) == (int)lane) hash_s[hs] = entry_short(cp + 2, w);
             }
             __syncwarp();
             if (hits)
@@ -1267,13 +1281,16 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
                     // the next lane probed ip1: its hash and its (batch-resolved) long candidate are hl1 / idxl1 of :175, :199
                     hl1 = __shfl_sync(FULL, hl, first + 1);
                     idxl1 = __shfl_sync(FULL, cand_l, first + 1);
+                    tagl1 = __shfl_sync(FULL, tag_l, first + 1);
                     w1 = __shfl_sync(FULL, w, first + 1);
                 }
                 else
                 {
                     w1 = rd64(s, P1);
                     hl1 = hash_long(w1, hl_bits);
-                    idxl1 = hash_l[hl1];
+                    const uint4 e1 = hash_l[hl1];
+                    idxl1 = e1.x;
+                    tagl1 = (uint64_t)e1.y | ((uint64_t)e1.z << 32);
                 }
                 found = true;
                 break;
@@ -1307,7 +1324,7 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
                 m = f_cand - 2;
                 m_len = count_equal_w(s, ip + 8, m + 8, iend, lane) + 8;
             }
-            else if (idxl1 > lowest_index && rd64(s, idxl1 - 2) == w1) // _search_next_long (:238-259)
+            else if (idxl1 > lowest_index && tagl1 == w1) // _search_next_long (:238-259)
             {
                 ip = P1;
                 m = idxl1 - 2;
@@ -1324,7 +1341,7 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
             m_len += back;
             offset_2 = offset_1;
             offset_1 = offset;
-            if (f_step < 4 && lane == 0) hash_l[hl1] = P1 + 2; // :261-273
+            if (f_step < 4 && lane == 0) hash_l[hl1] = entry_long(P1 + 2, w1); // :261-273
         }
         {
             const uint32_t ll = ip - anchor;
@@ -1340,14 +1357,15 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
         {
             // complementary insertions (:286-291), in the reference's order; all lanes compute, lane 0 stores
             const uint32_t insert = curr + 2; // an index; its position is curr
-            const uint32_t h_a = hash_long(rd64(s, insert - 2), hl_bits), h_b = hash_long(rd64(s, ip - 2), hl_bits);
-            const uint32_t h_c = hash_short(s, insert - 2, hs_bits, mls), h_d = hash_short(s, ip - 1, hs_bits, mls);
+            const uint64_t w_a = rd64(s, insert - 2), w_b = rd64(s, ip - 2), w_d = rd64(s, ip - 1);
+            const uint32_t h_a = hash_long(w_a, hl_bits), h_b = hash_long(w_b, hl_bits);
+            const uint32_t h_c = hash_short_w(w_a, hs_bits, mls), h_d = hash_short_w(w_d, hs_bits, mls);
             if (lane == 0)
             {
-                hash_l[h_a] = insert;
-                hash_l[h_b] = ip;     // index of position ip - 2
-                hash_s[h_c] = insert;
-                hash_s[h_d] = ip + 1; // index of position ip - 1
+                hash_l[h_a] = entry_long(insert, w_a);
+                hash_l[h_b] = entry_long(ip, w_b);      // index of position ip - 2
+                hash_s[h_c] = entry_short(insert, w_a);
+                hash_s[h_d] = entry_short(ip + 1, w_d); // index of position ip - 1
             }
             // immediate repcodes (:294-308)
             while ((int32_t)ip <= ilimit && offset_2 > 0 && rd32(s, ip) == rd32(s, ip - offset_2))
@@ -1357,8 +1375,8 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
                 const uint64_t wi = rd64(s, ip);
                 if (lane == 0)
                 {
-                    hash_s[hash_short(s, ip, hs_bits, mls)] = ip + 2;
-                    hash_l[hash_long(wi, hl_bits)] = ip + 2;
+                    hash_s[hash_short_w(wi, hs_bits, mls)] = entry_short(ip + 2, wi);
+                    hash_l[hash_long(wi, hl_bits)] = entry_long(ip + 2, wi);
                     W->seq_lit[nb] = 0; W->seq_len[nb] = r_len; W->seq_off[nb] = 1;
                 }
                 nb++;
@@ -1411,9 +1429,9 @@ __device__ uint32_t zstd_compress_frame(ZstdWorker* W, WarpShared* sh, const uin
     const uint32_t window_log = W->window_log;
     {
         // fresh context: both tables start zeroed (ZSTD_reset_matchState, zstd_compress.c:1970-2050)
-        uint4* hl = reinterpret_cast<uint4*>(W->hash_long);
+        uint4* hl = W->hash_long;
         uint4* hs = reinterpret_cast<uint4*>(W->hash_small);
-        const uint32_t nl = (1u << W->hash_log) / 4, ns = (1u << W->chain_log) / 4;
+        const uint32_t nl = 1u << W->hash_log, ns = (1u << W->chain_log) / 2;
         for (uint32_t i = lane; i < nl; i += 32) hl[i] = make_uint4(0, 0, 0, 0);
         for (uint32_t i = lane; i < ns; i += 32) hs[i] = make_uint4(0, 0, 0, 0);
     }
