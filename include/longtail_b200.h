@@ -258,6 +258,27 @@ LT_B200_EXPORT int lt_b200_zstd_compress_host(lt_b200_context* context, uint32_t
 LT_B200_EXPORT int lt_b200_zstd_decompress_host(lt_b200_context* context, uint32_t count, const void* const* src, const uint32_t* src_size,
                                                 void* const* dst, const uint64_t* dst_capacity, uint64_t* out_size);
 
+/* ---- the step after PutStoredBlock: an on-disk block sink in the layout of the reference's fsblockstore
+ * (lib/fsblockstore/longtail_fsblockstore.c): <store>/chunks/<4 hex>/0x<16 hex>.lrb per block (:66-129) and <store>/store.lsi, the
+ * serialised Longtail_StoreIndex (src/longtail.c:8913-8977).  An unmodified longtail opens the directory with
+ * Longtail_CreateFSBlockStoreAPI.  Host code, no GPU needed.
+ *   open     creates the directory; `writer_threads` file writers work behind the sink (0 = write inside the sink call)
+ *   sink     an lt_b200_block_sink (pass the store as `user` to lt_b200_write_blocks_device): existing block files are not rewritten
+ *            (SafeWriteStoredBlock :243-320), new ones are written under a temporary name and renamed
+ *   flush    waits for the writers; store.lsi := blocks added since the last flush, in sink order, merged in front of the index on disk
+ *            (UpdateStoreIndex :330-352, Longtail_MergeStoreIndex src/longtail.c:9155-9290) under flock(store.lsi.sync)
+ *   existing_chunks  the chunk hashes store.lsi lists — the `existing_hashes` of lt_b200_missing_chunks (out_hashes may be NULL to size)
+ *   close    flush + release */
+#define LT_B200_STORE_INDEX_VERSION 0x01000000u /* LONGTAIL_STORE_INDEX_VERSION_1_0_0, src/longtail.c:16-23 */
+typedef struct lt_b200_fs_store lt_b200_fs_store;
+LT_B200_EXPORT int lt_b200_fs_store_open(const char* store_path, uint32_t writer_threads, lt_b200_fs_store** out_store);
+LT_B200_EXPORT int lt_b200_fs_store_sink(void* store, const struct lt_b200_stored_block_view* block);
+LT_B200_EXPORT int lt_b200_fs_store_flush(lt_b200_fs_store* store);
+LT_B200_EXPORT int lt_b200_fs_store_existing_chunks(lt_b200_fs_store* store, uint64_t* out_hashes, uint32_t capacity, uint32_t* out_count);
+LT_B200_EXPORT int lt_b200_fs_store_stats(lt_b200_fs_store* store, uint64_t* out_blocks_written, uint64_t* out_bytes_written,
+                                          uint64_t* out_blocks_skipped);
+LT_B200_EXPORT int lt_b200_fs_store_close(lt_b200_fs_store* store);
+
 /* Arena offsets of the unique chunks (first occurrences, VersionIndex order) found by the last lt_b200_index_device_assets
  * call on this context — the `chunk_arena_offsets` of a fresh-store lt_b200_write_blocks_device. */
 LT_B200_EXPORT int lt_b200_unique_chunk_offsets(lt_b200_context* context, uint64_t* out_offsets, uint32_t count);

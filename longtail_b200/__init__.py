@@ -29,6 +29,56 @@ class LongtailB200Error(RuntimeError):
         self.errno = code
 
 
+class FsStore:
+    """On-disk block sink in the reference's fsblockstore layout (include/longtail_b200.h, lt_b200_fs_store_*): host code, no GPU."""
+
+    def __init__(self, path, writer_threads=4):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        err = self.lib.lt_b200_fs_store_open(os.fsencode(path), C.c_uint32(writer_threads), C.byref(self.handle))
+        if err:
+            raise LongtailB200Error(err, "fs_store_open(%s)" % path)
+
+    def put(self, block_hash, image):
+        """hand one serialised stored block (bytes) to the sink, as lt_b200_write_blocks_device would"""
+        buf = np.frombuffer(image, dtype=np.uint8)
+        n = int(np.frombuffer(image, dtype=np.uint32, count=1, offset=12)[0])
+        tag = int(np.frombuffer(image, dtype=np.uint32, count=1, offset=16)[0])
+        v = StoredBlockView(int(block_hash), buf.ctypes.data, buf.size, n, tag, 0, 0)
+        err = self.lib.lt_b200_fs_store_sink(self.handle, C.byref(v))
+        if err:
+            raise LongtailB200Error(err, "fs_store_sink")
+
+    def flush(self):
+        err = self.lib.lt_b200_fs_store_flush(self.handle)
+        if err:
+            raise LongtailB200Error(err, "fs_store_flush")
+
+    def existing_chunks(self):
+        n = C.c_uint32(0)
+        err = self.lib.lt_b200_fs_store_existing_chunks(self.handle, None, 0, C.byref(n))
+        if err:
+            raise LongtailB200Error(err, "fs_store_existing_chunks")
+        out = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            err = self.lib.lt_b200_fs_store_existing_chunks(self.handle, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+            if err:
+                raise LongtailB200Error(err, "fs_store_existing_chunks")
+        return out
+
+    def stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.lib.lt_b200_fs_store_stats(self.handle, C.byref(a), C.byref(b), C.byref(c))
+        return {"blocks_written": a.value, "bytes_written": b.value, "blocks_skipped": c.value}
+
+    def close(self):
+        if self.handle:
+            err = self.lib.lt_b200_fs_store_close(self.handle)
+            self.handle = C.c_void_p()
+            if err:
+                raise LongtailB200Error(err, "fs_store_close")
+
+
 class Range(C.Structure):
     _fields_ = [("arena_offset", C.c_uint64), ("size", C.c_uint32), ("tag", C.c_uint32)]
 
@@ -98,6 +148,12 @@ def load_library():
     lib.lt_b200_write_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_uint32, C.c_uint32, C.c_uint32, BLOCK_SINK, C.c_void_p]
     lib.lt_b200_unique_chunk_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.lt_b200_fs_store_open.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.lt_b200_fs_store_sink.argtypes = [C.c_void_p, C.POINTER(StoredBlockView)]
+    lib.lt_b200_fs_store_flush.argtypes = [C.c_void_p]
+    lib.lt_b200_fs_store_close.argtypes = [C.c_void_p]
+    lib.lt_b200_fs_store_existing_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.lt_b200_fs_store_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.lt_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.lt_b200_profile_reset.argtypes = [C.c_void_p]
     lib.lt_b200_profile_read.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -320,12 +376,20 @@ class Context:
         return out[:h.size].astype(bool)
 
     def write_blocks_device(self, dptr, arena_size, chunk_hashes, chunk_sizes, chunk_tags, chunk_offsets, max_block_size=8388608,
-                            max_chunks_per_block=1024, hash_type=HASH_BLAKE3, keep_bytes=True):
-        """-> list of (block_hash, serialised stored block bytes | size) in store order"""
+                            max_chunks_per_block=1024, hash_type=HASH_BLAKE3, keep_bytes=True, fs_store=None):
+        """-> list of (block_hash, serialised stored block bytes | size) in store order; with fs_store (an FsStore) the blocks go
+        straight to its C sink (no Python in the loop) and the result is None"""
         h = np.ascontiguousarray(chunk_hashes, dtype=np.uint64)
         s = np.ascontiguousarray(chunk_sizes, dtype=np.uint32)
         t = np.ascontiguousarray(chunk_tags, dtype=np.uint32)
         o = np.ascontiguousarray(chunk_offsets, dtype=np.uint64)
+        if fs_store is not None:
+            cb = C.cast(self.lib.lt_b200_fs_store_sink, BLOCK_SINK)
+            self._check(self.lib.lt_b200_write_blocks_device(self.handle, C.c_void_p(dptr), int(arena_size), h.size, h.ctypes.data_as(C.c_void_p),
+                                                             s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                                                             int(hash_type), int(max_block_size), int(max_chunks_per_block), cb, fs_store.handle),
+                        "write_blocks_device")
+            return None
         blocks = []
 
         def sink(_user, view):

@@ -22,12 +22,14 @@
 #include "lib/brotli/longtail_brotli.h"
 #include "lib/compressblockstore/longtail_compressblockstore.h"
 #include "lib/compressionregistry/longtail_full_compression_registry.h"
+#include "lib/filestorage/longtail_filestorage.h"
 #include "lib/fsblockstore/longtail_fsblockstore.h"
 #include "lib/memstorage/longtail_memstorage.h"
 #include "lib/longtail_platform.h"
 
 #include <errno.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -561,3 +563,156 @@ REF_EXPORT int ref_upsync_existing(uint32_t count, const char** paths, const uin
                        keep_bytes, out_buf, out_size, seconds, out_stored_bytes, existing_count, existing_hashes);
 }
 
+
+/* ---------------------------------------------------------------- upsync into an fsblockstore directory
+ * Reference behaviour the B200 fs sink (longtail_b200/csrc/fs_store.cpp) is checked against: cmd/main.c:UpSync (:1052-1153) with
+ * compressblockstore -> fsblockstore -> filestorage.  The existing content is asked from the store itself, so a second call on the
+ * same directory is an incremental upsync. */
+struct sync_existing
+{
+    struct Longtail_AsyncGetExistingContentAPI api;
+    struct Longtail_StoreIndex* index;
+    int err;
+    volatile int done;
+};
+static void sync_existing_done(struct Longtail_AsyncGetExistingContentAPI* api, struct Longtail_StoreIndex* index, int err)
+{
+    struct sync_existing* s = (struct sync_existing*)api;
+    s->index = index;
+    s->err = err;
+    __sync_synchronize();
+    s->done = 1;
+}
+struct sync_flush
+{
+    struct Longtail_AsyncFlushAPI api;
+    int err;
+    volatile int done;
+};
+static void sync_flush_done(struct Longtail_AsyncFlushAPI* api, int err)
+{
+    struct sync_flush* s = (struct sync_flush*)api;
+    s->err = err;
+    __sync_synchronize();
+    s->done = 1;
+}
+struct sync_get
+{
+    struct Longtail_AsyncGetStoredBlockAPI api;
+    struct Longtail_StoredBlock* block;
+    int err;
+    volatile int done;
+};
+static void sync_get_done(struct Longtail_AsyncGetStoredBlockAPI* api, struct Longtail_StoredBlock* block, int err)
+{
+    struct sync_get* s = (struct sync_get*)api;
+    s->block = block;
+    s->err = err;
+    __sync_synchronize();
+    s->done = 1;
+}
+
+REF_EXPORT int ref_upsync_to_dir(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
+                                 const uint16_t* perms, const uint32_t* tags, uint32_t hash_type,
+                                 uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block,
+                                 uint32_t workers, const char* dir, uint32_t* out_blocks_written)
+{
+    struct Longtail_HashAPI* hash = make_hash(hash_type);
+    if (!hash) return EINVAL;
+    struct Longtail_JobAPI* job = Longtail_CreateBikeshedJobAPI(workers, 0);
+    struct Longtail_ChunkerAPI* chunker = Longtail_CreateHPCDCChunkerAPI();
+    struct Longtail_StorageAPI* storage = make_asset_storage(count, paths, datas, sizes);
+    struct Longtail_FileInfos* fi = make_file_infos(count, paths, sizes, perms);
+    struct Longtail_CompressionRegistryAPI* registry = Longtail_CreateFullCompressionRegistry();
+    struct Longtail_StorageAPI* fs = Longtail_CreateFSStorageAPI();
+    struct Longtail_BlockStoreAPI* fs_store = Longtail_CreateFSBlockStoreAPI(job, fs, dir, 0, 0);
+    struct Longtail_BlockStoreAPI* store = Longtail_CreateCompressBlockStoreAPI(fs_store, registry);
+    struct Longtail_VersionIndex* vi = 0;
+    struct Longtail_StoreIndex* missing = 0;
+    struct sync_existing ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.api.OnComplete = sync_existing_done;
+    int err = Longtail_CreateVersionIndex(storage, hash, chunker, job, 0, 0, 0, "root", fi, tags, target_chunk_size, 0, &vi);
+    if (!err) err = store->GetExistingContent(store, *vi->m_ChunkCount, vi->m_ChunkHashes, 0, &ex.api);
+    if (!err)
+    {
+        while (!ex.done) sched_yield();
+        err = ex.err;
+    }
+    if (!err) err = Longtail_CreateMissingContent(hash, ex.index, vi, max_block_size, max_chunks_per_block, &missing);
+    if (!err && out_blocks_written) *out_blocks_written = *missing->m_BlockCount;
+    if (!err) err = Longtail_WriteContent(storage, store, job, 0, 0, 0, missing, vi, "root");
+    if (!err)
+    {
+        struct sync_flush fl;
+        memset(&fl, 0, sizeof(fl));
+        fl.api.OnComplete = sync_flush_done;
+        err = store->Flush(store, &fl.api);
+        if (!err)
+        {
+            while (!fl.done) sched_yield();
+            err = fl.err;
+        }
+    }
+    Longtail_Free(missing);
+    Longtail_Free(ex.index);
+    Longtail_Free(vi);
+    free(fi);
+    SAFE_DISPOSE_API(store);
+    SAFE_DISPOSE_API(fs_store);
+    SAFE_DISPOSE_API(fs);
+    SAFE_DISPOSE_API(registry);
+    SAFE_DISPOSE_API(storage);
+    SAFE_DISPOSE_API(chunker);
+    SAFE_DISPOSE_API(job);
+    SAFE_DISPOSE_API(hash);
+    return err;
+}
+
+/* The UNMODIFIED reference opens `dir` as a block store (fsblockstore behind compressblockstore), takes the block list from store.lsi and
+ * reads every block back, decompressed.  out[0] = blocks, out[1] = chunks, out[2] = uncompressed payload bytes,
+ * out[3] = order-independent digest (sum over blocks of fnv1a(block hash, chunk hashes, chunk sizes, payload)). */
+REF_EXPORT int ref_read_store_dir(const char* dir, uint64_t out[4])
+{
+    struct Longtail_JobAPI* job = Longtail_CreateBikeshedJobAPI(0, 0);
+    struct Longtail_CompressionRegistryAPI* registry = Longtail_CreateFullCompressionRegistry();
+    struct Longtail_StorageAPI* fs = Longtail_CreateFSStorageAPI();
+    struct Longtail_BlockStoreAPI* fs_store = Longtail_CreateFSBlockStoreAPI(job, fs, dir, 0, 0);
+    struct Longtail_BlockStoreAPI* store = Longtail_CreateCompressBlockStoreAPI(fs_store, registry);
+    struct Longtail_StoreIndex* index = 0;
+    char* index_path = fs->ConcatPath(fs, dir, "store.lsi");
+    int err = Longtail_ReadStoreIndex(fs, index_path, &index);
+    Longtail_Free(index_path);
+    memset(out, 0, sizeof(uint64_t) * 4);
+    for (uint32_t b = 0; !err && b < *index->m_BlockCount; ++b)
+    {
+        struct sync_get g;
+        memset(&g, 0, sizeof(g));
+        g.api.OnComplete = sync_get_done;
+        err = store->GetStoredBlock(store, index->m_BlockHashes[b], &g.api);
+        if (err) break;
+        while (!g.done) sched_yield();
+        err = g.err;
+        if (err) break;
+        const struct Longtail_BlockIndex* bi = g.block->m_BlockIndex;
+        const uint32_t n = *bi->m_ChunkCount;
+        if (*bi->m_BlockHash != index->m_BlockHashes[b] || n != index->m_BlockChunkCounts[b]) err = EBADF;
+        uint64_t h = 1469598103934665603ull;
+        const uint8_t* parts[4] = {(const uint8_t*)bi->m_BlockHash, (const uint8_t*)bi->m_ChunkHashes, (const uint8_t*)bi->m_ChunkSizes, (const uint8_t*)g.block->m_BlockData};
+        const size_t lens[4] = {8, 8 * (size_t)n, 4 * (size_t)n, g.block->m_BlockChunksDataSize};
+        for (int k = 0; k < 4; ++k)
+            for (size_t i = 0; i < lens[k]; ++i) { h ^= parts[k][i]; h *= 1099511628211ull; }
+        out[0] += 1;
+        out[1] += n;
+        out[2] += g.block->m_BlockChunksDataSize;
+        out[3] += h;
+        if (g.block->Dispose) g.block->Dispose(g.block);
+    }
+    Longtail_Free(index);
+    SAFE_DISPOSE_API(store);
+    SAFE_DISPOSE_API(fs_store);
+    SAFE_DISPOSE_API(fs);
+    SAFE_DISPOSE_API(registry);
+    SAFE_DISPOSE_API(job);
+    return err;
+}

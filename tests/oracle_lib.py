@@ -276,3 +276,25 @@ class Reference:
             return list(secs), stored.value
         res = parse_upsync(out)
         return (res, list(secs)) if want_seconds else res
+
+
+def ref_upsync_to_dir(ref, assets, target_chunk_size, directory, max_block_size=8388608, max_chunks_per_block=1024, hash_type=HASH_BLAKE3,
+                      tags=None, perms=None, workers=0):
+    """the unmodified reference's upsync into an fsblockstore directory (incremental when the directory already holds a store);
+    -> number of blocks it wrote"""
+    a = _AssetArgs(assets, tags, perms)
+    written = C.c_uint32(0)
+    err = ref.lib.ref_upsync_to_dir(C.c_uint32(a.n), a.paths, a.datas, a.sizes, a.perms, a.tags, C.c_uint32(hash_type), C.c_uint32(target_chunk_size),
+                                    C.c_uint32(max_block_size), C.c_uint32(max_chunks_per_block), C.c_uint32(workers), directory.encode(),
+                                    C.byref(written))
+    assert err == 0, err
+    return written.value
+
+
+def ref_read_store_dir(ref, directory):
+    """the unmodified reference opens the directory as a block store and reads every block of store.lsi back (decompressed)
+    -> (blocks, chunks, payload bytes, order-independent digest)"""
+    out = (C.c_uint64 * 4)()
+    err = ref.lib.ref_read_store_dir(directory.encode(), out)
+    assert err == 0, err
+    return tuple(int(x) for x in out)

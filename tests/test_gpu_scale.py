@@ -118,3 +118,54 @@ def test_incremental_upsync_missing_chunks(workload):
     assert len(blocks) == len(want_blocks) and len(blocks) > 30
     for (h, got), (hw, want) in zip(blocks, want_blocks):
         assert h == hw and got == want, "block %016x differs" % hw
+
+
+def test_upsync_to_disk_matches_reference_fsblockstore(workload, tmp_path):
+    """lt_b200_write_blocks_device -> lt_b200_fs_store_sink (C to C, writer threads) leaves the same directory as
+    the reference's compressblockstore -> fsblockstore: every chunks/xxxx/0x....lrb and store.lsi byte for byte; then an incremental
+    upsync of a changed version (existing chunks from store.lsi -> lt_b200_missing_chunks -> only the new blocks) does too, and the
+    unmodified reference reads both stores back identically"""
+    import longtail_b200
+    w = workload
+    ctx = w["ctx"]
+    n = 40  # ~450 MiB of the set
+    assets, sizes, offs, tags = w["assets"][:n], w["sizes"][:n], w["offs"][:n], w["tags"][:n]
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "ref")
+    ref = ol.Reference()
+
+    def tree(root):
+        out = {}
+        for d, _, files in os.walk(root):
+            for f in files:
+                if f != "store.lsi.sync":
+                    out[os.path.relpath(os.path.join(d, f), root)] = open(os.path.join(d, f), "rb").read()
+        return out
+
+    def upsync_ours(count):
+        al = longtail_b200.AssetList([p for p, _ in assets[:count]], sizes[:count])
+        v = ctx.index_device_assets(w["arena"], w["arena_bytes"], al, offs[:count], tags[:count], target_chunk_size=TARGET)
+        vi = longtail_b200.parse_version_index(v)
+        uoff = ctx.unique_chunk_offsets(vi["chunk_count"])
+        st = longtail_b200.FsStore(ours, writer_threads=4)
+        missing = ctx.missing_chunks(vi["chunk_hashes"], st.existing_chunks())
+        ctx.write_blocks_device(w["arena"], w["arena_bytes"], vi["chunk_hashes"][missing], vi["chunk_sizes"][missing], vi["chunk_tags"][missing],
+                                uoff[missing], fs_store=st)
+        st.flush()
+        stats = st.stats()
+        st.close()
+        return stats
+
+    s1 = upsync_ours(25)
+    n1 = ol.ref_upsync_to_dir(ref, assets[:25], TARGET, theirs, tags=tags[:25], workers=0)
+    assert s1["blocks_written"] == n1 and n1 > 10
+    a, b = tree(ours), tree(theirs)
+    assert sorted(a) == sorted(b) and len(a) == n1 + 1
+    assert all(a[k] == b[k] for k in a), [k for k in a if a[k] != b[k]][:3]
+    # the version grows by 15 assets (half of their segments are shared with what the store holds)
+    s2 = upsync_ours(n)
+    n2 = ol.ref_upsync_to_dir(ref, assets, TARGET, theirs, tags=tags, workers=0)
+    assert s2["blocks_written"] == n2 and n2 > 5 and s2["blocks_skipped"] == 0
+    a, b = tree(ours), tree(theirs)
+    assert sorted(a) == sorted(b) and len(a) == n1 + n2 + 1
+    assert all(a[k] == b[k] for k in a), [k for k in a if a[k] != b[k]][:3]
+    assert ol.ref_read_store_dir(ref, ours) == ol.ref_read_store_dir(ref, theirs)
