@@ -179,6 +179,33 @@ def compress_leg(ctx, torch, stream, codec, gib, cpu_sample_gib, want_cpu):
                "d2h_bytes": stored, "note": "value = asset bytes / (index + gather + codec kernel device time); e2e adds the block-store "
                                             "hand-over: every StoredBlock copied to pinned host memory and passed to the sink"}
     out.update(res)
+    # the step after PutStoredBlock: the same write with the fsblockstore-layout disk sink (C sink, writer threads)
+    # into a RAM-backed directory, so the number is the sink's own cost (copy, open/write/rename per block, store.lsi), not a disk's
+    out["fs_store"] = None
+    try:
+        import shutil
+        import tempfile
+
+        import psutil
+        base = os.environ.get("LT_B200_FS_STORE_DIR", "/dev/shm")
+        if codec == "lz4" and os.path.isdir(base) and psutil.virtual_memory().available > 4 * res["stored_bytes"] and shutil.disk_usage(base).free > 2 * res["stored_bytes"]:
+            d = tempfile.mkdtemp(prefix="lt_b200_store_", dir=base)
+            try:
+                st = longtail_b200.FsStore(d, writer_threads=8)
+                t4 = time.perf_counter()
+                ctx.write_blocks_device(arena, arena_bytes, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"], uoff, fs_store=st)
+                st.flush()
+                t5 = time.perf_counter()
+                stats = st.stats()
+                st.close()
+                out["fs_store"] = {"dir": base, "writer_threads": 8, "blocks_written": stats["blocks_written"], "bytes_written": stats["bytes_written"],
+                                   "write_wall_ms": round(1e3 * (t5 - t4), 1), "stored_GBps": round(stats["bytes_written"] / (t5 - t4) / 1e9, 2),
+                                   "e2e_GiBps": round(nbytes / ((t1 - t0) + (t5 - t4)) / GIB, 3),
+                                   "note": "index + WriteContent with every block written as chunks/xxxx/0x....lrb plus store.lsi (reference fsblockstore layout)"}
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+    except Exception as e:  # the sink leg is informative; the bench line must not depend on /dev/shm
+        out["fs_store"] = {"error": str(e)[:200]}
     if want_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as ol
