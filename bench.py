@@ -252,7 +252,7 @@ def run_reference(args):
     import oracle_lib as ol
     ref = ol.Reference()
     if not ref.available:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_shim.so missing (built from /root/reference by `make -C oracle ref`)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libref_shim.so missing (built from /root/reference by `make -C oracle ref`)"})
         return
     cores = ref.cpu_count()
     nbytes = int(args.cpu_gib * GIB)
@@ -263,7 +263,7 @@ def run_reference(args):
     total = sum(t)
     value = nbytes * args.steps / total / GIB
     sample = "first %.1f GiB of the %.0f GiB file, Longtail_CreateVersionIndex, bikeshed %d workers + caller" % (args.cpu_gib, args.gib, cores)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -271,7 +271,7 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 4), "unit": "GiB/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def run_b200(args):
@@ -514,7 +514,7 @@ def run_b200(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "write_content": compress,
         }
-        print(json.dumps(line))
+        emit(line)
     if host_buf is not None:
         ctx.pinned_free(host_buf)
     if arena is not None:
@@ -524,8 +524,24 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _RESULT_OUT
     args = parse_args()
+    # Libraries write banners to fd 1 (NCCL prints "NCCL version ..." there when NCCL_DEBUG is set): keep the real stdout for the result
+    # line only and send everything else to stderr.
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
