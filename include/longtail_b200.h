@@ -299,6 +299,22 @@ LT_B200_EXPORT int lt_b200_index_stream_assets(lt_b200_context* context, const s
                                                uint32_t hash_type, uint32_t target_chunk_size, lt_b200_read_batch_func read_batch,
                                                void* user, const void** out_buffer, uint64_t* out_size);
 
+/* ---- the step before the hot path: Longtail_GetFilesRecursively2 (src/longtail.c:1656-1893) over the
+ * file system and a threaded reader behind lt_b200_index_stream_assets.  Host code.
+ *   scan_directory   lists `root_path` recursively with `threads` workers; entries, their order (strcmp over the relative names before
+ *                    directories get their trailing '/'), sizes and permissions (st_mode & 0x1FF) are the reference's.  Entries that are
+ *                    neither regular files nor directories: ENOTSUP.
+ *   file_list_assets the result as the lt_b200_assets every index verb takes (valid until file_list_free)
+ *   index_file_list  CreateVersionIndex over the scanned tree: `reader_threads` threads pread the parts into the pinned staging of the
+ *                    streaming verb while the previous batch is on the device; asset_tags may be NULL */
+typedef struct lt_b200_file_list lt_b200_file_list;
+LT_B200_EXPORT int lt_b200_scan_directory(const char* root_path, uint32_t threads, lt_b200_file_list** out_list);
+LT_B200_EXPORT const struct lt_b200_assets* lt_b200_file_list_assets(const lt_b200_file_list* list);
+LT_B200_EXPORT void lt_b200_file_list_free(lt_b200_file_list* list);
+LT_B200_EXPORT int lt_b200_index_file_list(lt_b200_context* context, const lt_b200_file_list* list, const uint32_t* asset_tags,
+                                           uint32_t hash_type, uint32_t target_chunk_size, uint32_t reader_threads,
+                                           const void** out_buffer, uint64_t* out_size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,31 @@ class LongtailB200Error(RuntimeError):
         self.errno = code
 
 
+class FileList:
+    """Longtail_GetFilesRecursively2 over a real directory (lt_b200_scan_directory): entries in the reference's order; host code."""
+
+    def __init__(self, root, threads=8):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        err = self.lib.lt_b200_scan_directory(os.fsencode(root), C.c_uint32(threads), C.byref(self.handle))
+        if err:
+            raise LongtailB200Error(err, "scan_directory(%s)" % root)
+        class _Raw(C.Structure):  # Assets with path_data as a plain address (c_char_p fields stop at the first NUL)
+            _fields_ = [("asset_count", C.c_uint32), ("path_data_size", C.c_uint32), ("sizes", C.POINTER(C.c_uint64)),
+                        ("path_start_offsets", C.POINTER(C.c_uint32)), ("permissions", C.POINTER(C.c_uint16)), ("path_data", C.c_void_p)]
+        a = _Raw.from_address(self.lib.lt_b200_file_list_assets(self.handle))
+        n = a.asset_count
+        self.sizes = [int(a.sizes[i]) for i in range(n)]
+        self.permissions = [int(a.permissions[i]) for i in range(n)]
+        data = C.string_at(a.path_data, a.path_data_size)
+        self.paths = [data[a.path_start_offsets[i]:data.index(b"\0", a.path_start_offsets[i])].decode() for i in range(n)]
+
+    def close(self):
+        if self.handle:
+            self.lib.lt_b200_file_list_free(self.handle)
+            self.handle = C.c_void_p()
+
+
 class FsStore:
     """On-disk block sink in the reference's fsblockstore layout (include/longtail_b200.h, lt_b200_fs_store_*): host code, no GPU."""
 
@@ -148,6 +173,12 @@ def load_library():
     lib.lt_b200_write_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_uint32, C.c_uint32, C.c_uint32, BLOCK_SINK, C.c_void_p]
     lib.lt_b200_unique_chunk_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.lt_b200_scan_directory.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.lt_b200_file_list_assets.restype = C.c_void_p
+    lib.lt_b200_file_list_assets.argtypes = [C.c_void_p]
+    lib.lt_b200_file_list_free.argtypes = [C.c_void_p]
+    lib.lt_b200_index_file_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_uint64)]
     lib.lt_b200_fs_store_open.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
     lib.lt_b200_fs_store_sink.argtypes = [C.c_void_p, C.POINTER(StoredBlockView)]
     lib.lt_b200_fs_store_flush.argtypes = [C.c_void_p]
@@ -489,6 +520,15 @@ class Context:
         self._check(self.lib.lt_b200_index_device_assets(self.handle, C.c_void_p(dptr), int(arena_size), C.byref(st), offs.ctypes.data_as(C.c_void_p),
                                                          None if tg is None else tg.ctypes.data_as(C.c_void_p), int(hash_type),
                                                          int(target_chunk_size), C.byref(buf), C.byref(size)), "index_device_assets")
+        return self._result(buf, size, copy)
+
+    def index_file_list(self, file_list, tags=None, hash_type=HASH_BLAKE3, target_chunk_size=32768, reader_threads=8, copy=True):
+        """CreateVersionIndex over a scanned directory: reader threads pread the parts into pinned staging behind the streaming verb"""
+        tg = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint32)
+        buf, size = C.c_void_p(), C.c_uint64(0)
+        self._check(self.lib.lt_b200_index_file_list(self.handle, file_list.handle, None if tg is None else tg.ctypes.data_as(C.c_void_p),
+                                                     int(hash_type), int(target_chunk_size), int(reader_threads), C.byref(buf), C.byref(size)),
+                    "index_file_list")
         return self._result(buf, size, copy)
 
     def index_host_assets(self, assets, datas, tags=None, hash_type=HASH_BLAKE3, target_chunk_size=32768, copy=True):

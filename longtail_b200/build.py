@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "liblongtail_b200.so")
-CUDA_SOURCES = ["hpcdc.cu", "blake3.cu", "blake2s.cu", "meow.cu", "lz4.cu", "zstd.cu", "zstd_dec.cu", "util.cu", "capi.cu", "longtail_api.cpp", "fs_store.cpp"]
+CUDA_SOURCES = ["hpcdc.cu", "blake3.cu", "blake2s.cu", "meow.cu", "lz4.cu", "zstd.cu", "zstd_dec.cu", "util.cu", "capi.cu", "longtail_api.cpp", "fs_store.cpp", "dir_scan.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
               "-Xptxas", "-v"]
 

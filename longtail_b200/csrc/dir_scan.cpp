@@ -1,0 +1,238 @@
+// dir_scan.cpp — the step BEFORE the hot path: what Longtail_GetFilesRecursively2 (src/longtail.c:1656-1893)
+// does for cmd/main.c:UpSync, and a reader that keeps lt_b200_index_stream_assets fed.
+//
+//  * scan: every directory is listed with readdir + stat like the reference's file storage (lib/longtail_platform.c:2025-2180: "." and ".."
+//    skipped, permissions = st_mode & 0x1FF, directories have size 0); an entry is named by its path relative to the root; the result is
+//    sorted with strcmp over those names BEFORE directories receive their trailing '/' (SortScannedPaths, src/longtail.c:1600-1620, then
+//    :1866-1872) — so "a.b" sorts before "a/" 's children but the directory "a" itself sorts by the name "a";
+//  * read: the streaming verb hands out batches of {asset, offset, size, destination in pinned staging}; a pool of threads preads them
+//    (the reference issues one StorageAPI.Read per chunker refill from its job threads, src/longtail.c:1923-1960).
+//
+// Host code only.  Entries that are neither regular files nor directories (the reference's iterator hands them on with a NULL name and
+// fails) are rejected with ENOTSUP.
+#include "../../include/longtail_b200.h"
+
+#include <dirent.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Entry
+{
+    std::string name; // relative to the root, no trailing '/'
+    uint64_t size;
+    uint16_t permissions;
+    bool is_dir;
+};
+
+// one directory: ScanFolder (src/longtail.c:1440-1570)
+int list_directory(const std::string& root, const std::string& sub, std::vector<Entry>* out)
+{
+    const std::string full = sub.empty() ? root : root + "/" + sub;
+    DIR* d = opendir(full.c_str());
+    if (!d) return errno == ENOENT ? 0 : errno; // a folder that vanished lists as empty (:1465-1482)
+    int err = 0;
+    for (;;)
+    {
+        errno = 0;
+        struct dirent* e = readdir(d);
+        if (!e)
+        {
+            err = errno;
+            break;
+        }
+        const char* n = e->d_name;
+        if (n[0] == '.' && (n[1] == 0 || (n[1] == '.' && n[2] == 0))) continue;
+        const std::string path = full + "/" + n;
+        struct stat st;
+        if (stat(path.c_str(), &st) != 0)
+        {
+            err = errno;
+            break;
+        }
+        const bool is_dir = S_ISDIR(st.st_mode);
+        if (!is_dir && !S_ISREG(st.st_mode)) { err = ENOTSUP; break; }
+        if (e->d_type != DT_UNKNOWN && e->d_type != (is_dir ? DT_DIR : DT_REG)) { err = ENOTSUP; break; } // a symbolic link: the reference has no name for it
+        Entry en;
+        en.name = sub.empty() ? std::string(n) : sub + "/" + n;
+        en.is_dir = is_dir;
+        en.size = is_dir ? 0 : (uint64_t)st.st_size;
+        en.permissions = (uint16_t)(st.st_mode & 0x1FF);
+        out->push_back(std::move(en));
+    }
+    closedir(d);
+    return err;
+}
+
+} // namespace
+
+struct lt_b200_file_list
+{
+    struct lt_b200_assets assets;
+    std::vector<uint64_t> sizes;
+    std::vector<uint32_t> offsets;
+    std::vector<uint16_t> permissions;
+    std::string path_data;
+    std::string root;
+};
+
+extern "C" int lt_b200_scan_directory(const char* root_path, uint32_t threads, lt_b200_file_list** out_list)
+{
+    if (!root_path || !out_list) return EINVAL;
+    std::string root = root_path;
+    while (root.size() > 1 && root.back() == '/') root.pop_back();
+    std::vector<Entry> all;
+    std::vector<std::string> level(1, std::string());
+    if (threads == 0) threads = 1;
+    // level by level, the folders of one level in parallel (the reference: one ScanFolder job per folder, :1681-1747)
+    while (!level.empty())
+    {
+        std::vector<std::vector<Entry>> found(level.size());
+        std::atomic<size_t> next(0);
+        std::atomic<int> first_err(0);
+        auto work = [&]() {
+            for (;;)
+            {
+                const size_t i = next.fetch_add(1);
+                if (i >= level.size()) return;
+                const int err = list_directory(root, level[i], &found[i]);
+                if (err)
+                {
+                    int expected = 0;
+                    first_err.compare_exchange_strong(expected, err);
+                }
+            }
+        };
+        const uint32_t n = (uint32_t)std::min<size_t>(threads, level.size());
+        std::vector<std::thread> pool;
+        for (uint32_t t = 1; t < n; ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        if (first_err.load()) return first_err.load();
+        std::vector<std::string> deeper;
+        for (auto& f : found)
+            for (auto& e : f)
+            {
+                if (e.is_dir) deeper.push_back(e.name);
+                all.push_back(std::move(e));
+            }
+        level.swap(deeper);
+    }
+    std::sort(all.begin(), all.end(), [](const Entry& a, const Entry& b) { return strcmp(a.name.c_str(), b.name.c_str()) < 0; });
+    if (all.size() > 0xfffffffeull) return E2BIG;
+    lt_b200_file_list* l = new (std::nothrow) lt_b200_file_list();
+    if (!l) return ENOMEM;
+    l->root = root;
+    for (const Entry& e : all)
+    {
+        l->offsets.push_back((uint32_t)l->path_data.size());
+        l->path_data += e.name;
+        if (e.is_dir) l->path_data += '/';
+        l->path_data += '\0';
+        l->sizes.push_back(e.size);
+        l->permissions.push_back(e.permissions);
+    }
+    if (l->path_data.size() > 0xffffffffull) { delete l; return E2BIG; }
+    l->assets.asset_count = (uint32_t)all.size();
+    l->assets.path_data_size = (uint32_t)l->path_data.size();
+    l->assets.sizes = l->sizes.data();
+    l->assets.path_start_offsets = l->offsets.data();
+    l->assets.permissions = l->permissions.data();
+    l->assets.path_data = l->path_data.data();
+    *out_list = l;
+    return 0;
+}
+
+extern "C" const struct lt_b200_assets* lt_b200_file_list_assets(const lt_b200_file_list* list) { return list ? &list->assets : nullptr; }
+
+extern "C" void lt_b200_file_list_free(lt_b200_file_list* list) { delete list; }
+
+namespace {
+
+struct ReadContext
+{
+    const lt_b200_file_list* list;
+    uint32_t threads;
+};
+
+// lt_b200_read_batch_func: jobs are handed to `threads` readers; a reader keeps the file of consecutive jobs of one asset open
+int read_batch(void* user, const struct lt_b200_read_job* jobs, uint32_t job_count)
+{
+    const ReadContext* rc = static_cast<const ReadContext*>(user);
+    std::atomic<uint32_t> next(0);
+    std::atomic<int> first_err(0);
+    auto work = [&]() {
+        int fd = -1;
+        uint32_t open_asset = 0xffffffffu;
+        for (;;)
+        {
+            // a few jobs at a time, so that one reader works through neighbouring parts of the same file
+            const uint32_t i0 = next.fetch_add(4), i1 = std::min(job_count, i0 + 4);
+            if (i0 >= job_count) break;
+            for (uint32_t i = i0; i < i1 && !first_err.load(); ++i)
+            {
+                const lt_b200_read_job& j = jobs[i];
+                if (j.asset_index != open_asset)
+                {
+                    if (fd >= 0) close(fd);
+                    const std::string path = rc->list->root + "/" + (rc->list->path_data.data() + rc->list->offsets[j.asset_index]);
+                    fd = open(path.c_str(), O_RDONLY);
+                    open_asset = j.asset_index;
+                    if (fd < 0)
+                    {
+                        int expected = 0;
+                        first_err.compare_exchange_strong(expected, errno ? errno : EIO);
+                        open_asset = 0xffffffffu;
+                        break;
+                    }
+                }
+                uint8_t* dst = static_cast<uint8_t*>(j.dst);
+                uint64_t off = j.offset;
+                uint32_t left = j.size;
+                while (left)
+                {
+                    const ssize_t n = pread(fd, dst, left, (off_t)off);
+                    if (n < 0 && errno == EINTR) continue;
+                    if (n <= 0)
+                    {
+                        int expected = 0;
+                        first_err.compare_exchange_strong(expected, n < 0 ? errno : EIO); // the file shrank since the scan
+                        break;
+                    }
+                    dst += n;
+                    off += (uint64_t)n;
+                    left -= (uint32_t)n;
+                }
+            }
+        }
+        if (fd >= 0) close(fd);
+    };
+    const uint32_t n = std::max(1u, std::min(rc->threads, (job_count + 3) / 4));
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < n; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    return first_err.load();
+}
+
+} // namespace
+
+extern "C" int lt_b200_index_file_list(lt_b200_context* context, const lt_b200_file_list* list, const uint32_t* asset_tags, uint32_t hash_type,
+                                       uint32_t target_chunk_size, uint32_t reader_threads, const void** out_buffer, uint64_t* out_size)
+{
+    if (!context || !list) return EINVAL;
+    ReadContext rc = {list, reader_threads ? reader_threads : 1};
+    return lt_b200_index_stream_assets(context, &list->assets, asset_tags, hash_type, target_chunk_size, read_batch, &rc, out_buffer, out_size);
+}

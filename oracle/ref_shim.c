@@ -716,3 +716,78 @@ REF_EXPORT int ref_read_store_dir(const char* dir, uint64_t out[4])
     SAFE_DISPOSE_API(job);
     return err;
 }
+
+/* ---------------------------------------------------------------- directory scan + index through the reference's file storage
+ * (SURVEY.md section 8f row 4): cmd/main.c:UpSync's Longtail_GetFilesRecursively2 + Longtail_CreateVersionIndex over a real directory.
+ * ref_scan_directory serialises the FileInfos: u32 count, then per entry { u64 size, u16 permissions, u32 path length, path bytes }. */
+REF_EXPORT int ref_scan_directory(const char* root, uint32_t workers, void** out_buf, uint64_t* out_size)
+{
+    struct Longtail_StorageAPI* fs = Longtail_CreateFSStorageAPI();
+    struct Longtail_JobAPI* job = workers ? Longtail_CreateBikeshedJobAPI(workers, 0) : 0;
+    struct Longtail_FileInfos* fi = 0;
+    int err = Longtail_GetFilesRecursively2(fs, job, 0, 0, 0, root, &fi);
+    if (!err)
+    {
+        size_t total = 4;
+        for (uint32_t i = 0; i < fi->m_Count; ++i) total += 8 + 2 + 4 + strlen(&fi->m_PathData[fi->m_PathStartOffsets[i]]);
+        uint8_t* out = (uint8_t*)malloc(total);
+        uint8_t* p = out;
+        memcpy(p, &fi->m_Count, 4); p += 4;
+        for (uint32_t i = 0; i < fi->m_Count; ++i)
+        {
+            const char* path = &fi->m_PathData[fi->m_PathStartOffsets[i]];
+            uint32_t n = (uint32_t)strlen(path);
+            memcpy(p, &fi->m_Sizes[i], 8); p += 8;
+            memcpy(p, &fi->m_Permissions[i], 2); p += 2;
+            memcpy(p, &n, 4); p += 4;
+            memcpy(p, path, n); p += n;
+        }
+        *out_buf = out;
+        *out_size = (uint64_t)(p - out);
+    }
+    Longtail_Free(fi);
+    if (job) SAFE_DISPOSE_API(job);
+    SAFE_DISPOSE_API(fs);
+    return err;
+}
+
+REF_EXPORT int ref_index_directory(const char* root, uint32_t hash_type, uint32_t target_chunk_size, uint32_t workers, uint32_t tag,
+                                   void** out_buf, uint64_t* out_size)
+{
+    struct Longtail_HashAPI* hash = make_hash(hash_type);
+    if (!hash) return EINVAL;
+    struct Longtail_StorageAPI* fs = Longtail_CreateFSStorageAPI();
+    struct Longtail_JobAPI* job = Longtail_CreateBikeshedJobAPI(workers, 0);
+    struct Longtail_ChunkerAPI* chunker = Longtail_CreateHPCDCChunkerAPI();
+    struct Longtail_FileInfos* fi = 0;
+    struct Longtail_VersionIndex* vi = 0;
+    int err = Longtail_GetFilesRecursively2(fs, job, 0, 0, 0, root, &fi);
+    uint32_t* tags = 0;
+    if (!err)
+    {
+        tags = (uint32_t*)malloc(sizeof(uint32_t) * (fi->m_Count ? fi->m_Count : 1));
+        for (uint32_t i = 0; i < fi->m_Count; ++i) tags[i] = tag;
+        err = Longtail_CreateVersionIndex(fs, hash, chunker, job, 0, 0, 0, root, fi, tags, target_chunk_size, 0, &vi);
+    }
+    if (!err)
+    {
+        void* buf = 0;
+        size_t size = 0;
+        err = Longtail_WriteVersionIndexToBuffer(vi, &buf, &size);
+        if (!err)
+        {
+            *out_buf = malloc(size ? size : 1);
+            memcpy(*out_buf, buf, size);
+            *out_size = size;
+            Longtail_Free(buf);
+        }
+    }
+    free(tags);
+    Longtail_Free(vi);
+    Longtail_Free(fi);
+    SAFE_DISPOSE_API(chunker);
+    SAFE_DISPOSE_API(job);
+    SAFE_DISPOSE_API(fs);
+    SAFE_DISPOSE_API(hash);
+    return err;
+}

@@ -298,3 +298,31 @@ def ref_read_store_dir(ref, directory):
     err = ref.lib.ref_read_store_dir(directory.encode(), out)
     assert err == 0, err
     return tuple(int(x) for x in out)
+
+
+def ref_scan_directory(ref, root, workers=0):
+    """Longtail_GetFilesRecursively2 of the unmodified reference over its own file storage -> [(path, size, permissions)]"""
+    buf, size = C.c_void_p(), C.c_uint64(0)
+    err = ref.lib.ref_scan_directory(root.encode(), C.c_uint32(workers), C.byref(buf), C.byref(size))
+    assert err == 0, err
+    raw = C.string_at(buf, size.value)
+    ref.lib.ref_free(buf)
+    n = struct.unpack_from("<I", raw, 0)[0]
+    out, p = [], 4
+    for _ in range(n):
+        sz, perm, ln = struct.unpack_from("<QHI", raw, p)
+        p += 14
+        out.append((raw[p:p + ln].decode(), sz, perm))
+        p += ln
+    return out
+
+
+def ref_index_directory(ref, root, target_chunk_size, hash_type=HASH_BLAKE3, workers=4, tag=0):
+    """GetFilesRecursively2 + CreateVersionIndex of the unmodified reference over a real directory -> serialised VersionIndex"""
+    buf, size = C.c_void_p(), C.c_uint64(0)
+    err = ref.lib.ref_index_directory(root.encode(), C.c_uint32(hash_type), C.c_uint32(target_chunk_size), C.c_uint32(workers), C.c_uint32(tag),
+                                      C.byref(buf), C.byref(size))
+    assert err == 0, err
+    out = C.string_at(buf, size.value)
+    ref.lib.ref_free(buf)
+    return out

@@ -1,0 +1,79 @@
+"""lt_b200_scan_directory against the unmodified reference's Longtail_GetFilesRecursively2 over its own file
+storage (same entries, order, sizes, permissions), and — on the GPU — CreateVersionIndex over the scanned tree with the threaded reader
+against the reference indexing the same directory."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from synth import synth_bytes
+
+
+def make_tree(root):
+    """names chosen to exercise the ordering rule: strcmp over relative names BEFORE directories get their '/' ("a.b" < "a/x" but "a" < "a.b"),
+    upper/lower case, empty directories and files, nested empties, files spanning several parts at a small target"""
+    files = {"a/x.bin": 300000, "a/y/z.txt": 1234, "a.b": 77, "a-b/q": 5000, "A/upper.bin": 70000, "b": 0, "c/empty.dat": 0,
+             "c/d/e/f/deep.bin": 150000, "zz/big.bin": 3 * 1024 * 1024 + 17, "a/x.bin.bak": 300000, "0": 48, "_under/score": 49}
+    for i, (rel, n) in enumerate(sorted(files.items())):
+        p = os.path.join(root, rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        synth_bytes(40 + (0 if rel.endswith(".bak") else i), n, ("rand", "text", "nib", "rec")[i % 4] if not rel.endswith(".bak") else "rand").tofile(p) if n else open(p, "wb").close()
+    # the .bak file must duplicate a/x.bin byte for byte (dedup across assets)
+    open(os.path.join(root, "a/x.bin.bak"), "wb").write(open(os.path.join(root, "a/x.bin"), "rb").read())
+    for d in ("empty_dir", "c/d/also_empty", "a/y/w"):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+    os.chmod(os.path.join(root, "a/x.bin"), 0o640)
+    os.chmod(os.path.join(root, "zz/big.bin"), 0o755)
+    os.chmod(os.path.join(root, "empty_dir"), 0o700)
+    return files
+
+
+def test_scan_matches_reference(reference, tmp_path):
+    if reference is None:
+        pytest.skip("oracle/_ref/libref_shim.so not built")
+    import longtail_b200
+    root = str(tmp_path / "tree")
+    os.makedirs(root)
+    make_tree(root)
+    want = ol.ref_scan_directory(reference, root, workers=0)
+    assert want == ol.ref_scan_directory(reference, root, workers=4)
+    for threads in (1, 8):
+        fl = longtail_b200.FileList(root, threads=threads)
+        got = list(zip(fl.paths, fl.sizes, fl.permissions))
+        fl.close()
+        assert got == want
+    names = [p for p, _, _ in want]
+    assert names.index("a/") < names.index("a-b/") < names.index("a.b") < names.index("a/x.bin")  # "a" < "a-b" < "a.b" < "a/x.bin"
+    assert "empty_dir/" in names and "c/d/also_empty/" in names and dict((p, s) for p, s, _ in want)["b"] == 0
+
+
+def test_scan_errors(tmp_path):
+    import longtail_b200
+    root = tmp_path / "t"
+    root.mkdir()
+    (root / "f").write_bytes(b"x")
+    os.symlink(str(root / "f"), str(root / "link"))
+    with pytest.raises(longtail_b200.LongtailB200Error):
+        longtail_b200.FileList(str(root))  # the reference's iterator has no name for a symbolic link; rejected instead of guessed
+    fl = longtail_b200.FileList(str(tmp_path / "missing"))  # a root that does not exist lists as empty, like ScanFolder's ENOENT branch
+    assert fl.paths == []
+    fl.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("target,readers", [(64, 1), (64, 8), (32768, 4)])
+def test_index_directory_matches_reference(reference, tmp_path, target, readers):
+    if reference is None:
+        pytest.skip("oracle/_ref/libref_shim.so not built")
+    import longtail_b200
+    root = str(tmp_path / "tree")
+    os.makedirs(root)
+    make_tree(root)
+    ctx = longtail_b200.Context(0)
+    fl = longtail_b200.FileList(root)
+    tags = [ol.COMP_LZ4] * len(fl.paths)
+    got = ctx.index_file_list(fl, tags, target_chunk_size=target, reader_threads=readers)
+    fl.close()
+    ctx.close()
+    assert got == ol.ref_index_directory(reference, root, target, workers=4, tag=ol.COMP_LZ4)
