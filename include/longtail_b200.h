@@ -315,6 +315,16 @@ LT_B200_EXPORT int lt_b200_index_file_list(lt_b200_context* context, const lt_b2
                                            uint32_t hash_type, uint32_t target_chunk_size, uint32_t reader_threads,
                                            const void** out_buffer, uint64_t* out_size);
 
+/* cmd/main.c:UpSync (:972-1153) for a scanned tree that fits one GPU: the tree is read once into a device arena (reader threads ->
+ * pinned staging -> HBM), then CreateVersionIndex, CreateMissingContent against the chunks `store` already lists and WriteContent all run
+ * on the resident bytes; stored blocks leave through lt_b200_fs_store_sink and the store is flushed.  *out_version_index is the serialised
+ * VersionIndex (pinned memory owned by the context, valid until its next index call) — what UpSync writes to the .lvi file.
+ * ENOMEM when the tree does not fit the device. */
+LT_B200_EXPORT int lt_b200_upsync_file_list(lt_b200_context* context, const lt_b200_file_list* list, const uint32_t* asset_tags,
+                                            uint32_t hash_type, uint32_t target_chunk_size, uint32_t max_block_size,
+                                            uint32_t max_chunks_per_block, uint32_t reader_threads, lt_b200_fs_store* store,
+                                            const void** out_version_index, uint64_t* out_size, uint32_t* out_blocks_written);
+
 #ifdef __cplusplus
 }
 #endif

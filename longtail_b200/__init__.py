@@ -179,6 +179,8 @@ def load_library():
     lib.lt_b200_file_list_free.argtypes = [C.c_void_p]
     lib.lt_b200_index_file_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
                                             C.POINTER(C.c_uint64)]
+    lib.lt_b200_upsync_file_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                             C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     lib.lt_b200_fs_store_open.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
     lib.lt_b200_fs_store_sink.argtypes = [C.c_void_p, C.POINTER(StoredBlockView)]
     lib.lt_b200_fs_store_flush.argtypes = [C.c_void_p]
@@ -530,6 +532,17 @@ class Context:
                                                      int(hash_type), int(target_chunk_size), int(reader_threads), C.byref(buf), C.byref(size)),
                     "index_file_list")
         return self._result(buf, size, copy)
+
+    def upsync_file_list(self, file_list, fs_store, tags=None, hash_type=HASH_BLAKE3, target_chunk_size=32768, max_block_size=8388608,
+                         max_chunks_per_block=1024, reader_threads=8):
+        """cmd/main.c:UpSync for a scanned tree that fits the GPU -> (serialised VersionIndex, stored blocks written)"""
+        tg = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint32)
+        buf, size, written = C.c_void_p(), C.c_uint64(0), C.c_uint32(0)
+        self._check(self.lib.lt_b200_upsync_file_list(self.handle, file_list.handle, None if tg is None else tg.ctypes.data_as(C.c_void_p),
+                                                      int(hash_type), int(target_chunk_size), int(max_block_size), int(max_chunks_per_block),
+                                                      int(reader_threads), fs_store.handle, C.byref(buf), C.byref(size), C.byref(written)),
+                    "upsync_file_list")
+        return self._result(buf, size, True), written.value
 
     def index_host_assets(self, assets, datas, tags=None, hash_type=HASH_BLAKE3, target_chunk_size=32768, copy=True):
         """datas: list of contiguous uint8 numpy arrays (pinned for full PCIe speed), one per asset"""

@@ -236,3 +236,136 @@ extern "C" int lt_b200_index_file_list(lt_b200_context* context, const lt_b200_f
     ReadContext rc = {list, reader_threads ? reader_threads : 1};
     return lt_b200_index_stream_assets(context, &list->assets, asset_tags, hash_type, target_chunk_size, read_batch, &rc, out_buffer, out_size);
 }
+
+// ---------------------------------------------------------------- a whole upsync of a scanned tree (cmd/main.c:UpSync, :972-1153)
+// The tree is loaded ONCE into a device arena (180 GB of HBM hold most asset trees whole): readers pread into two pinned staging
+// buffers while the previous one crosses PCIe.  Then everything stays on the device: CreateVersionIndex, DiffHashes against the chunks the
+// store already lists, block packing, payload gather, compression, and the stored blocks leave through the fsblockstore-layout sink.
+extern "C" int lt_b200_upsync_file_list(lt_b200_context* context, const lt_b200_file_list* list, const uint32_t* asset_tags, uint32_t hash_type,
+                                        uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block, uint32_t reader_threads,
+                                        lt_b200_fs_store* store, const void** out_version_index, uint64_t* out_size, uint32_t* out_blocks_written)
+{
+    if (!context || !list || !store || !out_version_index || !out_size) return EINVAL;
+    const uint32_t n = list->assets.asset_count;
+    std::vector<uint64_t> arena_off(n ? n : 1);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        arena_off[i] = total;
+        total += (list->sizes[i] + 255u) & ~(uint64_t)255u;
+    }
+    const uint64_t arena_bytes = total + 4096;
+    void* arena = nullptr;
+    int err = lt_b200_device_alloc(context, arena_bytes, &arena);
+    if (err) return err; // ENOMEM: the tree does not fit this GPU; shard the file list across ranks (longtail_b200/distributed.py)
+    const uint64_t stage_bytes = 256ull << 20;
+    void* stage[2] = {nullptr, nullptr};
+    err = lt_b200_host_alloc_pinned(context, stage_bytes, &stage[0]);
+    if (!err) err = lt_b200_host_alloc_pinned(context, stage_bytes, &stage[1]);
+    ReadContext rc = {list, reader_threads ? reader_threads : 1};
+    // pieces of at most 8 MiB, packed into staging batches; the arena keeps each asset contiguous at arena_off
+    struct Piece { uint32_t asset; uint64_t offset; uint32_t size; };
+    std::vector<Piece> pieces;
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint64_t o = 0; o < list->sizes[i]; o += 8u << 20)
+            pieces.push_back({i, o, (uint32_t)std::min<uint64_t>(8u << 20, list->sizes[i] - o)});
+    struct Batch { size_t first, last; uint64_t bytes; };
+    auto plan = [&](size_t first) {
+        Batch b = {first, first, 0};
+        while (b.last < pieces.size() && (b.bytes + pieces[b.last].size <= stage_bytes || b.last == first)) b.bytes += pieces[b.last++].size;
+        return b;
+    };
+    auto read_into = [&](const Batch& b, void* buf) -> int {
+        std::vector<lt_b200_read_job> jobs;
+        uint64_t at = 0;
+        for (size_t k = b.first; k < b.last; ++k)
+        {
+            jobs.push_back({pieces[k].asset, pieces[k].size, pieces[k].offset, static_cast<uint8_t*>(buf) + at});
+            at += pieces[k].size;
+        }
+        return jobs.empty() ? 0 : read_batch(&rc, jobs.data(), (uint32_t)jobs.size());
+    };
+    if (!err && !pieces.empty())
+    {
+        Batch cur = plan(0);
+        int which = 0;
+        err = read_into(cur, stage[0]);
+        while (!err)
+        {
+            const bool has_next = cur.last < pieces.size();
+            Batch next = has_next ? plan(cur.last) : cur;
+            int read_err = 0;
+            std::thread reader;
+            if (has_next) reader = std::thread([&]() { read_err = read_into(next, stage[which ^ 1]); });
+            uint64_t at = 0;
+            for (size_t k = cur.first; k < cur.last && !err; ++k) // consecutive pieces of one asset are consecutive in both buffers: one copy per run
+            {
+                size_t e = k;
+                uint64_t run = 0;
+                while (e < cur.last && pieces[e].asset == pieces[k].asset) run += pieces[e++].size;
+                err = lt_b200_copy_to_device(context, static_cast<uint8_t*>(arena) + arena_off[pieces[k].asset] + pieces[k].offset,
+                                             static_cast<uint8_t*>(stage[which]) + at, run);
+                at += run;
+                k = e - 1;
+            }
+            if (has_next) reader.join();
+            if (!err) err = read_err;
+            if (!has_next) break;
+            cur = next;
+            which ^= 1;
+        }
+    }
+    const void* vi = nullptr;
+    uint64_t vi_size = 0;
+    if (!err) err = lt_b200_index_device_assets(context, static_cast<const uint8_t*>(arena), arena_bytes, &list->assets, arena_off.data(), asset_tags, hash_type,
+                                                target_chunk_size, &vi, &vi_size);
+    if (!err)
+    {
+        // the unique chunks of the version, in version order, from the serialised index (src/longtail.c:2566-2584): 6 x u32, then
+        // u64[A] x 3, u32[A] x 2, u32[I], u64 chunk_hash[C], u32 chunk_size[C], u32 chunk_tag[C]
+        const uint8_t* p = static_cast<const uint8_t*>(vi);
+        uint32_t head[6];
+        memcpy(head, p, sizeof(head));
+        const uint64_t A = head[3], C = head[4], I = head[5];
+        const uint8_t* q = p + 24 + 24 * A + 8 * A + 4 * I;
+        std::vector<uint64_t> hashes(C ? C : 1), offsets(C ? C : 1);
+        std::vector<uint32_t> sizes(C ? C : 1), tags(C ? C : 1);
+        memcpy(hashes.data(), q, 8 * C);
+        memcpy(sizes.data(), q + 8 * C, 4 * C);
+        memcpy(tags.data(), q + 12 * C, 4 * C);
+        if (C) err = lt_b200_unique_chunk_offsets(context, offsets.data(), (uint32_t)C);
+        // Longtail_CreateMissingContent: only what the store does not list yet, in version order
+        uint32_t have = 0;
+        std::vector<uint64_t> existing;
+        if (!err) err = lt_b200_fs_store_existing_chunks(store, nullptr, 0, &have);
+        if (!err && have)
+        {
+            existing.resize(have);
+            err = lt_b200_fs_store_existing_chunks(store, existing.data(), have, &have);
+        }
+        std::vector<uint8_t> missing(C ? C : 1, 1);
+        if (!err && C) err = lt_b200_missing_chunks(context, (uint32_t)C, hashes.data(), have, have ? existing.data() : nullptr, missing.data());
+        uint32_t m = 0;
+        for (uint64_t i = 0; i < C && !err; ++i)
+            if (missing[i])
+            {
+                hashes[m] = hashes[i]; sizes[m] = sizes[i]; tags[m] = tags[i]; offsets[m] = offsets[i];
+                ++m;
+            }
+        uint64_t before = 0, after = 0;
+        lt_b200_fs_store_stats(store, &before, nullptr, nullptr);
+        if (!err && m)
+            err = lt_b200_write_blocks_device(context, static_cast<const uint8_t*>(arena), arena_bytes, m, hashes.data(), sizes.data(), tags.data(), offsets.data(),
+                                              hash_type, max_block_size, max_chunks_per_block, lt_b200_fs_store_sink, store);
+        if (!err) err = lt_b200_fs_store_flush(store);
+        lt_b200_fs_store_stats(store, &after, nullptr, nullptr);
+        if (out_blocks_written) *out_blocks_written = (uint32_t)(after - before);
+        // write_blocks_device reuses pinned staging of the context, the index buffer is a different one and stays valid (see the header)
+        *out_version_index = vi;
+        *out_size = vi_size;
+    }
+    if (stage[0]) lt_b200_host_free_pinned(context, stage[0]);
+    if (stage[1]) lt_b200_host_free_pinned(context, stage[1]);
+    lt_b200_device_free(context, arena);
+    return err;
+}

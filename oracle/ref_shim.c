@@ -791,3 +791,80 @@ REF_EXPORT int ref_index_directory(const char* root, uint32_t hash_type, uint32_
     SAFE_DISPOSE_API(hash);
     return err;
 }
+
+/* cmd/main.c:UpSync over real directories: source tree `source_root` (file storage) -> store directory `store_dir` (compressblockstore ->
+ * fsblockstore); the serialised VersionIndex is returned.  A second call with the same store is an incremental upsync. */
+REF_EXPORT int ref_upsync_dir_to_dir(const char* source_root, const char* store_dir, uint32_t hash_type, uint32_t target_chunk_size,
+                                     uint32_t max_block_size, uint32_t max_chunks_per_block, uint32_t workers, uint32_t tag,
+                                     void** out_buf, uint64_t* out_size, uint32_t* out_blocks_written)
+{
+    struct Longtail_HashAPI* hash = make_hash(hash_type);
+    if (!hash) return EINVAL;
+    struct Longtail_StorageAPI* fs = Longtail_CreateFSStorageAPI();
+    struct Longtail_JobAPI* job = Longtail_CreateBikeshedJobAPI(workers, 0);
+    struct Longtail_ChunkerAPI* chunker = Longtail_CreateHPCDCChunkerAPI();
+    struct Longtail_CompressionRegistryAPI* registry = Longtail_CreateFullCompressionRegistry();
+    struct Longtail_BlockStoreAPI* fs_store = Longtail_CreateFSBlockStoreAPI(job, fs, store_dir, 0, 0);
+    struct Longtail_BlockStoreAPI* store = Longtail_CreateCompressBlockStoreAPI(fs_store, registry);
+    struct Longtail_FileInfos* fi = 0;
+    struct Longtail_VersionIndex* vi = 0;
+    struct Longtail_StoreIndex* missing = 0;
+    uint32_t* tags = 0;
+    struct sync_existing ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.api.OnComplete = sync_existing_done;
+    int err = Longtail_GetFilesRecursively2(fs, job, 0, 0, 0, source_root, &fi);
+    if (!err)
+    {
+        tags = (uint32_t*)malloc(sizeof(uint32_t) * (fi->m_Count ? fi->m_Count : 1));
+        for (uint32_t i = 0; i < fi->m_Count; ++i) tags[i] = tag;
+        err = Longtail_CreateVersionIndex(fs, hash, chunker, job, 0, 0, 0, source_root, fi, tags, target_chunk_size, 0, &vi);
+    }
+    if (!err) err = store->GetExistingContent(store, *vi->m_ChunkCount, vi->m_ChunkHashes, 0, &ex.api);
+    if (!err)
+    {
+        while (!ex.done) sched_yield();
+        err = ex.err;
+    }
+    if (!err) err = Longtail_CreateMissingContent(hash, ex.index, vi, max_block_size, max_chunks_per_block, &missing);
+    if (!err && out_blocks_written) *out_blocks_written = *missing->m_BlockCount;
+    if (!err) err = Longtail_WriteContent(fs, store, job, 0, 0, 0, missing, vi, source_root);
+    if (!err)
+    {
+        struct sync_flush fl;
+        memset(&fl, 0, sizeof(fl));
+        fl.api.OnComplete = sync_flush_done;
+        err = store->Flush(store, &fl.api);
+        if (!err)
+        {
+            while (!fl.done) sched_yield();
+            err = fl.err;
+        }
+    }
+    if (!err)
+    {
+        void* buf = 0;
+        size_t size = 0;
+        err = Longtail_WriteVersionIndexToBuffer(vi, &buf, &size);
+        if (!err)
+        {
+            *out_buf = malloc(size ? size : 1);
+            memcpy(*out_buf, buf, size);
+            *out_size = size;
+            Longtail_Free(buf);
+        }
+    }
+    free(tags);
+    Longtail_Free(missing);
+    Longtail_Free(ex.index);
+    Longtail_Free(vi);
+    Longtail_Free(fi);
+    SAFE_DISPOSE_API(store);
+    SAFE_DISPOSE_API(fs_store);
+    SAFE_DISPOSE_API(registry);
+    SAFE_DISPOSE_API(chunker);
+    SAFE_DISPOSE_API(job);
+    SAFE_DISPOSE_API(fs);
+    SAFE_DISPOSE_API(hash);
+    return err;
+}

@@ -326,3 +326,16 @@ def ref_index_directory(ref, root, target_chunk_size, hash_type=HASH_BLAKE3, wor
     out = C.string_at(buf, size.value)
     ref.lib.ref_free(buf)
     return out
+
+
+def ref_upsync_dir_to_dir(ref, source_root, store_dir, target_chunk_size, max_block_size=8388608, max_chunks_per_block=1024,
+                          hash_type=HASH_BLAKE3, workers=0, tag=0):
+    """cmd/main.c:UpSync of the unmodified reference: real source directory -> fsblockstore directory -> (VersionIndex bytes, blocks written)"""
+    buf, size, written = C.c_void_p(), C.c_uint64(0), C.c_uint32(0)
+    err = ref.lib.ref_upsync_dir_to_dir(source_root.encode(), store_dir.encode(), C.c_uint32(hash_type), C.c_uint32(target_chunk_size),
+                                        C.c_uint32(max_block_size), C.c_uint32(max_chunks_per_block), C.c_uint32(workers), C.c_uint32(tag),
+                                        C.byref(buf), C.byref(size), C.byref(written))
+    assert err == 0, err
+    out = C.string_at(buf, size.value)
+    ref.lib.ref_free(buf)
+    return out, written.value

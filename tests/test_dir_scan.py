@@ -77,3 +77,47 @@ def test_index_directory_matches_reference(reference, tmp_path, target, readers)
     fl.close()
     ctx.close()
     assert got == ol.ref_index_directory(reference, root, target, workers=4, tag=ol.COMP_LZ4)
+
+
+@pytest.mark.gpu
+def test_upsync_directory_to_directory_matches_reference(reference, tmp_path):
+    """cmd/main.c:UpSync end to end on the device: scan -> load the tree into HBM -> index -> missing chunks -> blocks -> fsblockstore
+    directory; VersionIndex, every .lrb and store.lsi identical to the unmodified reference doing the same, then the tree changes and both
+    upsync again into their stores (incremental)"""
+    if reference is None:
+        pytest.skip("oracle/_ref/libref_shim.so not built")
+    import longtail_b200
+    src = str(tmp_path / "tree")
+    os.makedirs(src)
+    make_tree(src)
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "ref")
+    kw = dict(max_block_size=262144, max_chunks_per_block=64)
+    ctx = longtail_b200.Context(0)
+
+    def tree(root):
+        return {os.path.relpath(os.path.join(d, f), root): open(os.path.join(d, f), "rb").read()
+                for d, _, files in os.walk(root) for f in files if f != "store.lsi.sync"}
+
+    def both():
+        fl = longtail_b200.FileList(src)
+        st = longtail_b200.FsStore(ours, writer_threads=4)
+        vi, n = ctx.upsync_file_list(fl, st, [ol.COMP_ZSTD_DEFAULT] * len(fl.paths), target_chunk_size=64, reader_threads=4, **kw)
+        st.close()
+        fl.close()
+        want_vi, want_n = ol.ref_upsync_dir_to_dir(reference, src, theirs, 64, workers=0, tag=ol.COMP_ZSTD_DEFAULT, **kw)
+        assert vi == want_vi and n == want_n and n > 0
+        a, b = tree(ours), tree(theirs)
+        assert sorted(a) == sorted(b)
+        assert all(a[k] == b[k] for k in a), [k for k in a if a[k] != b[k]][:3]
+        return n
+
+    n1 = both()
+    synth_bytes(555, 400000, "rec").tofile(os.path.join(src, "a/new.bin"))
+    os.remove(os.path.join(src, "a.b"))
+    with open(os.path.join(src, "zz/big.bin"), "r+b") as f:  # an edit in the middle of a multi-part file
+        f.seek(1500000)
+        f.write(b"edited" * 100)
+    n2 = both()
+    assert n2 < n1
+    assert ol.ref_read_store_dir(reference, ours) == ol.ref_read_store_dir(reference, theirs)
+    ctx.close()
