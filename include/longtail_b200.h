@@ -216,6 +216,14 @@ LT_B200_EXPORT int lt_b200_write_blocks_device(lt_b200_context* context, const u
                                                const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
                                                uint32_t max_block_size, uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user);
 
+/* lt_b200_write_blocks_device for blocks whose composition is GIVEN (a Longtail_StoreIndex: block b holds the next block_chunk_counts[b]
+ * chunks of the chunk arrays; its tag is the tag of its first chunk) instead of packed greedily — what Longtail_WriteContent does with the
+ * store index it is handed (src/longtail.c:4760-4912). */
+LT_B200_EXPORT int lt_b200_write_given_blocks_device(lt_b200_context* context, const uint8_t* device_arena, uint64_t arena_size,
+                                                     uint32_t chunk_count, const uint64_t* chunk_hashes, const uint32_t* chunk_sizes,
+                                                     const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
+                                                     uint32_t block_count, const uint32_t* block_chunk_counts, lt_b200_block_sink sink, void* user);
+
 /* DiffHashes of Longtail_CreateMissingContent (src/longtail.c:6620-6743, :6882-6998) on the device: out_missing[i] = 1 when
  * chunk_hashes[i] (the version's unique chunks, HOST array) is absent from existing_hashes (the chunk hashes of the store index, HOST
  * array).  The chunks to write are the flagged ones in their given order; pass them to lt_b200_write_blocks_device. */

@@ -92,6 +92,18 @@ LT_B200_EXPORT struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockSt
     struct Longtail_BlockStoreAPI* backing_block_store,
     struct Longtail_CompressionRegistryAPI* compression_registry);
 
+/* Longtail_WriteContent (src/longtail.c:4760-4912) TOGETHER WITH the compress block store it normally writes into: same parameter list,
+ * but `backing_block_store_api` is the store that would sit BELOW Longtail_CreateCompressBlockStoreAPI — it receives the finished
+ * (compressed) stored blocks, byte-identical to what compressblockstore would have forwarded.  The version's assets are read once through
+ * source_storage_api (fanned out over job_api) into a device arena; payload gather (WriteContentBlockJob :4559-4758), block hashes,
+ * compression and serialisation run on the device for the blocks exactly as store_index lists them.  Errors as the reference: EINVAL for
+ * missing arguments or a store-index chunk the version does not hold (:4826-4832), the first storage / PutStoredBlock error otherwise;
+ * ENOTSUP for block tags without a device codec. */
+LT_B200_EXPORT int Longtail_B200_WriteContent(
+    struct Longtail_StorageAPI* source_storage_api, struct Longtail_BlockStoreAPI* backing_block_store_api, struct Longtail_JobAPI* job_api,
+    struct Longtail_ProgressAPI* progress_api, struct Longtail_CancelAPI* optional_cancel_api, Longtail_CancelAPI_HCancelToken optional_cancel_token,
+    struct Longtail_StoreIndex* store_index, struct Longtail_VersionIndex* version_index, const char* assets_folder);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1187,10 +1187,48 @@ extern "C" int lt_b200_pack_blocks(uint32_t chunk_count, const uint32_t* chunk_s
     return 0;
 }
 
+namespace {
+int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
+                      const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
+                      const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
+                      uint32_t max_chunks_per_block, uint32_t given_block_count, const uint32_t* given_block_chunk_counts,
+                      lt_b200_block_sink sink, void* user);
+}
+
 extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
                                            const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
                                            const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
                                            uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user)
+{
+    return write_blocks_impl(c, d_arena, arena_size, chunk_count, chunk_hashes, chunk_sizes, chunk_tags, chunk_arena_offsets, hash_type, max_block_size,
+                             max_chunks_per_block, 0, nullptr, sink, user);
+}
+
+extern "C" int lt_b200_write_given_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
+                                                 const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
+                                                 const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t block_count,
+                                                 const uint32_t* block_chunk_counts, lt_b200_block_sink sink, void* user)
+{
+    if (block_count && !block_chunk_counts) return EINVAL;
+    uint64_t sum = 0;
+    uint32_t most = 1;
+    for (uint32_t b = 0; b < block_count; ++b)
+    {
+        if (!block_chunk_counts[b]) return EINVAL;
+        sum += block_chunk_counts[b];
+        if (block_chunk_counts[b] > most) most = block_chunk_counts[b];
+    }
+    if (sum != chunk_count) return EINVAL;
+    return write_blocks_impl(c, d_arena, arena_size, chunk_count, chunk_hashes, chunk_sizes, chunk_tags, chunk_arena_offsets, hash_type, 0xffffffffu, most,
+                             block_count, block_chunk_counts, sink, user);
+}
+
+namespace {
+int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
+                      const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
+                      const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
+                      uint32_t max_chunks_per_block, uint32_t given_block_count, const uint32_t* given_block_chunk_counts,
+                      lt_b200_block_sink sink, void* user)
 {
     if (!c || !sink || (chunk_count && (!chunk_hashes || !chunk_sizes || !chunk_arena_offsets))) return EINVAL;
     if (max_chunks_per_block == 0) return EINVAL;
@@ -1205,15 +1243,26 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
     struct Block { uint32_t first, count, raw, tag; };
     std::vector<Block> blocks;
     const uint64_t limit = (uint64_t)max_block_size + max_block_size / 10;
+    uint32_t given = 0;
     for (uint32_t i = 0; i < chunk_count;)
     {
         Block b = {i, 1, chunk_sizes[i], chunk_tags ? chunk_tags[i] : 0u};
         if (b.tag != 0 && b.tag != LT_B200_COMPRESSION_LZ4 && !is_zstd_level3(b.tag))
             return fail(c, ENOTSUP, "compression type 0x%08x has no device implementation", b.tag);
         if (chunk_arena_offsets[i] + chunk_sizes[i] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", i);
+        const uint32_t want = given_block_chunk_counts ? given_block_chunk_counts[given++] : 0u; // the caller's blocks, as given (a store index)
         while (i + b.count < chunk_count)
         {
             const uint32_t j = i + b.count;
+            if (given_block_chunk_counts)
+            {
+                if (b.count == want) break;
+                if (chunk_arena_offsets[j] + chunk_sizes[j] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", j);
+                if ((uint64_t)b.raw + chunk_sizes[j] > 0x7E000000ull) return fail(c, E2BIG, "block %u too large", given - 1);
+                b.raw += chunk_sizes[j];
+                ++b.count;
+                continue;
+            }
             if ((chunk_tags ? chunk_tags[j] : 0u) != b.tag) break;
             if (b.count == max_chunks_per_block) break;
             if ((uint64_t)b.raw + chunk_sizes[j] > limit) break;
@@ -1437,6 +1486,7 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
     (void)done_chunks;
     return 0;
 }
+} // namespace
 
 // ================================================================ CompressionAPI batch entry points (host buffers)
 

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -896,6 +897,194 @@ void store_dispose(struct Longtail_API* api)
 }
 
 } // namespace
+
+// ---------------------------------------------------------------- WriteContent + compress block store in one verb
+namespace {
+
+struct PutWait
+{
+    struct Longtail_AsyncPutStoredBlockAPI api;
+    std::mutex m;
+    std::condition_variable cv;
+    bool done = false;
+    int err = 0;
+};
+void put_wait_done(struct Longtail_AsyncPutStoredBlockAPI* api, int err)
+{
+    PutWait* w = reinterpret_cast<PutWait*>(api);
+    std::lock_guard<std::mutex> g(w->m);
+    w->err = err;
+    w->done = true;
+    w->cv.notify_all();
+}
+
+struct WriteSink
+{
+    struct Longtail_BlockStoreAPI* store;
+    struct Longtail_ProgressAPI* progress;
+    struct Longtail_CancelAPI* cancel;
+    Longtail_CancelAPI_HCancelToken token;
+    uint32_t total, done;
+};
+
+// lt_b200_block_sink: the byte image becomes a Longtail_StoredBlock whose index points into it (Longtail_InitStoredBlockFromData,
+// src/longtail.c:4056-4109); the image is only valid during the call, so the put is awaited here
+int write_content_sink(void* user, const struct lt_b200_stored_block_view* v)
+{
+    WriteSink* ws = static_cast<WriteSink*>(user);
+    if (ws->cancel && ws->cancel->IsCancelled(ws->cancel, ws->token) == ECANCELED) return ECANCELED;
+    uint8_t* p = static_cast<uint8_t*>(const_cast<void*>(v->data));
+    const uint32_t n = v->chunk_count;
+    struct Longtail_BlockIndex bi;
+    bi.m_BlockHash = reinterpret_cast<TLongtail_Hash*>(p);
+    bi.m_HashIdentifier = reinterpret_cast<uint32_t*>(p + 8);
+    bi.m_ChunkCount = reinterpret_cast<uint32_t*>(p + 12);
+    bi.m_Tag = reinterpret_cast<uint32_t*>(p + 16);
+    bi.m_ChunkHashes = reinterpret_cast<TLongtail_Hash*>(p + 20);
+    bi.m_ChunkSizes = reinterpret_cast<uint32_t*>(p + 20 + 8 * (size_t)n);
+    struct Longtail_StoredBlock sb;
+    sb.Dispose = nullptr;
+    sb.m_BlockIndex = &bi;
+    sb.m_BlockData = p + block_index_data_size(n);
+    sb.m_BlockChunksDataSize = (uint32_t)(v->size - block_index_data_size(n));
+    PutWait w;
+    w.api.m_API.Dispose = nullptr;
+    w.api.OnComplete = put_wait_done;
+    int err = ws->store->PutStoredBlock(ws->store, &sb, &w.api);
+    if (err) return err; // a non-zero return means OnComplete is not called (src/longtail.c:4747-4757)
+    {
+        std::unique_lock<std::mutex> g(w.m);
+        w.cv.wait(g, [&w] { return w.done; });
+        err = w.err;
+    }
+    ++ws->done;
+    if (!err && ws->progress) ws->progress->OnProgress(ws->progress, ws->total, ws->done);
+    return err;
+}
+
+} // namespace
+
+extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_storage_api, struct Longtail_BlockStoreAPI* backing_block_store_api,
+                                          struct Longtail_JobAPI* job_api, struct Longtail_ProgressAPI* progress_api,
+                                          struct Longtail_CancelAPI* optional_cancel_api, Longtail_CancelAPI_HCancelToken optional_cancel_token,
+                                          struct Longtail_StoreIndex* store_index, struct Longtail_VersionIndex* version_index, const char* assets_folder)
+{
+    // same argument validation as src/longtail.c:4781-4786
+    if (!source_storage_api || !backing_block_store_api || !job_api || !version_index || !store_index || !assets_folder) return EINVAL;
+    const uint32_t block_count = *store_index->m_BlockCount;
+    if (block_count == 0) return 0; // :4788-4792
+    const uint32_t hash_type = *version_index->m_HashIdentifier;
+    const uint32_t A = *version_index->m_AssetCount, C = *version_index->m_ChunkCount, SC = *store_index->m_ChunkCount;
+
+    // CreateAssetPartLookup (:4429-4500): a chunk's bytes come from its first occurrence, assets and chunks in version order
+    std::unordered_map<uint64_t, std::pair<uint32_t, uint64_t>> where; // chunk hash -> (asset, offset inside the asset)
+    where.reserve((size_t)C * 2);
+    for (uint32_t a = 0; a < A; ++a)
+    {
+        uint64_t off = 0;
+        const uint32_t first = version_index->m_AssetChunkIndexStarts[a];
+        for (uint32_t k = 0; k < version_index->m_AssetChunkCounts[a]; ++k)
+        {
+            const uint32_t ci = version_index->m_AssetChunkIndexes[first + k];
+            where.emplace(version_index->m_ChunkHashes[ci], std::make_pair(a, off));
+            off += version_index->m_ChunkSizes[ci];
+        }
+    }
+    std::unordered_map<uint64_t, uint32_t> version_chunk; // :4821-4824
+    version_chunk.reserve((size_t)C * 2);
+    for (uint32_t c = 0; c < C; ++c) version_chunk[version_index->m_ChunkHashes[c]] = c;
+
+    // the chunks in store order with the sizes the VERSION gives them (:4826-4834), the tag of their block, and the assets they need
+    std::vector<uint64_t> hashes(SC), offsets(SC);
+    std::vector<uint32_t> sizes(SC), tags(SC), counts(block_count);
+    std::vector<uint8_t> needed(A ? A : 1, 0);
+    for (uint32_t b = 0; b < block_count; ++b)
+    {
+        counts[b] = store_index->m_BlockChunkCounts[b];
+        if (counts[b] == 0) return EINVAL;
+        const uint32_t tag = store_index->m_BlockTags[b];
+        if (tag != 0 && tag != TYPE_LZ4 && !is_zstd_level3(tag)) return ENOTSUP;
+        for (uint32_t k = 0; k < counts[b]; ++k)
+        {
+            const uint32_t c = store_index->m_BlockChunksOffsets[b] + k;
+            const uint64_t h = store_index->m_ChunkHashes[c];
+            auto vc = version_chunk.find(h);
+            auto w = where.find(h);
+            if (vc == version_chunk.end() || w == where.end()) return EINVAL;
+            hashes[c] = h;
+            sizes[c] = version_index->m_ChunkSizes[vc->second];
+            tags[c] = tag;
+            needed[w->second.first] = 1;
+        }
+    }
+    // arena layout: only the assets that hold a needed chunk
+    std::vector<uint64_t> arena_off(A ? A : 1, 0);
+    uint64_t total = 0;
+    for (uint32_t a = 0; a < A; ++a)
+        if (needed[a])
+        {
+            arena_off[a] = total;
+            total += (version_index->m_AssetSizes[a] + 255u) & ~(uint64_t)255u;
+        }
+    for (uint32_t c = 0; c < SC; ++c)
+    {
+        const auto& w = where[hashes[c]];
+        offsets[c] = arena_off[w.first] + w.second;
+    }
+
+    std::lock_guard<std::mutex> g(g_gpu);
+    int err = ensure_ctx();
+    if (err) return err;
+    const uint64_t arena_bytes = total + 4096;
+    void* arena = nullptr;
+    err = lt_b200_device_alloc(g_ctx, arena_bytes, &arena);
+    if (err) return err;
+    // the reader of the index verb: StorageAPI reads fanned out over the caller's JobAPI, paths from the version index
+    struct Longtail_FileInfos names;
+    memset(&names, 0, sizeof(names));
+    names.m_Count = A;
+    names.m_PathStartOffsets = version_index->m_NameOffsets;
+    names.m_PathData = version_index->m_NameData;
+    ReadCtx rc = {source_storage_api, assets_folder, &names, job_api, nullptr, optional_cancel_api, optional_cancel_token, 0, 0};
+    const uint64_t stage_bytes = 256ull << 20, piece = 8ull << 20;
+    void* stage = nullptr;
+    err = lt_b200_host_alloc_pinned(g_ctx, stage_bytes, &stage);
+    std::vector<lt_b200_read_job> jobs;
+    std::vector<uint64_t> dst_off;
+    uint64_t used = 0;
+    auto flush = [&]() -> int {
+        if (jobs.empty()) return 0;
+        int e = read_batch(&rc, jobs.data(), (uint32_t)jobs.size());
+        for (size_t i = 0; i < jobs.size() && !e; ++i)
+            e = lt_b200_copy_to_device(g_ctx, static_cast<uint8_t*>(arena) + dst_off[i], jobs[i].dst, jobs[i].size);
+        jobs.clear();
+        dst_off.clear();
+        used = 0;
+        return e;
+    };
+    for (uint32_t a = 0; a < A && !err; ++a)
+    {
+        if (!needed[a]) continue;
+        for (uint64_t o = 0; o < version_index->m_AssetSizes[a] && !err; o += piece)
+        {
+            const uint32_t n = (uint32_t)std::min<uint64_t>(piece, version_index->m_AssetSizes[a] - o);
+            if (used + n > stage_bytes) err = flush();
+            jobs.push_back({a, n, o, static_cast<uint8_t*>(stage) + used});
+            dst_off.push_back(arena_off[a] + o);
+            used += n;
+        }
+    }
+    if (!err) err = flush();
+    if (!err)
+    {
+        WriteSink ws = {backing_block_store_api, progress_api, optional_cancel_api, optional_cancel_token, block_count, 0};
+        err = lt_b200_write_given_blocks_device(g_ctx, static_cast<const uint8_t*>(arena), arena_bytes, SC, hashes.data(), sizes.data(), tags.data(),
+                                                offsets.data(), hash_type, block_count, counts.data(), write_content_sink, &ws);
+    }
+    if (stage) lt_b200_host_free_pinned(g_ctx, stage);
+    lt_b200_device_free(g_ctx, arena);
+    return err;
+}
 
 extern "C" struct Longtail_CompressionAPI* Longtail_CreateB200LZ4CompressionAPI(void)
 {

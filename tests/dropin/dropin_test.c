@@ -305,6 +305,51 @@ int main(int argc, char** argv)
         int e2 = write_content(storage, s_codec, jobs, ref_hash, vi, block_size, per_block, &m_codec);
         CHECK(e2 == 0, "WriteContent through the B200 %s CompressionAPI: %d", codec_name, e2);
         CHECK(k_ref->count > 3 && k_ref->count == k_b200->count && k_ref->count == k_codec->count, "block counts %u %u %u", k_ref->count, k_b200->count, k_codec->count);
+        /* (c) Longtail_B200_WriteContent: WriteContent and the compress block store in one verb, into a plain store, for the store index
+         *     the reference computed; and for a store index with a DIFFERENT block composition (two blocks merged) to show that the
+         *     blocks are written as given, not re-packed */
+        struct keep_store* k_verb = make_keep_store();
+        int e3 = Longtail_B200_WriteContent(storage, &k_verb->api, jobs, 0, 0, 0, m_ref, vi, "root");
+        CHECK(e3 == 0, "Longtail_B200_WriteContent: %d", e3);
+        CHECK(k_verb->count == k_ref->count, "Longtail_B200_WriteContent block count %u vs %u", k_verb->count, k_ref->count);
+        uint32_t same_c = 0;
+        for (uint32_t i = 0; i < k_ref->count; ++i)
+        {
+            const struct kept_block* c = find_block(k_verb, k_ref->blocks[i].hash);
+            if (c && c->size == k_ref->blocks[i].size && memcmp(c->data, k_ref->blocks[i].data, c->size) == 0) ++same_c;
+        }
+        CHECK(same_c == k_ref->count, "Longtail_B200_WriteContent: %u of %u stored blocks identical", same_c, k_ref->count);
+        SAFE_DISPOSE_API(&k_verb->api);
+        {
+            struct Longtail_StoreIndex* regrouped = 0;
+            struct Longtail_StoreIndex* empty = 0;
+            Longtail_CreateStoreIndexFromBlocks(0, 0, &empty);
+            CHECK(Longtail_CreateMissingContent(ref_hash, empty, vi, block_size * 2, per_block * 2, &regrouped) == 0, "larger blocks");
+            struct keep_store* k_r2 = make_keep_store();
+            struct keep_store* k_v2 = make_keep_store();
+            struct Longtail_BlockStoreAPI* s_r2 = Longtail_CreateCompressBlockStoreAPI(&k_r2->api, full);
+            CHECK(Longtail_WriteContent(storage, s_r2, jobs, 0, 0, 0, regrouped, vi, "root") == 0, "reference WriteContent, larger blocks");
+            int e4 = Longtail_B200_WriteContent(storage, &k_v2->api, jobs, 0, 0, 0, regrouped, vi, "root");
+            CHECK(e4 == 0, "Longtail_B200_WriteContent, larger blocks: %d", e4);
+            uint32_t same_d = 0;
+            for (uint32_t i = 0; i < k_r2->count; ++i)
+            {
+                const struct kept_block* d = find_block(k_v2, k_r2->blocks[i].hash);
+                if (d && d->size == k_r2->blocks[i].size && memcmp(d->data, k_r2->blocks[i].data, d->size) == 0) ++same_d;
+            }
+            CHECK(k_r2->count == k_v2->count && same_d == k_r2->count && k_r2->count < k_ref->count, "larger blocks: %u of %u identical (%u before)", same_d, k_r2->count, k_ref->count);
+            printf("Longtail_B200_WriteContent (%s): %u + %u blocks identical to WriteContent -> compressblockstore\n", codec_name, same_c, same_d);
+            /* a store index that names a chunk the version does not hold: EINVAL, like src/longtail.c:4826-4832 */
+            uint64_t saved = regrouped->m_ChunkHashes[0];
+            regrouped->m_ChunkHashes[0] = 0x1234567890abcdefull;
+            struct keep_store* k_bad = make_keep_store();
+            CHECK(Longtail_B200_WriteContent(storage, &k_bad->api, jobs, 0, 0, 0, regrouped, vi, "root") == EINVAL, "unknown chunk must be EINVAL");
+            regrouped->m_ChunkHashes[0] = saved;
+            SAFE_DISPOSE_API(&k_bad->api);
+            SAFE_DISPOSE_API(s_r2);
+            SAFE_DISPOSE_API(&k_r2->api); SAFE_DISPOSE_API(&k_v2->api);
+            Longtail_Free(regrouped); Longtail_Free(empty);
+        }
         uint32_t same_a = 0, same_b = 0, lz4_blocks = 0;
         for (uint32_t i = 0; i < k_ref->count; ++i)
         {
