@@ -121,3 +121,21 @@ def test_upsync_directory_to_directory_matches_reference(reference, tmp_path):
     assert n2 < n1
     assert ol.ref_read_store_dir(reference, ours) == ol.ref_read_store_dir(reference, theirs)
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sub", ["longtail_b200/csrc", "longtail_b200/_lib", "tests/golden"])
+def test_index_real_directories_of_this_repository(reference, sub):
+    """real files (sources, object files, the shared library, fixtures) instead of synthetic bytes: the VersionIndex of the tree equals the
+    reference's, default target chunk size of the CLI"""
+    if reference is None:
+        pytest.skip("oracle/_ref/libref_shim.so not built")
+    import longtail_b200
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), sub)
+    ctx = longtail_b200.Context(0)
+    fl = longtail_b200.FileList(root)
+    assert len(fl.paths) > 3
+    got = ctx.index_file_list(fl, None, target_chunk_size=32768, reader_threads=8)
+    fl.close()
+    ctx.close()
+    assert got == ol.ref_index_directory(reference, root, 32768, workers=8, tag=0)
