@@ -134,7 +134,7 @@ def test_index_real_directories_of_this_repository(reference, sub):
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), sub)
     ctx = longtail_b200.Context(0)
     fl = longtail_b200.FileList(root)
-    assert len(fl.paths) > 3
+    assert len(fl.paths) >= 3
     got = ctx.index_file_list(fl, None, target_chunk_size=32768, reader_threads=8)
     fl.close()
     ctx.close()
