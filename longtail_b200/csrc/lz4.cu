@@ -184,6 +184,10 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
                     w_next = valid_next ? rd64(src, p_next) : 0ull;
                 }
                 const uint32_t h = valid ? lz4_hash_word<U16>(w) : 0xffffffffu - lane;
+                // the table entry is requested BEFORE the intra-batch conflict resolution: it does not depend on it, and MATCH.ANY plus
+                // the dependent shuffles take about as long as the load itself (a lane that ends up using a lower lane's position drops it)
+                TabEntry e = {0u, 0u};
+                if (valid) e = tab_get<U16>(table, h);
                 const uint32_t same = __match_any_sync(FULL, h);
                 const uint32_t lower = same & ((1u << lane) - 1u);
                 // candidate = what the sequential loop would find in the table: the closest lower lane of this batch with the
@@ -191,8 +195,6 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
                 const int from = lower ? 31 - __clz(lower) : (int)lane;
                 const uint32_t from_lane = __shfl_sync(FULL, p, from);
                 const uint32_t from_tag = __shfl_sync(FULL, (uint32_t)w, from);
-                TabEntry e = {0u, 0u};
-                if (!lower && valid) e = tab_get<U16>(table, h);
                 const uint32_t cand = lower ? from_lane : e.pos;
                 const uint32_t tag = lower ? from_tag : e.tag;
                 bool hit = false;

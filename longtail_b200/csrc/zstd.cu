@@ -1235,6 +1235,15 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
             const uint64_t w = readable ? rd64(s, cp) : 0ull;
             const uint32_t hl = readable ? hash_long(w, hl_bits) : 0xffffffffu - lane;
             const uint32_t hs = readable ? hash_short_w(w, hs_bits, mls) : 0xffffffffu - lane;
+            // both table entries are requested BEFORE the intra-batch conflict resolution: they do not depend on it, and the two MATCH.ANY
+            // plus the dependent shuffles take about as long as the loads (a lane that ends up using a lower lane's position drops them)
+            uint4 el = make_uint4(0u, 0u, 0u, 0u);
+            uint2 es = make_uint2(0u, 0u);
+            if (readable)
+            {
+                el = hash_l[hl];
+                es = hash_s[hs];
+            }
             const uint32_t valids = __ballot_sync(FULL, valid);
             const uint32_t below = (1u << lane) - 1u;
             const uint32_t same_l = __match_any_sync(FULL, hl);
@@ -1245,10 +1254,6 @@ __device__ uint32_t dfast_block_w(ZstdWorker* W, const uint8_t* __restrict__ s, 
             const uint32_t from_s = __shfl_sync(FULL, cp, src_s);
             const uint64_t from_wl = __shfl_sync(FULL, w, src_l);
             const uint32_t from_ws = __shfl_sync(FULL, (uint32_t)w, src_s);
-            uint4 el = make_uint4(0u, 0u, 0u, 0u);
-            uint2 es = make_uint2(0u, 0u);
-            if (!low_l && readable) el = hash_l[hl];
-            if (!low_s && readable) es = hash_s[hs];
             const uint32_t cand_l = low_l ? from_l + 2 : el.x;
             const uint32_t cand_s = low_s ? from_s + 2 : es.x;
             const uint64_t tag_l = low_l ? from_wl : ((uint64_t)el.y | ((uint64_t)el.z << 32)); // the 8 bytes at the long candidate
