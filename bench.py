@@ -309,6 +309,7 @@ def run_b200(args):
     all_assets = longtail_b200.AssetList(["f%05d.bin" % r for r in range(world)], [nbytes] * world)
     my_asset = longtail_b200.AssetList(["f%05d.bin" % rank], [nbytes])
     jobs = ltd.plan_jobs([nbytes] * world, TARGET_CHUNK_SIZE)
+    job_asset_ids = ltd.job_assets(jobs)  # once, outside the timed steps
     my_jobs = [j for j in jobs if j[0] == rank]
     ranges = [(start, size, 0) for _, start, size in my_jobs]
     index_bytes = [0]
@@ -328,7 +329,7 @@ def run_b200(args):
             jc, gh, gs, gt = ltd.allgather_tables(counts, hashes, sizes, tags)
             stream.synchronize()
             if rank == 0:
-                acc = ltd.asset_chunk_counts(jobs, jc.cpu().numpy(), world)
+                acc = ltd.asset_chunk_counts(job_asset_ids, jc.cpu().numpy(), world)
                 v = ctx.build_version_index_device(all_assets, acc, gh.numel(), gh.data_ptr(), gs.data_ptr(), gt.data_ptr(),
                                                    target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
                 index_bytes[0] = len(v)

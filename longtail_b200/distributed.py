@@ -42,12 +42,16 @@ def shard_jobs(jobs, world):
     return [(bounds[r], max(bounds[r], bounds[r + 1])) for r in range(world)]
 
 
+def job_assets(jobs):
+    """the asset index of every job as an array — computed once per job list, so that the per-step merge below is vectorised"""
+    return np.fromiter((j[0] for j in jobs), dtype=np.int64, count=len(jobs))
+
+
 def asset_chunk_counts(jobs, job_chunk_counts, asset_count):
-    """sum the per-job chunk counts per asset (src/longtail.c:2499-2517)"""
-    out = np.zeros(asset_count, dtype=np.uint32)
-    for (a, _, _), n in zip(jobs, job_chunk_counts):
-        out[a] += int(n)
-    return out
+    """sum the per-job chunk counts per asset (src/longtail.c:2499-2517); `jobs` is the job list or job_assets(jobs)"""
+    assets = jobs if isinstance(jobs, np.ndarray) else job_assets(jobs)
+    counts = np.asarray(job_chunk_counts, dtype=np.int64)[:assets.size]
+    return np.bincount(assets, weights=counts, minlength=int(asset_count)).astype(np.uint32)
 
 
 def allgather_tables(local_job_counts, hashes, sizes, tags, group=None):
