@@ -21,6 +21,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
+#include <stdio.h>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -246,6 +248,9 @@ extern "C" int lt_b200_upsync_file_list(lt_b200_context* context, const lt_b200_
                                         lt_b200_fs_store* store, const void** out_version_index, uint64_t* out_size, uint32_t* out_blocks_written)
 {
     if (!context || !list || !store || !out_version_index || !out_size) return EINVAL;
+    const bool trace = getenv("LT_B200_TRACE") != nullptr; // phase times on stderr
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     const uint32_t n = list->assets.asset_count;
     std::vector<uint64_t> arena_off(n ? n : 1);
     uint64_t total = 0;
@@ -315,10 +320,12 @@ extern "C" int lt_b200_upsync_file_list(lt_b200_context* context, const lt_b200_
             which ^= 1;
         }
     }
+    const double t_loaded = now();
     const void* vi = nullptr;
     uint64_t vi_size = 0;
     if (!err) err = lt_b200_index_device_assets(context, static_cast<const uint8_t*>(arena), arena_bytes, &list->assets, arena_off.data(), asset_tags, hash_type,
                                                 target_chunk_size, &vi, &vi_size);
+    const double t_indexed = now();
     if (!err)
     {
         // the unique chunks of the version, in version order, from the serialised index (src/longtail.c:2566-2584): 6 x u32, then
@@ -364,6 +371,9 @@ extern "C" int lt_b200_upsync_file_list(lt_b200_context* context, const lt_b200_
         *out_version_index = vi;
         *out_size = vi_size;
     }
+    if (trace)
+        fprintf(stderr, "lt_b200_upsync_file_list: %.2f GiB: read + H2D %.3f s, index %.3f s, missing + blocks + sink + flush %.3f s\n", total / 1073741824.0,
+                t_loaded - t_start, t_indexed - t_loaded, now() - t_indexed);
     if (stage[0]) lt_b200_host_free_pinned(context, stage[0]);
     if (stage[1]) lt_b200_host_free_pinned(context, stage[1]);
     lt_b200_device_free(context, arena);

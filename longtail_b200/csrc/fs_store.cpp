@@ -216,10 +216,16 @@ struct lt_b200_fs_store
     std::unordered_map<uint64_t, int> block_state; // 0 = being written, 1 = stored (m_BlockState)
     std::vector<BlockRec> added;                   // in put order
     uint32_t in_flight = 0;
-    bool stop = false;
+    std::atomic<bool> stop{false};
     int first_error = 0;
     uint64_t blocks_written = 0, bytes_written = 0, blocks_skipped = 0;
     size_t queue_limit = 32;
+    // the copy of a block image out of the caller's staging memory is shared between the sink thread and a few copier threads
+    struct CopyPart { uint8_t* dst; const uint8_t* src; size_t size; std::atomic<uint32_t>* left; };
+    std::mutex copy_lock;
+    std::condition_variable wake_copier;
+    std::deque<CopyPart> copy_queue;
+    std::vector<std::thread> copiers;
 };
 
 namespace {
@@ -299,6 +305,49 @@ void writer_main(lt_b200_fs_store* s)
     }
 }
 
+void copier_main(lt_b200_fs_store* s)
+{
+    for (;;)
+    {
+        lt_b200_fs_store::CopyPart c;
+        {
+            std::unique_lock<std::mutex> g(s->copy_lock);
+            s->wake_copier.wait(g, [s] { return s->stop || !s->copy_queue.empty(); });
+            if (s->copy_queue.empty()) return;
+            c = s->copy_queue.front();
+            s->copy_queue.pop_front();
+        }
+        memcpy(c.dst, c.src, c.size);
+        c.left->fetch_sub(1, std::memory_order_acq_rel);
+    }
+}
+
+// dst[0..size) = src[0..size) with the copier threads' help; returns when the whole image has been copied
+void copy_shared(lt_b200_fs_store* s, uint8_t* dst, const uint8_t* src, size_t size)
+{
+    const size_t parts = s->copiers.empty() || size < (2u << 20) ? 1 : s->copiers.size() + 1;
+    if (parts == 1)
+    {
+        memcpy(dst, src, size);
+        return;
+    }
+    const size_t per = ((size + parts - 1) / parts + 4095) & ~(size_t)4095;
+    std::atomic<uint32_t> left(0);
+    uint32_t queued = 0;
+    {
+        std::lock_guard<std::mutex> g(s->copy_lock);
+        for (size_t off = per; off < size; off += per)
+        {
+            s->copy_queue.push_back({dst + off, src + off, size - off < per ? size - off : per, &left});
+            ++queued;
+        }
+        left.store(queued);
+    }
+    s->wake_copier.notify_all();
+    memcpy(dst, src, per < size ? per : size);
+    while (left.load(std::memory_order_acquire)) std::this_thread::yield();
+}
+
 void drain(lt_b200_fs_store* s)
 {
     std::unique_lock<std::mutex> g(s->lock);
@@ -323,6 +372,7 @@ extern "C" int lt_b200_fs_store_open(const char* store_path, uint32_t writer_thr
     s->tmp_ext[17] = 0;
     s->queue_limit = writer_threads ? 4 * (size_t)writer_threads : 0;
     for (uint32_t i = 0; i < writer_threads; ++i) s->writers.emplace_back(writer_main, s);
+    for (uint32_t i = 0; i < (writer_threads >= 4 ? 3u : 0u); ++i) s->copiers.emplace_back(copier_main, s);
     *out_store = s;
     return 0;
 }
@@ -368,7 +418,7 @@ extern "C" int lt_b200_fs_store_sink(void* user, const struct lt_b200_stored_blo
         finish_job(s, j, ENOMEM, false);
         return ENOMEM;
     }
-    memcpy(j.data, block->data, j.size);
+    copy_shared(s, static_cast<uint8_t*>(j.data), static_cast<const uint8_t*>(block->data), j.size);
     {
         std::unique_lock<std::mutex> g(s->lock);
         s->wake_producer.wait(g, [s] { return s->queue.size() < s->queue_limit; });
@@ -468,6 +518,11 @@ extern "C" int lt_b200_fs_store_close(lt_b200_fs_store* s)
     }
     s->wake_writer.notify_all();
     for (auto& t : s->writers) t.join();
+    {
+        std::lock_guard<std::mutex> g(s->copy_lock); // stop is read under this lock by the copiers
+    }
+    s->wake_copier.notify_all();
+    for (auto& t : s->copiers) t.join();
     delete s;
     return err;
 }

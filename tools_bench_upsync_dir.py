@@ -38,7 +38,7 @@ try:
         t0 = time.perf_counter()
         files = longtail_b200.FileList(src, threads=16)
         t1 = time.perf_counter()
-        store = longtail_b200.FsStore(ours, writer_threads=8)
+        store = longtail_b200.FsStore(ours, writer_threads=12)
         vi, blocks = ctx.upsync_file_list(files, store, [longtail_b200.COMPRESSION_LZ4] * len(files.paths), target_chunk_size=65536, reader_threads=16)
         store.close()
         files.close()
