@@ -121,3 +121,46 @@ def test_rejects_foreign_store_index_and_bad_image(fs, tmp_path):
         st.put(1, b"\x00" * 24 + b"\x07" * 8)  # hash in the image differs from the view's
     st.close()  # nothing was added: the foreign index is left alone
     assert (root / "store.lsi").read_bytes()[:4] == b"\x02\x00\x00\x00"
+
+
+def test_two_stores_one_directory_concurrently(fs, reference, tmp_path):
+    """two store objects (as two uploading processes would hold) put overlapping block sets into one directory from two threads and flush:
+    every block file exists once, complete; store.lsi lists the union exactly once (flock + merge with the index on disk), and the
+    unmodified reference reads the whole store back"""
+    if reference is None:
+        pytest.skip("oracle/_ref/libref_shim.so not built")
+    import threading
+    assets = version(30, extra=[("e/more.bin", synth_bytes(31, 900000, "rec"))])
+    blocks, _ = reference.upsync(assets, 16384, max_block_size=131072, max_chunks_per_block=32, tags=TAGS4 + [ol.COMP_LZ4])
+    assert len(blocks) > 12
+    root = str(tmp_path / "shared")
+    halves = [blocks[:2 * len(blocks) // 3], blocks[len(blocks) // 3:]]  # the middle third is put by both
+    errors = []
+
+    def upload(part):
+        try:
+            st = fs.FsStore(root, writer_threads=3)
+            for h, image in part:
+                st.put(h, image)
+            st.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=upload, args=(p,)) for p in halves]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    files = tree(root)
+    lrb = {k: v for k, v in files.items() if k.endswith(".lrb")}
+    assert len(lrb) == len(blocks)
+    by_hash = {"chunks/%s/0x%016x.lrb" % (("%016x" % h)[:4], h): img for h, img in blocks}
+    assert lrb == by_hash
+    assert not [k for k in files if k != "store.lsi" and not k.endswith(".lrb")]  # no temporary file left behind
+    lsi = files["store.lsi"]
+    nb = int(np.frombuffer(lsi, dtype=np.uint32, count=1, offset=8)[0])
+    hashes = np.frombuffer(lsi, dtype=np.uint64, count=nb, offset=16)
+    assert sorted(hashes.tolist()) == sorted(h for h, _ in blocks)
+    got = ol.ref_read_store_dir(reference, root)
+    assert got[0] == len(blocks)
