@@ -1,5 +1,5 @@
 """end-to-end upsync of a real directory tree on a RAM-backed file system, this repository vs the unmodified reference on the same box:
-    python tools_bench_upsync_dir.py [GiB] [files]
+    python tests/tools_bench_upsync_dir.py [GiB] [files]
 scan -> read -> CreateVersionIndex -> CreateMissingContent -> WriteContent (LZ4) -> fsblockstore directory + store.lsi.
 Both sides read the same files from /dev/shm and write their store there, so the number compares the pipelines, not a disk."""
 import os
@@ -10,10 +10,11 @@ import time
 
 import numpy as np
 
-import longtail_b200
-
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
-import oracle_lib as ol  # noqa: E402  (the reference arm of this tool; the product never loads it)
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import longtail_b200  # noqa: E402
+import oracle_lib as ol  # noqa: E402  (the reference arm of this measurement; it lives under tests/ because only tests may run the checker)
 
 gib = float(sys.argv[1]) if len(sys.argv) > 1 else 8.0
 nfiles = int(sys.argv[2]) if len(sys.argv) > 2 else 64

@@ -1,7 +1,8 @@
 """debug: compare the GPU WriteContent with the reference upsync block by block on the bench's configs[2] sample"""
 import sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
 import numpy as np
 import longtail_b200, oracle_lib as ol
 import bench
