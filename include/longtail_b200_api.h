@@ -85,8 +85,8 @@ LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CompressionRegistry_Crea
  * background thread, the caller's block stays alive until OnComplete as in the reference (:151-176) — and forwards the
  * compressed block to the backing store; GetStoredBlock fetches from the backing store and decodes on the GPU;
  * tag 0 passes through untouched; PruneBlocks returns ENOTSUP (:483-493); stats count what the reference counts (:199-201,
- * :362-363).  PutStoredBlock handles 'lz42', 'ztd1' and 'ztd2' (ZStd level 3); GetStoredBlock decodes 'lz42'.  Compression types without a
- * device kernel make PutStoredBlock / GetStoredBlock fail with ENOTSUP.
+ * :362-363).  PutStoredBlock handles 'lz42', 'ztd1' and 'ztd2' (ZStd level 3); GetStoredBlock decodes 'lz42' and every 'ztd?' id (frames of all
+ * levels).  Compression types without a device kernel make PutStoredBlock / GetStoredBlock fail with ENOTSUP.
  * `compression_registry` is accepted for signature compatibility and not used. */
 LT_B200_EXPORT struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockStoreAPI(
     struct Longtail_BlockStoreAPI* backing_block_store,
