@@ -195,11 +195,11 @@ LT_B200_EXPORT int lt_b200_index_host_assets(lt_b200_context* context, const str
  * Replaces, for chunks whose bytes are resident in a device arena: Longtail_CreateStoreIndex's packing
  * (src/longtail.c:6745-6880), Longtail_CreateBlockIndex (:3712-3770), WriteContentBlockJob's payload gather (:4559-4758) and
  * compressblockstore's CompressBlock (lib/compressblockstore/longtail_compressblockstore.c:67-141) with the LZ4 backend
- * (lib/lz4/longtail_lz4.c:52-77).  `chunk_*` are HOST arrays listing the chunks to store, in store order (for a fresh store:
+ * (lib/lz4/longtail_lz4.c:52-77) or the ZStd level 3 backend (lib/zstd/longtail_zstd.c:107-140).  `chunk_*` are HOST arrays listing the chunks to store, in store order (for a fresh store:
  * the unique chunks of the VersionIndex in order — DiffHashes keeps that order, src/longtail.c:6718-6740).
  * Every finished block is handed to `sink` in store order as the exact byte image Longtail_WriteStoredBlockToBuffer
- * (src/longtail.c:4111-4150) would produce; the memory is only valid during the call.  Tags: 0 = stored raw, 'lz42' = LZ4;
- * anything else returns ENOTSUP. */
+ * (src/longtail.c:4111-4150) would produce; the memory is only valid during the call.  Tags: 0 = stored raw, 'lz42' = LZ4,
+ * 'ztd1' / 'ztd2' = ZStd level 3; anything else returns ENOTSUP. */
 struct lt_b200_stored_block_view
 {
     uint64_t block_hash;
