@@ -164,3 +164,20 @@ def test_two_stores_one_directory_concurrently(fs, reference, tmp_path):
     assert sorted(hashes.tolist()) == sorted(h for h, _ in blocks)
     got = ol.ref_read_store_dir(reference, root)
     assert got[0] == len(blocks)
+
+
+@pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])
+def test_fs_store_under_sanitizers(tmp_path, sanitizer):
+    """fs_store.cpp compiled with ThreadSanitizer / AddressSanitizer + UBSan: two stores, 60 blocks of 3 MiB each, 30 of them put by both,
+    flushes in between — no report, and store.lsi lists the union"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "race")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=" + sanitizer, "-o", exe, os.path.join(root, "tests", "host", "fs_store_race.cpp"),
+                        os.path.join(root, "longtail_b200", "csrc", "fs_store.cpp"), "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("this toolchain lacks -fsanitize=" + sanitizer)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe, str(tmp_path / "store")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr[-3000:]
+    assert "chunks listed: 450" in r.stdout and "Sanitizer" not in r.stderr
