@@ -323,24 +323,399 @@ __device__ uint32_t lz4_encode_block(const uint8_t* __restrict__ src, uint32_t n
     return op;
 }
 
+
+// ======================================================================================================================
+// v2 encoder — byU32 blocks of at most 16 MiB (every block of the default 8 MiB / 1024-chunk packing): the hash table lives in
+// SHARED memory as ONE 32-bit word per slot, {position mod 2^17 | valid | 14-bit tag of the 4 bytes at that position}, 16 KiB per
+// warp, 13 warps per SM.  What the table answers is unchanged (lz4.c:1085-1092: the latest position with this hash, usable when it
+// is at most 65 535 bytes back and starts with the same 4 bytes):
+//   * a position is only ever compared with positions at most 65 535 bytes ahead of it, so 17 bits identify it as long as no
+//     entry older than 2^17 bytes survives: every <= 48 KiB of progress the warp sweeps the table and invalidates the entries
+//     that are out of reach for good (128 words per lane, ~3 % of the probe work on dense data);
+//   * the tag answers LZ4_read32(match) == LZ4_read32(ip) without touching the source; a tag match (true match, or one in 2^14
+//     by chance) is verified against the source in the same round trip that fetches the bytes of the match extension.
+// A probe batch (32 positions of the skip schedule) is: read the slots, write the own entries, read back.  If every lane reads
+// its own entry back, the 32 hashes were distinct; if in addition no tag matched, the table already is what the sequential
+// loop would have left and the batch is done — no MATCH.ANY, no global memory round trip.  Everything else (intra-batch
+// conflicts, a hit, the end of the block) goes through the general path, which resolves the batch exactly like v1 and
+// repairs the slots the eager writes touched.
+namespace v2 {
+
+constexpr uint32_t POS_MASK = 0x1ffffu;
+constexpr uint32_t VALID = 0x20000u;
+constexpr uint32_t HI_MASK = 0xfffe0000u;  // valid bit + tag
+constexpr uint32_t TAG_MASK = 0xfffc0000u;
+constexpr uint32_t TABLE_WORDS = 4096;
+constexpr uint32_t SWEEP_TRIGGER = 49152;  // sweep when a probe would lie this far beyond the last sweep position
+constexpr uint32_t MAX_N = 16u << 20;      // probe batches span < 32 KiB up to here (step <= 725)
+constexpr uint32_t DEFER_MIN = 256;        // literal runs from this length on are copied by k_lz4_copy
+constexpr uint32_t JOB_PIECE = 65536;      // ... in pieces of at most this many bytes (one warp each)
+
+__device__ __forceinline__ uint32_t entry_of(uint32_t p, uint32_t w32) { return ((w32 * 2246822519u) & TAG_MASK) | (p & POS_MASK) | VALID; }
+__device__ __forceinline__ uint32_t hash5(uint64_t w) { return (uint32_t)(((w << 24) * 889523592379ull) >> 52); }
+__device__ __forceinline__ uint64_t ld_word(const uint8_t* __restrict__ s, uint32_t p, uint32_t n) { return p < n ? rd64(s, p) : 0ull; }
+
+// invalidate every entry more than 65 535 bytes behind q.  Exact while all valid entries are less than 2^17 bytes behind q.
+__device__ __forceinline__ void sweep(uint32_t* table, uint32_t q, uint32_t lane)
+{
+    uint4* t4 = reinterpret_cast<uint4*>(table);
+#pragma unroll 4
+    for (uint32_t i = lane; i < TABLE_WORDS / 4; i += 32)
+    {
+        uint4 v = t4[i];
+        if (((q - v.x) & POS_MASK) > LZ4_MAX_DISTANCE) v.x = 0;
+        if (((q - v.y) & POS_MASK) > LZ4_MAX_DISTANCE) v.y = 0;
+        if (((q - v.z) & POS_MASK) > LZ4_MAX_DISTANCE) v.z = 0;
+        if (((q - v.w) & POS_MASK) > LZ4_MAX_DISTANCE) v.w = 0;
+        t4[i] = v;
+    }
+}
+// Invariant: every valid entry lies at or after sweep_base - 65535.  `top` = the highest position inserted so far.
+__device__ __noinline__ uint32_t sweep_to(uint32_t* table, uint32_t sweep_base, uint32_t q, uint32_t top, uint32_t lane)
+{
+    __syncwarp();
+    if (q - sweep_base > 65536u) // only after a match longer than 16 KiB
+    {
+        if (q > top + LZ4_MAX_DISTANCE)
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(table);
+            for (uint32_t i = lane; i < TABLE_WORDS / 4; i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            return q;
+        }
+        while (q - sweep_base > 65536u)
+        {
+            sweep(table, sweep_base + 65536u, lane);
+            sweep_base += 65536u;
+        }
+    }
+    sweep(table, q, lane);
+    __syncwarp();
+    return q;
+}
+
+// lane l: fx = the words at ip0 + 4l and m0 + 4l xor-ed (lane 0 = the 4 bytes of the match itself, lanes 1.. = LZ4_count's first
+// 124 bytes, lz4.c:1181); beq = the bytes l + 1 before both positions are equal (catch-up, lz4.c:1104-1109).  One round trip.
+__device__ __forceinline__ void load_match_words(const uint8_t* __restrict__ src, uint32_t ip0, uint32_t m0, uint32_t anchor, uint32_t matchlimit,
+                                                 uint32_t lane, uint32_t& fx, bool& beq)
+{
+    const uint32_t pa = ip0 + 4u * lane;
+    fx = 0xffffffffu;
+    if (lane == 0 || pa < matchlimit) fx = rd32(src, pa) ^ rd32(src, m0 + 4u * lane);
+    beq = false;
+    if (ip0 > anchor + lane && m0 > lane) beq = src[ip0 - 1u - lane] == src[m0 - 1u - lane];
+}
+
+__device__ __forceinline__ void emit_runs(uint8_t* __restrict__ dst, uint32_t op, const uint8_t* __restrict__ src, uint32_t from, uint32_t lit,
+                                              uint32_t lane, CopyJobs& cj)
+{
+    if (lit >= DEFER_MIN)
+    {
+        const uint32_t pieces = (lit + JOB_PIECE - 1u) / JOB_PIECE;
+        for (uint32_t i = lane; i < pieces; i += 32)
+        {
+            const uint32_t o = i * JOB_PIECE;
+            cj.jobs[cj.count + i] = make_uint3(op + o, from + o, min(JOB_PIECE, lit - o));
+        }
+        cj.count += pieces;
+    }
+    else if (lit)
+        copy_bytes(dst + op, src + from, lit, lane);
+}
+
+__device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t n, uint8_t* __restrict__ dst, uint32_t* table, const uint32_t lane,
+                                 CopyJobs& cj)
+{
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t mflimit_plus_one = n - 11, matchlimit = n - 5;
+    uint32_t op = 0, anchor = 0;
+    {
+        // zeroed table = every slot points at position 0 (lz4.c:1004-1010); inserting position 0 itself changes nothing
+        const uint32_t init = entry_of(0u, rd32(src, 0));
+        uint4* t4 = reinterpret_cast<uint4*>(table);
+        for (uint32_t i = lane; i < TABLE_WORDS / 4; i += 32) t4[i] = make_uint4(init, init, init, init);
+    }
+    __syncwarp();
+    uint32_t sweep_base = 0;
+    uint32_t S = 1; // start of the current search
+    bool finished = false;
+    uint32_t pA = S + lane; // probe_pos(S, k) = S + k for k <= 64
+    uint64_t wA = ld_word(src, pA, n);
+    for (;;)
+    {
+        // ---------------- search (lz4.c:1043-1100): 32 probes per batch, the source words two batches ahead in flight
+        uint32_t k0 = 0;
+        uint32_t pB = probe_pos(S, 32u + lane);
+        uint64_t wB = ld_word(src, pB, n);
+        uint32_t ip0 = 0, m0 = 0, fx = 0;
+        bool beq = false;
+        for (;;)
+        {
+            const uint32_t p = pA;
+            const uint64_t w = wA;
+            pA = pB;
+            wA = wB;
+            pB = probe_pos(S, k0 + 64u + lane);
+            wB = ld_word(src, pB, n);
+            const uint32_t p_last = probe_pos(S, k0 + 31u);
+            if (p_last >= sweep_base + SWEEP_TRIGGER)
+            {
+                const uint32_t q = probe_pos(S, k0);
+                sweep_base = sweep_to(table, sweep_base, q, q, lane);
+            }
+            const bool all_valid = p_last + probe_advance(k0 + 31u) <= mflimit_plus_one; // else: goto _last_literals inside this batch
+            const uint32_t lo = (uint32_t)w;
+            const uint32_t h = hash5(w);
+            const uint32_t mine = entry_of(p, lo);
+            uint32_t e = 0;
+            bool valid = true;
+            if (all_valid)
+            {
+                e = table[h];
+                __syncwarp();
+                table[h] = mine;
+                __syncwarp();
+                const uint32_t r = table[h];
+                const bool pot = ((e ^ mine) & HI_MASK) == 0u && ((p - e) & POS_MASK) <= LZ4_MAX_DISTANCE;
+                if (!__any_sync(FULL, pot || r != mine))
+                {
+                    k0 += 32;
+                    continue;
+                }
+            }
+            else
+            {
+                valid = p < n && p + probe_advance(k0 + lane) <= mflimit_plus_one;
+                if (valid) e = table[h];
+                __syncwarp();
+            }
+            // ---- general path: what v1 does for every batch.  A lane's candidate is the closest lower lane of this batch with the
+            // same hash, else the table entry it read before the batch wrote anything
+            const uint32_t same = __match_any_sync(FULL, valid ? h : 0x10000u + lane);
+            const uint32_t lower = same & lt_mask;
+            const int from = lower ? 31 - __clz(lower) : (int)lane;
+            const uint32_t p_from = __shfl_sync(FULL, p, from);
+            const uint32_t lo_from = __shfl_sync(FULL, lo, from);
+            uint32_t cand;
+            bool pot;
+            if (lower)
+            {
+                cand = p_from;
+                pot = valid && lo_from == lo && p - cand <= LZ4_MAX_DISTANCE;
+            }
+            else
+            {
+                const uint32_t age = (p - e) & POS_MASK;
+                cand = p - age;
+                pot = valid && ((e ^ mine) & HI_MASK) == 0u && age <= LZ4_MAX_DISTANCE;
+            }
+            uint32_t pots = __ballot_sync(FULL, pot);
+            const uint32_t valids = __ballot_sync(FULL, valid);
+            uint32_t first_hit = 32;
+            while (pots) // the first candidate that really starts with the same 4 bytes
+            {
+                const uint32_t f = (uint32_t)__ffs(pots) - 1u;
+                ip0 = __shfl_sync(FULL, p, f);
+                m0 = __shfl_sync(FULL, cand, f);
+                load_match_words(src, ip0, m0, anchor, matchlimit, lane, fx, beq);
+                if (__shfl_sync(FULL, fx, 0) == 0u)
+                {
+                    first_hit = f;
+                    break;
+                }
+                pots &= pots - 1u;
+            }
+            // table: the writes of the valid lanes up to and including the first hit are committed (the last writer of a hash value
+            // wins); a slot only lanes beyond the hit wrote eagerly gets its old content back
+            const uint32_t commit = valids & (first_hit >= 31u ? FULL : ((2u << first_hit) - 1u));
+            const uint32_t group = same & commit;
+            if (valid)
+            {
+                if (group)
+                {
+                    if ((uint32_t)(31 - __clz(group)) == lane) table[h] = mine;
+                }
+                else if (all_valid && (uint32_t)__ffs(same) - 1u == lane)
+                    table[h] = e;
+            }
+            __syncwarp();
+            if (first_hit < 32) break;
+            if (valids != FULL)
+            {
+                finished = true;
+                break;
+            }
+            k0 += 32;
+        }
+        if (finished) break;
+
+        // ---------------- catch up (lz4.c:1104-1109)
+        uint32_t top = ip0;
+        uint32_t back;
+        {
+            const uint32_t m = __ballot_sync(FULL, beq);
+            back = m == FULL ? 32u : (uint32_t)__ffs(~m) - 1u;
+        }
+        if (back == 32u)
+            for (;;)
+            {
+                bool eq = false;
+                const uint32_t d = back + lane;
+                if (ip0 > anchor + d && m0 > d) eq = src[ip0 - 1u - d] == src[m0 - 1u - d];
+                const uint32_t m = __ballot_sync(FULL, eq);
+                const uint32_t run = m == FULL ? 32u : (uint32_t)__ffs(~m) - 1u;
+                back += run;
+                if (run < 32) break;
+            }
+        uint32_t ip = ip0 - back, match = m0 - back; // where the sequence's match starts; ip0 / m0 / fx describe its forward part
+        uint32_t extra = back;                        // matched bytes in front of ip0
+        for (;;) // _next_match (lz4.c:1140-1296)
+        {
+            // match length beyond MINMATCH: LZ4_count(ip0+4, m0+4, matchlimit) — lanes 1..31 hold the first 124 bytes in fx
+            uint32_t fwd;
+            {
+                const uint32_t pa = ip0 + 4u * lane;
+                uint32_t eqb = 4;
+                bool stop = false;
+                if (lane)
+                {
+                    eqb = 0;
+                    if (pa < matchlimit)
+                    {
+                        eqb = fx ? (uint32_t)(__ffs(fx) - 1) >> 3 : 4u;
+                        const uint32_t room = matchlimit - pa;
+                        if (eqb > room) eqb = room;
+                    }
+                    stop = eqb < 4u;
+                }
+                const uint32_t stops = __ballot_sync(FULL, stop);
+                if (stops)
+                {
+                    const uint32_t f = (uint32_t)__ffs(stops) - 1u;
+                    fwd = 4u * (f - 1u) + __shfl_sync(FULL, eqb, f);
+                }
+                else
+                {
+                    fwd = 124;
+                    uint32_t a = ip0 + 128, b = m0 + 128;
+                    for (;;)
+                    {
+                        const uint32_t pa2 = a + 4u * lane;
+                        uint32_t eq2 = 0;
+                        bool stop2 = true;
+                        if (pa2 < matchlimit)
+                        {
+                            const uint32_t x = rd32(src, pa2) ^ rd32(src, b + 4u * lane);
+                            eq2 = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                            const uint32_t room = matchlimit - pa2;
+                            if (eq2 > room) eq2 = room;
+                            stop2 = eq2 < 4u;
+                        }
+                        const uint32_t stops2 = __ballot_sync(FULL, stop2);
+                        if (stops2)
+                        {
+                            const uint32_t f = (uint32_t)__ffs(stops2) - 1u;
+                            fwd += 4u * f + __shfl_sync(FULL, eq2, f);
+                            break;
+                        }
+                        fwd += 128;
+                        a += 128;
+                        b += 128;
+                    }
+                }
+            }
+            // token, literals, offset, match length (lz4.c:1112-1226); a chained match (post-match test below) has no literals
+            const uint32_t code = extra + fwd;
+            const uint32_t lit = ip - anchor;
+            const uint32_t token_pos = op++;
+            if (lit >= 15) op = put_length(dst, op, lit - 15, lane);
+            emit_runs(dst, op, src, anchor, lit, lane, cj);
+            op += lit;
+            const uint32_t off = ip - match;
+            if (lane == 0)
+            {
+                dst[op] = (uint8_t)off; // LZ4_writeLE16 (lz4.c:1157-1163)
+                dst[op + 1] = (uint8_t)(off >> 8);
+                dst[token_pos] = (uint8_t)((lit >= 15 ? 15u : lit) << 4 | (code >= 15 ? 15u : code));
+            }
+            op += 2;
+            if (code >= 15) op = put_length(dst, op, code - 15, lane);
+            ip = ip0 + 4u + fwd;
+            anchor = ip;
+            if (ip >= mflimit_plus_one) // lz4.c:1233
+            {
+                finished = true;
+                break;
+            }
+            // fill the table with ip-2, then test ip itself (lz4.c:1236-1294); every lane does the same (no broadcast needed).  The
+            // words of the next search's first batch are requested in the same round trip.
+            if (ip >= sweep_base + SWEEP_TRIGGER) sweep_base = sweep_to(table, sweep_base, ip - 2u, top, lane);
+            const uint64_t w2 = rd64(src, ip - 2u), w0 = rd64(src, ip);
+            S = ip + 1u;
+            pA = S + lane;
+            wA = ld_word(src, pA, n);
+            const uint32_t mine0 = entry_of(ip, (uint32_t)w0);
+            const uint32_t h0 = hash5(w0);
+            table[hash5(w2)] = entry_of(ip - 2u, (uint32_t)w2);
+            __syncwarp();
+            const uint32_t e = table[h0];
+            __syncwarp();
+            table[h0] = mine0;
+            __syncwarp();
+            const uint32_t age = (ip - e) & POS_MASK;
+            if (((e ^ mine0) & HI_MASK) == 0u && age <= LZ4_MAX_DISTANCE)
+            {
+                const uint32_t cand = ip - age;
+                load_match_words(src, ip, cand, ip, matchlimit, lane, fx, beq);
+                if (__shfl_sync(FULL, fx, 0) == 0u)
+                {
+                    ip0 = ip;
+                    m0 = cand;
+                    match = cand;
+                    extra = 0;
+                    top = ip;
+                    continue; // token = 0 literals, straight to the next match
+                }
+            }
+            break;
+        }
+        if (finished) break;
+        // lz4.c:1298: forwardH = hash(++ip), a fresh search (step 1, searchMatchNb reset) from S = ip + 1
+    }
+    // last literals (lz4.c:1302-1329)
+    const uint32_t last = n - anchor;
+    const uint32_t token_pos = op++;
+    if (lane == 0) dst[token_pos] = (uint8_t)((last >= 15 ? 15u : last) << 4);
+    if (last >= 15) op = put_length(dst, op, last - 15, lane);
+    emit_runs(dst, op, src, anchor, last, lane, cj);
+    op += last;
+    return op;
+}
+
+} // namespace v2
+
 } // namespace
 
 // one warp (= one CTA) per block.  dst layout per block: [u32 raw_size][u32 compressed_size][codec bytes]  — the payload
-// header compressblockstore writes (lib/compressblockstore/longtail_compressblockstore.c:103-137)
+// header compressblockstore writes (lib/compressblockstore/longtail_compressblockstore.c:103-137).
+// v1 kernel: blocks the v2 kernel does not take (byU16 blocks below 64 KiB, blocks above 16 MiB), or every block when v2 is off.
+__device__ __forceinline__ bool lz4_v2_takes(uint32_t n) { return n >= LZ4_64K_LIMIT && n <= v2::MAX_N; }
+
 __global__ void __launch_bounds__(32)
 k_lz4_blocks(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len,
              uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
              uint3* __restrict__ copy_jobs, const uint32_t* __restrict__ copy_job_start, uint32_t* __restrict__ copy_job_count,
-             uint32_t block_count, uint32_t* __restrict__ g_tables)
+             uint32_t block_count, uint32_t* __restrict__ g_tables, uint32_t v2_on)
 {
     extern __shared__ __align__(16) uint32_t s_shared_table[];
     const uint32_t b = blockIdx.x;
     if (b >= block_count) return;
-    // the hash table lives in HBM/L2 when the caller provides room (32 instead of 14 resident warps per SM), else in shared memory
+    const uint32_t n = raw_len[b];
+    if (v2_on && lz4_v2_takes(n)) return;
+    // the hash table lives in HBM/L2 when the caller provides room (32 instead of 7 resident warps per SM), else in shared memory
     uint32_t* s_table = g_tables ? g_tables + (size_t)b * (LZ4_TABLE_BYTES / 4) : s_shared_table;
     const uint32_t lane = threadIdx.x;
     const uint8_t* src = raw_base + raw_off[b];
-    const uint32_t n = raw_len[b];
     uint8_t* dst = out_base + out_off[b];
     CopyJobs cj = {copy_jobs + copy_job_start[b], 0};
     uint32_t c = n < LZ4_64K_LIMIT ? lz4_encode_block<true>(src, n, dst + 8, s_table, lane, cj)
@@ -354,20 +729,79 @@ k_lz4_blocks(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ 
     }
 }
 
-// the deferred literal runs of k_lz4_blocks: grid = (block, slice); every CTA copies its slice of every job of its block
+// v2 kernel: one warp (= one CTA) and one 16 KiB shared-memory table per block, 13 CTAs per SM; the grid is the work queue
+__global__ void __launch_bounds__(32)
+k_lz4_blocks_v2(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len,
+                uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
+                uint3* __restrict__ copy_jobs, const uint32_t* __restrict__ copy_job_start, uint32_t* __restrict__ copy_job_count,
+                uint32_t block_count)
+{
+    extern __shared__ __align__(16) uint32_t s_shared_table[];
+    const uint32_t b = blockIdx.x;
+    if (b >= block_count) return;
+    const uint32_t n = raw_len[b];
+    if (!lz4_v2_takes(n)) return;
+    const uint32_t lane = threadIdx.x;
+    const uint8_t* src = raw_base + raw_off[b];
+    uint8_t* dst = out_base + out_off[b];
+    CopyJobs cj = {copy_jobs + copy_job_start[b], 0};
+    const uint32_t c = v2::encode_block(src, n, dst + 8, s_shared_table, lane, cj);
+    if (lane == 0)
+    {
+        reinterpret_cast<uint32_t*>(dst)[0] = n;
+        reinterpret_cast<uint32_t*>(dst)[1] = c;
+        out_len[b] = c + 8;
+        copy_job_count[b] = cj.count;
+    }
+}
+
+// dst[0..n) = src[0..n) by one warp: 16-byte stores assembled from the (arbitrarily aligned) source with funnel shifts
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, uint32_t lane)
+{
+    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
+    if (lane < head) d[lane] = s[lane];
+    const uint8_t* s2 = s + head;
+    uint4* d4 = reinterpret_cast<uint4*>(d + head);
+    const uint32_t vecs = n - head >= 20u ? (n - head - 4u) >> 4 : 0u; // the funnel reads one word ahead: stay 4 bytes clear of the end
+    const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - ((uintptr_t)s2 & 3u));
+#pragma unroll 2
+    for (uint32_t v = lane; v < vecs; v += 32)
+    {
+        const uint32_t* w = sw + 4 * v;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        d4[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    for (uint32_t i = head + vecs * 16u + lane; i < n; i += 32) d[i] = s[i];
+}
+
+// the deferred literal runs of the encoders: grid = (block, slice).  A block with many jobs (v2: pieces of <= 64 KiB) hands them to
+// the warps of its CTAs round robin; a block with a few long jobs (v1: the whole incompressible block) is cut into slices instead.
 constexpr uint32_t LZ4_COPY_SLICES = 8;
-__global__ void __launch_bounds__(256)
+constexpr uint32_t LZ4_COPY_WARPS = 8;
+__global__ void __launch_bounds__(LZ4_COPY_WARPS * 32)
 k_lz4_copy(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, uint8_t* __restrict__ out_base,
            const uint64_t* __restrict__ out_off, const uint3* __restrict__ copy_jobs, const uint32_t* __restrict__ copy_job_start,
            const uint32_t* __restrict__ copy_job_count)
 {
     const uint32_t b = blockIdx.x;
     const uint32_t njobs = copy_job_count[b];
+    const uint3* jobs = copy_jobs + copy_job_start[b];
     const uint8_t* src = raw_base + raw_off[b];
     uint8_t* dst = out_base + out_off[b] + 8;
+    if (njobs >= 2 * LZ4_COPY_SLICES * LZ4_COPY_WARPS)
+    {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        for (uint32_t j = blockIdx.y * LZ4_COPY_WARPS + warp; j < njobs; j += LZ4_COPY_SLICES * LZ4_COPY_WARPS)
+        {
+            const uint3 job = jobs[j];
+            warp_copy(dst + job.x, src + job.y, job.z, lane);
+        }
+        return;
+    }
     for (uint32_t j = 0; j < njobs; ++j)
     {
-        const uint3 job = copy_jobs[copy_job_start[b] + j];
+        const uint3 job = jobs[j];
         // slice boundaries on 16-byte multiples of the job
         const uint32_t per = ((job.z + LZ4_COPY_SLICES - 1) / LZ4_COPY_SLICES + 15u) & ~15u;
         const uint32_t lo = min(job.z, per * blockIdx.y), hi = min(job.z, lo + per);
@@ -504,26 +938,29 @@ cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, con
     return cudaGetLastError();
 }
 
-uint32_t lz4_copy_job_capacity(uint32_t raw_len) { return raw_len / LZ4_DEFER_MIN + 2; }
+uint32_t lz4_copy_job_capacity(uint32_t raw_len) { return raw_len / v2::DEFER_MIN + 2; }
 
 cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
                               const uint64_t* d_out_off, uint32_t* d_out_len, uint3* d_copy_jobs, const uint32_t* d_copy_job_start,
                               uint32_t* d_copy_job_count, uint32_t block_count, uint32_t* d_tables, cudaStream_t st)
 {
     if (!block_count) return cudaSuccess;
-    static int carveout = -2;
-    if (carveout == -2)
+    static int v2_on = -1;
+    if (v2_on < 0)
     {
-        const char* e = getenv("LT_B200_LZ4_CARVEOUT"); // experiment knob: percent of the SM's L1/shared storage given to shared memory
-        carveout = e ? atoi(e) : -1;
-        if (carveout >= 0) cudaFuncSetAttribute(k_lz4_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        const char* e = getenv("LT_B200_LZ4_V1"); // A/B knob: 1 = the round-1 encoder (tables in HBM/L2) for every block
+        v2_on = e && atoi(e) ? 0 : 1;
+        // 13 CTAs of 16 KiB + 1 KiB per SM need the largest shared-memory carve-out
+        cudaFuncSetAttribute(k_lz4_blocks_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    // d_tables (16 KiB per block, in HBM/L2) lifts the residency from 14 warps per SM (shared-memory bound) to 32; the per-block
-    // latency is the same either way (measured: 278.8 vs 277.7 ms on 2 334 blocks), so batches beyond ~2 000 blocks finish sooner
+    // v1 takes the blocks v2 leaves (byU16, > 16 MiB): d_tables (32 KiB per block, in HBM/L2) lifts its residency from 7 warps per SM to 32
     k_lz4_blocks<<<block_count, 32, d_tables ? 0 : LZ4_TABLE_BYTES, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs,
-                                                                         d_copy_job_start, d_copy_job_count, block_count, d_tables);
-    k_lz4_copy<<<dim3(block_count, LZ4_COPY_SLICES), 256, 0, st>>>(d_raw, d_raw_off, d_out, d_out_off, d_copy_jobs, d_copy_job_start,
-                                                                 d_copy_job_count);
+                                                                         d_copy_job_start, d_copy_job_count, block_count, d_tables, (uint32_t)v2_on);
+    if (v2_on)
+        k_lz4_blocks_v2<<<block_count, 32, v2::TABLE_WORDS * 4, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs,
+                                                                    d_copy_job_start, d_copy_job_count, block_count);
+    k_lz4_copy<<<dim3(block_count, LZ4_COPY_SLICES), LZ4_COPY_WARPS * 32, 0, st>>>(d_raw, d_raw_off, d_out, d_out_off, d_copy_jobs, d_copy_job_start,
+                                                                                 d_copy_job_count);
     return cudaGetLastError();
 }
 

@@ -66,6 +66,51 @@ def test_lz4_vs_oracle(ctx, oracle, n, kind):
     assert oracle.lz4_decompress(comp, n) == x.tobytes()
 
 
+def _with_repeats(n, seed, dist, length, every):
+    """random bytes with copies of `length` bytes taken `dist` bytes back, every `every` bytes"""
+    x = synth_bytes(seed, n, "rand")
+    for i in range(max(dist, 100000), n - length - 16, every):
+        x[i:i + length] = x[i - dist:i - dist + length]
+    return x
+
+
+# the shared-memory-table encoder (k_lz4_blocks_v2) keeps 17 position bits + a 14-bit tag per slot and sweeps stale entries:
+# matches at the edge of the 65 535-byte window, matches longer than the window and longer than 2^17 (table cleared / multi-step
+# sweep), the v1 <-> v2 hand-over sizes (65 546 / 65 547 bytes, 16 MiB / 16 MiB + 1) and every synthetic class at block size
+@pytest.mark.parametrize("name,make", [
+    ("rep65535", lambda: _with_repeats(3 << 20, 901, 65535, 5000, 200001)),
+    ("rep65536", lambda: _with_repeats(3 << 20, 902, 65536, 5000, 200003)),
+    ("rep60000x200k", lambda: _with_repeats(4 << 20, 903, 60000, 200000, 700001)),
+    ("rep70000x100k", lambda: _with_repeats(4 << 20, 904, 70000, 100000, 500009)),
+    ("rep300x70000", lambda: _with_repeats(2 << 20, 905, 300, 70000, 150001)),
+    ("zero_then_rand", lambda: np.concatenate([np.zeros(200000, np.uint8), synth_bytes(906, 300000, "rand"), np.zeros(140000, np.uint8),
+                                               synth_bytes(907, 100000, "text")])),
+    ("text_9m", lambda: synth_bytes(908, 9200000, "text")),
+    ("nib_9m", lambda: synth_bytes(909, 9200000, "nib")),
+    ("rec_9m", lambda: synth_bytes(910, 9200000, "rec")),
+    ("bit_2m", lambda: synth_bytes(911, 2 << 20, "bit")),
+    ("rand_16m", lambda: synth_bytes(912, 16 << 20, "rand")),
+    ("text_16m_plus1", lambda: synth_bytes(913, (16 << 20) + 1, "text")),
+    ("mixed_9m", lambda: np.concatenate([synth_bytes(914 + i, 1 << 20, k) for i, k in enumerate(["rand", "text", "nib", "text", "rec", "rand", "nib", "text", "zero"])])),
+], ids=lambda v: v if isinstance(v, str) else "")
+def test_lz4_shared_table_encoder_vs_oracle(ctx, oracle, name, make):
+    x = make()
+    comp, _ = gpu_lz4(ctx, x)
+    want = oracle.lz4_compress(x)
+    assert len(comp) == len(want)
+    assert comp == want
+
+
+def test_lz4_many_blocks_one_launch(ctx, oracle):
+    """more blocks than resident warps of one wave, of mixed kinds and sizes, through the CompressionAPI batch entry point"""
+    kinds = ["text", "nib", "rand", "rec", "zero", "p3", "bit"]
+    bufs = [synth_bytes(3000 + i, 66000 + 37 * i + (i % 5) * 40000, kinds[i % len(kinds)]) for i in range(300)]
+    bufs += [synth_bytes(4000 + i, 1000 + 977 * i, kinds[i % len(kinds)]) for i in range(40)]
+    got = ctx.lz4_compress_host(bufs)
+    for b, g in zip(bufs, got):
+        assert g == oracle.lz4_compress(b)
+
+
 def test_lz4_size_pin(ctx):
     # reference test/test.cpp:2185-2192: this input compresses to 38 bytes of LZ4 payload
     data = np.concatenate([np.full(1147, 0x0D, np.uint8), np.full(4711, 0x4D, np.uint8)])
