@@ -216,6 +216,16 @@ LT_B200_EXPORT int lt_b200_write_blocks_device(lt_b200_context* context, const u
                                                const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
                                                uint32_t max_block_size, uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user);
 
+/* lt_b200_write_blocks_device with flags.  LT_B200_WRITE_DEVICE_SINK: the serialised images stay in HBM — `data` of every view is a
+ * DEVICE address (for a consumer that reads device memory: a GPUDirect NIC / storage path, a peer GPU); without it every image is
+ * copied once into pinned host staging, batch k's copies overlapping batch k + 1's kernels when device memory allows two batches. */
+#define LT_B200_WRITE_DEVICE_SINK 1u
+LT_B200_EXPORT int lt_b200_write_blocks_device_ex(lt_b200_context* context, const uint8_t* device_arena, uint64_t arena_size,
+                                                  uint32_t chunk_count, const uint64_t* chunk_hashes, const uint32_t* chunk_sizes,
+                                                  const uint32_t* chunk_tags, const uint64_t* chunk_arena_offsets, uint32_t hash_type,
+                                                  uint32_t max_block_size, uint32_t max_chunks_per_block, uint32_t flags,
+                                                  lt_b200_block_sink sink, void* user);
+
 /* lt_b200_write_blocks_device for blocks whose composition is GIVEN (a Longtail_StoreIndex: block b holds the next block_chunk_counts[b]
  * chunks of the chunk arrays; its tag is the tag of its first chunk) instead of packed greedily — what Longtail_WriteContent does with the
  * store index it is handed (src/longtail.c:4760-4912). */

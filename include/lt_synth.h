@@ -13,6 +13,12 @@
  *   - each segment has an entropy class: 0 = uniform random bytes, 1 = 4-bit entropy
  *     (byte & 0x0f), 2 = text-like (order-0 skewed letter distribution); `class_mode` selects
  *     "all random" (0) or "one third each, chosen per segment" (1).
+ *
+ * PAK-like model (`class_mode` 2): the asset is a concatenation of MEMBERS of
+ * 64 KiB .. 64 MiB (log-uniform, multiples of 16 bytes), each followed by zero padding up to the next 2 KiB
+ * boundary; a member has one entropy class (one third each).  So that any byte range can be produced without
+ * walking the file from its start, members are laid out per 64 MiB SLOT: the member list of slot s is a pure
+ * function of (seed, asset, s) and the slot's last member is cut at the slot end.
  */
 #ifndef LT_SYNTH_H
 #define LT_SYNTH_H
@@ -97,11 +103,92 @@ LT_SYNTH_FN void lt_synth_block16(uint64_t key, uint64_t block, uint32_t cls, ui
     }
 }
 
+#define LT_SYNTH_PAK_SLOT_BYTES (64ull << 20)
+#define LT_SYNTH_PAK_ALIGN 2048u
+
+/* size of member m of slot `slot`: 65536 * 2^(10 u), u uniform in [0, 1) with 16 fractional bits, rounded to 16 bytes */
+LT_SYNTH_FN uint64_t lt_synth_pak_member_size(uint64_t slot_key, uint32_t m)
+{
+    uint64_t h = lt_synth_mix(slot_key + (uint64_t)(m + 1) * 0xD6E8FEB86659FD93ull);
+    uint32_t e = (uint32_t)(h >> 48) & 0xffffu;  /* exponent in 1/65536 units of the 10 octaves */
+    uint32_t oct = (e * 10u) >> 16;              /* whole octaves 0..9 */
+    uint32_t frac = (e * 10u) & 0xffffu;         /* position inside the octave: size grows linearly from 2^oct to 2^(oct+1) */
+    uint64_t size = ((uint64_t)65536 << oct) + ((((uint64_t)65536 << oct) * frac) >> 16);
+    return (size + 15u) & ~(uint64_t)15u;
+}
+
+/* where byte `offset` of a PAK-like asset comes from: *out_pad = 1 for padding (zero bytes), else the keyed stream position */
+LT_SYNTH_FN void lt_synth_pak_locate(const struct lt_synth_spec* s, uint64_t asset_id, uint64_t offset,
+                                     uint64_t* out_key, uint64_t* out_rel, uint32_t* out_class, uint32_t* out_pad)
+{
+    uint64_t slot = offset / LT_SYNTH_PAK_SLOT_BYTES;
+    uint64_t in_slot = offset % LT_SYNTH_PAK_SLOT_BYTES;
+    uint64_t slot_key = lt_synth_mix(s->seed * 0x9E3779B97F4A7C15ull + asset_id * 0xD1B54A32D192ED03ull + slot * 0xA0761D6478BD642Full + 0x51ull);
+    uint64_t pos = 0;
+    for (uint32_t m = 0;; ++m)
+    {
+        uint64_t size = lt_synth_pak_member_size(slot_key, m);
+        uint64_t end = pos + size;
+        if (in_slot < end || end >= LT_SYNTH_PAK_SLOT_BYTES)
+        {
+            uint64_t h = lt_synth_mix(slot_key ^ ((uint64_t)(m + 1) * 0x94D049BB133111EBull));
+            *out_key = h;
+            *out_rel = in_slot - pos;
+            *out_class = (uint32_t)((h >> 40) % 3u);
+            *out_pad = 0;
+            return;
+        }
+        uint64_t padded = (end + (LT_SYNTH_PAK_ALIGN - 1u)) & ~(uint64_t)(LT_SYNTH_PAK_ALIGN - 1u);
+        if (in_slot < padded)
+        {
+            *out_key = 0;
+            *out_rel = 0;
+            *out_class = 0;
+            *out_pad = 1;
+            return;
+        }
+        pos = padded;
+    }
+}
+
+/* the 16 bytes at `offset` (a multiple of 16) of asset `asset_id` under any class_mode */
+LT_SYNTH_FN void lt_synth_asset_block16(const struct lt_synth_spec* s, uint64_t asset_id, uint64_t offset, uint8_t out[16])
+{
+    if (s->class_mode == 2)
+    {
+        uint64_t key, rel;
+        uint32_t cls, pad;
+        lt_synth_pak_locate(s, asset_id, offset, &key, &rel, &cls, &pad);
+        if (pad)
+        {
+            for (int i = 0; i < 16; ++i) out[i] = 0;
+            return;
+        }
+        lt_synth_block16(key, rel / 16, cls, out);
+        return;
+    }
+    uint64_t key, base;
+    uint32_t cls;
+    lt_synth_segment(s, asset_id, offset, &key, &base, &cls);
+    lt_synth_block16(key, (base + offset % LT_SYNTH_SEGMENT_BYTES) / 16, cls, out);
+}
+
 /* Fill dst[0..len) with asset bytes [offset, offset+len).  offset must be a multiple of 16;
  * len may be ragged. */
 LT_SYNTH_FN void lt_synth_fill(const struct lt_synth_spec* s, uint64_t asset_id, uint64_t offset,
                                uint8_t* dst, uint64_t len)
 {
+    if (s->class_mode == 2)
+    {
+        for (uint64_t i = 0; i < len; i += 16)
+        {
+            uint8_t tmp[16];
+            lt_synth_asset_block16(s, asset_id, offset + i, tmp);
+            uint64_t m = len - i < 16 ? len - i : 16;
+            for (uint64_t j = 0; j < m; ++j) dst[i + j] = tmp[j];
+        }
+        return;
+    }
     uint64_t done = 0;
     while (done < len)
     {

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 using namespace ltb;
@@ -31,13 +32,13 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
-    WS_LZ4_TABLES, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
+    WS_LZ4_TABLES, WS_LZ4_V2, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_CHUNK_SIZES, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
     WS_COUNT
 };
 
 enum HostSlot
 {
-    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_BLK_META, HS_BLK_OUT_LEN, HS_BLK_STAGE, HS_COUNT
+    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_BLK_META, HS_BLK_OUT_LEN, HS_BLK_OUT_LEN_B, HS_BLK_TAB, HS_BLK_TAB_B, HS_BLK_STAGE, HS_COUNT
 };
 
 struct Buf
@@ -54,6 +55,8 @@ struct lt_b200_context
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr; // second compute stream (the global-table LZ4 warps run next to the shared-memory ones)
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaEvent_t compute_done[2] = {nullptr, nullptr};
     uint32_t* d_table = nullptr;
@@ -312,6 +315,9 @@ extern "C" int lt_b200_context_create(int device_ordinal, lt_b200_context** out_
     if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc(&c->d_table, sizeof(k_hpcdc_table)) != cudaSuccess ||
         cudaMemcpy(c->d_table, k_hpcdc_table, sizeof(k_hpcdc_table), cudaMemcpyHostToDevice) != cudaSuccess)
     {
@@ -352,6 +358,9 @@ extern "C" void lt_b200_context_destroy(lt_b200_context* c)
         if (c->compute_done[i]) cudaEventDestroy(c->compute_done[i]);
     }
     cudaStreamDestroy(c->stream);
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    if (c->aux_fork) cudaEventDestroy(c->aux_fork);
+    if (c->aux_join) cudaEventDestroy(c->aux_join);
     cudaStreamDestroy(c->copy_stream);
     delete c;
 }
@@ -1192,7 +1201,7 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
                       const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
                       const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
                       uint32_t max_chunks_per_block, uint32_t given_block_count, const uint32_t* given_block_chunk_counts,
-                      lt_b200_block_sink sink, void* user);
+                      uint32_t flags, lt_b200_block_sink sink, void* user);
 }
 
 extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
@@ -1201,7 +1210,16 @@ extern "C" int lt_b200_write_blocks_device(lt_b200_context* c, const uint8_t* d_
                                            uint32_t max_chunks_per_block, lt_b200_block_sink sink, void* user)
 {
     return write_blocks_impl(c, d_arena, arena_size, chunk_count, chunk_hashes, chunk_sizes, chunk_tags, chunk_arena_offsets, hash_type, max_block_size,
-                             max_chunks_per_block, 0, nullptr, sink, user);
+                             max_chunks_per_block, 0, nullptr, 0, sink, user);
+}
+
+extern "C" int lt_b200_write_blocks_device_ex(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
+                                              const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
+                                              const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
+                                              uint32_t max_chunks_per_block, uint32_t flags, lt_b200_block_sink sink, void* user)
+{
+    return write_blocks_impl(c, d_arena, arena_size, chunk_count, chunk_hashes, chunk_sizes, chunk_tags, chunk_arena_offsets, hash_type, max_block_size,
+                             max_chunks_per_block, 0, nullptr, flags, sink, user);
 }
 
 extern "C" int lt_b200_write_given_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
@@ -1220,15 +1238,30 @@ extern "C" int lt_b200_write_given_blocks_device(lt_b200_context* c, const uint8
     }
     if (sum != chunk_count) return EINVAL;
     return write_blocks_impl(c, d_arena, arena_size, chunk_count, chunk_hashes, chunk_sizes, chunk_tags, chunk_arena_offsets, hash_type, 0xffffffffu, most,
-                             block_count, block_chunk_counts, sink, user);
+                             block_count, block_chunk_counts, 0, sink, user);
 }
 
 namespace {
+
+// One batch of stored blocks in flight: its device buffers, its launch tables (one pinned host image, one device image) and the
+// event that marks its kernels done.  With room for two of them the device -> host copies of batch k overlap the kernels of k + 1.
+struct WriteSlot
+{
+    int ws_raw, ws_out, ws_tab, ws_jobs, hs_tab, hs_len;
+    cudaEvent_t done;
+    // filled by launch
+    uint32_t b0 = 0, nb = 0, n_lz = 0, n_zs = 0;
+    std::vector<uint64_t> img_off;  // offset of each block's serialised image (block index + payload) in the out buffer
+    std::vector<uint32_t> hdr_size;
+    std::vector<uint32_t> lz_idx, zs_idx;
+    bool busy = false;
+};
+
 int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
                       const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
                       const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t max_block_size,
                       uint32_t max_chunks_per_block, uint32_t given_block_count, const uint32_t* given_block_chunk_counts,
-                      lt_b200_block_sink sink, void* user)
+                      uint32_t flags, lt_b200_block_sink sink, void* user)
 {
     if (!c || !sink || (chunk_count && (!chunk_hashes || !chunk_sizes || !chunk_arena_offsets))) return EINVAL;
     if (max_chunks_per_block == 0) return EINVAL;
@@ -1237,6 +1270,7 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     if (hash_type != LT_B200_HASH_BLAKE3 && hash_type != LT_B200_HASH_BLAKE2 && hash_type != LT_B200_HASH_MEOW)
         return fail(c, ENOTSUP, "hash type 0x%08x has no device implementation", hash_type);
     if (!chunk_count) return 0;
+    const bool device_sink = (flags & LT_B200_WRITE_DEVICE_SINK) != 0;
 
     // ---- Longtail_CreateStoreIndex's greedy packing (src/longtail.c:6796-6860): in order; a block closes on a tag change, at
     // max_chunks_per_block chunks, or when the next chunk would exceed max_block_size + max_block_size/10
@@ -1249,7 +1283,7 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
         Block b = {i, 1, chunk_sizes[i], chunk_tags ? chunk_tags[i] : 0u};
         if (b.tag != 0 && b.tag != LT_B200_COMPRESSION_LZ4 && !is_zstd_level3(b.tag))
             return fail(c, ENOTSUP, "compression type 0x%08x has no device implementation", b.tag);
-        if (chunk_arena_offsets[i] + chunk_sizes[i] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", i);
+        if (chunk_arena_offsets[i] > arena_size || chunk_sizes[i] > arena_size - chunk_arena_offsets[i]) return fail(c, EINVAL, "chunk %u lies outside the arena", i);
         const uint32_t want = given_block_chunk_counts ? given_block_chunk_counts[given++] : 0u; // the caller's blocks, as given (a store index)
         while (i + b.count < chunk_count)
         {
@@ -1257,16 +1291,15 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
             if (given_block_chunk_counts)
             {
                 if (b.count == want) break;
-                if (chunk_arena_offsets[j] + chunk_sizes[j] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", j);
-                if ((uint64_t)b.raw + chunk_sizes[j] > 0x7E000000ull) return fail(c, E2BIG, "block %u too large", given - 1);
-                b.raw += chunk_sizes[j];
-                ++b.count;
-                continue;
             }
-            if ((chunk_tags ? chunk_tags[j] : 0u) != b.tag) break;
-            if (b.count == max_chunks_per_block) break;
-            if ((uint64_t)b.raw + chunk_sizes[j] > limit) break;
-            if (chunk_arena_offsets[j] + chunk_sizes[j] > arena_size) return fail(c, EINVAL, "chunk %u lies outside the arena", j);
+            else
+            {
+                if ((chunk_tags ? chunk_tags[j] : 0u) != b.tag) break;
+                if (b.count == max_chunks_per_block) break;
+                if ((uint64_t)b.raw + chunk_sizes[j] > limit) break;
+            }
+            if (chunk_arena_offsets[j] > arena_size || chunk_sizes[j] > arena_size - chunk_arena_offsets[j]) return fail(c, EINVAL, "chunk %u lies outside the arena", j);
+            if ((uint64_t)b.raw + chunk_sizes[j] > 0x7E000000ull) return fail(c, E2BIG, "block %zu too large", blocks.size()); // LZ4_MAX_INPUT_SIZE, u32 fields
             b.raw += chunk_sizes[j];
             ++b.count;
         }
@@ -1275,8 +1308,10 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     }
     const uint32_t nblocks = (uint32_t)blocks.size();
 
-    // ---- block hashes = HashBuffer over each block's chunk-hash array (Longtail_CreateBlockIndex, src/longtail.c:3712-3770)
+    // ---- block hashes = HashBuffer over each block's chunk-hash array (Longtail_CreateBlockIndex, src/longtail.c:3712-3770); the chunk
+    // hashes and sizes stay on the device for the block indexes written in front of every payload
     TRY(ws_reserve(c, WS_BLK_HASHES, sizeof(uint64_t) * (size_t)chunk_count + 16));
+    TRY(ws_reserve(c, WS_BLK_CHUNK_SIZES, sizeof(uint32_t) * (size_t)chunk_count + 16));
     TRY(ws_reserve(c, WS_BLK_SEG_OFF, sizeof(uint64_t) * (size_t)nblocks));
     TRY(ws_reserve(c, WS_BLK_SEG_LEN, sizeof(uint32_t) * (size_t)nblocks));
     TRY(ws_reserve(c, WS_BLK_HASH_OUT, sizeof(uint64_t) * (size_t)nblocks));
@@ -1292,6 +1327,7 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
         upper += h_seg_len[b] / 1024;
     }
     CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_HASHES), chunk_hashes, sizeof(uint64_t) * (size_t)chunk_count, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_CHUNK_SIZES), chunk_sizes, sizeof(uint32_t) * (size_t)chunk_count, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_SEG_OFF), h_seg_off, sizeof(uint64_t) * (size_t)nblocks, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_SEG_LEN), h_seg_len, sizeof(uint32_t) * (size_t)nblocks, cudaMemcpyHostToDevice, c->stream));
     TRY(hash_segments_device(c, hash_type, ws<uint8_t>(c, WS_BLK_HASHES), 8ull * chunk_count, ws<uint64_t>(c, WS_BLK_SEG_OFF),
@@ -1300,191 +1336,267 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     CU(cudaMemcpyAsync(h_blk_hash, ws<void>(c, WS_BLK_HASH_OUT), sizeof(uint64_t) * (size_t)nblocks, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
 
-    // ---- batches of blocks bounded by a device-memory budget: gather -> LZ4 -> copy out -> sink, in store order
+    // ---- batches of blocks bounded by a device-memory budget: gather -> codec -> block indexes, all on the device; then every block's
+    // serialised image (Longtail_WriteStoredBlockToBuffer, src/longtail.c:4111-4150) is handed to the sink in store order — as a device
+    // address (LT_B200_WRITE_DEVICE_SINK) or after one device -> host copy into pinned staging
+    auto lz4_bound = [](uint64_t n) { return n + n / 255 + 16; }; // lib/lz4/ext/lz4.h:215
+    auto block_need = [&](const Block& bl, uint64_t* raw_need, uint64_t* out_need, uint64_t* job_need) {
+        const uint64_t hdr = (20 + 12ull * bl.count + 15) & ~15ull;
+        const uint64_t pay = bl.tag ? 8 + (is_zstd_level3(bl.tag) ? lt_b200_zstd_bound(bl.raw) : lz4_bound(bl.raw)) : bl.raw;
+        *raw_need = bl.tag ? (((uint64_t)bl.raw + 16 + 15) & ~15ull) : 0;
+        *out_need = hdr + ((pay + 16 + 15) & ~15ull);
+        *job_need = bl.tag == LT_B200_COMPRESSION_LZ4 ? sizeof(uint3) * (uint64_t)lz4_copy_job_capacity(bl.raw) : 0;
+    };
+    uint64_t need_all = 0, need_max = 0;
+    for (const Block& bl : blocks)
+    {
+        uint64_t r, o, j;
+        block_need(bl, &r, &o, &j);
+        need_all += r + o + j;
+        if (r + o + j > need_max) need_max = r + o + j;
+    }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    // a batch should hold enough blocks to occupy every resident codec warp (~3000 ZStd frames, ~2000 LZ4 blocks of ~9 MiB, twice
-    // that in bytes for input + output), memory permitting
-    uint64_t budget = (uint64_t)(free_b * 0.45);
+    // what the grow-only workspace already holds for these buffers counts as available
+    const uint64_t held = c->ws[WS_BLK_RAW].cap + c->ws[WS_BLK_OUT].cap + c->ws[WS_BLK_JOBS].cap + c->ws[WS_BLK_RAW_B].cap + c->ws[WS_BLK_OUT_B].cap +
+                          c->ws[WS_BLK_JOBS_B].cap;
+    uint64_t avail = (uint64_t)((free_b + held) * 0.92);
+    // the codec kernels want a batch to fill every resident warp (13 x 148 LZ4 blocks); two batches in flight only when both can be that large
+    const uint64_t full_batch = std::min<uint64_t>(need_all, (uint64_t)13 * c->sm_count * need_max);
+    const bool host_sink_pipeline = !device_sink && avail >= 2 * full_batch + (64ull << 20) && need_all > full_batch;
+    const uint32_t nslots = host_sink_pipeline ? 2u : 1u;
+    uint64_t budget = avail / nslots;
     if (budget > (64ull << 30)) budget = 64ull << 30;
-    if (budget < (64ull << 20)) budget = 64ull << 20;
-    auto lz4_bound = [](uint64_t n) { return n + n / 255 + 16; }; // lib/lz4/ext/lz4.h:215
-    std::vector<uint64_t> src_off, dst_off, raw_off, out_off;
-    std::vector<uint32_t> len, raw_len;
-    uint32_t done_chunks = 0;
-    for (uint32_t b0 = 0; b0 < nblocks;)
-    {
-        uint64_t raw_bytes = 0, out_bytes = 0;
-        uint32_t b1 = b0;
-        raw_off.clear(); out_off.clear(); raw_len.clear(); src_off.clear(); dst_off.clear(); len.clear();
-        while (b1 < nblocks)
-        {
-            const Block& bl = blocks[b1];
-            const uint64_t r = ((uint64_t)bl.raw + 16 + 15) & ~15ull;
-            const uint64_t o = bl.tag ? ((8 + (is_zstd_level3(bl.tag) ? lt_b200_zstd_bound(bl.raw) : lz4_bound(bl.raw)) + 15) & ~15ull) : 0;
-            if (b1 > b0 && raw_bytes + out_bytes + r + o > budget) break;
-            raw_off.push_back(raw_bytes);
-            out_off.push_back(out_bytes);
-            raw_len.push_back(bl.raw);
-            uint64_t w = raw_bytes;
-            for (uint32_t k = 0; k < bl.count; ++k)
-            {
-                src_off.push_back(chunk_arena_offsets[bl.first + k]);
-                dst_off.push_back(w);
-                len.push_back(chunk_sizes[bl.first + k]);
-                w += chunk_sizes[bl.first + k];
-            }
-            raw_bytes += r;
-            out_bytes += o;
-            ++b1;
-        }
+    if (budget < need_max + (1ull << 20)) budget = need_max + (1ull << 20);
+
+    WriteSlot slots[2] = {{WS_BLK_RAW, WS_BLK_OUT, WS_BLK_TAB, WS_BLK_JOBS, HS_BLK_TAB, HS_BLK_OUT_LEN, c->copy_done[0]},
+                          {WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_TAB_B, WS_BLK_JOBS_B, HS_BLK_TAB_B, HS_BLK_OUT_LEN_B, c->copy_done[1]}};
+    TRY(ws_reserve(c, WS_LZ4_V2, lz4_v2_scratch_bytes()));
+
+    // launch the kernels of blocks [b0, b1) into slot s
+    auto launch = [&](WriteSlot& s, uint32_t b0, uint32_t b1) -> int {
         const uint32_t nb = b1 - b0;
-        const uint32_t nc = (uint32_t)len.size();
-        TRY(ws_reserve(c, WS_BLK_RAW, raw_bytes + 64));
-        TRY(ws_reserve(c, WS_BLK_OUT, out_bytes + 64));
-        TRY(ws_reserve(c, WS_BLK_SRC_OFF, sizeof(uint64_t) * (size_t)nc));
-        TRY(ws_reserve(c, WS_BLK_DST_OFF, sizeof(uint64_t) * (size_t)nc));
-        TRY(ws_reserve(c, WS_BLK_LEN, sizeof(uint32_t) * (size_t)nc));
-        TRY(ws_reserve(c, WS_BLK_RAW_OFF, sizeof(uint64_t) * (size_t)nb));
-        TRY(ws_reserve(c, WS_BLK_RAW_LEN, sizeof(uint32_t) * (size_t)nb));
-        TRY(ws_reserve(c, WS_BLK_OUT_OFF, sizeof(uint64_t) * (size_t)nb));
-        TRY(ws_reserve(c, WS_BLK_OUT_LEN, sizeof(uint32_t) * (size_t)nb));
-        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_SRC_OFF), src_off.data(), sizeof(uint64_t) * (size_t)nc, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_DST_OFF), dst_off.data(), sizeof(uint64_t) * (size_t)nc, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_LEN), len.data(), sizeof(uint32_t) * (size_t)nc, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_OFF), raw_off.data(), sizeof(uint64_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_LEN), raw_len.data(), sizeof(uint32_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_OUT_OFF), out_off.data(), sizeof(uint64_t) * (size_t)nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream)); // the host vectors are reused by the next batch
-        {
-            ProfScope ps(c, LT_B200_KERNEL_GATHER, raw_bytes);
-            launch_gather_chunks(d_arena, ws<uint64_t>(c, WS_BLK_SRC_OFF), ws<uint64_t>(c, WS_BLK_DST_OFF), ws<uint32_t>(c, WS_BLK_LEN),
-                                 ws<uint8_t>(c, WS_BLK_RAW), nc, c->stream);
-        }
-        // LZ4 over the compressed-tag blocks of the batch: the kernel is launched over all blocks; raw ones are skipped by length 0
-        // in the launch table — simpler: launch over the whole batch and let tag-0 blocks be served straight from the raw buffer
-        std::vector<uint32_t> lz_idx;
-        std::vector<uint32_t> zs_idx;
+        s.b0 = b0; s.nb = nb;
+        s.img_off.assign(nb, 0); s.hdr_size.assign(nb, 0); s.lz_idx.clear(); s.zs_idx.clear();
+        uint64_t raw_bytes = 0, out_bytes = 0, job_count = 0;
+        uint32_t nc = 0;
+        std::vector<uint64_t> raw_off(nb), pay_off(nb);
         for (uint32_t i = 0; i < nb; ++i)
         {
-            if (blocks[b0 + i].tag == LT_B200_COMPRESSION_LZ4) lz_idx.push_back(i);
-            else if (blocks[b0 + i].tag) zs_idx.push_back(i);
+            const Block& bl = blocks[b0 + i];
+            uint64_t r, o, j;
+            block_need(bl, &r, &o, &j);
+            const uint64_t hdr = 20 + 12ull * bl.count, hdr_pad = (hdr + 15) & ~15ull;
+            raw_off[i] = raw_bytes;
+            pay_off[i] = out_bytes + hdr_pad;       // 16-byte aligned; the block index sits right in front of it
+            s.img_off[i] = pay_off[i] - hdr;
+            s.hdr_size[i] = (uint32_t)hdr;
+            raw_bytes += r; out_bytes += o; nc += bl.count;
+            if (bl.tag == LT_B200_COMPRESSION_LZ4) { s.lz_idx.push_back(i); job_count += lz4_copy_job_capacity(bl.raw); }
+            else if (bl.tag) s.zs_idx.push_back(i);
         }
-        if (!lz_idx.empty())
+        s.n_lz = (uint32_t)s.lz_idx.size(); s.n_zs = (uint32_t)s.zs_idx.size();
+        // the LZ4 encoder prefetches the source a few batches of probes ahead: keep that inside the allocation
+        TRY(ws_reserve(c, s.ws_raw, raw_bytes + (128u << 10)));
+        TRY(ws_reserve(c, s.ws_out, out_bytes + 64));
+        TRY(ws_reserve(c, s.ws_jobs, sizeof(uint3) * (size_t)(job_count + 1)));
+        uint8_t* d_raw = ws<uint8_t>(c, s.ws_raw);
+        uint8_t* d_out = ws<uint8_t>(c, s.ws_out);
+        // one table image: u64 src_off[nc] dst_abs[nc] hdr_dst[nb] lz_raw_off[nlz] lz_out_off[nlz] | u32 len[nc] blk_first[nb] blk_count[nb] blk_tag[nb]
+        //                  lz_raw_len[nlz] lz_job_start[nlz] | outputs: u32 lz_out_len[nlz] lz_job_count[nlz]
+        const size_t n64 = 2 * (size_t)nc + nb + 2 * (size_t)s.n_lz;
+        const size_t n32 = (size_t)nc + 3 * (size_t)nb + 4 * (size_t)s.n_lz;
+        const size_t tab_bytes = 8 * n64 + 4 * n32 + 64;
+        TRY(ws_reserve(c, s.ws_tab, tab_bytes));
+        TRY(hs_reserve(c, s.hs_tab, tab_bytes));
+        uint64_t* h64 = hs<uint64_t>(c, s.hs_tab);
+        uint32_t* h32 = reinterpret_cast<uint32_t*>(h64 + n64);
+        uint64_t* d64 = ws<uint64_t>(c, s.ws_tab);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(d64 + n64);
+        uint64_t *h_src = h64, *h_dst = h64 + nc, *h_hdr = h64 + 2 * (size_t)nc, *h_lro = h_hdr + nb, *h_loo = h_lro + s.n_lz;
+        uint32_t *h_len = h32, *h_first = h32 + nc, *h_count = h_first + nb, *h_tag = h_count + nb, *h_lrl = h_tag + nb, *h_ljs = h_lrl + s.n_lz;
+        uint32_t ci = 0;
+        for (uint32_t i = 0; i < nb; ++i)
         {
-            // compact launch tables for the LZ4 blocks
-            std::vector<uint64_t> lro(lz_idx.size()), loo(lz_idx.size());
-            std::vector<uint32_t> lrl(lz_idx.size()), ljs(lz_idx.size());
-            uint32_t job_cap = 0;
-            for (size_t i = 0; i < lz_idx.size(); ++i)
+            const Block& bl = blocks[b0 + i];
+            // compressed blocks gather into the raw buffer, stored-raw blocks straight into their place in the image
+            uint64_t w = bl.tag ? (uint64_t)(uintptr_t)(d_raw + raw_off[i]) : (uint64_t)(uintptr_t)(d_out + pay_off[i]);
+            for (uint32_t k = 0; k < bl.count; ++k, ++ci)
             {
-                lro[i] = raw_off[lz_idx[i]]; loo[i] = out_off[lz_idx[i]]; lrl[i] = raw_len[lz_idx[i]];
-                ljs[i] = job_cap;
-                job_cap += lz4_copy_job_capacity(lrl[i]);
+                h_src[ci] = chunk_arena_offsets[bl.first + k];
+                h_dst[ci] = w;
+                h_len[ci] = chunk_sizes[bl.first + k];
+                w += chunk_sizes[bl.first + k];
             }
-            TRY(ws_reserve(c, WS_BLK_JOBS, sizeof(uint3) * (size_t)job_cap));
-            TRY(ws_reserve(c, WS_BLK_JOB_START, sizeof(uint32_t) * lz_idx.size()));
-            TRY(ws_reserve(c, WS_BLK_JOB_COUNT, sizeof(uint32_t) * lz_idx.size()));
-            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_JOB_START), ljs.data(), sizeof(uint32_t) * ljs.size(), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_OFF), lro.data(), sizeof(uint64_t) * lro.size(), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_OUT_OFF), loo.data(), sizeof(uint64_t) * loo.size(), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(ws<void>(c, WS_BLK_RAW_LEN), lrl.data(), sizeof(uint32_t) * lrl.size(), cudaMemcpyHostToDevice, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
+            h_hdr[i] = s.img_off[i];
+            h_first[i] = bl.first; h_count[i] = bl.count; h_tag[i] = bl.tag;
+        }
+        uint32_t job_at = 0;
+        for (uint32_t q = 0; q < s.n_lz; ++q)
+        {
+            const uint32_t i = s.lz_idx[q];
+            h_lro[q] = raw_off[i]; h_loo[q] = pay_off[i]; h_lrl[q] = blocks[b0 + i].raw; h_ljs[q] = job_at;
+            job_at += lz4_copy_job_capacity(blocks[b0 + i].raw);
+        }
+        CU(cudaMemcpyAsync(d64, h64, 8 * n64 + 4 * (n32 - 2 * (size_t)s.n_lz), cudaMemcpyHostToDevice, c->stream));
+        {
+            ProfScope ps(c, LT_B200_KERNEL_GATHER, raw_bytes);
+            launch_gather_chunks(d_arena, d64, d64 + nc, d32, nullptr, nc, c->stream);
+        }
+        uint32_t* d_lz_out_len = d32 + nc + 3 * (size_t)nb + 2 * (size_t)s.n_lz;
+        if (s.n_lz)
+        {
             uint64_t lz_bytes = 0;
-            for (uint32_t v : lrl) lz_bytes += v;
-            TRY(ws_reserve(c, WS_LZ4_TABLES, LZ4_TABLE_BYTES_PER_BLOCK * lz_idx.size()));
+            for (uint32_t q = 0; q < s.n_lz; ++q) lz_bytes += h_lrl[q];
+            TRY(ws_reserve(c, WS_LZ4_TABLES, LZ4_TABLE_BYTES_PER_BLOCK * (size_t)s.n_lz));
             ProfScope ps(c, LT_B200_KERNEL_LZ4, lz_bytes);
-            CU(launch_lz4_blocks(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
-                                 ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), ws<uint3>(c, WS_BLK_JOBS),
-                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), (uint32_t)lz_idx.size(),
-                                 ws<uint32_t>(c, WS_LZ4_TABLES), c->stream));
+            CU(launch_lz4_blocks(d_raw, d64 + 2 * (size_t)nc + nb, d32 + nc + 3 * (size_t)nb, d_out, d64 + 2 * (size_t)nc + nb + s.n_lz, d_lz_out_len,
+                                 ws<uint3>(c, s.ws_jobs), d32 + nc + 3 * (size_t)nb + s.n_lz, d_lz_out_len + s.n_lz, s.n_lz,
+                                 ws<uint32_t>(c, WS_LZ4_TABLES), ws<void>(c, WS_LZ4_V2), c->sm_count, c->stream));
         }
-        // ZStd level 3 over the 'ztd1' / 'ztd2' blocks of the batch: one frame per block
-        if (!zs_idx.empty())
+        if (s.n_zs) // ZStd level 3 over the 'ztd1' / 'ztd2' blocks of the batch: one frame per block
         {
-            std::vector<uint64_t> zro(zs_idx.size()), zoo(zs_idx.size());
-            std::vector<uint32_t> zrl(zs_idx.size());
+            std::vector<uint64_t> zro(s.n_zs), zoo(s.n_zs);
+            std::vector<uint32_t> zrl(s.n_zs);
             uint64_t zs_bytes = 0;
-            for (size_t i = 0; i < zs_idx.size(); ++i)
+            for (uint32_t q = 0; q < s.n_zs; ++q)
             {
-                zro[i] = raw_off[zs_idx[i]]; zoo[i] = out_off[zs_idx[i]]; zrl[i] = raw_len[zs_idx[i]];
-                zs_bytes += zrl[i];
+                const uint32_t i = s.zs_idx[q];
+                zro[q] = raw_off[i]; zoo[q] = pay_off[i]; zrl[q] = blocks[b0 + i].raw;
+                zs_bytes += zrl[q];
             }
-            TRY(zstd_launch(c, ws<uint8_t>(c, WS_BLK_RAW), zro, zrl, ws<uint8_t>(c, WS_BLK_OUT), zoo, zs_bytes));
+            TRY(zstd_launch(c, d_raw, zro, zrl, d_out, zoo, zs_bytes));
         }
-        c->launches += 3;
-        TRY(hs_reserve(c, HS_BLK_OUT_LEN, sizeof(uint32_t) * 2 * (size_t)nb + 16));
-        uint32_t* h_out_len = hs<uint32_t>(c, HS_BLK_OUT_LEN);
-        uint32_t* h_zs_len = h_out_len + nb;
-        if (!lz_idx.empty())
-            CU(cudaMemcpyAsync(h_out_len, ws<void>(c, WS_BLK_OUT_LEN), sizeof(uint32_t) * lz_idx.size(), cudaMemcpyDeviceToHost, c->stream));
-        if (!zs_idx.empty())
-            CU(cudaMemcpyAsync(h_zs_len, ws<void>(c, WS_ZSTD_OUT_LEN), sizeof(uint32_t) * zs_idx.size(), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        launch_block_headers(d_out, d64 + 2 * (size_t)nc, d32 + nc, d32 + nc + nb, d32 + nc + 2 * (size_t)nb, ws<uint64_t>(c, WS_BLK_HASH_OUT) + b0,
+                             ws<uint64_t>(c, WS_BLK_HASHES), ws<uint32_t>(c, WS_BLK_CHUNK_SIZES), hash_type, nb, c->stream);
+        c->launches += 5;
+        TRY(hs_reserve(c, s.hs_len, sizeof(uint32_t) * 2 * (size_t)nb + 16));
+        uint32_t* h_out_len = hs<uint32_t>(c, s.hs_len);
+        if (s.n_lz) CU(cudaMemcpyAsync(h_out_len, d_lz_out_len, sizeof(uint32_t) * s.n_lz, cudaMemcpyDeviceToHost, c->stream));
+        if (s.n_zs) CU(cudaMemcpyAsync(h_out_len + nb, ws<void>(c, WS_ZSTD_OUT_LEN), sizeof(uint32_t) * s.n_zs, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(s.done, c->stream));
+        s.busy = true;
+        return 0;
+    };
+
+    // hand the finished blocks of slot s to the sink, in store order
+    auto drain = [&](WriteSlot& s) -> int {
+        if (!s.busy) return 0;
+        s.busy = false;
+        CU(cudaEventSynchronize(s.done));
         CU(cudaGetLastError());
+        const uint32_t nb = s.nb, b0 = s.b0;
+        const uint32_t* h_out_len = hs<uint32_t>(c, s.hs_len);
         std::vector<uint32_t> payload_len(nb);
         for (uint32_t i = 0; i < nb; ++i) payload_len[i] = blocks[b0 + i].raw;
-        for (size_t i = 0; i < lz_idx.size(); ++i) payload_len[lz_idx[i]] = h_out_len[i];
-        for (size_t i = 0; i < zs_idx.size(); ++i)
+        for (uint32_t q = 0; q < s.n_lz; ++q) payload_len[s.lz_idx[q]] = h_out_len[q];
+        for (uint32_t q = 0; q < s.n_zs; ++q)
         {
-            if (h_zs_len[i] == 0xffffffffu) return fail(c, EINVAL, "ZStd encoder failed on block %u", b0 + zs_idx[i]);
-            payload_len[zs_idx[i]] = h_zs_len[i];
+            if (h_out_len[nb + q] == 0xffffffffu) return fail(c, EINVAL, "ZStd encoder failed on block %u", b0 + s.zs_idx[q]);
+            payload_len[s.zs_idx[q]] = h_out_len[nb + q];
         }
-
-        // ---- serialise (Longtail_WriteStoredBlockToBuffer, src/longtail.c:4111-4150) into pinned staging, a few blocks at a time
-        const uint64_t stage_cap = 256ull << 20;
-        uint32_t i = 0;
-        while (i < nb)
+        const uint8_t* d_out = ws<uint8_t>(c, s.ws_out);
+        auto view_of = [&](uint32_t k, const void* data) {
+            const Block& bl = blocks[b0 + k];
+            lt_b200_stored_block_view v;
+            v.block_hash = h_blk_hash[b0 + k];
+            v.data = data;
+            v.size = (uint64_t)s.hdr_size[k] + payload_len[k];
+            v.chunk_count = bl.count;
+            v.tag = bl.tag;
+            v.raw_payload_size = bl.raw;
+            v.first_chunk = bl.first;
+            return v;
+        };
+        if (device_sink)
         {
+            for (uint32_t k = 0; k < nb; ++k)
+            {
+                const lt_b200_stored_block_view v = view_of(k, d_out + s.img_off[k]);
+                const int err = sink(user, &v);
+                if (err) return fail(c, err, "block sink failed with %d", err);
+            }
+            return 0;
+        }
+        // pinned staging, two halves: while the sink consumes one half the copies into the other are in flight on the copy stream
+        const uint64_t half_cap = 256ull << 20;
+        uint64_t biggest = 0;
+        for (uint32_t k = 0; k < nb; ++k) biggest = std::max<uint64_t>(biggest, (uint64_t)s.hdr_size[k] + payload_len[k]);
+        const uint64_t half = std::max<uint64_t>(half_cap, (biggest + 63) & ~63ull);
+        TRY(hs_reserve(c, HS_BLK_STAGE, 2 * half + 64));
+        uint8_t* stage = hs<uint8_t>(c, HS_BLK_STAGE);
+        struct Group { uint32_t i, j; std::vector<uint64_t> at; };
+        auto issue = [&](uint32_t i, int which, Group* g) -> int {
+            g->i = i; g->at.clear();
             uint64_t used = 0;
             uint32_t j = i;
-            std::vector<uint64_t> at;
             while (j < nb)
             {
-                const Block& bl = blocks[b0 + j];
-                const uint64_t need = ((20 + 12ull * bl.count + payload_len[j]) + 63) & ~63ull;
-                if (j > i && used + need > stage_cap) break;
-                at.push_back(used);
+                const uint64_t need = (((uint64_t)s.hdr_size[j] + payload_len[j]) + 63) & ~63ull;
+                if (j > i && used + need > half) break;
+                g->at.push_back(used);
+                CU(cudaMemcpyAsync(stage + (size_t)which * half + used, d_out + s.img_off[j], (size_t)s.hdr_size[j] + payload_len[j], cudaMemcpyDeviceToHost,
+                                   c->copy_stream));
                 used += need;
                 ++j;
             }
-            TRY(hs_reserve(c, HS_BLK_STAGE, used + 64));
-            uint8_t* stage = hs<uint8_t>(c, HS_BLK_STAGE);
-            for (uint32_t k = i; k < j; ++k)
+            g->j = j;
+            CU(cudaEventRecord(c->compute_done[which], c->copy_stream));
+            return 0;
+        };
+        Group g[2];
+        int which = 0;
+        TRY(issue(0, 0, &g[0]));
+        while (g[which].i < nb)
+        {
+            Group& cur = g[which];
+            if (cur.j < nb) TRY(issue(cur.j, which ^ 1, &g[which ^ 1])); else g[which ^ 1].i = g[which ^ 1].j = nb;
+            CU(cudaEventSynchronize(c->compute_done[which]));
+            for (uint32_t k = cur.i; k < cur.j; ++k)
             {
-                const Block& bl = blocks[b0 + k];
-                uint8_t* p = stage + at[k - i];
-                memcpy(p, &h_blk_hash[b0 + k], 8);
-                memcpy(p + 8, &hash_type, 4);
-                memcpy(p + 12, &bl.count, 4);
-                memcpy(p + 16, &bl.tag, 4);
-                memcpy(p + 20, chunk_hashes + bl.first, 8ull * bl.count);
-                memcpy(p + 20 + 8ull * bl.count, chunk_sizes + bl.first, 4ull * bl.count);
-                const uint8_t* d_payload = bl.tag ? ws<uint8_t>(c, WS_BLK_OUT) + out_off[k] : ws<uint8_t>(c, WS_BLK_RAW) + raw_off[k];
-                CU(cudaMemcpyAsync(p + 20 + 12ull * bl.count, d_payload, payload_len[k], cudaMemcpyDeviceToHost, c->stream));
+                const lt_b200_stored_block_view v = view_of(k, stage + (size_t)which * half + cur.at[k - cur.i]);
+                const int err = sink(user, &v);
+                if (err)
+                {
+                    cudaStreamSynchronize(c->copy_stream);
+                    return fail(c, err, "block sink failed with %d", err);
+                }
             }
-            CU(cudaStreamSynchronize(c->stream));
-            for (uint32_t k = i; k < j; ++k)
-            {
-                const Block& bl = blocks[b0 + k];
-                lt_b200_stored_block_view v;
-                v.block_hash = h_blk_hash[b0 + k];
-                v.data = stage + at[k - i];
-                v.size = 20 + 12ull * bl.count + payload_len[k];
-                v.chunk_count = bl.count;
-                v.tag = bl.tag;
-                v.raw_payload_size = bl.raw;
-                v.first_chunk = bl.first;
-                int err = sink(user, &v);
-                if (err) return fail(c, err, "block sink failed with %d", err);
-            }
-            i = j;
+            which ^= 1;
         }
-        done_chunks += nc;
+        return 0;
+    };
+
+    int rc = 0;
+    uint32_t batch = 0;
+    WriteSlot* prev = nullptr;
+    for (uint32_t b0 = 0; b0 < nblocks && !rc; ++batch)
+    {
+        uint64_t used = 0;
+        uint32_t b1 = b0;
+        while (b1 < nblocks)
+        {
+            uint64_t r, o, j;
+            block_need(blocks[b1], &r, &o, &j);
+            if (b1 > b0 && used + r + o + j > budget) break;
+            used += r + o + j;
+            ++b1;
+        }
+        WriteSlot& s = slots[batch % nslots];
+        if (nslots == 1 && prev) rc = drain(*prev);
+        if (!rc) rc = launch(s, b0, b1);
+        if (!rc && nslots == 2 && prev) rc = drain(*prev); // overlaps the kernels just launched
+        prev = &s;
         b0 = b1;
     }
-    (void)done_chunks;
-    return 0;
+    if (!rc && prev) rc = drain(*prev);
+    if (rc)
+    {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_stream);
+        for (WriteSlot& s : slots) s.busy = false;
+    }
+    return rc;
 }
 } // namespace
 
@@ -1550,10 +1662,12 @@ int codec_host_batch(lt_b200_context* c, uint32_t count, const void* const* src,
         if (compress)
         {
             TRY(ws_reserve(c, WS_LZ4_TABLES, LZ4_TABLE_BYTES_PER_BLOCK * (size_t)nb));
+            TRY(ws_reserve(c, WS_LZ4_V2, lz4_v2_scratch_bytes()));
             ProfScope ps(c, LT_B200_KERNEL_LZ4, in_bytes);
             CU(launch_lz4_blocks(ws<uint8_t>(c, WS_BLK_RAW), ws<uint64_t>(c, WS_BLK_RAW_OFF), ws<uint32_t>(c, WS_BLK_RAW_LEN), ws<uint8_t>(c, WS_BLK_OUT),
                                  ws<uint64_t>(c, WS_BLK_OUT_OFF), ws<uint32_t>(c, WS_BLK_OUT_LEN), ws<uint3>(c, WS_BLK_JOBS),
-                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), nb, ws<uint32_t>(c, WS_LZ4_TABLES), c->stream));
+                                 ws<uint32_t>(c, WS_BLK_JOB_START), ws<uint32_t>(c, WS_BLK_JOB_COUNT), nb, ws<uint32_t>(c, WS_LZ4_TABLES),
+                                 ws<void>(c, WS_LZ4_V2), c->sm_count, c->stream));
             c->launches += 2;
         }
         else if (mode == CODEC_LZ4_DECODE)

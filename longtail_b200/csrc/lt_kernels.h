@@ -41,10 +41,16 @@ cudaError_t launch_meow_segments(const uint8_t* d_base, const uint64_t* d_off, c
 uint32_t lz4_copy_job_capacity(uint32_t raw_len);
 cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, uint8_t* d_out,
                               const uint64_t* d_out_off, const uint32_t* d_out_cap, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st);
+// d_v2_scratch: lz4_v2_scratch_bytes() bytes (the work-queue head of the shared-memory-table encoder)
+size_t lz4_v2_scratch_bytes();
 cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
                               const uint64_t* d_out_off, uint32_t* d_out_len, uint3* d_copy_jobs, const uint32_t* d_copy_job_start,
-                              uint32_t* d_copy_job_count, uint32_t block_count, uint32_t* d_tables, cudaStream_t st);
+                              uint32_t* d_copy_job_count, uint32_t block_count, uint32_t* d_tables, void* d_v2_scratch, int sm_count,
+                              cudaStream_t st);
 constexpr size_t LZ4_TABLE_BYTES_PER_BLOCK = 32768; // d_tables: one hash table per block (nullptr = shared memory, 7 warps per SM)
+void launch_block_headers(uint8_t* d_out, const uint64_t* d_img_off, const uint32_t* d_blk_first, const uint32_t* d_blk_count,
+                          const uint32_t* d_blk_tag, const uint64_t* d_blk_hash, const uint64_t* d_chunk_hashes, const uint32_t* d_chunk_sizes,
+                          uint32_t hash_type, uint32_t nb, cudaStream_t st);
 void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, const uint64_t* d_dst_off, const uint32_t* d_len,
                           uint8_t* d_out, uint32_t count, cudaStream_t st);
 

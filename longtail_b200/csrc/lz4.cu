@@ -420,8 +420,46 @@ __device__ __forceinline__ void emit_runs(uint8_t* __restrict__ dst, uint32_t op
         cj.count += pieces;
     }
     else if (lit)
-        copy_bytes(dst + op, src + from, lit, lane);
+    {
+        // fewer than 256 bytes: at most 8 per lane, all loads in flight before the first store
+        const uint8_t* s = src + from + lane;
+        uint8_t* d = dst + op + lane;
+        const uint32_t rounds = (lit + 31u) >> 5;
+        uint8_t v[8];
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i)
+            if (i < rounds && lane + 32u * i < lit) v[i] = s[32u * i];
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i)
+            if (i < rounds && lane + 32u * i < lit) d[32u * i] = v[i];
+    }
 }
+
+// the three aligned words around position p, requested now and shifted into place only when they are used (two batches later):
+// the funnel shift would otherwise wait for the load right where it is issued
+struct Raw
+{
+    uint32_t a, b, c;
+};
+__device__ __forceinline__ Raw load_raw(const uint8_t* __restrict__ s, uint32_t p, uint32_t n)
+{
+    Raw r = {0u, 0u, 0u};
+    if (p < n)
+    {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s + (p & ~3u));
+        r.a = w[0];
+        r.b = w[1];
+        r.c = w[2];
+    }
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// The probes of a search that starts at S (lz4.c:1023-1053), in batches of 32: batch k0 (a multiple of 32) holds probes k0 .. k0+31.
+// Every probe of the batch advances by step = (k0 >> 6) + 1, except the first one of a batch with k0 = 64, 128, ... which advances by
+// one less.  So with pf = the position of the batch's first probe, lane l probes pf + l * step - (l && short_first).
+__device__ __forceinline__ uint32_t batch_step(uint32_t k0) { return (k0 >> 6) + 1u; }
+__device__ __forceinline__ uint32_t batch_short_first(uint32_t k0) { return (k0 & 63u) == 0u && k0 != 0u ? 1u : 0u; }
 
 __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t n, uint8_t* __restrict__ dst, uint32_t* table, const uint32_t lane,
                                  CopyJobs& cj)
@@ -439,35 +477,41 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
     uint32_t sweep_base = 0;
     uint32_t S = 1; // start of the current search
     bool finished = false;
-    uint32_t pA = S + lane; // probe_pos(S, k) = S + k for k <= 64
-    uint64_t wA = ld_word(src, pA, n);
+    uint32_t pA = S + lane;
+    Raw rawA = load_raw(src, pA, n);
     for (;;)
     {
         // ---------------- search (lz4.c:1043-1100): 32 probes per batch, the source words two batches ahead in flight
         uint32_t k0 = 0;
-        uint32_t pB = probe_pos(S, 32u + lane);
-        uint64_t wB = ld_word(src, pB, n);
+        uint32_t pf = S;        // first position of batch k0
+        uint32_t pfC = S + 64u; // first position of batch k0 + 64
+        uint32_t pB = S + 32u + lane;
+        Raw rawB = load_raw(src, pB, n);
         uint32_t ip0 = 0, m0 = 0, fx = 0;
         bool beq = false;
         for (;;)
         {
             const uint32_t p = pA;
-            const uint64_t w = wA;
+            const uint32_t sh = (p & 3u) * 8u;
+            const uint32_t lo = __funnelshift_r(rawA.a, rawA.b, sh);
+            const uint32_t hi = __funnelshift_r(rawA.b, rawA.c, sh);
             pA = pB;
-            wA = wB;
-            pB = probe_pos(S, k0 + 64u + lane);
-            wB = ld_word(src, pB, n);
-            const uint32_t p_last = probe_pos(S, k0 + 31u);
-            if (p_last >= sweep_base + SWEEP_TRIGGER)
+            rawA = rawB;
             {
-                const uint32_t q = probe_pos(S, k0);
-                sweep_base = sweep_to(table, sweep_base, q, q, lane);
+                const uint32_t kc = k0 + 64u, stepC = batch_step(kc), sfC = (kc & 63u) == 0u ? 1u : 0u;
+                pB = pfC + lane * stepC - (lane ? sfC : 0u);
+                rawB = load_raw(src, pB, n);
+                const uint32_t far = pB + 2048u + 256u * stepC; // the stream some ten batches ahead: HBM -> L2
+                if (far < n) prefetch_l2(src + far);
+                pfC += 32u * stepC - sfC;
             }
-            const bool all_valid = p_last + probe_advance(k0 + 31u) <= mflimit_plus_one; // else: goto _last_literals inside this batch
-            const uint32_t lo = (uint32_t)w;
-            const uint32_t h = hash5(w);
+            const uint32_t step = batch_step(k0), sf = batch_short_first(k0);
+            const uint32_t span = 32u * step - sf; // = the next batch's first position - pf
+            if (pf + span - step >= sweep_base + SWEEP_TRIGGER) sweep_base = sweep_to(table, sweep_base, pf, pf, lane);
+            const bool all_valid = pf + span <= mflimit_plus_one; // else: goto _last_literals inside this batch
+            const uint32_t h = hash5((uint64_t)lo | ((uint64_t)hi << 32));
             const uint32_t mine = entry_of(p, lo);
-            uint32_t e = 0;
+            uint32_t e = 0, r = 0;
             bool valid = true;
             if (all_valid)
             {
@@ -475,32 +519,47 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
                 __syncwarp();
                 table[h] = mine;
                 __syncwarp();
-                const uint32_t r = table[h];
+                r = table[h];
                 const bool pot = ((e ^ mine) & HI_MASK) == 0u && ((p - e) & POS_MASK) <= LZ4_MAX_DISTANCE;
                 if (!__any_sync(FULL, pot || r != mine))
                 {
                     k0 += 32;
+                    pf += span;
                     continue;
                 }
             }
             else
             {
-                valid = p < n && p + probe_advance(k0 + lane) <= mflimit_plus_one;
+                valid = p < n && p + (lane == 0 && sf ? step - 1u : step) <= mflimit_plus_one;
                 if (valid) e = table[h];
                 __syncwarp();
             }
-            // ---- general path: what v1 does for every batch.  A lane's candidate is the closest lower lane of this batch with the
-            // same hash, else the table entry it read before the batch wrote anything
-            const uint32_t same = __match_any_sync(FULL, valid ? h : 0x10000u + lane);
+            // ---- general path.  A lane's candidate is the closest lower lane of this batch with the same hash, else the table entry
+            // it read before the batch wrote anything.  `same` = the lanes with this lane's hash: found from the eager writes (a lane
+            // that did not read its own entry back shares its slot), MATCH.ANY only for the batch at the end of the block
+            uint32_t same = 1u << lane;
+            if (all_valid)
+            {
+                uint32_t confl = __ballot_sync(FULL, r != mine);
+                while (confl)
+                {
+                    const uint32_t hc = __shfl_sync(FULL, h, __ffs(confl) - 1);
+                    const uint32_t g = __ballot_sync(FULL, h == hc);
+                    if (h == hc) same = g;
+                    confl &= ~g;
+                }
+            }
+            else
+                same = __match_any_sync(FULL, valid ? h : 0x10000u + lane);
             const uint32_t lower = same & lt_mask;
             const int from = lower ? 31 - __clz(lower) : (int)lane;
-            const uint32_t p_from = __shfl_sync(FULL, p, from);
-            const uint32_t lo_from = __shfl_sync(FULL, lo, from);
+            uint32_t lo_from = lo;
+            if (__any_sync(FULL, lower != 0u)) lo_from = __shfl_sync(FULL, lo, from);
             uint32_t cand;
             bool pot;
             if (lower)
             {
-                cand = p_from;
+                cand = pf + from * step - (from ? sf : 0u);
                 pot = valid && lo_from == lo && p - cand <= LZ4_MAX_DISTANCE;
             }
             else
@@ -512,13 +571,13 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
             uint32_t pots = __ballot_sync(FULL, pot);
             const uint32_t valids = __ballot_sync(FULL, valid);
             uint32_t first_hit = 32;
-            while (pots) // the first candidate that really starts with the same 4 bytes
+            while (pots) // the first candidate that really starts with the same 4 bytes (lane 0 of fx compares them)
             {
                 const uint32_t f = (uint32_t)__ffs(pots) - 1u;
-                ip0 = __shfl_sync(FULL, p, f);
+                ip0 = pf + f * step - (f ? sf : 0u);
                 m0 = __shfl_sync(FULL, cand, f);
                 load_match_words(src, ip0, m0, anchor, matchlimit, lane, fx, beq);
-                if (__shfl_sync(FULL, fx, 0) == 0u)
+                if ((__ballot_sync(FULL, fx != 0u) & 1u) == 0u)
                 {
                     first_hit = f;
                     break;
@@ -546,6 +605,7 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
                 break;
             }
             k0 += 32;
+            pf += span;
         }
         if (finished) break;
 
@@ -653,7 +713,7 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
             const uint64_t w2 = rd64(src, ip - 2u), w0 = rd64(src, ip);
             S = ip + 1u;
             pA = S + lane;
-            wA = ld_word(src, pA, n);
+            rawA = load_raw(src, pA, n);
             const uint32_t mine0 = entry_of(ip, (uint32_t)w0);
             const uint32_t h0 = hash5(w0);
             table[hash5(w2)] = entry_of(ip - 2u, (uint32_t)w2);
@@ -729,29 +789,35 @@ k_lz4_blocks(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ 
     }
 }
 
-// v2 kernel: one warp (= one CTA) and one 16 KiB shared-memory table per block, 13 CTAs per SM; the grid is the work queue
+// v2 kernel: persistent warps (one per CTA, 13 per SM: 16 KiB of table + 1 KiB of system shared memory each) pull blocks from a queue
 __global__ void __launch_bounds__(32)
 k_lz4_blocks_v2(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ raw_off, const uint32_t* __restrict__ raw_len,
                 uint8_t* __restrict__ out_base, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
                 uint3* __restrict__ copy_jobs, const uint32_t* __restrict__ copy_job_start, uint32_t* __restrict__ copy_job_count,
-                uint32_t block_count)
+                uint32_t block_count, uint32_t* __restrict__ queue)
 {
     extern __shared__ __align__(16) uint32_t s_shared_table[];
-    const uint32_t b = blockIdx.x;
-    if (b >= block_count) return;
-    const uint32_t n = raw_len[b];
-    if (!lz4_v2_takes(n)) return;
     const uint32_t lane = threadIdx.x;
-    const uint8_t* src = raw_base + raw_off[b];
-    uint8_t* dst = out_base + out_off[b];
-    CopyJobs cj = {copy_jobs + copy_job_start[b], 0};
-    const uint32_t c = v2::encode_block(src, n, dst + 8, s_shared_table, lane, cj);
-    if (lane == 0)
+    for (;;)
     {
-        reinterpret_cast<uint32_t*>(dst)[0] = n;
-        reinterpret_cast<uint32_t*>(dst)[1] = c;
-        out_len[b] = c + 8;
-        copy_job_count[b] = cj.count;
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(queue, 1u);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= block_count) return;
+        const uint32_t n = raw_len[b];
+        if (!lz4_v2_takes(n)) continue;
+        const uint8_t* src = raw_base + raw_off[b];
+        uint8_t* dst = out_base + out_off[b];
+        CopyJobs cj = {copy_jobs + copy_job_start[b], 0};
+        const uint32_t c = v2::encode_block(src, n, dst + 8, s_shared_table, lane, cj);
+        if (lane == 0)
+        {
+            reinterpret_cast<uint32_t*>(dst)[0] = n;
+            reinterpret_cast<uint32_t*>(dst)[1] = c;
+            out_len[b] = c + 8;
+            copy_job_count[b] = cj.count;
+        }
+        __syncwarp();
     }
 }
 
@@ -863,6 +929,44 @@ k_gather_chunks(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ 
     for (uint32_t i = head + vecs * 16u + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
 }
 
+// The block index in front of every payload (Longtail_WriteStoredBlockToBuffer, src/longtail.c:4111-4150; layout of
+// Longtail_BlockIndex's data, :3585-3637): u64 block hash, u32 hash id, u32 chunk count, u32 tag, u64 chunk hashes[], u32 chunk sizes[].
+// One CTA per block; the image starts at a 4-byte aligned offset, so 64-bit fields go out as two words.
+__global__ void __launch_bounds__(128)
+k_block_headers(uint8_t* __restrict__ out_base, const uint64_t* __restrict__ img_off, const uint32_t* __restrict__ blk_first,
+                const uint32_t* __restrict__ blk_count, const uint32_t* __restrict__ blk_tag, const uint64_t* __restrict__ blk_hash,
+                const uint64_t* __restrict__ chunk_hashes, const uint32_t* __restrict__ chunk_sizes, uint32_t hash_type, uint32_t nb)
+{
+    const uint32_t b = blockIdx.x;
+    if (b >= nb) return;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out_base + img_off[b]);
+    const uint32_t first = blk_first[b], count = blk_count[b];
+    if (threadIdx.x == 0)
+    {
+        const uint64_t h = blk_hash[b];
+        dst[0] = (uint32_t)h;
+        dst[1] = (uint32_t)(h >> 32);
+        dst[2] = hash_type;
+        dst[3] = count;
+        dst[4] = blk_tag[b];
+    }
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x)
+    {
+        const uint64_t h = chunk_hashes[first + i];
+        dst[5 + 2 * i] = (uint32_t)h;
+        dst[6 + 2 * i] = (uint32_t)(h >> 32);
+        dst[5 + 2 * count + i] = chunk_sizes[first + i];
+    }
+}
+
+void launch_block_headers(uint8_t* d_out, const uint64_t* d_img_off, const uint32_t* d_blk_first, const uint32_t* d_blk_count,
+                          const uint32_t* d_blk_tag, const uint64_t* d_blk_hash, const uint64_t* d_chunk_hashes, const uint32_t* d_chunk_sizes,
+                          uint32_t hash_type, uint32_t nb, cudaStream_t st)
+{
+    if (!nb) return;
+    k_block_headers<<<nb, 128, 0, st>>>(d_out, d_img_off, d_blk_first, d_blk_count, d_blk_tag, d_blk_hash, d_chunk_hashes, d_chunk_sizes, hash_type, nb);
+}
+
 // LZ4 block decoder (LZ4_decompress_safe semantics, lib/lz4/longtail_lz4.c:79-101): one warp per block, the token stream is
 // walked by all lanes in lock step (uniform control flow), literal and match bytes are moved lane-parallel.  An overlapping
 // match (offset < length) repeats its first `offset` bytes, so byte i of the match is byte (i mod offset) of that period.
@@ -940,16 +1044,21 @@ cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, con
 
 uint32_t lz4_copy_job_capacity(uint32_t raw_len) { return raw_len / v2::DEFER_MIN + 2; }
 
+size_t lz4_v2_scratch_bytes() { return 256; }
+
 cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, const uint32_t* d_raw_len, uint8_t* d_out,
                               const uint64_t* d_out_off, uint32_t* d_out_len, uint3* d_copy_jobs, const uint32_t* d_copy_job_start,
-                              uint32_t* d_copy_job_count, uint32_t block_count, uint32_t* d_tables, cudaStream_t st)
+                              uint32_t* d_copy_job_count, uint32_t block_count, uint32_t* d_tables, void* d_v2_scratch, int sm_count,
+                              cudaStream_t st)
 {
     if (!block_count) return cudaSuccess;
-    static int v2_on = -1;
+    static int v2_on = -1, smem_per_sm = 13;
     if (v2_on < 0)
     {
         const char* e = getenv("LT_B200_LZ4_V1"); // A/B knob: 1 = the round-1 encoder (tables in HBM/L2) for every block
         v2_on = e && atoi(e) ? 0 : 1;
+        const char* m = getenv("LT_B200_LZ4_SMEM_CTAS"); // A/B knob: shared-memory CTAs per SM (default: all 13 that fit)
+        if (m) smem_per_sm = atoi(m) < 1 ? 1 : (atoi(m) > 13 ? 13 : atoi(m));
         // 13 CTAs of 16 KiB + 1 KiB per SM need the largest shared-memory carve-out
         cudaFuncSetAttribute(k_lz4_blocks_v2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
@@ -957,8 +1066,13 @@ cudaError_t launch_lz4_blocks(const uint8_t* d_raw, const uint64_t* d_raw_off, c
     k_lz4_blocks<<<block_count, 32, d_tables ? 0 : LZ4_TABLE_BYTES, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs,
                                                                          d_copy_job_start, d_copy_job_count, block_count, d_tables, (uint32_t)v2_on);
     if (v2_on)
-        k_lz4_blocks_v2<<<block_count, 32, v2::TABLE_WORDS * 4, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs,
-                                                                    d_copy_job_start, d_copy_job_count, block_count);
+    {
+        uint32_t* queue = static_cast<uint32_t*>(d_v2_scratch);
+        cudaMemsetAsync(queue, 0, 4, st);
+        const uint32_t ctas = min(block_count, (uint32_t)(smem_per_sm * sm_count));
+        k_lz4_blocks_v2<<<ctas, 32, v2::TABLE_WORDS * 4, st>>>(d_raw, d_raw_off, d_raw_len, d_out, d_out_off, d_out_len, d_copy_jobs, d_copy_job_start,
+                                                             d_copy_job_count, block_count, queue);
+    }
     k_lz4_copy<<<dim3(block_count, LZ4_COPY_SLICES), LZ4_COPY_WARPS * 32, 0, st>>>(d_raw, d_raw_off, d_out, d_out_off, d_copy_jobs, d_copy_job_start,
                                                                                  d_copy_job_count);
     return cudaGetLastError();

@@ -256,11 +256,8 @@ __global__ void k_synth_fill(uint8_t* __restrict__ dst, uint64_t len, lt_synth_s
     for (; b < blocks; b += stride)
     {
         const uint64_t off = offset + b * 16;
-        uint64_t key, base;
-        uint32_t cls;
-        lt_synth_segment(&spec, asset_id, off, &key, &base, &cls);
         uint8_t tmp[16];
-        lt_synth_block16(key, (base + off % LT_SYNTH_SEGMENT_BYTES) / 16, cls, tmp);
+        lt_synth_asset_block16(&spec, asset_id, off, tmp);
         if (b * 16 + 16 <= len && (((uintptr_t)dst) & 15) == 0)
             *reinterpret_cast<uint4*>(dst + b * 16) = *reinterpret_cast<uint4*>(tmp);
         else
