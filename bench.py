@@ -1,22 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — the headline benchmark of BASELINE.json: GiB/s of CreateVersionIndex (content-defined chunking + BLAKE3
-per chunk + dedup + VersionIndex) and the fraction of the HBM-read roofline.
+"""bench.py — BASELINE.json's headline metric: GiB/s of the chunk -> hash -> compress indexing path (CreateVersionIndex +
+CreateMissingContent + WriteContent through the compress block store) and the fraction of the HBM roofline.
 
-Workload (config.workload): BASELINE.json configs[1] — "1xB200: chunk+BLAKE3 only (no compression) on one 64 GiB synthetic
-file, 64 KiB target chunk size" (SURVEY.md §8d config 2): uniform-random bytes from the counter-based generator of
-include/lt_synth.h (seed 1), target_chunk_size 65536, tag 0.  With N GPUs every rank indexes its own 64 GiB file (weak
-scaling); the per-rank chunk tables are merged with one allgather and rank 0 builds the VersionIndex of all N files.
+Workloads (config.workload names the one `value` is measured on):
+  headline, every N   BASELINE.json configs[2] per GPU: 10 000 synthetic assets totalling 128 GiB with 50 % byte redundancy
+                      (sizes log-uniform in [64 KiB, 256 MiB], 1 MiB segments half of which come from a
+                      shared 8 GiB pool, random / 4-bit / text-like segments), target chunk 65 536, BLAKE3, tag 'lz42', blocks of
+                      8 MiB / 1 024 chunks.  With N > 1 every rank holds its own 10 000 assets of ONE version (the pool is shared, so
+                      chunks repeat across ranks): the job list is sharded by (asset, part), the chunk tables are merged with NCCL, the
+                      dedup is global, the blocks are packed over the global unique-chunk list and written by the ranks — configs[4]'s
+                      full upsync (CreateVersionIndex + CreateMissingContent + WriteContent, NCCL all-gather of the chunk-hash table) at
+                      N x 128 GiB.  Weak scaling.
+  index_only, N = 1   configs[1]: chunk + BLAKE3 only on one 64 GiB uniform-random file (the chunker / hash kernels' roofline numbers)
+  zstd_pak, every N   configs[3]'s shape per GPU: a 32 GiB slice of ONE PAK-like file (64 KiB - 64 MiB members, 2 KiB zero padding), parts
+                      sharded across the ranks, tag 'ztd2' (ZStd level 3) — 8 x 32 GiB = the 256 GiB file of configs[3]
 
-A step = one full pass: chunk + hash every part, merge, content hashes, dedup, serialised VersionIndex copied to the host.
-  value  inputs already resident in HBM (CUDA events on the context stream, max over ranks)
-  e2e    the same verb through the C ABI with the asset bytes in pinned HOST memory, host->device copies inside the timing
+A step = one full pass over the workload.
+  value  inputs resident in HBM, stored blocks left in HBM (device sink): CUDA events on the context stream, max over ranks
+  e2e    the same verbs with the asset bytes in pinned HOST memory and every stored block copied to pinned host memory:
+         lt_b200_upsync_host_assets, wall clock
   roofline / cpu_baseline  as the task contract describes; see DESIGN.md §Measurement
 
-`--impl reference` times the UNMODIFIED reference (oracle/_ref/libref_shim.so: Longtail_CreateVersionIndex with the bikeshed
-JobAPI on all host threads) on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libref_shim.so: Longtail_CreateVersionIndex + CreateMissingContent +
+WriteContent through its compressblockstore with the bikeshed JobAPI on all host threads) on a bounded sample of the same workload.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -27,9 +37,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GIB = 1 << 30
 TARGET_CHUNK_SIZE = 65536
-SEED = 1
-# BASELINE.json's metric, verbatim.  The configuration it is quoted on at N = 1 (configs[1]) has no compression stage: `value` is
-# chunk + BLAKE3 + VersionIndex; the chunk + hash + compress legs of configs[2] (LZ4) and configs[3]'s codec (ZStd) are under `write_content`.
+MAX_BLOCK_SIZE = 8388608
+MAX_CHUNKS_PER_BLOCK = 1024
+SEED_CONFIG2 = 2
+SEED_RANDOM = 1
+SEED_PAK = 3
 METRIC = "GiB/s end-to-end chunk+hash+compress (CreateVersionIndex); % HBM roofline"
 try:
     with open(os.path.join(ROOT, "BASELINE.json")) as _f:
@@ -44,14 +56,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gib", type=float, default=64.0, help="size of the synthetic file per GPU (GiB)")
-    ap.add_argument("--e2e-gib", type=float, default=None, help="size of the host-resident file for the e2e leg (default: --gib, bounded by host RAM)")
-    ap.add_argument("--cpu-gib", type=float, default=8.0, help="bounded sample for the CPU baseline / the reference arm")
-    ap.add_argument("--compress-gib", type=float, default=32.0, help="size of the configs[2]-shaped asset set of the LZ4 leg (0 = skip; 128 = the full config)")
-    ap.add_argument("--zstd-gib", type=float, default=32.0, help="size of the asset set of the ZStd leg (0 = skip)")
+    ap.add_argument("--gib", type=float, default=128.0, help="size of the configs[2] asset set per GPU (GiB); 128 = the full config")
+    ap.add_argument("--index-gib", type=float, default=64.0, help="size of the configs[1] file of the index_only leg (0 = skip)")
+    ap.add_argument("--zstd-gib", type=float, default=32.0, help="size of the PAK-like slice per GPU of the zstd_pak leg (0 = skip)")
+    ap.add_argument("--e2e-gib", type=float, default=None, help="host-resident part of the asset set for the e2e leg (default: all that fits host RAM)")
+    ap.add_argument("--cpu-gib", type=float, default=16.0, help="bounded sample of the reference arm per step (BASELINE.md: a fixed 16 GiB prefix)")
+    ap.add_argument("--verify-gib", type=float, default=1.0, help="N > 1: per-rank size of the multi-GPU parity run against the reference (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--verify", action="store_true", help="small sizes only: compare the final VersionIndex with the CPU checker, byte for byte")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the reference runs (parity and cpu_baseline)")
     return ap.parse_args()
 
 
@@ -89,7 +101,6 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        # under load = the SM clock samples of the upper half (idle samples before the first step would drag the median down)
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
         mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
         reasons = set()
@@ -101,26 +112,8 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def host_sample(nbytes, threads, asset_id=0):
-    """the first nbytes of synthetic file `asset_id`, generated on the host (oracle/_ref/libsynth_host.so)"""
-    import ctypes as C
-
-    import numpy as np
-
-    import longtail_b200
-    path = os.path.join(ROOT, "oracle", "_ref", "libsynth_host.so")
-    if not os.path.exists(path):
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-    lib = C.CDLL(path)
-    buf = np.empty(nbytes, dtype=np.uint8)
-    spec = longtail_b200.SynthSpec(SEED, 0, 1, 0, 0)
-    lib.synth_fill_mt(C.byref(spec), C.c_uint64(asset_id), C.c_uint64(0), buf.ctypes.data_as(C.c_void_p), C.c_uint64(nbytes), C.c_uint32(threads))
-    return buf
-
-
 def config3_asset_sizes(total_bytes, count):
     """sizes log-uniform in [64 KiB, 256 MiB], rescaled to the total, 256-byte granules"""
-    import math
     x, sizes = 12345, []
     for _ in range(count):
         x = (x * 6364136223846793005 + 1442695040888963407) & ((1 << 64) - 1)
@@ -130,182 +123,123 @@ def config3_asset_sizes(total_bytes, count):
     return [max(4096, int(v * scale) // 256 * 256) for v in sizes]
 
 
-def compress_leg(ctx, torch, stream, codec, gib, cpu_sample_gib, want_cpu):
-    """configs[2] shape (10 000 assets per 128 GiB, 50 % byte redundancy, random / 4-bit / text-like segments) through
-    CreateVersionIndex + WriteContent with the codec tag on every asset: gather + compress on the device, every StoredBlock
-    copied to a host sink (memory is the sink: SURVEY.md section 8d)."""
+class Config2Set:
+    """the configs[2] asset set of one rank: names, sizes, arena offsets, generator parameters"""
+
+    def __init__(self, gib, rank, world):
+        self.total_target = int(gib * GIB)
+        self.count = max(8, int(round(10000 * gib / 128.0)))
+        self.sizes = config3_asset_sizes(self.total_target, self.count)
+        self.offsets, off = [], 0
+        for sz in self.sizes:
+            self.offsets.append(off)
+            off += (sz + 255) & ~255
+        self.arena_bytes = off + 4096
+        self.nbytes = sum(self.sizes)
+        self.pool = max(8, int(8192 * gib / 128.0))  # the shared pool: 8 GiB at full size (1 MiB segments)
+        self.first_id = rank * self.count
+        self.names = ["a/%06d.bin" % (self.first_id + i) for i in range(self.count)]
+        self.all_names = ["a/%06d.bin" % i for i in range(self.count * world)]
+        self.all_sizes = self.sizes * world
+
+    def fill(self, ctx, arena):
+        for i, (o, sz) in enumerate(zip(self.offsets, self.sizes)):
+            ctx.synth_fill(arena + o, sz, seed=SEED_CONFIG2, asset_id=self.first_id + i, class_mode=1, shared_permille=500, pool_segments=self.pool)
+        ctx.synchronize()
+
+
+def synth_host_lib():
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libsynth_host.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    return C.CDLL(path)
+
+
+def host_assets(cs, limit_bytes, threads, first_id=0):
+    """the first assets of a Config2Set (up to limit_bytes), generated on the HOST (oracle/_ref/libsynth_host.so) -> list of uint8 arrays"""
+    import ctypes as C
+
     import numpy as np
 
     import longtail_b200
-    tag = longtail_b200.COMPRESSION_LZ4 if codec == "lz4" else longtail_b200.COMPRESSION_ZSTD_DEFAULT
-    kernel = "k_lz4_blocks" if codec == "lz4" else "k_zstd_frames"
-    total = int(gib * GIB)
-    count = max(8, int(round(10000 * gib / 128.0)))
-    sizes = config3_asset_sizes(total, count)
-    offs, off = [], 0
-    for sz in sizes:
-        offs.append(off)
-        off += (sz + 255) & ~255
-    arena_bytes = off + 4096
-    arena = ctx.device_alloc(arena_bytes)
-    pool = max(8, int(8192 * gib / 128.0))  # the shared pool is 8 GiB at full size (1 MiB segments)
-    for i, (o, sz) in enumerate(zip(offs, sizes)):
-        ctx.synth_fill(arena + o, sz, seed=2, asset_id=i, class_mode=1, shared_permille=500, pool_segments=pool)
-    ctx.synchronize()
-    al = longtail_b200.AssetList(["a/%05d.bin" % i for i in range(count)], sizes)
-    tags = [tag] * count
-    nbytes = sum(sizes)
-    out = {"codec": codec, "assets": count, "bytes": nbytes}
-    res = None
-    for it in range(2):  # pass 0 warms up (workspace growth, pinned staging), pass 1 is reported
-        ctx.profile_reset()
-        ctx.profile_enable(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        v = ctx.index_device_assets(arena, arena_bytes, al, offs, tags, target_chunk_size=TARGET_CHUNK_SIZE)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        vi = longtail_b200.parse_version_index(v)
-        uoff = ctx.unique_chunk_offsets(vi["chunk_count"])
-        t2 = time.perf_counter()
-        blocks = ctx.write_blocks_device(arena, arena_bytes, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"], uoff, keep_bytes=False)
-        t3 = time.perf_counter()
-        ctx.profile_enable(False)
-        prof = ctx.profile_read()
-        unique = int(vi["chunk_sizes"].astype(np.uint64).sum())
-        stored = sum(sz for _, sz in blocks)
-        index_ms = e0.elapsed_time(e1)
-        dev_ms = index_ms + prof["k_gather_chunks"][0] + prof[kernel][0]
-        res = {"unique_bytes": unique, "unique_frac": round(unique / nbytes, 4), "blocks": len(blocks), "stored_bytes": stored,
-               "ratio": round(stored / max(unique, 1), 4), "index_ms": round(index_ms, 2), "gather_ms": round(prof["k_gather_chunks"][0], 2),
-               "codec_kernel_ms": round(prof[kernel][0], 2), "codec_kernel_GBps": round(unique / max(prof[kernel][0], 1e-9) / 1e6, 2),
-               "value_GiBps": round(nbytes / (dev_ms / 1e3) / GIB, 3),
-               "e2e_GiBps": round(nbytes / ((t1 - t0) + (t3 - t2)) / GIB, 3), "write_wall_ms": round(1e3 * (t3 - t2), 1),
-               "d2h_bytes": stored, "note": "value = asset bytes / (index + gather + codec kernel device time); e2e adds the block-store "
-                                            "hand-over: every StoredBlock copied to pinned host memory and passed to the sink"}
-    out.update(res)
-    # the step after PutStoredBlock (SURVEY.md section 8f row 2): the same write with the fsblockstore-layout disk sink (C sink, writer threads)
-    # into a RAM-backed directory, so the number is the sink's own cost (copy, open/write/rename per block, store.lsi), not a disk's
-    out["fs_store"] = None
-    try:
-        import shutil
-        import tempfile
-
-        import psutil
-        base = os.environ.get("LT_B200_FS_STORE_DIR", "/dev/shm")
-        if codec == "lz4" and os.path.isdir(base) and psutil.virtual_memory().available > 4 * res["stored_bytes"] and shutil.disk_usage(base).free > 2 * res["stored_bytes"]:
-            d = tempfile.mkdtemp(prefix="lt_b200_store_", dir=base)
-            try:
-                st = longtail_b200.FsStore(d, writer_threads=8)
-                t4 = time.perf_counter()
-                ctx.write_blocks_device(arena, arena_bytes, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"], uoff, fs_store=st)
-                st.flush()
-                t5 = time.perf_counter()
-                stats = st.stats()
-                st.close()
-                out["fs_store"] = {"dir": base, "writer_threads": 8, "blocks_written": stats["blocks_written"], "bytes_written": stats["bytes_written"],
-                                   "write_wall_ms": round(1e3 * (t5 - t4), 1), "stored_GBps": round(stats["bytes_written"] / (t5 - t4) / 1e9, 2),
-                                   "e2e_GiBps": round(nbytes / ((t1 - t0) + (t5 - t4)) / GIB, 3),
-                                   "note": "index + WriteContent with every block written as chunks/xxxx/0x....lrb plus store.lsi (reference fsblockstore layout)"}
-            finally:
-                shutil.rmtree(d, ignore_errors=True)
-    except Exception as e:  # the sink leg is informative; the bench line must not depend on /dev/shm
-        out["fs_store"] = {"error": str(e)[:200]}
-    if want_cpu:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_lib as ol
-        ref = ol.Reference()
-        if ref.available:
-            assets, acc = [], 0
-            for i, (o, sz) in enumerate(zip(offs, sizes)):
-                if acc + sz > cpu_sample_gib * GIB and assets:
-                    break
-                assets.append(("a/%05d.bin" % i, ctx.to_host(arena + o, sz)))
-                acc += sz
-            cores = ref.cpu_count()
-            secs, _stored = ref.upsync(assets, TARGET_CHUNK_SIZE, tags=[tag] * len(assets), workers=cores, keep_bytes=False)
-            # parity on the same sample: the GPU path over exactly these assets must store exactly as many bytes as the reference
-            k = len(assets)
-            sub = longtail_b200.AssetList(["a/%05d.bin" % i for i in range(k)], sizes[:k])
-            v = ctx.index_device_assets(arena, arena_bytes, sub, offs[:k], [tag] * k, target_chunk_size=TARGET_CHUNK_SIZE)
-            vi = longtail_b200.parse_version_index(v)
-            blocks = ctx.write_blocks_device(arena, arena_bytes, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"],
-                                             ctx.unique_chunk_offsets(vi["chunk_count"]), keep_bytes=False)
-            gpu_stored = sum(sz for _, sz in blocks)
-            if gpu_stored != _stored:
-                raise SystemExit("%s parity check failed: %d stored bytes on the GPU, %d in the reference" % (codec, gpu_stored, _stored))
-            out["parity"] = "sample of %d assets: %d blocks, %d stored bytes, identical to the reference's upsync" % (k, len(blocks), gpu_stored)
-            out["cpu_baseline"] = {"value": round(acc / sum(secs) / GIB, 4), "unit": "GiB/s", "cores": cores, "kind": "reference",
-                                   "sample": "first %d assets (%.2f GiB): CreateVersionIndex + CreateMissingContent + WriteContent through "
-                                             "compressblockstore, bikeshed %d workers" % (len(assets), acc / GIB, cores),
-                                   "seconds_index_missing_write": [round(x, 3) for x in secs]}
-    ctx.device_free(arena)
+    lib = synth_host_lib()
+    out, acc = [], 0
+    spec = longtail_b200.SynthSpec(SEED_CONFIG2, 500, cs.pool, 1, 0)
+    for i, sz in enumerate(cs.sizes):
+        if acc + sz > limit_bytes and out:
+            break
+        buf = np.empty(sz, dtype=np.uint8)
+        lib.synth_fill_mt(C.byref(spec), C.c_uint64(first_id + i), C.c_uint64(0), buf.ctypes.data_as(C.c_void_p), C.c_uint64(sz), C.c_uint32(threads))
+        out.append(buf)
+        acc += sz
     return out
 
 
-def reference_pass(ref, data, workers):
-    """one Longtail_CreateVersionIndex of the unmodified reference over `data` as a single asset; -> seconds (wall, inside C)"""
-    _, secs = ref.create_version_index([("f00000.bin", data)], TARGET_CHUNK_SIZE, workers=workers, want_seconds=True)
-    return secs
-
-
+# ---------------------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
+    cs = Config2Set(args.gib, 0, 1)
     ref = ol.Reference()
+    workload = "configs[2]: chunk+BLAKE3+LZ4 (CreateVersionIndex + CreateMissingContent + WriteContent), %d synthetic assets / %.0f GiB, 50 %% byte " \
+               "redundancy, target_chunk_size 65536" % (cs.count, args.gib)
     if not ref.available:
         # the reference was not compiled on this box: the oracle's single-threaded C restatement of the same path stands in (kind "port")
         o = ol.Oracle()
-        nbytes = int(min(args.cpu_gib, 1.0) * GIB)
-        data = host_sample(nbytes, 1)
+        datas = host_assets(cs, int(min(args.cpu_gib, 0.5) * GIB), 4)
+        assets = list(zip(cs.names, datas))
+        nbytes = sum(d.size for d in datas)
         t = []
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            o.create_version_index([("f00000.bin", data)], TARGET_CHUNK_SIZE)
+            o.upsync(assets, TARGET_CHUNK_SIZE, tags=[ol.COMP_LZ4] * len(assets))
             if i >= args.warmup:
                 t.append(time.perf_counter() - t0)
         total = sum(t)
         value = nbytes * args.steps / total / GIB
-        sample = "first %.1f GiB of the %.0f GiB file, oracle/lt_oracle.c (C restatement), 1 thread" % (nbytes / GIB, args.gib)
-        emit({"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps,
-              "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-              "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-              "config": {"workload": "configs[1]: chunk+BLAKE3, one %.0f GiB synthetic file, target_chunk_size 65536 (CPU sample: %s)" % (args.gib, sample)},
-              "cpu_baseline": {"value": round(value, 4), "unit": "GiB/s", "cores": 1, "kind": "port", "sample": sample},
-              "e2e": {"value": round(value, 4), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        return
-    cores = ref.cpu_count()
-    nbytes = int(args.cpu_gib * GIB)
-    data = host_sample(nbytes, cores)
-    for _ in range(args.warmup):
-        reference_pass(ref, data, cores)
-    t = [reference_pass(ref, data, cores) for _ in range(args.steps)]
-    total = sum(t)
-    value = nbytes * args.steps / total / GIB
-    sample = "first %.1f GiB of the %.0f GiB file, Longtail_CreateVersionIndex, bikeshed %d workers + caller" % (args.cpu_gib, args.gib, cores)
+        sample = "first %d assets (%.2f GiB), oracle/lt_oracle.c (C restatement), 1 thread" % (len(assets), nbytes / GIB)
+        cores, kind = 1, "port"
+    else:
+        cores = ref.cpu_count()
+        datas = host_assets(cs, int(args.cpu_gib * GIB), cores)
+        assets = list(zip(cs.names, datas))
+        nbytes = sum(d.size for d in datas)
+        tags = [ol.COMP_LZ4] * len(assets)
+
+        def one_pass():
+            secs, _stored = ref.upsync(assets, TARGET_CHUNK_SIZE, MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK, tags=tags, workers=cores, keep_bytes=False)
+            return sum(secs)
+
+        for _ in range(args.warmup):
+            one_pass()
+        t = [one_pass() for _ in range(args.steps)]
+        total = sum(t)
+        value = nbytes * args.steps / total / GIB
+        sample = "first %d assets (%.2f GiB) of the set: CreateVersionIndex + CreateMissingContent + WriteContent through compressblockstore " \
+                 "(LZ4), bikeshed %d workers + caller" % (len(assets), nbytes / GIB, cores)
+        kind = "reference"
     emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "configs[1]: chunk+BLAKE3, one %.0f GiB synthetic file, target_chunk_size 65536 (CPU sample: %s)" % (args.gib, sample)},
-        "cpu_baseline": {"value": round(value, 4), "unit": "GiB/s", "cores": cores, "kind": "reference", "sample": sample},
+        "config": {"workload": workload + " (CPU sample: %s)" % sample},
+        "cpu_baseline": {"value": round(value, 4), "unit": "GiB/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
 
 
+# ---------------------------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import longtail_b200
-    from longtail_b200 import distributed as ltd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -315,52 +249,36 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = longtail_b200.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-
-    nbytes = int(args.gib * GIB)
+    comm = None
+    if world > 1:
+        # the library's own NCCL communicator: rank 0 makes the id, torch.distributed only carries its 128 bytes
+        box = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = ctx.comm_create(box[0], rank, world)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    LZ4 = longtail_b200.COMPRESSION_LZ4
+    ZSTD = longtail_b200.COMPRESSION_ZSTD_DEFAULT
     part = TARGET_CHUNK_SIZE * 1024
-    mn, av, mx = longtail_b200.chunker_params(TARGET_CHUNK_SIZE)
-    arena = ctx.device_alloc(nbytes + 4096)
-    ctx.synth_fill(arena, nbytes, seed=SEED, asset_id=rank)
-    ctx.synchronize()
-
-    # the whole job: N files of nbytes each; this rank owns file `rank`
-    all_assets = longtail_b200.AssetList(["f%05d.bin" % r for r in range(world)], [nbytes] * world)
-    my_asset = longtail_b200.AssetList(["f%05d.bin" % rank], [nbytes])
-    jobs = ltd.plan_jobs([nbytes] * world, TARGET_CHUNK_SIZE)
-    job_asset_ids = ltd.job_assets(jobs)  # once, outside the timed steps
-    my_jobs = [j for j in jobs if j[0] == rank]
-    ranges = [(start, size, 0) for _, start, size in my_jobs]
-    index_bytes = [0]
-
-    def step_resident():
-        if world == 1:
-            v = ctx.index_device_assets(arena, nbytes + 4096, my_asset, [0], None, target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
-            index_bytes[0] = len(v)
-            return v
-        t = ctx.chunk_ranges(arena, nbytes + 4096, ranges, mn, av, mx, want_host=False)
-        dh, ds, dt, n = ctx.resident_table()
-        with torch.cuda.stream(stream):
-            counts = torch.as_tensor(t["range_chunk_counts"].astype(np.int64), device="cuda")
-            hashes = torch.as_tensor(ltd.DeviceArray(dh, n, "<i8"), device="cuda")
-            sizes = torch.as_tensor(ltd.DeviceArray(ds, n, "<i4"), device="cuda")
-            tags = torch.as_tensor(ltd.DeviceArray(dt, n, "<i4"), device="cuda")
-            jc, gh, gs, gt = ltd.allgather_tables(counts, hashes, sizes, tags)
-            stream.synchronize()
-            if rank == 0:
-                acc = ltd.asset_chunk_counts(job_asset_ids, jc.cpu().numpy(), world)
-                v = ctx.build_version_index_device(all_assets, acc, gh.numel(), gh.data_ptr(), gs.data_ptr(), gt.data_ptr(),
-                                                   target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
-                index_bytes[0] = len(v)
-                return v
-        return None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     def timed(fn, steps):
-        """-> (device ms over `steps` calls of fn, max over ranks)"""
+        """-> device ms over `steps` calls of fn (CUDA events on the context stream), max over ranks"""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -368,184 +286,312 @@ def run_b200(args):
             fn()
         e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1))
 
-    # ---- parity before anything is timed: 8 parts spread over the whole file (first, last, 6 pseudo-random) against the CPU checker,
-    # chunk sizes and chunk hashes bit for bit; then size-independent properties of the full-size VersionIndex
-    parity = "skipped"
-    if rank == 0:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
+    # ------------------------------------------------------------------ the sharded upsync of one version (any N)
+    class Upsync:
+        """CreateVersionIndex + CreateMissingContent (fresh store) + WriteContent of the version made of every rank's assets"""
+
+        def __init__(self, names, sizes, tags, my_first_asset, my_offsets, arena, arena_bytes, byte_range_base=None):
+            self.assets = longtail_b200.AssetList(names, sizes)
+            self.tags = tags
+            self.arena, self.arena_bytes = arena, arena_bytes
+            self.my_first_asset, self.my_offsets = my_first_asset, my_offsets
+            if comm is not None:
+                first, njobs = ctx.plan_shards(self.assets, TARGET_CHUNK_SIZE, world)
+                jobs = ctx.shard_jobs(self.assets, TARGET_CHUNK_SIZE, int(first[rank]), int(first[rank + 1] - first[rank]))
+                if byte_range_base is not None:
+                    # ONE asset sharded by byte range: this rank's arena holds its bytes [byte_range_base, byte_range_base + arena size)
+                    if jobs.size and (int(jobs["offset"].min()) < byte_range_base or
+                                      int((jobs["offset"] + jobs["size"]).max()) > byte_range_base + arena_bytes):
+                        raise SystemExit("shard plan does not follow the byte ranges the ranks hold")
+                    self.job_offsets = (jobs["offset"].astype(np.int64) - byte_range_base).astype(np.uint64)
+                else:
+                    local = jobs["asset_index"].astype(np.int64) - my_first_asset
+                    if local.size and (local.min() < 0 or local.max() >= len(my_offsets)):
+                        raise SystemExit("shard plan hands rank %d a job of an asset it does not hold" % rank)
+                    self.job_offsets = np.asarray(my_offsets, dtype=np.uint64)[local] + jobs["offset"]
+            self.index_bytes = 0
+
+        def index(self, want_host=True, copy=False):
+            if comm is None:
+                v = ctx.index_device_assets(self.arena, self.arena_bytes, self.assets, self.my_offsets, self.tags, target_chunk_size=TARGET_CHUNK_SIZE, copy=copy)
+                self.index_bytes = len(v)
+                return v
+            v = ctx.index_sharded(comm, self.arena, self.arena_bytes, self.assets, self.tags, self.job_offsets, TARGET_CHUNK_SIZE,
+                                  want_host=want_host, copy=copy)
+            self.index_bytes = v if isinstance(v, int) else len(v)
+            return v
+
+        def write(self, c_sink, device_sink, vi=None):
+            if comm is None:
+                if vi is None:
+                    raise ValueError("single-GPU write needs the parsed VersionIndex")
+                ctx.write_blocks_device(self.arena, self.arena_bytes, vi["chunk_hashes"], vi["chunk_sizes"], vi["chunk_tags"],
+                                        ctx.unique_chunk_offsets(vi["chunk_count"]), MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK, c_sink=c_sink,
+                                        device_sink=device_sink)
+                return None
+            return ctx.write_blocks_sharded(comm, c_sink, MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK, device_sink=device_sink)
+
+    def parity_against_reference(up, host_datas_of_all_ranks, names, tags, label):
+        """rank 0 runs the unmodified reference over the whole version; the VersionIndex must be byte-identical and every StoredBlock
+        (block hash, size, 64-bit digest of its serialised bytes, in store order) identical — the blocks of all ranks concatenated in
+        rank order.  -> (text for the JSON line, reference seconds or None)"""
         import oracle_lib as ol
-        nparts = (nbytes + part - 1) // part
-        picks = sorted({0, nparts - 1} | {(k * 2654435761 + 12345) % nparts for k in range(6)})
-        ranges_chk = [(pi * part, min(part, nbytes - pi * part), 0) for pi in picks]
-        got = ctx.chunk_ranges(arena, nbytes + 4096, ranges_chk, mn, av, mx)
         ref = ol.Reference()
-        checker = ref if ref.available else ol.Oracle()
-        exp_sizes, exp_hashes = [], []
-        for o, sz, _ in ranges_chk:
-            host = ctx.to_host(arena + o, sz)
-            e = checker.chunk(host, mn, av, mx)
-            offs = np.concatenate([[0], np.cumsum(e.astype(np.uint64))[:-1]]).astype(np.uint64)
-            exp_sizes.append(e)
-            exp_hashes.append(checker.hash_segments(ol.HASH_BLAKE3, host, offs, e))
-        ok = got["sizes"].tolist() == np.concatenate(exp_sizes).tolist() and got["hashes"].tolist() == np.concatenate(exp_hashes).tolist()
-        if not ok:
-            raise SystemExit("parity check failed: the CUDA path differs from the CPU checker")
-        # full-size properties: chunk sizes tile every part exactly, lie in [min, max] except a part's last chunk, the index is
-        # deterministic (two passes give identical bytes) and its asset content hash is the hash of the chunk-hash array
-        v1 = bytes(step_resident()) if world == 1 else None
-        if v1 is not None:
-            vi = longtail_b200.parse_version_index(v1)
-            v2 = bytes(step_resident())
-            sizes_all = vi["chunk_sizes"][vi["asset_chunk_indexes"]].astype(np.uint64)
-            props = (v1 == v2 and int(sizes_all.sum()) == nbytes and int(vi["chunk_sizes"].max()) <= mx
-                     and int((vi["chunk_sizes"] < mn).sum()) <= nparts
-                     and int(vi["content_hashes"][0]) == checker.hash(ol.HASH_BLAKE3, vi["chunk_hashes"][vi["asset_chunk_indexes"]].astype("<u8").tobytes()))
-            if not props:
-                raise SystemExit("full-size property check failed")
-        parity = "bit-exact vs %s on %d parts (%d MiB) spread over the file%s" % (
-            "reference" if ref.available else "oracle", len(picks), sum(r[1] for r in ranges_chk) >> 20,
-            "; full-size properties hold (sizes tile the file, [min,max], deterministic, content hash)" if v1 is not None else "")
-
-    if args.verify:
-        v = step_resident()
+        if not ref.available:
+            return "unpinned: oracle/_ref/libref_shim.so is not built on this box", None
+        sink = ol.DigestSink(ref)
+        v = up.index(want_host=True, copy=True)
+        vi = longtail_b200.parse_version_index(v) if comm is None or rank == 0 else None
+        up.write((sink.fn, sink.user), False, vi)
+        mine = sink.records()
+        sink.close()
+        if world > 1:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(mine, gathered, dst=0)
+        else:
+            gathered = [mine]
+        secs = None
         if rank == 0:
-            import oracle_lib as ol
-            ref = ol.Reference()
-            checker = ref if ref.available else ol.Oracle()
-            assets = [("f%05d.bin" % r, host_sample(nbytes, 8, asset_id=r)) for r in range(world)]
-            want = checker.create_version_index(assets, TARGET_CHUNK_SIZE)
-            if bytes(v) != want:
-                raise SystemExit("VERIFY FAILED: VersionIndex of %d GPUs differs from the CPU checker" % world)
-            print("verify ok: %d-byte VersionIndex of %d file(s) identical to the %s" % (len(want), world, "reference" if ref.available else "oracle"), file=sys.stderr)
-            parity += "; full VersionIndex verified"
+            got = np.concatenate(gathered, axis=0)
+            rec, want_v, secs = ref.upsync(list(zip(names, host_datas_of_all_ranks)), TARGET_CHUNK_SIZE, MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK,
+                                           tags=tags, workers=ref.cpu_count(), keep_bytes=2)
+            if bytes(v) != want_v:
+                raise SystemExit("PARITY FAILED (%s): the VersionIndex differs from the reference's" % label)
+            if got.shape != rec.shape or not np.array_equal(got, rec):
+                raise SystemExit("PARITY FAILED (%s): StoredBlocks differ from the reference's (%d vs %d blocks)" % (label, got.shape[0], rec.shape[0]))
+            text = "full: %d-byte VersionIndex memcmp-identical and all %d StoredBlocks (hash, size, 64-bit digest of the serialised bytes, store " \
+                   "order) identical to the unmodified reference on %s" % (len(want_v), rec.shape[0], label)
+        else:
+            text = ""
+        return text, secs
 
-    # ---- resident-in-HBM measurement
+    # ================================================================== headline: configs[2] per GPU
+    cs = Config2Set(args.gib, rank, world)
+    arena = ctx.device_alloc(cs.arena_bytes)
+    cs.fill(ctx, arena)
+    tags_all = [LZ4] * (cs.count * world)
+    up = Upsync(cs.all_names, cs.all_sizes, tags_all, cs.first_id, cs.offsets, arena, cs.arena_bytes)
+
+    # ---- host copy of this rank's assets in pinned memory: the e2e source and (N = 1) the reference's input
+    import psutil
+    avail = psutil.virtual_memory().available
+    want_host = cs.nbytes if args.e2e_gib is None else int(args.e2e_gib * GIB)
+    host_limit = int(min(want_host, 0.72 * avail / max(world, 1)))
+    host_buf, host_datas, host_count = None, [], 0
+    if not (args.no_e2e and args.no_cpu):
+        acc = 0
+        while host_count < cs.count and acc + cs.sizes[host_count] <= host_limit:
+            acc += cs.sizes[host_count]
+            host_count += 1
+        host_count = max(host_count, 1)
+        span = cs.offsets[host_count - 1] + cs.sizes[host_count - 1]
+        host_buf = ctx.pinned_alloc(span)
+        ctx.lib.lt_b200_copy_to_host(ctx.handle, host_buf.ctypes.data, arena, span)
+        host_datas = [host_buf[o:o + s] for o, s in zip(cs.offsets[:host_count], cs.sizes[:host_count])]
+    host_bytes = sum(d.size for d in host_datas)
+
+    # ---- parity before anything is timed
+    parity, cpu = "skipped (--no-cpu)", None
+    if not args.no_cpu:
+        if world == 1 and host_count == cs.count:
+            parity, secs = parity_against_reference(up, host_datas, cs.names, [LZ4] * cs.count, "the whole %.0f GiB asset set" % (cs.nbytes / GIB))
+            if secs is not None:
+                import oracle_lib as ol
+                cores = ol.Reference().cpu_count()
+                cpu = {"value": round(cs.nbytes / sum(secs) / GIB, 4), "unit": "GiB/s", "cores": cores, "kind": "reference",
+                       "sample": "the whole set (%d assets, %.1f GiB), one pass: CreateVersionIndex + CreateMissingContent + WriteContent through "
+                                 "compressblockstore (LZ4), bikeshed %d workers + caller" % (cs.count, cs.nbytes / GIB, cores),
+                       "seconds_index_missing_write": [round(x, 3) for x in secs]}
+        elif world == 1:
+            # host RAM does not hold the whole set: the reference runs over the first host_count assets, the B200 path over the same ones
+            sub = Upsync(cs.names[:host_count], cs.sizes[:host_count], [LZ4] * host_count, 0, cs.offsets[:host_count], arena, cs.arena_bytes)
+            parity, secs = parity_against_reference(sub, host_datas, cs.names[:host_count], [LZ4] * host_count,
+                                                    "the first %d assets (%.1f GiB; host RAM bounds the reference's input)" % (host_count, host_bytes / GIB))
+            if secs is not None:
+                import oracle_lib as ol
+                cores = ol.Reference().cpu_count()
+                cpu = {"value": round(host_bytes / sum(secs) / GIB, 4), "unit": "GiB/s", "cores": cores, "kind": "reference",
+                       "sample": "first %d assets (%.1f GiB), one pass of the reference upsync (LZ4), bikeshed %d workers + caller" % (host_count, host_bytes / GIB, cores)}
+        elif args.verify_gib > 0:
+            # N > 1: the whole multi-GPU path (sharded index, NCCL merge, split dedup, sharded WriteContent with chunk exchange) on a small
+            # version first, against the reference over all ranks' bytes on rank 0
+            vs = Config2Set(args.verify_gib, rank, world)
+            varena = ctx.device_alloc(vs.arena_bytes)
+            vs.fill(ctx, varena)
+            vup = Upsync(vs.all_names, vs.all_sizes, [LZ4] * (vs.count * world), vs.first_id, vs.offsets, varena, vs.arena_bytes)
+            # rank 0 makes every rank's assets again on the host (the generator is the same function on both sides, include/lt_synth.h)
+            everything = None
+            if rank == 0:
+                everything = []
+                for r in range(world):
+                    everything += host_assets(Config2Set(args.verify_gib, r, world), 1 << 62, os.cpu_count() or 8, first_id=r * vs.count)
+            parity, _ = parity_against_reference(vup, everything, vs.all_names, [LZ4] * (vs.count * world),
+                                                 "a %d x %.1f GiB version sharded over %d GPUs (the full-size run is checked by its invariants)" % (world, args.verify_gib, world))
+            ctx.device_free(varena)
+
+    # ---- resident-in-HBM measurement: index + write, blocks left in HBM
+    count_fn, count_user, acc = ctx.counting_sink()
+    state = {"vi": None}
+
+    def step_resident():
+        v = up.index(want_host=(rank == 0), copy=False)
+        vi = longtail_b200.parse_version_index(v) if rank == 0 else None
+        up.write((count_fn, count_user), True, vi)
+        state["vi"] = vi
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)  # let nvidia-smi come up; it then samples through the warm-up and the timed region
+        time.sleep(0.3)
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    acc[:] = 0
     launches0 = ctx.launch_count
     ctx.profile_reset()
     ctx.profile_enable(True)
     ms = timed(step_resident, args.steps)
-    clocks = sampler.finish() if rank == 0 else None
     ctx.profile_enable(False)
     prof = ctx.profile_read()
     launches = ctx.launch_count - launches0
-    value = world * nbytes * args.steps / (ms / 1e3) / GIB
+    clocks = sampler.finish() if rank == 0 else None
+    blocks_mine, stored_mine, raw_mine = int(acc[0]) // args.steps, int(acc[1]) // args.steps, int(acc[2]) // args.steps
+    blocks_all, stored_all, raw_all = int(sum_over_ranks(blocks_mine)), int(sum_over_ranks(stored_mine)), int(sum_over_ranks(raw_mine))
+    value = world * cs.nbytes * args.steps / (ms / 1e3) / GIB
+    # invariants of the full-size run: every unique byte lands in exactly one block, on every rank's count
+    if rank == 0 and state["vi"] is not None:
+        uniq = int(state["vi"]["chunk_sizes"].astype(np.uint64).sum())
+        if raw_all != uniq:
+            raise SystemExit("invariant failed: %d payload bytes in blocks, %d unique chunk bytes in the VersionIndex" % (raw_all, uniq))
 
-    # ---- end to end from pinned host memory
+    # ---- end to end from pinned host memory (this rank's assets; every stored block copied to pinned host memory)
     e2e = None
-    host_buf = None
-    if not args.no_e2e:
-        import psutil
-        avail = psutil.virtual_memory().available
-        want = args.e2e_gib if args.e2e_gib is not None else args.gib
-        e2e_bytes = int(min(want * GIB, 0.7 * avail / max(world, 1))) // part * part
-        e2e_bytes = max(e2e_bytes, part)
-        host_buf = ctx.pinned_alloc(e2e_bytes)
-        ctx.lib.lt_b200_copy_to_host(ctx.handle, host_buf.ctypes.data, arena, e2e_bytes)
-        e2e_asset = longtail_b200.AssetList(["f%05d.bin" % rank], [e2e_bytes])
+    if not args.no_e2e and host_count:
+        e2e_assets = longtail_b200.AssetList(cs.names[:host_count], cs.sizes[:host_count])
+        e2e_tags = [LZ4] * host_count
+        efn, euser, eacc = ctx.counting_sink()
+        ibytes = [0]
 
         def step_e2e():
-            v = ctx.index_host_assets(e2e_asset, [host_buf], None, target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
-            index_bytes[0] = len(v)
+            v, _ = ctx.upsync_host_assets(e2e_assets, host_datas, e2e_tags, (efn, euser), TARGET_CHUNK_SIZE, MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK, copy=False)
+            ibytes[0] = len(v)
 
-        for _ in range(1):
-            step_e2e()
+        ctx.device_free(arena)  # the verb brings its own arena
+        arena = None
+        step_e2e()
+        eacc[:] = 0
+        e2e_steps = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             step_e2e()
         barrier()
-        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(world * e2e_bytes * args.steps / float(wall.item()) / GIB, 3), "unit": "GiB/s",
-               "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": index_bytes[0],
-               "note": "lt_b200_index_host_assets over a %.1f GiB pinned host buffer per GPU, wall clock" % (e2e_bytes / GIB)}
-
-    # ---- CPU baseline (rank 0, N == 1): the unmodified reference on a bounded sample of the same bytes
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        import oracle_lib as ol
-        ref = ol.Reference()
-        cpu_bytes = int(min(args.cpu_gib * GIB, nbytes))
-        if host_buf is not None and host_buf.size >= cpu_bytes:
-            sample = host_buf[:cpu_bytes]
-        else:
-            sample = ctx.to_host(arena, cpu_bytes)
-        if ref.available:
-            cores = ref.cpu_count()
-            secs = reference_pass(ref, sample, cores)
-            cpu = {"value": round(cpu_bytes / secs / GIB, 4), "unit": "GiB/s", "cores": cores, "kind": "reference",
-                   "sample": "first %.1f GiB of the file, Longtail_CreateVersionIndex, bikeshed %d workers + caller, 1 pass" % (cpu_bytes / GIB, cores)}
-        else:
-            o = ol.Oracle()
-            small = sample[:min(cpu_bytes, 1 << 30)]
-            t0 = time.perf_counter()
-            o.create_version_index([("f00000.bin", small)], TARGET_CHUNK_SIZE)
-            secs = time.perf_counter() - t0
-            cpu = {"value": round(small.size / secs / GIB, 4), "unit": "GiB/s", "cores": 1, "kind": "port",
-                   "sample": "first %.1f GiB of the file, oracle/lt_oracle.c single thread" % (small.size / GIB)}
-
-    # ---- the compress half on a configs[2]-shaped asset set (rank 0, N == 1): LZ4 and ZStd level 3
-    compress = None
-    if rank == 0 and world == 1 and (args.compress_gib > 0 or args.zstd_gib > 0):
+        wall = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": round(world * host_bytes * e2e_steps / wall / GIB, 3), "unit": "GiB/s", "h2d_bytes_per_step": host_bytes,
+               "d2h_bytes_per_step": int(eacc[1]) // e2e_steps + ibytes[0], "steps": e2e_steps,
+               "note": "lt_b200_upsync_host_assets per GPU over %d assets (%.1f GiB) in pinned host memory: one H2D copy per asset, CreateVersionIndex, "
+                       "WriteContent with every StoredBlock copied to pinned host staging; wall clock, max over ranks%s"
+                       % (host_count, host_bytes / GIB, "" if host_count == cs.count else " (host RAM bounds the host-resident part of the set)")}
+    if host_buf is not None:
+        ctx.pinned_free(host_buf)
+        host_buf, host_datas = None, []
+    if arena is not None:
         ctx.device_free(arena)
         arena = None
-        if host_buf is not None:
-            ctx.pinned_free(host_buf)
-            host_buf = None
-        compress = {}
-        if args.compress_gib > 0:
-            compress["lz4"] = compress_leg(ctx, torch, stream, "lz4", args.compress_gib, 4.0, not args.no_cpu)
-        if args.zstd_gib > 0:
-            compress["zstd"] = compress_leg(ctx, torch, stream, "zstd", args.zstd_gib, 2.0, not args.no_cpu)
+
+    # ================================================================== index_only: configs[1] (N = 1)
+    index_only = None
+    if world == 1 and args.index_gib > 0:
+        nbytes = int(args.index_gib * GIB)
+        a1 = ctx.device_alloc(nbytes + 4096)
+        ctx.synth_fill(a1, nbytes, seed=SEED_RANDOM, asset_id=0)
+        ctx.synchronize()
+        al1 = longtail_b200.AssetList(["f00000.bin"], [nbytes])
+
+        def step_index():
+            ctx.index_device_assets(a1, nbytes + 4096, al1, [0], None, target_chunk_size=TARGET_CHUNK_SIZE, copy=False)
+
+        for _ in range(3):
+            step_index()
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        ms1 = timed(step_index, args.steps)
+        ctx.profile_enable(False)
+        p1 = ctx.profile_read()
+        index_only = {"workload": "configs[1]: chunk+BLAKE3 only, one %.0f GiB uniform-random file, target_chunk_size 65536" % args.index_gib,
+                      "value_GiBps": round(nbytes * args.steps / (ms1 / 1e3) / GIB, 3), "ms_per_step": round(ms1 / args.steps, 3),
+                      "per_kernel": {k: {"ms_per_step": round(v[0] / args.steps, 3), "GBps": round(v[2] / max(v[0], 1e-9) / 1e6, 1)}
+                                     for k, v in p1.items() if v[0] > 0}}
+        ctx.device_free(a1)
+
+    # ================================================================== zstd_pak: configs[3]'s shape, a slice of one PAK-like file per GPU
+    zstd_pak = None
+    if args.zstd_gib > 0:
+        zbytes = int(args.zstd_gib * GIB) // part * part
+        za = ctx.device_alloc(zbytes + 4096)
+        ctx.synth_fill(za, zbytes, seed=SEED_PAK, asset_id=0, offset=rank * zbytes, class_mode=2)
+        ctx.synchronize()
+        # ONE file of world x zbytes; rank r holds bytes [r * zbytes, (r + 1) * zbytes) — whole parts, so the byte-range shards need no stitch
+        zup = Upsync(["pak/data.pak"], [zbytes * world], [ZSTD], 0, [0], za, zbytes + 4096, byte_range_base=rank * zbytes)
+        zfn, zuser, zacc = ctx.counting_sink()
+
+        def step_zstd():
+            v = zup.index(want_host=(rank == 0), copy=False)
+            zup.write((zfn, zuser), True, longtail_b200.parse_version_index(v) if rank == 0 else None)
+
+        step_zstd()
+        zacc[:] = 0
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        zsteps = max(1, min(args.steps, 2))
+        msz = timed(step_zstd, zsteps)
+        ctx.profile_enable(False)
+        pz = ctx.profile_read()
+        zraw, zstored = sum_over_ranks(int(zacc[2]) // zsteps), sum_over_ranks(int(zacc[1]) // zsteps)
+        zstd_pak = {"workload": "configs[3] shape: chunk+BLAKE3+ZStd-level-3 on one %.0f GiB PAK-like file, %.0f GiB of whole parts per GPU" % (world * zbytes / GIB, zbytes / GIB),
+                    "value_GiBps": round(world * zbytes * zsteps / (msz / 1e3) / GIB, 3), "ms_per_step": round(msz / zsteps, 1),
+                    "unique_bytes": int(zraw), "stored_bytes": int(zstored), "ratio": round(zstored / max(zraw, 1), 4),
+                    "codec_kernel_ms_rank0": round(pz["k_zstd_frames"][0] / zsteps, 1),
+                    "codec_kernel_GBps_rank0": round(pz["k_zstd_frames"][2] / max(pz["k_zstd_frames"][0], 1e-9) / 1e6, 2)}
+        ctx.device_free(za)
 
     if rank == 0:
         peak, peak_src = peaks()
-        # dominant kernel = the one with the largest share of device time
+        step_ms = ms / args.steps
+        per_kernel = {k: {"ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[1] // args.steps,
+                          "GBps": round(v[2] / max(v[0], 1e-9) / 1e6, 1), "share_of_step": round(v[0] / ms, 4)} for k, v in prof.items() if v[0] > 0}
         name = max(prof, key=lambda k: prof[k][0])
         kms, kn, kbytes = prof[name]
-        achieved = (kbytes / max(kn, 1)) / ((kms / max(kn, 1)) / 1e3) / 1e9 if kms > 0 else 0.0
-        shares = {k: round(v[0] / (ms / 1.0), 4) for k, v in prof.items()}
-        per_kernel = {k: {"ms_per_launch": round(v[0] / max(v[1], 1), 4), "launches": v[1],
-                          "GBps": round((v[2] / max(v[1], 1)) / ((v[0] / max(v[1], 1)) / 1e3) / 1e9, 1) if v[0] > 0 else None} for k, v in prof.items()}
-        # DRAM traffic per launch of the dominant kernel: (dram__bytes_read + dram__bytes_write) / algorithmic bytes as captured by
-        # `ncu --set full` on an 8 GiB launch (profiles/r01p_*_ncu.txt), applied to this run's algorithmic bytes per launch
-        ncu_traffic_ratio = {"k_blake3_leaves": (8.963703e9 + 0.340567e9) / 8.589934592e9, "k_hpcdc_scan": (8.609740e9 + 0.019096e9) / 8.589934592e9}
-        traffic = round(kbytes / max(kn, 1) * ncu_traffic_ratio[name]) if name in ncu_traffic_ratio else None
+        achieved = kbytes / max(kms, 1e-9) / 1e6
+        # algorithmic traffic of the whole step per asset byte (SURVEY.md §8d): 1 (chunk + hash read) + u (gather read) + u (gather write)
+        # + u (codec read) + c*u (codec write), u = unique fraction, c = compression ratio
+        u = raw_all / float(world * cs.nbytes)
+        c = stored_all / float(max(raw_all, 1))
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "GiB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic",
-            "config": {"workload": "configs[1]: chunk+BLAKE3 only (no compression), one %.0f GiB synthetic file per GPU, target_chunk_size 65536; "
-                                   "the compress stage of the metric's name is measured on configs[2]'s shape under write_content"
-                                   % args.gib, "bytes_per_gpu": nbytes, "l2": "inputs (%.0f GiB) far larger than L2; no flush needed" % args.gib,
-                       "parity": parity, "index_bytes": index_bytes[0]},
+            "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "configs[2] per GPU: chunk+BLAKE3+LZ4 (CreateVersionIndex + CreateMissingContent + WriteContent through the compress "
+                                   "block store) on %d synthetic assets totalling %.1f GiB per GPU with 50 %% byte redundancy, target_chunk_size 65536, "
+                                   "blocks 8 MiB / 1024 chunks%s" % (cs.count, cs.nbytes / GIB, "" if world == 1 else
+                                                                      "; %d GPUs = ONE version of %d assets / %.0f GiB: configs[4]'s full upsync with the NCCL "
+                                                                      "all-gather of the chunk-hash table" % (world, cs.count * world, world * cs.nbytes / GIB)),
+                       "bytes_per_gpu": cs.nbytes, "assets_per_gpu": cs.count, "l2": "inputs (%.0f GiB per GPU) far larger than L2; no flush needed" % (cs.nbytes / GIB),
+                       "parity": parity, "index_bytes": up.index_bytes, "unique_frac": round(u, 4), "blocks": blocks_all, "stored_bytes": stored_all,
+                       "compression_ratio": round(c, 4), "blocks_rank0": blocks_mine},
             "hbm_roofline_frac_whole_step": round(value * GIB / 1e9 / world / peak, 4),
-            "roofline": {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": traffic,
-                         "traffic_source": "ncu --set full on an 8 GiB launch (profiles/r01p_leaves_ncu.txt, r01p_scan_ncu.txt): DRAM read+write / algorithmic bytes = "
-                                           "1.083 (leaves: chaining values written) and 1.005 (scan), scaled to this launch", "peak_source": peak_src,
-                         "share_of_step": shares, "per_kernel": per_kernel,
-                         "note": "algorithmic bytes = 1 B read per asset byte (SURVEY.md §8d); both hot kernels are integer-issue bound, see DESIGN.md"},
+            "hbm_roofline_frac_whole_step_all_traffic": round(value * GIB / 1e9 / world / peak * (1 + 3 * u + c * u), 4),
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "traffic_source": "see profiles/r02_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "peak_source": peak_src, "per_kernel": per_kernel,
+                         "note": "algorithmic bytes of the codec kernel = the unique payload bytes it reads (SURVEY.md §8d); rank 0's kernels; the LZ4 "
+                                 "parse is a latency-bound serial chain per stored block, see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "write_content": compress,
+            "index_only": index_only, "zstd_pak": zstd_pak,
         }
         emit(line)
-    if host_buf is not None:
-        ctx.pinned_free(host_buf)
-    if arena is not None:
-        ctx.device_free(arena)
+    if comm is not None:
+        ctx.comm_destroy(comm)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

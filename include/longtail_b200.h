@@ -82,6 +82,8 @@ LT_B200_EXPORT int lt_b200_host_alloc_pinned(lt_b200_context* context, uint64_t 
 LT_B200_EXPORT int lt_b200_host_free_pinned(lt_b200_context* context, void* host_ptr);
 LT_B200_EXPORT int lt_b200_copy_to_device(lt_b200_context* context, void* device_dst, const void* host_src, uint64_t bytes);
 LT_B200_EXPORT int lt_b200_copy_to_host(lt_b200_context* context, void* host_dst, const void* device_src, uint64_t bytes);
+/* copy_to_device queued on the context's stream without waiting: host_src must stay valid until the next synchronising call on the context */
+LT_B200_EXPORT int lt_b200_copy_to_device_async(lt_b200_context* context, void* device_dst, const void* host_src, uint64_t bytes);
 
 /* Deterministic synthetic asset bytes written straight into HBM (include/lt_synth.h).  Bench/test input only. */
 struct lt_b200_synth_spec
@@ -226,6 +228,10 @@ LT_B200_EXPORT int lt_b200_write_blocks_device_ex(lt_b200_context* context, cons
                                                   uint32_t max_block_size, uint32_t max_chunks_per_block, uint32_t flags,
                                                   lt_b200_block_sink sink, void* user);
 
+/* an lt_b200_block_sink that only counts (benchmarks, dry runs): user = uint64_t[4] {blocks, stored bytes, raw payload bytes, xor of the
+ * block hashes}; it never dereferences `data`, so it also serves LT_B200_WRITE_DEVICE_SINK */
+LT_B200_EXPORT int lt_b200_counting_sink(void* user, const struct lt_b200_stored_block_view* block);
+
 /* lt_b200_write_blocks_device for blocks whose composition is GIVEN (a Longtail_StoreIndex: block b holds the next block_chunk_counts[b]
  * chunks of the chunk arrays; its tag is the tag of its first chunk) instead of packed greedily — what Longtail_WriteContent does with the
  * store index it is handed (src/longtail.c:4760-4912). */
@@ -342,6 +348,57 @@ LT_B200_EXPORT int lt_b200_upsync_file_list(lt_b200_context* context, const lt_b
                                             uint32_t hash_type, uint32_t target_chunk_size, uint32_t max_block_size,
                                             uint32_t max_chunks_per_block, uint32_t reader_threads, lt_b200_fs_store* store,
                                             const void** out_version_index, uint64_t* out_size, uint32_t* out_blocks_written);
+
+/* cmd/main.c:UpSync (:972-1153) for assets in HOST memory (pinned for full PCIe speed) that fit one GPU: one host -> device copy per asset
+ * into a device arena, then CreateVersionIndex, CreateMissingContent against `existing_hashes` (NULL / 0: a fresh store) and WriteContent
+ * on the resident bytes; the stored blocks leave through `sink` (flags as lt_b200_write_blocks_device_ex).  *out_version_index: pinned
+ * memory owned by the context, valid until its next index call.  ENOMEM when the assets do not fit the device. */
+LT_B200_EXPORT int lt_b200_upsync_host_assets(lt_b200_context* context, const struct lt_b200_assets* assets, const uint8_t* const* asset_data,
+                                              const uint32_t* asset_tags, uint32_t hash_type, uint32_t target_chunk_size, uint32_t max_block_size,
+                                              uint32_t max_chunks_per_block, uint32_t existing_count, const uint64_t* existing_hashes,
+                                              uint32_t flags, lt_b200_block_sink sink, void* user, const void** out_version_index,
+                                              uint64_t* out_size, uint32_t* out_chunks_written);
+
+/* ---- multi-GPU: one process per GPU of one node, NCCL over NVLink / NVSwitch.  The reference has no distributed
+ * runtime (its only parallelism is the bikeshed thread pool behind Longtail_JobAPI); what is sharded here is its own job unit, one
+ * (asset, part) pair with parts of target_chunk_size * 1024 bytes (src/longtail.c:2396-2457): parts never share chunker state, so ranks
+ * chunk + hash disjoint slices and exchange only the chunk tables.
+ *
+ *   comm_unique_id    rank 0 makes the NCCL id and hands it to the other processes by any means (a file, an environment variable, MPI, a
+ *                     torch.distributed store: the library does not care)
+ *   comm_create       joins `world` processes (collective); one communicator per context
+ *   plan_shards       host helper: out_first_job[r] .. out_first_job[r + 1] are rank r's jobs — contiguous slices of the job list in asset /
+ *                     part order (empty parts left out), balanced by bytes; shard_jobs describes them so that the caller can put each
+ *                     job's bytes into its rank's device arena
+ *   index_sharded     Longtail_CreateVersionIndex over all ranks (collective): chunk + hash of this rank's jobs (job_arena_offsets[j] = where
+ *                     the bytes of its j-th job sit in device_arena), variable-size all-gather of the chunk tables, first-occurrence dedup
+ *                     split by hash with one all-reduce, the same VersionIndex laid out on every rank; the host copy only where want_host
+ *   write_blocks_sharded  Longtail_CreateMissingContent (fresh store) + Longtail_WriteContent over all ranks (collective, after index_sharded):
+ *                     every rank derives the same block packing, takes a contiguous run of blocks balanced by bytes, receives the chunks whose
+ *                     first occurrence lives on another rank point to point, and hands its finished blocks to its own sink in store order.
+ *                     The union over the ranks, in rank order, is the block list of the reference's single-process upsync. */
+#define LT_B200_COMM_ID_BYTES 128
+typedef struct lt_b200_comm lt_b200_comm;
+struct lt_b200_shard_job
+{
+    uint32_t asset_index;
+    uint32_t size;
+    uint64_t offset; /* byte offset inside the asset */
+};
+LT_B200_EXPORT int lt_b200_comm_unique_id(uint8_t out_id[LT_B200_COMM_ID_BYTES]);
+LT_B200_EXPORT int lt_b200_comm_create(lt_b200_context* context, const uint8_t id[LT_B200_COMM_ID_BYTES], uint32_t rank, uint32_t world,
+                                       lt_b200_comm** out_comm);
+LT_B200_EXPORT void lt_b200_comm_destroy(lt_b200_comm* comm);
+LT_B200_EXPORT int lt_b200_plan_shards(const struct lt_b200_assets* assets, uint32_t target_chunk_size, uint32_t world,
+                                       uint32_t* out_first_job /* [world + 1] */, uint32_t* out_job_count);
+LT_B200_EXPORT int lt_b200_shard_jobs(const struct lt_b200_assets* assets, uint32_t target_chunk_size, uint32_t first_job, uint32_t job_count,
+                                      struct lt_b200_shard_job* out_jobs);
+LT_B200_EXPORT int lt_b200_index_sharded(lt_b200_context* context, lt_b200_comm* comm, const uint8_t* device_arena, uint64_t arena_size,
+                                         const struct lt_b200_assets* assets, const uint32_t* asset_tags, const uint64_t* job_arena_offsets,
+                                         uint32_t hash_type, uint32_t target_chunk_size, int want_host, const void** out_buffer, uint64_t* out_size);
+LT_B200_EXPORT int lt_b200_write_blocks_sharded(lt_b200_context* context, lt_b200_comm* comm, uint32_t max_block_size, uint32_t max_chunks_per_block,
+                                                uint32_t flags, lt_b200_block_sink sink, void* user, uint32_t* out_my_blocks,
+                                                uint32_t* out_total_blocks);
 
 #ifdef __cplusplus
 }

@@ -172,6 +172,20 @@ def load_library():
                                                        C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.lt_b200_write_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_uint32, C.c_uint32, C.c_uint32, BLOCK_SINK, C.c_void_p]
+    lib.lt_b200_write_blocks_device_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.lt_b200_upsync_host_assets.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    lib.lt_b200_comm_unique_id.argtypes = [C.c_void_p]
+    lib.lt_b200_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.lt_b200_comm_destroy.argtypes = [C.c_void_p]
+    lib.lt_b200_plan_shards.argtypes = [C.POINTER(Assets), C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.lt_b200_shard_jobs.argtypes = [C.POINTER(Assets), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.lt_b200_index_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Assets), C.c_void_p, C.c_void_p, C.c_uint32,
+                                          C.c_uint32, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.lt_b200_write_blocks_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                 C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.lt_b200_unique_chunk_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.lt_b200_scan_directory.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
     lib.lt_b200_file_list_assets.restype = C.c_void_p
@@ -194,6 +208,8 @@ def load_library():
     return lib
 
 
+WRITE_DEVICE_SINK = 1
+COMM_ID_BYTES = 128
 KERNEL_NAMES = {0: "k_hpcdc_scan", 1: "k_hpcdc_walk", 2: "k_blake3_leaves", 3: "k_blake3_merge", 4: "k_gather_chunks", 5: "k_lz4_blocks", 6: "k_blake2s_segments", 7: "k_meow_segments", 8: "k_zstd_frames", 9: "k_lz4_decode", 10: "k_zstd_decode"}
 
 
@@ -259,6 +275,29 @@ class AssetList:
         a.permissions = self.permissions.ctypes.data_as(C.POINTER(C.c_uint16))
         a.path_data = self.path_data
         return a
+
+
+def plan_shards(assets, target_chunk_size, world):
+    """host helper (no GPU): -> (first_job[world + 1], job count) — contiguous slices of the reference's (asset, part) job list, balanced by bytes"""
+    lib = load_library()
+    first = np.zeros(world + 1, dtype=np.uint32)
+    n = C.c_uint32(0)
+    a = assets.as_struct()
+    err = lib.lt_b200_plan_shards(C.byref(a), int(target_chunk_size), int(world), first.ctypes.data_as(C.c_void_p), C.byref(n))
+    if err:
+        raise LongtailB200Error(err, "lt_b200_plan_shards")
+    return first, n.value
+
+
+def shard_jobs(assets, target_chunk_size, first_job, job_count):
+    """host helper (no GPU): -> structured array (asset_index, size, offset) of jobs [first_job, first_job + job_count)"""
+    lib = load_library()
+    out = np.zeros(max(int(job_count), 1), dtype=np.dtype([("asset_index", "<u4"), ("size", "<u4"), ("offset", "<u8")]))
+    a = assets.as_struct()
+    err = lib.lt_b200_shard_jobs(C.byref(a), int(target_chunk_size), int(first_job), int(job_count), out.ctypes.data_as(C.c_void_p))
+    if err:
+        raise LongtailB200Error(err, "lt_b200_shard_jobs")
+    return out[:int(job_count)]
 
 
 class Context:
@@ -408,14 +447,26 @@ class Context:
                                                     e.ctypes.data_as(C.c_void_p) if e.size else None, out.ctypes.data_as(C.c_void_p)), "missing_chunks")
         return out[:h.size].astype(bool)
 
+    def counting_sink(self):
+        """-> (fn, user, acc): the library's counting sink and its uint64[4] accumulator {blocks, stored bytes, raw bytes, xor of hashes}"""
+        acc = np.zeros(4, dtype=np.uint64)
+        return C.cast(self.lib.lt_b200_counting_sink, C.c_void_p), acc.ctypes.data_as(C.c_void_p), acc
+
     def write_blocks_device(self, dptr, arena_size, chunk_hashes, chunk_sizes, chunk_tags, chunk_offsets, max_block_size=8388608,
-                            max_chunks_per_block=1024, hash_type=HASH_BLAKE3, keep_bytes=True, fs_store=None):
+                            max_chunks_per_block=1024, hash_type=HASH_BLAKE3, keep_bytes=True, fs_store=None, c_sink=None, device_sink=False):
         """-> list of (block_hash, serialised stored block bytes | size) in store order; with fs_store (an FsStore) the blocks go
-        straight to its C sink (no Python in the loop) and the result is None"""
+        straight to its C sink (no Python in the loop) and the result is None; c_sink = (function pointer, user pointer) of any C
+        lt_b200_block_sink; device_sink leaves the block images in HBM (LT_B200_WRITE_DEVICE_SINK)"""
         h = np.ascontiguousarray(chunk_hashes, dtype=np.uint64)
         s = np.ascontiguousarray(chunk_sizes, dtype=np.uint32)
         t = np.ascontiguousarray(chunk_tags, dtype=np.uint32)
         o = np.ascontiguousarray(chunk_offsets, dtype=np.uint64)
+        if c_sink is not None:
+            self._check(self.lib.lt_b200_write_blocks_device_ex(self.handle, C.c_void_p(dptr), int(arena_size), h.size, h.ctypes.data_as(C.c_void_p),
+                                                                s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                                                                int(hash_type), int(max_block_size), int(max_chunks_per_block),
+                                                                WRITE_DEVICE_SINK if device_sink else 0, c_sink[0], c_sink[1]), "write_blocks_device_ex")
+            return None
         if fs_store is not None:
             cb = C.cast(self.lib.lt_b200_fs_store_sink, BLOCK_SINK)
             self._check(self.lib.lt_b200_write_blocks_device(self.handle, C.c_void_p(dptr), int(arena_size), h.size, h.ctypes.data_as(C.c_void_p),
@@ -435,6 +486,69 @@ class Context:
                                                          s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
                                                          int(hash_type), int(max_block_size), int(max_chunks_per_block), cb, None), "write_blocks_device")
         return blocks
+
+    def upsync_host_assets(self, assets, datas, tags, c_sink, target_chunk_size=32768, max_block_size=8388608, max_chunks_per_block=1024,
+                           hash_type=HASH_BLAKE3, existing_hashes=None, device_sink=False, copy=True):
+        """the whole upsync for assets in host memory (list of uint8 arrays, pinned for full PCIe speed): H2D once, CreateVersionIndex,
+        CreateMissingContent, WriteContent into c_sink = (fn, user); -> (serialised VersionIndex, chunks written)"""
+        st = assets.as_struct()
+        ptrs = (C.c_void_p * max(len(datas), 1))(*[d.ctypes.data if d.size else None for d in datas])
+        tg = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint32)
+        eh = None if existing_hashes is None else np.ascontiguousarray(existing_hashes, dtype=np.uint64)
+        buf, size, written = C.c_void_p(), C.c_uint64(0), C.c_uint32(0)
+        self._check(self.lib.lt_b200_upsync_host_assets(self.handle, C.byref(st), ptrs, None if tg is None else tg.ctypes.data_as(C.c_void_p),
+                                                        int(hash_type), int(target_chunk_size), int(max_block_size), int(max_chunks_per_block),
+                                                        0 if eh is None else int(eh.size), None if eh is None else eh.ctypes.data_as(C.c_void_p),
+                                                        WRITE_DEVICE_SINK if device_sink else 0, c_sink[0], c_sink[1], C.byref(buf), C.byref(size),
+                                                        C.byref(written)), "upsync_host_assets")
+        return self._result(buf, size, copy), written.value
+
+    # ---- multi-GPU (one process per GPU; include/longtail_b200.h "multi-GPU")
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        err = self.lib.lt_b200_comm_unique_id(buf)
+        if err:
+            raise LongtailB200Error(err, "lt_b200_comm_unique_id failed (NCCL not loadable?)")
+        return bytes(buf)
+
+    def comm_create(self, unique_id, rank, world):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self.lib.lt_b200_comm_create(self.handle, buf, int(rank), int(world), C.byref(h)), "comm_create")
+        return h
+
+    def comm_destroy(self, comm):
+        self.lib.lt_b200_comm_destroy(comm)
+
+    def plan_shards(self, assets, target_chunk_size, world):
+        return plan_shards(assets, target_chunk_size, world)
+
+    def shard_jobs(self, assets, target_chunk_size, first_job, job_count):
+        return shard_jobs(assets, target_chunk_size, first_job, job_count)
+
+    def index_sharded(self, comm, dptr, arena_size, assets, asset_tags, job_arena_offsets, target_chunk_size, hash_type=HASH_BLAKE3,
+                      want_host=True, copy=True):
+        """collective CreateVersionIndex; -> serialised VersionIndex (bytes / view) where want_host, else its size"""
+        a = assets.as_struct()
+        tags = None if asset_tags is None else np.ascontiguousarray(asset_tags, dtype=np.uint32)
+        offs = np.ascontiguousarray(job_arena_offsets, dtype=np.uint64)
+        buf, size = C.c_void_p(), C.c_uint64(0)
+        self._check(self.lib.lt_b200_index_sharded(self.handle, comm, C.c_void_p(dptr), int(arena_size), C.byref(a),
+                                                   tags.ctypes.data_as(C.c_void_p) if tags is not None else None,
+                                                   offs.ctypes.data_as(C.c_void_p) if offs.size else None, int(hash_type),
+                                                   int(target_chunk_size), 1 if want_host else 0, C.byref(buf), C.byref(size)), "index_sharded")
+        if not want_host:
+            return int(size.value)
+        return self._result(buf, size, copy)
+
+    def write_blocks_sharded(self, comm, c_sink, max_block_size=8388608, max_chunks_per_block=1024, device_sink=False):
+        """collective WriteContent of a fresh store after index_sharded; this rank's blocks go to c_sink = (fn, user);
+        -> (blocks written by this rank, blocks of the whole store)"""
+        mine, total = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.lt_b200_write_blocks_sharded(self.handle, comm, int(max_block_size), int(max_chunks_per_block),
+                                                          WRITE_DEVICE_SINK if device_sink else 0, c_sink[0], c_sink[1], C.byref(mine), C.byref(total)),
+                    "write_blocks_sharded")
+        return mine.value, total.value
 
     def lz4_compress_host(self, buffers):
         """CompressionAPI.Compress for 'lz42' over a list of host buffers in one launch -> list of LZ4 blocks (bytes)"""

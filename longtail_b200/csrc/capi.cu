@@ -11,7 +11,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 using namespace ltb;
@@ -32,7 +36,7 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
-    WS_LZ4_TABLES, WS_LZ4_V2, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_CHUNK_SIZES, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
+    WS_LZ4_TABLES, WS_LZ4_V2, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_CHUNK_SIZES, WS_UFIRST, WS_G_COUNTS, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND, WS_X_RECV, WS_X_TAB, WS_PACK_A, WS_PACK_B, WS_PACK_C, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
     WS_COUNT
 };
 
@@ -79,6 +83,69 @@ struct lt_b200_context
     uint64_t prof_bytes[LT_B200_KERNEL_COUNT] = {0};
 };
 
+// ---------------------------------------------------------------- NCCL, loaded on first use
+// Only the multi-GPU verbs need NCCL; it is dlopen'ed (libnccl.so.2: the copy already in the process, e.g. torch's, wins) so that a
+// single-GPU caller has no such dependency.
+struct NcclApi
+{
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_lock;
+
+static int nccl_load()
+{
+    std::lock_guard<std::mutex> lock(g_nccl_lock);
+    if (g_nccl.lib) return 0;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return ENOSYS;
+    NcclApi a;
+    a.lib = lib;
+#define LT_NCCL_SYM(field, name) *reinterpret_cast<void**>(&a.field) = dlsym(lib, name); if (!a.field) { dlclose(lib); return ENOSYS; }
+    LT_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    LT_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    LT_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    LT_NCCL_SYM(Broadcast, "ncclBroadcast")
+    LT_NCCL_SYM(AllReduce, "ncclAllReduce")
+    LT_NCCL_SYM(AllGather, "ncclAllGather")
+    LT_NCCL_SYM(Send, "ncclSend")
+    LT_NCCL_SYM(Recv, "ncclRecv")
+    LT_NCCL_SYM(GroupStart, "ncclGroupStart")
+    LT_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    LT_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef LT_NCCL_SYM
+    g_nccl = a;
+    return 0;
+}
+
+// One communicator per context: `world` processes, one GPU each (the reference has no distributed runtime at all — SURVEY.md F1; the
+// unit that is sharded is its own job, one (asset, part) pair, src/longtail.c:2396-2457)
+struct lt_b200_comm
+{
+    lt_b200_context* ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    uint32_t rank = 0, world = 1;
+    // state left by the last lt_b200_index_sharded for lt_b200_write_blocks_sharded
+    std::vector<uint32_t> rank_chunk_start; // [world + 1] first global chunk ordinal of every rank's slice
+    std::vector<uint32_t> rank_unique_start; // [world + 1] first unique chunk whose first occurrence lies in every rank's slice
+    uint32_t global_chunks = 0, global_unique = 0;
+    const uint8_t* d_arena = nullptr;
+    uint64_t arena_size = 0;
+    uint32_t hash_type = 0;
+};
+
 namespace {
 
 int fail(lt_b200_context* c, int code, const char* fmt, ...)
@@ -108,6 +175,12 @@ int cuda_fail(lt_b200_context* c, cudaError_t e, const char* what)
     do {                           \
         int r__ = (call);          \
         if (r__) return r__;       \
+    } while (0)
+
+#define NC(call)                                                                                      \
+    do {                                                                                              \
+        ncclResult_t n__ = (call);                                                                    \
+        if (n__ != ncclSuccess) return fail(c, EIO, "%s: %s", #call, g_nccl.GetErrorString(n__));     \
     } while (0)
 
 int ws_reserve(lt_b200_context* c, int slot, size_t bytes)
@@ -448,6 +521,15 @@ extern "C" int lt_b200_copy_to_device(lt_b200_context* c, void* dst, const void*
     return 0;
 }
 
+// queued on the context stream without waiting (the next verb on this context runs after it); host_src must stay valid until then
+extern "C" int lt_b200_copy_to_device_async(lt_b200_context* c, void* dst, const void* src, uint64_t bytes)
+{
+    if (!c || (bytes && (!dst || !src))) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
 extern "C" int lt_b200_copy_to_host(lt_b200_context* c, void* dst, const void* src, uint64_t bytes)
 {
     if (!c) return EINVAL;
@@ -613,7 +695,8 @@ namespace {
 // device-side table to index: [d_hash, d_len, d_tag] x chunk_count already resident
 int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, const uint32_t* asset_chunk_counts, uint32_t chunk_count,
                                   const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t hash_type,
-                                  uint32_t target_chunk_size, const void** out_buffer, uint64_t* out_size, const uint64_t* d_chunk_off = nullptr)
+                                  uint32_t target_chunk_size, const void** out_buffer, uint64_t* out_size, const uint64_t* d_chunk_off = nullptr,
+                                  lt_b200_comm* comm = nullptr, bool want_host = true)
 {
     c->unique_chunks = 0;
     c->unique_offsets_valid = false;
@@ -667,7 +750,8 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
     if (chunk_count)
     {
         uint32_t cap = 1024;
-        while (cap < 2ull * chunk_count && cap < 0x80000000u) cap <<= 1;
+        const uint64_t keys_here = comm && comm->world > 1 ? 2ull * (chunk_count / comm->world) + 4096 : chunk_count;
+        while (cap < 2ull * keys_here && cap < 0x80000000u) cap <<= 1;
         TRY(ws_reserve(c, WS_DEDUP_KEYS, sizeof(uint64_t) * (size_t)cap));
         TRY(ws_reserve(c, WS_DEDUP_VALS, sizeof(uint32_t) * ((size_t)cap + 1)));
         TRY(ws_reserve(c, WS_DEDUP_FIRST, sizeof(uint32_t) * (size_t)chunk_count));
@@ -688,11 +772,23 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
         db.uidx = ws<uint32_t>(c, WS_DEDUP_UIDX);
         CU(cudaMemsetAsync(db.keys, 0xff, sizeof(uint64_t) * (size_t)cap, c->stream));
         CU(cudaMemsetAsync(db.vals, 0xff, sizeof(uint32_t) * ((size_t)cap + 1), c->stream));
-        launch_dedup_insert(d_hash, chunk_count, db, c->stream);
-        launch_dedup_lookup(d_hash, chunk_count, db, c->stream);
+        if (comm && comm->world > 1)
+        {
+            // every rank holds the whole table; the random-access part of the dedup is split by hash and one all-reduce merges the answers
+            launch_dedup_insert_part(d_hash, chunk_count, db, comm->world, comm->rank, c->stream);
+            launch_dedup_lookup_part(d_hash, chunk_count, db, comm->world, comm->rank, c->stream);
+            NC(g_nccl.AllReduce(db.first, db.first, chunk_count, ncclUint32, ncclSum, comm->comm, c->stream));
+            launch_mark_first(db, chunk_count, c->stream);
+        }
+        else
+        {
+            launch_dedup_insert(d_hash, chunk_count, db, c->stream);
+            launch_dedup_lookup(d_hash, chunk_count, db, c->stream);
+        }
         launch_exclusive_scan(db.is_first, chunk_count, db.uidx, ws<uint32_t>(c, WS_SCAN_TMP), c->stream);
+        TRY(ws_reserve(c, WS_UFIRST, sizeof(uint32_t) * (size_t)chunk_count));
         launch_dedup_emit(d_hash, d_len, d_tag, chunk_count, db, ws<uint32_t>(c, WS_ACI), ws<uint64_t>(c, WS_UHASH), ws<uint32_t>(c, WS_ULEN),
-                          ws<uint32_t>(c, WS_UTAG), d_chunk_off, ws<uint64_t>(c, WS_UOFF), c->stream);
+                          ws<uint32_t>(c, WS_UTAG), d_chunk_off, ws<uint64_t>(c, WS_UOFF), c->stream, ws<uint32_t>(c, WS_UFIRST));
         c->launches += 6;
         CU(cudaMemcpyAsync(&unique, db.uidx + chunk_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
@@ -702,7 +798,7 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
     // ---- serialised layout, assembled in device memory then copied out once (src/longtail.c:2566-2584)
     const size_t total = 24 + (size_t)A * (8 + 8 + 8 + 4 + 4 + 4 + 2) + 4 * (size_t)chunk_count + 16 * (size_t)unique + a->path_data_size;
     TRY(ws_reserve(c, WS_INDEX_OUT, total + 16));
-    TRY(hs_reserve(c, HS_INDEX_OUT, total + 16));
+    if (want_host) TRY(hs_reserve(c, HS_INDEX_OUT, total + 16));
     TRY(hs_reserve(c, HS_SMALL, 64));
     uint8_t* d_out = ws<uint8_t>(c, WS_INDEX_OUT);
     uint32_t* hdr = hs<uint32_t>(c, HS_SMALL);
@@ -737,9 +833,9 @@ int build_index_from_device_table(lt_b200_context* c, const lt_b200_assets* a, c
     CU(put_h(a->permissions, 2 * (size_t)A));                       // m_Permissions
     CU(put_h(a->path_data, a->path_data_size));                     // m_NameData
     if (o != total) return fail(c, EFAULT, "index layout mismatch %zu != %zu", o, total);
-    CU(cudaMemcpyAsync(hs<void>(c, HS_INDEX_OUT), d_out, total, cudaMemcpyDeviceToHost, c->stream));
+    if (want_host) CU(cudaMemcpyAsync(hs<void>(c, HS_INDEX_OUT), d_out, total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    *out_buffer = hs<void>(c, HS_INDEX_OUT);
+    *out_buffer = want_host ? hs<void>(c, HS_INDEX_OUT) : nullptr;
     *out_size = total;
     c->unique_chunks = unique;
     c->unique_offsets_valid = d_chunk_off != nullptr;
@@ -1222,6 +1318,18 @@ extern "C" int lt_b200_write_blocks_device_ex(lt_b200_context* c, const uint8_t*
                              max_chunks_per_block, 0, nullptr, flags, sink, user);
 }
 
+// a sink that only counts: user = uint64_t[4] {blocks, stored bytes, raw payload bytes, xor of the block hashes}
+extern "C" int lt_b200_counting_sink(void* user, const lt_b200_stored_block_view* block)
+{
+    uint64_t* acc = static_cast<uint64_t*>(user);
+    if (!acc || !block) return EINVAL;
+    acc[0] += 1;
+    acc[1] += block->size;
+    acc[2] += block->raw_payload_size;
+    acc[3] ^= block->block_hash;
+    return 0;
+}
+
 extern "C" int lt_b200_write_given_blocks_device(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena_size, uint32_t chunk_count,
                                                  const uint64_t* chunk_hashes, const uint32_t* chunk_sizes, const uint32_t* chunk_tags,
                                                  const uint64_t* chunk_arena_offsets, uint32_t hash_type, uint32_t block_count,
@@ -1599,6 +1707,362 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     return rc;
 }
 } // namespace
+
+// ================================================================ multi-GPU: one process per GPU, NCCL over NVLink
+//
+// The path shards by the reference's own job unit — one (asset, part) pair, parts of target_chunk_size * 1024 bytes, every part its own
+// chunker instance (src/longtail.c:2396-2457) — so ranks chunk + hash disjoint, contiguous slices of the job list with no data-path
+// collective.  One exchange follows: the per-job chunk counts and the (hash, size, tag) tables are all-gathered (variable sizes: one
+// grouped set of broadcasts, no padding) so that every rank holds the table in global order; the first-occurrence dedup
+// (:2952-2970) is split by hash over the ranks and merged with one all-reduce; then every rank lays out the same VersionIndex.
+// WriteContent shards by stored block, balanced by bytes; the few chunks whose first occurrence lives on another rank move point to point.
+
+namespace {
+
+struct ShardJob { uint32_t asset; uint64_t offset; uint32_t size; };
+
+// the reference's job list without its empty parts, in asset / part order
+void shard_jobs(const lt_b200_assets* a, uint32_t target_chunk_size, std::vector<ShardJob>& jobs)
+{
+    const uint64_t part_size = (uint64_t)target_chunk_size * 1024;
+    for (uint32_t i = 0; i < a->asset_count; ++i)
+        for (uint64_t start = 0; start < a->sizes[i]; start += part_size)
+        {
+            ShardJob j = {i, start, (uint32_t)std::min<uint64_t>(part_size, a->sizes[i] - start)};
+            jobs.push_back(j);
+        }
+}
+
+// contiguous slices of the job list with (nearly) equal bytes: slice r ends where the running total first reaches (r + 1) / world of all
+void shard_plan(const std::vector<ShardJob>& jobs, uint32_t world, std::vector<uint32_t>& first_job)
+{
+    uint64_t total = 0;
+    for (const ShardJob& j : jobs) total += j.size;
+    first_job.assign(world + 1, (uint32_t)jobs.size());
+    first_job[0] = 0;
+    uint64_t run = 0;
+    uint32_t r = 1;
+    for (uint32_t i = 0; i < jobs.size() && r < world; ++i)
+    {
+        run += jobs[i].size;
+        while (r < world && run * world >= total * r) first_job[r++] = i + 1;
+    }
+}
+
+} // namespace
+
+extern "C" int lt_b200_comm_unique_id(uint8_t out_id[LT_B200_COMM_ID_BYTES])
+{
+    if (!out_id) return EINVAL;
+    if (nccl_load()) return ENOSYS;
+    static_assert(sizeof(ncclUniqueId) <= LT_B200_COMM_ID_BYTES, "ncclUniqueId does not fit LT_B200_COMM_ID_BYTES");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return EIO;
+    memset(out_id, 0, LT_B200_COMM_ID_BYTES);
+    memcpy(out_id, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" int lt_b200_comm_create(lt_b200_context* c, const uint8_t id_bytes[LT_B200_COMM_ID_BYTES], uint32_t rank, uint32_t world, lt_b200_comm** out)
+{
+    if (!c || !id_bytes || !out || world == 0 || rank >= world) return EINVAL;
+    *out = nullptr;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    if (nccl_load()) return fail(c, ENOSYS, "libnccl.so.2 could not be loaded");
+    lt_b200_comm* m = new (std::nothrow) lt_b200_comm();
+    if (!m) return ENOMEM;
+    m->ctx = c;
+    m->rank = rank;
+    m->world = world;
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    const ncclResult_t r = g_nccl.CommInitRank(&m->comm, (int)world, id, (int)rank);
+    if (r != ncclSuccess)
+    {
+        delete m;
+        return fail(c, EIO, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" void lt_b200_comm_destroy(lt_b200_comm* m)
+{
+    if (!m) return;
+    if (m->comm)
+    {
+        cudaSetDevice(m->ctx->device);
+        cudaStreamSynchronize(m->ctx->stream);
+        g_nccl.CommDestroy(m->comm);
+    }
+    delete m;
+}
+
+extern "C" int lt_b200_plan_shards(const lt_b200_assets* a, uint32_t target_chunk_size, uint32_t world, uint32_t* out_first_job, uint32_t* out_job_count)
+{
+    if (!a || !out_first_job || world == 0 || target_chunk_size == 0) return EINVAL;
+    std::vector<ShardJob> jobs;
+    shard_jobs(a, target_chunk_size, jobs);
+    std::vector<uint32_t> first;
+    shard_plan(jobs, world, first);
+    memcpy(out_first_job, first.data(), sizeof(uint32_t) * (world + 1));
+    if (out_job_count) *out_job_count = (uint32_t)jobs.size();
+    return 0;
+}
+
+extern "C" int lt_b200_shard_jobs(const lt_b200_assets* a, uint32_t target_chunk_size, uint32_t first_job, uint32_t job_count, lt_b200_shard_job* out_jobs)
+{
+    if (!a || (job_count && !out_jobs) || target_chunk_size == 0) return EINVAL;
+    std::vector<ShardJob> jobs;
+    shard_jobs(a, target_chunk_size, jobs);
+    if ((uint64_t)first_job + job_count > jobs.size()) return EINVAL;
+    for (uint32_t i = 0; i < job_count; ++i)
+    {
+        out_jobs[i].asset_index = jobs[first_job + i].asset;
+        out_jobs[i].size = jobs[first_job + i].size;
+        out_jobs[i].offset = jobs[first_job + i].offset;
+    }
+    return 0;
+}
+
+extern "C" int lt_b200_index_sharded(lt_b200_context* c, lt_b200_comm* m, const uint8_t* d_arena, uint64_t arena_size, const lt_b200_assets* a,
+                                     const uint32_t* asset_tags, const uint64_t* job_arena_offsets, uint32_t hash_type,
+                                     uint32_t target_chunk_size, int want_host, const void** out_buffer, uint64_t* out_size)
+{
+    if (!c || !m || m->ctx != c || !out_buffer || !out_size) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    TRY(validate_assets(c, a));
+    if (target_chunk_size == 0 || target_chunk_size > (1u << 20)) return fail(c, EINVAL, "target_chunk_size %u outside (0, 1 MiB]", target_chunk_size);
+    uint32_t mn, av, mx;
+    target_to_params(target_chunk_size, &mn, &av, &mx);
+    const uint32_t world = m->world, rank = m->rank;
+    std::vector<ShardJob> jobs;
+    shard_jobs(a, target_chunk_size, jobs);
+    std::vector<uint32_t> first_job;
+    shard_plan(jobs, world, first_job);
+    const uint32_t total_jobs = (uint32_t)jobs.size(), j0 = first_job[rank], j1 = first_job[rank + 1];
+    if (j1 > j0 && !job_arena_offsets) return EINVAL;
+
+    // ---- this rank's slice: chunk + hash, table left resident
+    std::vector<lt_b200_range> ranges(j1 - j0);
+    for (uint32_t j = j0; j < j1; ++j)
+    {
+        lt_b200_range r = {job_arena_offsets[j - j0], jobs[j].size, asset_tags ? asset_tags[jobs[j].asset] : 0u};
+        ranges[j - j0] = r;
+    }
+    lt_b200_chunk_table table;
+    TRY(lt_b200_chunk_ranges(c, d_arena, arena_size, ranges.data(), (uint32_t)ranges.size(), mn, av, mx, hash_type, 0, &table));
+
+    // ---- exchange 1: chunk count of every job (each rank contributes its slice)
+    TRY(ws_reserve(c, WS_G_COUNTS, sizeof(uint32_t) * ((size_t)total_jobs + 1)));
+    uint32_t* g_counts = ws<uint32_t>(c, WS_G_COUNTS);
+    std::vector<uint32_t> all_counts(total_jobs + 1, 0);
+    if (world > 1)
+    {
+        if (j1 > j0) CU(cudaMemcpyAsync(g_counts + j0, table.range_chunk_counts, sizeof(uint32_t) * (j1 - j0), cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.GroupStart());
+        for (uint32_t r = 0; r < world; ++r)
+            if (first_job[r + 1] > first_job[r])
+                NC(g_nccl.Broadcast(g_counts + first_job[r], g_counts + first_job[r], first_job[r + 1] - first_job[r], ncclUint32, (int)r, m->comm, c->stream));
+        NC(g_nccl.GroupEnd());
+        CU(cudaMemcpyAsync(all_counts.data(), g_counts, sizeof(uint32_t) * total_jobs, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    else
+        for (uint32_t j = 0; j < total_jobs; ++j) all_counts[j] = table.range_chunk_counts[j];
+    std::vector<uint32_t> asset_chunks(a->asset_count, 0);
+    m->rank_chunk_start.assign(world + 1, 0);
+    uint64_t run = 0;
+    for (uint32_t r = 0, j = 0; r < world; ++r)
+    {
+        m->rank_chunk_start[r] = (uint32_t)run;
+        for (; j < first_job[r + 1]; ++j)
+        {
+            run += all_counts[j];
+            asset_chunks[jobs[j].asset] += all_counts[j];
+        }
+    }
+    if (run >= 0xffffffffull) return fail(c, E2BIG, "%llu chunks exceed the VersionIndex's 32-bit indexes", (unsigned long long)run);
+    const uint32_t N = (uint32_t)run;
+    m->rank_chunk_start[world] = N;
+    if (m->rank_chunk_start[rank + 1] - m->rank_chunk_start[rank] != table.chunk_count) return fail(c, EFAULT, "chunk count exchange out of step");
+
+    // ---- exchange 2: the (hash, size, tag) tables, every rank's slice broadcast into place
+    const uint64_t* g_hash = ws<uint64_t>(c, WS_CHUNK_HASH);
+    const uint32_t* g_len = ws<uint32_t>(c, WS_CHUNK_LEN);
+    const uint32_t* g_tag = ws<uint32_t>(c, WS_CHUNK_TAG);
+    if (world > 1)
+    {
+        TRY(ws_reserve(c, WS_G_HASH, sizeof(uint64_t) * (size_t)N + 16));
+        TRY(ws_reserve(c, WS_G_LEN, sizeof(uint32_t) * (size_t)N + 16));
+        TRY(ws_reserve(c, WS_G_TAG, sizeof(uint32_t) * (size_t)N + 16));
+        NC(g_nccl.GroupStart());
+        for (uint32_t r = 0; r < world; ++r)
+        {
+            const uint32_t s0 = m->rank_chunk_start[r], n = m->rank_chunk_start[r + 1] - s0;
+            if (!n) continue;
+            NC(g_nccl.Broadcast(ws<uint64_t>(c, WS_CHUNK_HASH), ws<uint64_t>(c, WS_G_HASH) + s0, n, ncclUint64, (int)r, m->comm, c->stream));
+            NC(g_nccl.Broadcast(ws<uint32_t>(c, WS_CHUNK_LEN), ws<uint32_t>(c, WS_G_LEN) + s0, n, ncclUint32, (int)r, m->comm, c->stream));
+            NC(g_nccl.Broadcast(ws<uint32_t>(c, WS_CHUNK_TAG), ws<uint32_t>(c, WS_G_TAG) + s0, n, ncclUint32, (int)r, m->comm, c->stream));
+        }
+        NC(g_nccl.GroupEnd());
+        g_hash = ws<uint64_t>(c, WS_G_HASH);
+        g_len = ws<uint32_t>(c, WS_G_LEN);
+        g_tag = ws<uint32_t>(c, WS_G_TAG);
+        c->launches += 2;
+    }
+
+    // ---- the one VersionIndex, on every rank (the host copy only where it is wanted)
+    TRY(build_index_from_device_table(c, a, asset_chunks.data(), N, g_hash, g_len, g_tag, hash_type, target_chunk_size, out_buffer, out_size, nullptr, m,
+                                      want_host != 0));
+    // where the unique chunks' first occurrences live: rank r holds unique chunks [rank_unique_start[r], rank_unique_start[r + 1])
+    m->rank_unique_start.assign(world + 1, c->unique_chunks);
+    for (uint32_t r = 0; r < world; ++r)
+        if (m->rank_chunk_start[r] < N)
+            CU(cudaMemcpyAsync(&m->rank_unique_start[r], ws<uint32_t>(c, WS_DEDUP_UIDX) + m->rank_chunk_start[r], sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    m->global_chunks = N;
+    m->global_unique = c->unique_chunks;
+    m->d_arena = d_arena;
+    m->arena_size = arena_size;
+    m->hash_type = hash_type;
+    return 0;
+}
+
+extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m, uint32_t max_block_size, uint32_t max_chunks_per_block, uint32_t flags,
+                                            lt_b200_block_sink sink, void* user, uint32_t* out_my_blocks, uint32_t* out_total_blocks)
+{
+    if (!c || !m || m->ctx != c || !sink || max_chunks_per_block == 0) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    if (m->rank_unique_start.size() != m->world + 1) return fail(c, EINVAL, "lt_b200_index_sharded has not run on this communicator");
+    const uint32_t world = m->world, rank = m->rank, U = m->global_unique;
+    if (out_my_blocks) *out_my_blocks = 0;
+    if (out_total_blocks) *out_total_blocks = 0;
+    if (!U) return 0;
+
+    // ---- the same plan on every rank: Longtail_CreateStoreIndex's packing over the unique chunks in VersionIndex order
+    // (src/longtail.c:6796-6860), then contiguous runs of blocks per rank with (nearly) equal payload bytes
+    std::vector<uint32_t> u_len(U), u_tag(U);
+    CU(cudaMemcpyAsync(u_len.data(), ws<void>(c, WS_ULEN), sizeof(uint32_t) * (size_t)U, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(u_tag.data(), ws<void>(c, WS_UTAG), sizeof(uint32_t) * (size_t)U, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> blk_first(U), blk_count(U);
+    uint32_t B = 0;
+    TRY(lt_b200_pack_blocks(U, u_len.data(), u_tag.data(), max_block_size, max_chunks_per_block, blk_first.data(), blk_count.data(), &B));
+    std::vector<uint64_t> blk_end_bytes(B);
+    uint64_t total_bytes = 0;
+    for (uint32_t b = 0; b < B; ++b)
+    {
+        for (uint32_t k = 0; k < blk_count[b]; ++k) total_bytes += u_len[blk_first[b] + k];
+        blk_end_bytes[b] = total_bytes;
+    }
+    std::vector<uint32_t> rank_blk(world + 1, B);
+    rank_blk[0] = 0;
+    for (uint32_t b = 0, r = 1; b < B && r < world; ++b)
+        while (r < world && blk_end_bytes[b] * world >= total_bytes * r) rank_blk[r++] = b + 1;
+    auto chunk_lo = [&](uint32_t r) { return rank_blk[r] < B ? blk_first[rank_blk[r]] : U; }; // first unique chunk rank r writes
+    if (out_total_blocks) *out_total_blocks = B;
+    const uint32_t my_b0 = rank_blk[rank], my_b1 = rank_blk[rank + 1];
+    const uint32_t cs = chunk_lo(rank), ce = chunk_lo(rank + 1);
+
+    // ---- exchange: owner o holds unique chunks [us_o, ue_o); writer w needs [cs_w, ce_w).  Local offsets of my own first occurrences:
+    const uint32_t my_c0 = m->rank_chunk_start[rank], my_cn = m->rank_chunk_start[rank + 1] - my_c0;
+    const uint32_t us = m->rank_unique_start[rank], ue = m->rank_unique_start[rank + 1];
+    std::vector<uint64_t> local_off(my_cn);
+    std::vector<uint32_t> u_first(ue > us ? ue - us : 0);
+    if (my_cn) CU(cudaMemcpyAsync(local_off.data(), ws<void>(c, WS_CHUNK_OFF), sizeof(uint64_t) * (size_t)my_cn, cudaMemcpyDeviceToHost, c->stream));
+    if (ue > us) CU(cudaMemcpyAsync(u_first.data(), ws<uint32_t>(c, WS_UFIRST) + us, sizeof(uint32_t) * (size_t)(ue - us), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    auto off_of = [&](uint32_t u) { return local_off[u_first[u - us] - my_c0]; }; // arena offset of unique chunk u (mine)
+
+    struct Seg { uint32_t peer, a, b; uint64_t bytes, at; };
+    std::vector<Seg> sends, recvs;
+    uint64_t send_bytes = 0, recv_bytes = 0;
+    for (uint32_t w = 0; w < world; ++w)
+    {
+        if (w == rank) continue;
+        const uint32_t a = std::max(chunk_lo(w), us), b = std::min(chunk_lo(w + 1), ue); // what writer w needs from me
+        if (a < b)
+        {
+            Seg s = {w, a, b, 0, send_bytes};
+            for (uint32_t u = a; u < b; ++u) s.bytes += u_len[u];
+            send_bytes += (s.bytes + 15) & ~15ull;
+            sends.push_back(s);
+        }
+        const uint32_t ra = std::max(cs, m->rank_unique_start[w]), rb = std::min(ce, m->rank_unique_start[w + 1]); // what I need from owner w
+        if (ra < rb)
+        {
+            Seg s = {w, ra, rb, 0, recv_bytes};
+            for (uint32_t u = ra; u < rb; ++u) s.bytes += u_len[u];
+            recv_bytes += (s.bytes + 15) & ~15ull;
+            recvs.push_back(s);
+        }
+    }
+    if (world > 1)
+    {
+        TRY(ws_reserve(c, WS_X_SEND, send_bytes + 64));
+        TRY(ws_reserve(c, WS_X_RECV, recv_bytes + 64));
+        if (!sends.empty())
+        {
+            size_t n = 0;
+            for (const Seg& s : sends) n += s.b - s.a;
+            std::vector<uint64_t> src(n), dst(n);
+            std::vector<uint32_t> len(n);
+            size_t i = 0;
+            for (const Seg& s : sends)
+            {
+                uint64_t w = s.at;
+                for (uint32_t u = s.a; u < s.b; ++u, ++i)
+                {
+                    src[i] = off_of(u);
+                    dst[i] = w;
+                    len[i] = u_len[u];
+                    w += u_len[u];
+                }
+            }
+            TRY(ws_reserve(c, WS_X_TAB, 20 * n + 64));
+            uint64_t* d_src = ws<uint64_t>(c, WS_X_TAB);
+            uint64_t* d_dst = d_src + n;
+            uint32_t* d_len = reinterpret_cast<uint32_t*>(d_dst + n);
+            CU(cudaMemcpyAsync(d_src, src.data(), 8 * n, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_dst, dst.data(), 8 * n, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_len, len.data(), 4 * n, cudaMemcpyHostToDevice, c->stream));
+            launch_gather_chunks(m->d_arena, d_src, d_dst, d_len, ws<uint8_t>(c, WS_X_SEND), (uint32_t)n, c->stream);
+            CU(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
+        }
+        NC(g_nccl.GroupStart());
+        for (const Seg& s : sends) NC(g_nccl.Send(ws<uint8_t>(c, WS_X_SEND) + s.at, s.bytes, ncclUint8, (int)s.peer, m->comm, c->stream));
+        for (const Seg& s : recvs) NC(g_nccl.Recv(ws<uint8_t>(c, WS_X_RECV) + s.at, s.bytes, ncclUint8, (int)s.peer, m->comm, c->stream));
+        NC(g_nccl.GroupEnd());
+        c->launches += 2;
+    }
+
+    // ---- this rank's blocks: chunks [cs, ce) with their bytes at absolute device addresses (own arena or the receive buffer)
+    if (out_my_blocks) *out_my_blocks = my_b1 - my_b0;
+    if (cs >= ce) return 0;
+    const uint32_t n = ce - cs;
+    std::vector<uint64_t> hashes(n), addr(n);
+    CU(cudaMemcpyAsync(hashes.data(), ws<uint64_t>(c, WS_UHASH) + cs, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    for (uint32_t u = std::max(cs, us); u < std::min(ce, ue); ++u) addr[u - cs] = (uint64_t)(uintptr_t)m->d_arena + off_of(u);
+    for (const Seg& s : recvs)
+    {
+        uint64_t w = (uint64_t)(uintptr_t)ws<uint8_t>(c, WS_X_RECV) + s.at;
+        for (uint32_t u = s.a; u < s.b; ++u)
+        {
+            addr[u - cs] = w;
+            w += u_len[u];
+        }
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> counts(blk_count.begin() + my_b0, blk_count.begin() + my_b1);
+    uint32_t most = 1;
+    for (uint32_t v : counts) most = std::max(most, v);
+    return write_blocks_impl(c, nullptr, ~0ull, n, hashes.data(), u_len.data() + cs, u_tag.data() + cs, addr.data(), m->hash_type, 0xffffffffu, most,
+                             my_b1 - my_b0, counts.data(), flags, sink, user);
+}
 
 // ================================================================ CompressionAPI batch entry points (host buffers)
 

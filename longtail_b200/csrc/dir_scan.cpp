@@ -379,3 +379,73 @@ extern "C" int lt_b200_upsync_file_list(lt_b200_context* context, const lt_b200_
     lt_b200_device_free(context, arena);
     return err;
 }
+
+// cmd/main.c:UpSync (:972-1153) for assets that sit in HOST memory (pinned for full PCIe speed) and fit one GPU: every asset is copied once
+// into a device arena, then CreateVersionIndex, CreateMissingContent against `existing_hashes` (may be NULL: a fresh store) and WriteContent
+// run on the resident bytes; stored blocks leave through `sink`.  The reference reads every file twice (once to index it, once to compose
+// the blocks, src/longtail.c:2076, :4675); here the bytes cross PCIe once.
+extern "C" int lt_b200_upsync_host_assets(lt_b200_context* context, const lt_b200_assets* assets, const uint8_t* const* asset_data,
+                                          const uint32_t* asset_tags, uint32_t hash_type, uint32_t target_chunk_size, uint32_t max_block_size,
+                                          uint32_t max_chunks_per_block, uint32_t existing_count, const uint64_t* existing_hashes, uint32_t flags,
+                                          lt_b200_block_sink sink, void* user, const void** out_version_index, uint64_t* out_size,
+                                          uint32_t* out_chunks_written)
+{
+    if (!context || !assets || !sink || !out_version_index || !out_size || (assets->asset_count && !asset_data)) return EINVAL;
+    const uint32_t n = assets->asset_count;
+    std::vector<uint64_t> arena_off(n ? n : 1);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        arena_off[i] = total;
+        total += (assets->sizes[i] + 255u) & ~(uint64_t)255u;
+    }
+    const uint64_t arena_bytes = total + 4096;
+    void* arena = nullptr;
+    int err = lt_b200_device_alloc(context, arena_bytes, &arena);
+    if (err) return err; // ENOMEM: shard the asset list across GPUs (lt_b200_index_sharded)
+    for (uint32_t i = 0; i < n && !err; ++i)
+        if (assets->sizes[i])
+        {
+            if (!asset_data[i]) err = EINVAL;
+            else err = lt_b200_copy_to_device_async(context, static_cast<uint8_t*>(arena) + arena_off[i], asset_data[i], assets->sizes[i]);
+        }
+    const void* vi = nullptr;
+    uint64_t vi_size = 0;
+    if (!err) err = lt_b200_index_device_assets(context, static_cast<const uint8_t*>(arena), arena_bytes, assets, arena_off.data(), asset_tags, hash_type,
+                                                target_chunk_size, &vi, &vi_size);
+    if (!err)
+    {
+        const uint8_t* p = static_cast<const uint8_t*>(vi);
+        uint32_t head[6];
+        memcpy(head, p, sizeof(head));
+        const uint64_t A = head[3], C = head[4], I = head[5];
+        const uint8_t* q = p + 24 + 24 * A + 8 * A + 4 * I; // the unique chunks of the version, in version order (src/longtail.c:2566-2584)
+        std::vector<uint64_t> hashes(C ? C : 1), offsets(C ? C : 1);
+        std::vector<uint32_t> sizes(C ? C : 1), tags(C ? C : 1);
+        memcpy(hashes.data(), q, 8 * C);
+        memcpy(sizes.data(), q + 8 * C, 4 * C);
+        memcpy(tags.data(), q + 12 * C, 4 * C);
+        if (C) err = lt_b200_unique_chunk_offsets(context, offsets.data(), (uint32_t)C);
+        uint32_t m = (uint32_t)C;
+        if (!err && C && existing_count)
+        {
+            std::vector<uint8_t> missing(C, 1);
+            err = lt_b200_missing_chunks(context, (uint32_t)C, hashes.data(), existing_count, existing_hashes, missing.data());
+            m = 0;
+            for (uint64_t i = 0; i < C && !err; ++i)
+                if (missing[i])
+                {
+                    hashes[m] = hashes[i]; sizes[m] = sizes[i]; tags[m] = tags[i]; offsets[m] = offsets[i];
+                    ++m;
+                }
+        }
+        if (!err && m)
+            err = lt_b200_write_blocks_device_ex(context, static_cast<const uint8_t*>(arena), arena_bytes, m, hashes.data(), sizes.data(), tags.data(),
+                                                 offsets.data(), hash_type, max_block_size, max_chunks_per_block, flags, sink, user);
+        if (out_chunks_written) *out_chunks_written = m;
+        *out_version_index = vi;
+        *out_size = vi_size;
+    }
+    lt_b200_device_free(context, arena);
+    return err;
+}

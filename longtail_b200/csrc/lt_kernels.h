@@ -90,7 +90,12 @@ void launch_dedup_lookup(const uint64_t* d_hash, uint32_t count, const DedupBuff
 void launch_set_contains(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, uint8_t* d_present, cudaStream_t st);
 void launch_dedup_emit(const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, const DedupBuffers& b,
                        uint32_t* d_asset_chunk_index, uint64_t* d_unique_hash, uint32_t* d_unique_len, uint32_t* d_unique_tag,
-                       const uint64_t* d_chunk_off, uint64_t* d_unique_off, cudaStream_t st);
+                       const uint64_t* d_chunk_off, uint64_t* d_unique_off, cudaStream_t st, uint32_t* d_unique_first = nullptr);
+// the dedup split by hash across ranks (every rank holds the whole hash list): insert / resolve only the keys rank `rank` owns, first[] = 0
+// elsewhere; after an all-reduce (sum) of first[] over the ranks, launch_mark_first derives is_first[]
+void launch_dedup_insert_part(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, uint32_t world, uint32_t rank, cudaStream_t st);
+void launch_dedup_lookup_part(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, uint32_t world, uint32_t rank, cudaStream_t st);
+void launch_mark_first(const DedupBuffers& b, uint32_t count, cudaStream_t st);
 void launch_fill_u32(uint32_t* d, uint32_t value, size_t count, cudaStream_t st);
 
 // ---- synth.cu : deterministic synthetic asset bytes (include/lt_synth.h)

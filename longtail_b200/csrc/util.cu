@@ -179,11 +179,84 @@ __global__ void k_dedup_lookup(const uint64_t* __restrict__ hash, uint32_t count
     is_first[i] = f == i ? 1u : 0u;
 }
 
+// ---- the same, split by hash across `world` ranks: every rank holds the whole (allgathered) hash list but inserts and resolves only
+// the keys it owns; an all-reduce (sum) of `first` — zero where a rank does not own the key — then gives every rank every answer, and
+// the random-access part of the dedup is 1/world of the single-GPU work on each rank.
+__device__ __forceinline__ uint32_t dedup_owner(uint64_t key, uint32_t world) { return (uint32_t)(((key * 0xD6E8FEB86659FD93ull) >> 40) % world); }
+
+__global__ void k_dedup_insert_part(const uint64_t* __restrict__ hash, uint32_t count, uint64_t* keys, uint32_t* vals, uint32_t capacity,
+                                    uint32_t world, uint32_t rank)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t key = hash[i];
+    if (dedup_owner(key, world) != rank) return;
+    if (key == DEDUP_EMPTY)
+    {
+        atomicMin(&vals[capacity], i);
+        return;
+    }
+    const uint32_t mask = capacity - 1;
+    for (uint32_t s = dedup_slot(key, mask);; s = (s + 1) & mask)
+    {
+        unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&keys[s]), (unsigned long long)DEDUP_EMPTY, (unsigned long long)key);
+        if (prev == DEDUP_EMPTY || prev == key)
+        {
+            atomicMin(&vals[s], i);
+            return;
+        }
+    }
+}
+
+__global__ void k_dedup_lookup_part(const uint64_t* __restrict__ hash, uint32_t count, const uint64_t* __restrict__ keys,
+                                    const uint32_t* __restrict__ vals, uint32_t capacity, uint32_t* __restrict__ first, uint32_t world, uint32_t rank)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t key = hash[i];
+    uint32_t f = 0;
+    if (dedup_owner(key, world) == rank)
+    {
+        if (key == DEDUP_EMPTY)
+            f = vals[capacity];
+        else
+        {
+            const uint32_t mask = capacity - 1;
+            uint32_t s = dedup_slot(key, mask);
+            while (keys[s] != key) s = (s + 1) & mask;
+            f = vals[s];
+        }
+    }
+    first[i] = f;
+}
+
+__global__ void k_mark_first(const uint32_t* __restrict__ first, uint32_t count, uint32_t* __restrict__ is_first)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) is_first[i] = first[i] == i ? 1u : 0u;
+}
+
+void launch_dedup_insert_part(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, uint32_t world, uint32_t rank, cudaStream_t st)
+{
+    if (!count) return;
+    k_dedup_insert_part<<<(count + 255) / 256, 256, 0, st>>>(d_hash, count, b.keys, b.vals, b.capacity, world, rank);
+}
+void launch_dedup_lookup_part(const uint64_t* d_hash, uint32_t count, const DedupBuffers& b, uint32_t world, uint32_t rank, cudaStream_t st)
+{
+    if (!count) return;
+    k_dedup_lookup_part<<<(count + 255) / 256, 256, 0, st>>>(d_hash, count, b.keys, b.vals, b.capacity, b.first, world, rank);
+}
+void launch_mark_first(const DedupBuffers& b, uint32_t count, cudaStream_t st)
+{
+    if (!count) return;
+    k_mark_first<<<(count + 255) / 256, 256, 0, st>>>(b.first, count, b.is_first);
+}
+
 __global__ void k_dedup_emit(const uint64_t* __restrict__ hash, const uint32_t* __restrict__ len, const uint32_t* __restrict__ tag,
                              uint32_t count, const uint32_t* __restrict__ first, const uint32_t* __restrict__ is_first,
                              const uint32_t* __restrict__ uidx, uint32_t* __restrict__ asset_chunk_index,
                              uint64_t* __restrict__ unique_hash, uint32_t* __restrict__ unique_len, uint32_t* __restrict__ unique_tag,
-                             const uint64_t* __restrict__ chunk_off, uint64_t* __restrict__ unique_off)
+                             const uint64_t* __restrict__ chunk_off, uint64_t* __restrict__ unique_off, uint32_t* __restrict__ unique_first)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -191,6 +264,7 @@ __global__ void k_dedup_emit(const uint64_t* __restrict__ hash, const uint32_t* 
     if (is_first[i])
     {
         const uint32_t u = uidx[i];
+        if (unique_first) unique_first[u] = i; // ordinal of the first occurrence: which rank holds the bytes, and where
         unique_hash[u] = hash[i];
         unique_len[u] = len[i];
         unique_tag[u] = tag[i]; // tag of the first occurrence (src/longtail.c:2962)
@@ -239,11 +313,11 @@ void launch_dedup_lookup(const uint64_t* d_hash, uint32_t count, const DedupBuff
 
 void launch_dedup_emit(const uint64_t* d_hash, const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, const DedupBuffers& b,
                        uint32_t* d_asset_chunk_index, uint64_t* d_unique_hash, uint32_t* d_unique_len, uint32_t* d_unique_tag,
-                       const uint64_t* d_chunk_off, uint64_t* d_unique_off, cudaStream_t st)
+                       const uint64_t* d_chunk_off, uint64_t* d_unique_off, cudaStream_t st, uint32_t* d_unique_first)
 {
     if (!count) return;
     k_dedup_emit<<<(count + 255) / 256, 256, 0, st>>>(d_hash, d_len, d_tag, count, b.first, b.is_first, b.uidx, d_asset_chunk_index,
-                                                      d_unique_hash, d_unique_len, d_unique_tag, d_chunk_off, d_unique_off);
+                                                      d_unique_hash, d_unique_len, d_unique_tag, d_chunk_off, d_unique_off, d_unique_first);
 }
 
 // ---------------------------------------------------------------- synthetic assets (bench / test inputs only)

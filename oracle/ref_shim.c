@@ -362,11 +362,71 @@ REF_EXPORT int ref_create_version_index(uint32_t count, const char** paths, cons
 
 /* ---------------------------------------------------------------- WriteContent with a capturing sink */
 
+/* 64-bit digest of a byte string (four interleaved multiply-rotate lanes, ~10 GB/s): lets a 128 GiB upsync be compared block by block
+ * — the reference's serialised StoredBlocks here, the B200 path's in ref_digest_sink — without keeping 64 GiB of blocks around */
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+REF_EXPORT uint64_t ref_digest64(const void* data, uint64_t n)
+{
+    const uint8_t* p = (const uint8_t*)data;
+    uint64_t h[4] = {0x9E3779B97F4A7C15ull ^ n, 0xBF58476D1CE4E5B9ull, 0x94D049BB133111EBull, 0xD6E8FEB86659FD93ull};
+    uint64_t i = 0;
+    for (; i + 32 <= n; i += 32)
+    {
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        h[0] = rotl64(h[0] ^ w[0], 29) * 0xA0761D6478BD642Full;
+        h[1] = rotl64(h[1] ^ w[1], 31) * 0xE7037ED1A0B428DBull;
+        h[2] = rotl64(h[2] ^ w[2], 33) * 0x8EBC6AF09C88C6E3ull;
+        h[3] = rotl64(h[3] ^ w[3], 27) * 0x589965CC75374CC3ull;
+    }
+    uint64_t tail[4] = {0, 0, 0, 0};
+    memcpy(tail, p + i, n - i);
+    for (int k = 0; k < 4; ++k) h[k] = rotl64(h[k] ^ tail[k], 23) * 0x1D8E4E27C47D124Full;
+    uint64_t x = h[0] ^ rotl64(h[1], 17) ^ rotl64(h[2], 34) ^ rotl64(h[3], 51);
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+/* an lt_b200_block_sink (include/longtail_b200.h) that records {block hash, size, digest} of every block it is handed.
+ * user = a ref_digest_list made by ref_digest_list_create */
+struct ref_digest_list
+{
+    uint64_t* rec; /* 3 x u64 per block */
+    uint64_t count, cap;
+};
+struct ref_block_view /* = struct lt_b200_stored_block_view */
+{
+    uint64_t block_hash;
+    const void* data;
+    uint64_t size;
+    uint32_t chunk_count, tag, raw_payload_size, first_chunk;
+};
+REF_EXPORT struct ref_digest_list* ref_digest_list_create(void) { return (struct ref_digest_list*)calloc(1, sizeof(struct ref_digest_list)); }
+REF_EXPORT void ref_digest_list_free(struct ref_digest_list* l) { if (l) { free(l->rec); free(l); } }
+REF_EXPORT const uint64_t* ref_digest_list_data(const struct ref_digest_list* l, uint64_t* out_count) { *out_count = l->count; return l->rec; }
+REF_EXPORT int ref_digest_sink(void* user, const struct ref_block_view* v)
+{
+    struct ref_digest_list* l = (struct ref_digest_list*)user;
+    if (l->count == l->cap)
+    {
+        l->cap = l->cap ? l->cap * 2 : 1024;
+        l->rec = (uint64_t*)realloc(l->rec, l->cap * 24);
+        if (!l->rec) return ENOMEM;
+    }
+    uint64_t* r = l->rec + 3 * l->count++;
+    r[0] = v->block_hash;
+    r[1] = v->size;
+    r[2] = ref_digest64(v->data, v->size);
+    return 0;
+}
+
 struct captured_block
 {
     uint64_t hash;
     void* data;
     size_t size;
+    uint64_t digest;
 };
 
 struct capture_store
@@ -396,6 +456,7 @@ static int capture_put(struct Longtail_BlockStoreAPI* api, struct Longtail_Store
     int err = Longtail_WriteStoredBlockToBuffer(block, &buf, &size);
     if (!err)
     {
+        const uint64_t digest = s->keep_bytes == 2 ? ref_digest64(buf, size) : 0; /* outside the lock: the workers digest in parallel */
         pthread_mutex_lock(&s->lock);
         if (s->count == s->cap)
         {
@@ -406,7 +467,8 @@ static int capture_put(struct Longtail_BlockStoreAPI* api, struct Longtail_Store
         b->hash = *block->m_BlockIndex->m_BlockHash;
         b->size = size;
         b->data = 0;
-        if (s->keep_bytes)
+        b->digest = digest;
+        if (s->keep_bytes == 1)
         {
             b->data = malloc(size);
             memcpy(b->data, buf, size);
@@ -444,7 +506,7 @@ static struct capture_store* make_capture_store(int keep_bytes)
  * Output buffer (malloc'd): u32 block_count, then per block IN STORE-INDEX ORDER
  * { u64 block_hash, u64 size, u8 serialised_stored_block[size] } (Longtail_WriteStoredBlockToBuffer),
  * followed by the serialised VersionIndex { u64 size, bytes }.  With keep_bytes == 0 only sizes are
- * recorded (timing runs).  seconds[0..2] = CreateVersionIndex, CreateMissingContent, WriteContent. */
+ * recorded (timing runs); keep_bytes == 2 records { u64 block_hash, u64 size, u64 ref_digest64 } per block instead of the bytes.  seconds[0..2] = CreateVersionIndex, CreateMissingContent, WriteContent. */
 static int upsync_impl(uint32_t count, const char** paths, const uint8_t** datas, const uint64_t* sizes,
                           const uint16_t* perms, const uint32_t* tags, uint32_t hash_type,
                           uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block,
@@ -503,20 +565,21 @@ static int upsync_impl(uint32_t count, const char** paths, const uint8_t** datas
         {
             uint32_t block_count = *missing->m_BlockCount;
             size_t total = 4 + 8 + vsize;
-            for (uint32_t i = 0; i < sink->count; ++i) total += 16 + (keep_bytes ? sink->blocks[i].size : 0);
+            for (uint32_t i = 0; i < sink->count; ++i) total += 16 + (keep_bytes == 1 ? sink->blocks[i].size : 8);
             uint8_t* out = (uint8_t*)malloc(total);
             uint8_t* p = out;
             memcpy(p, &block_count, 4); p += 4;
             for (uint32_t b = 0; b < block_count && !err; ++b)
             {
                 uint64_t h = missing->m_BlockHashes[b];
-                uint32_t j = 0;
+                uint32_t j = b < sink->count && sink->blocks[b].hash == h ? b : 0; /* a single worker stores in order */
                 while (j < sink->count && sink->blocks[j].hash != h) ++j;
                 if (j == sink->count) { err = ENOENT; break; }
                 uint64_t sz = sink->blocks[j].size;
                 memcpy(p, &h, 8); p += 8;
                 memcpy(p, &sz, 8); p += 8;
-                if (keep_bytes) { memcpy(p, sink->blocks[j].data, sz); p += sz; }
+                if (keep_bytes == 1) { memcpy(p, sink->blocks[j].data, sz); p += sz; }
+                else if (keep_bytes == 2) { memcpy(p, &sink->blocks[j].digest, 8); p += 8; }
             }
             uint64_t vs = vsize;
             memcpy(p, &vs, 8); p += 8;

@@ -1,4 +1,7 @@
-"""Host-side sharding of the indexing path across GPUs (one process per GPU, torch.distributed for the plumbing).
+"""TEST INFRASTRUCTURE — a Python model of the sharded indexing path used by the gloo (CPU, world_size 2 / 3) tests; the product's multi-GPU path
+is C + NCCL behind the C ABI (lt_b200_index_sharded / lt_b200_write_blocks_sharded, longtail_b200/csrc/capi.cu).
+
+Host-side sharding of the indexing path across GPUs (one process per GPU, torch.distributed for the plumbing).
 
 The unit of work is the reference's own job: one (asset, part) pair, part = target_chunk_size * 1024 bytes
 (src/longtail.c:2396-2457).  Parts are independent chunker instances, so the global job list is cut into `world`
@@ -113,7 +116,7 @@ def pack_blocks(sizes, tags, max_block_size=8388608, max_chunks_per_block=1024):
     -> list of (first_unique_chunk, chunk_count).  Runs in the C library (lt_b200_pack_blocks, a host-only helper)."""
     import ctypes as C
 
-    from . import load_library
+    from longtail_b200 import load_library
     lib = load_library()
     sz = np.ascontiguousarray(sizes, dtype=np.uint32)
     tg = np.ascontiguousarray(tags, dtype=np.uint32)

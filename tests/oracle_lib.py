@@ -263,19 +263,51 @@ class Reference:
             eh = np.ascontiguousarray(existing_hashes, dtype=np.uint64)
             err = self.lib.ref_upsync_existing(C.c_uint32(a.n), a.paths, a.datas, a.sizes, a.perms, a.tags, C.c_uint32(hash_type),
                                                C.c_uint32(target_chunk_size), C.c_uint32(max_block_size), C.c_uint32(max_chunks_per_block),
-                                               C.c_uint32(workers), C.c_int(1 if keep_bytes else 0), C.byref(buf), C.byref(size), secs, C.byref(stored),
+                                               C.c_uint32(workers), C.c_int(int(keep_bytes)), C.byref(buf), C.byref(size), secs, C.byref(stored),
                                                C.c_uint32(eh.size), eh.ctypes.data_as(C.c_void_p))
         else:
             err = self.lib.ref_upsync(C.c_uint32(a.n), a.paths, a.datas, a.sizes, a.perms, a.tags, C.c_uint32(hash_type),
                                       C.c_uint32(target_chunk_size), C.c_uint32(max_block_size), C.c_uint32(max_chunks_per_block),
-                                      C.c_uint32(workers), C.c_int(1 if keep_bytes else 0), C.byref(buf), C.byref(size), secs, C.byref(stored))
+                                      C.c_uint32(workers), C.c_int(int(keep_bytes)), C.byref(buf), C.byref(size), secs, C.byref(stored))
         assert err == 0, err
         out = C.string_at(buf, size.value)
         self.lib.ref_free(buf)
         if not keep_bytes:
             return list(secs), stored.value
+        if keep_bytes == 2:
+            # -> (u64 array [blocks, 3] of {block hash, size, ref_digest64}, version index bytes, seconds)
+            (count,) = struct.unpack_from("<I", out, 0)
+            rec = np.frombuffer(out, dtype="<u8", count=3 * count, offset=4).reshape(count, 3).copy()
+            (vsize,) = struct.unpack_from("<Q", out, 4 + 24 * count)
+            return rec, out[12 + 24 * count:12 + 24 * count + vsize], list(secs)
         res = parse_upsync(out)
         return (res, list(secs)) if want_seconds else res
+
+
+class DigestSink:
+    """C block sink of the checker library (oracle/ref_shim.c: ref_digest_sink): records {block hash, size, ref_digest64} of every block
+    the B200 path hands over — pass .fn / .user to Context.write_blocks_device(c_sink=...)"""
+
+    def __init__(self, ref):
+        self.lib = ref.lib
+        self.lib.ref_digest_list_create.restype = C.c_void_p
+        self.lib.ref_digest_list_free.argtypes = [C.c_void_p]
+        self.lib.ref_digest_list_data.restype = C.c_void_p
+        self.lib.ref_digest_list_data.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        self.user = C.c_void_p(self.lib.ref_digest_list_create())
+        self.fn = C.cast(self.lib.ref_digest_sink, C.c_void_p)
+
+    def records(self):
+        n = C.c_uint64(0)
+        ptr = self.lib.ref_digest_list_data(self.user, C.byref(n))
+        if not n.value:
+            return np.zeros((0, 3), dtype="<u8")
+        return np.ctypeslib.as_array((C.c_uint64 * (3 * n.value)).from_address(ptr)).reshape(n.value, 3).copy()
+
+    def close(self):
+        if self.user:
+            self.lib.ref_digest_list_free(self.user)
+            self.user = None
 
 
 def ref_upsync_to_dir(ref, assets, target_chunk_size, directory, max_block_size=8388608, max_chunks_per_block=1024, hash_type=HASH_BLAKE3,

@@ -1,4 +1,4 @@
-"""The N>1 host logic (longtail_b200/distributed.py) on CPU: world_size 2, gloo.  Each rank produces the chunk table of its
+"""The N>1 host logic (tests/dist_model.py) on CPU: world_size 2, gloo.  Each rank produces the chunk table of its
 slice of the job list with the CPU oracle (standing in for the GPU), the tables are merged with allgather_tables, and the
 merged table must equal the single-process table in global job order."""
 import os
@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 
 
 def test_job_plan_matches_reference_part_rule():
-    from longtail_b200.distributed import plan_jobs, shard_jobs
+    from dist_model import plan_jobs, shard_jobs
     part = 16 * 1024
     sizes = [0, 1, part - 1, part, part + 1, 3 * part, 5 * part + 7]
     jobs = plan_jobs(sizes, 16)
@@ -33,7 +33,7 @@ def _worker(rank, world, port, out_path):
     import torch.distributed as dist
 
     import oracle_lib as ol
-    from longtail_b200 import distributed as ltd
+    import dist_model as ltd
     from synth import chunker_params, synth_bytes
 
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
@@ -105,7 +105,7 @@ def _write_worker(rank, world, port, out_dir):
     import torch.distributed as dist
 
     import oracle_lib as ol
-    from longtail_b200 import distributed as ltd
+    import dist_model as ltd
     from synth import chunker_params, synth_bytes
 
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)

@@ -1,6 +1,6 @@
-"""-m gpu, needs >= 2 GPUs (skipped otherwise): CreateVersionIndex + WriteContent sharded over two GPUs
-(tests/tools_multi_gpu_write.py: NCCL allgather of the chunk tables, blocks sharded by owner, foreign chunks of straddling blocks
-moved point to point) — every StoredBlock byte-identical to the single-process CPU upsync."""
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): the multi-GPU verbs of the C ABI (lt_b200_index_sharded, lt_b200_write_blocks_sharded: NCCL
+all-gather of the chunk tables, dedup split by hash, global block plan, chunk exchange point to point) over two GPUs under torchrun —
+VersionIndex and every StoredBlock byte-identical to the single-process reference upsync (tests/tools_multi_gpu_upsync.py)."""
 import os
 import subprocess
 import sys
@@ -19,13 +19,13 @@ def _gpus():
         return 0
 
 
-@pytest.mark.parametrize("codec", ["lz4", "zstd"])
-def test_write_content_two_gpus(codec):
+@pytest.mark.parametrize("codec,extra", [("lz4", []), ("zstd", []), ("none", []), ("zstd", ["--single-file"])])
+def test_sharded_upsync_two_gpus(codec, extra):
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
     port = 29700 + os.getpid() % 200
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "tools_multi_gpu_write.py"), "--gib", "0.25", "--codec", codec, "--verify"]
+           os.path.join(ROOT, "tests", "tools_multi_gpu_upsync.py"), "--gib", "0.25", "--codec", codec] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "VERIFY OK" in r.stderr
