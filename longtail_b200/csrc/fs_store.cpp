@@ -256,7 +256,11 @@ int write_block_file(lt_b200_fs_store* s, uint64_t hash, const void* data, size_
     int err = mkdir_p(tmp_path.substr(0, tmp_path.find_last_of('/')));
     if (err) return err;
     err = write_all(tmp_path, data, size);
-    if (err) return err;
+    if (err)
+    {
+        unlink(tmp_path.c_str()); // a short write (disk full) must not leave the temporary file behind
+        return err;
+    }
     if (rename(tmp_path.c_str(), final_path.c_str()) != 0)
     {
         err = errno;
@@ -432,21 +436,31 @@ extern "C" int lt_b200_fs_store_flush(lt_b200_fs_store* s)
 {
     if (!s) return EINVAL;
     drain(s);
-    std::vector<BlockRec> added;
+    // The records leave s->added only once store.lsi holds them: taken out here, put back in front when anything below fails, so that a
+    // retried flush indexes them.  Records of blocks that have not reached the disk yet (a sink that ran after drain) stay for the next flush.
+    std::vector<BlockRec> added, later;
     {
         std::lock_guard<std::mutex> g(s->lock);
         if (s->first_error) return s->first_error;
-        // only blocks that reached the disk enter the index
         for (auto& r : s->added)
-            if (s->block_state.count(r.hash) && s->block_state[r.hash] == 1) added.push_back(r);
-        s->added.clear();
+        {
+            auto it = s->block_state.find(r.hash);
+            if (it != s->block_state.end() && it->second == 1) added.push_back(std::move(r)); // only blocks that reached the disk enter the index
+            else later.push_back(std::move(r));
+        }
+        s->added.swap(later);
     }
+    auto give_back = [&](int e) {
+        std::lock_guard<std::mutex> g(s->lock);
+        s->added.insert(s->added.begin(), std::make_move_iterator(added.begin()), std::make_move_iterator(added.end()));
+        return e;
+    };
     const std::string index_path = s->root + "/store.lsi";
     if (added.empty() && is_file(index_path)) return 0;
     const std::string lock_path = s->root + "/store.lsi.sync";
     const int lock_fd = open(lock_path.c_str(), O_RDWR | O_CREAT, 0666);
-    if (lock_fd < 0) return errno;
-    if (flock(lock_fd, LOCK_EX) != 0) { const int e = errno; close(lock_fd); return e; }
+    if (lock_fd < 0) return give_back(errno);
+    if (flock(lock_fd, LOCK_EX) != 0) { const int e = errno; close(lock_fd); return give_back(e); }
     int err = 0;
     Index add_ix, disk_ix, merged;
     add_ix.version = LT_B200_STORE_INDEX_VERSION;
@@ -474,7 +488,7 @@ extern "C" int lt_b200_fs_store_flush(lt_b200_fs_store* s)
     }
     flock(lock_fd, LOCK_UN);
     close(lock_fd);
-    return err;
+    return err ? give_back(err) : 0;
 }
 
 extern "C" int lt_b200_fs_store_existing_chunks(lt_b200_fs_store* s, uint64_t* out_hashes, uint32_t capacity, uint32_t* out_count)

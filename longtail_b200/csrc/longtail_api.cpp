@@ -7,6 +7,7 @@
 
 #include <dlfcn.h>
 #include <errno.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -57,6 +58,17 @@ int ensure_ctx()
 {
     if (g_ctx) return 0;
     return lt_b200_context_create(g_device, &g_ctx);
+}
+// The two batched verbs (Longtail_B200_CreateVersionIndex / Longtail_B200_WriteContent) call back into foreign code — the caller's
+// StorageAPI and JobAPI, the backing store's PutStoredBlock — while they own a context.  Those callbacks may use the B200 hash /
+// compression / chunker objects from any thread, so the verbs run on a context and a lock of their own: a callback that needs g_gpu
+// never waits for the verb that is waiting for it.
+std::mutex g_verb;
+lt_b200_context* g_verb_ctx = nullptr;
+int ensure_verb_ctx()
+{
+    if (g_verb_ctx) return 0;
+    return lt_b200_context_create(g_device, &g_verb_ctx);
 }
 int ensure_arena(uint64_t bytes)
 {
@@ -280,21 +292,27 @@ int hash_buffer(struct Longtail_HashAPI* api, uint32_t length, const void* data,
     if (!out || (!data && length)) return EINVAL;
     const uint32_t type = hash_type_of(api);
     const uint8_t* p = static_cast<const uint8_t*>(data);
+    // a range handed out by one of our chunkers: its hash was computed in the chunker's GPU pass.  The registry lock only covers the
+    // search for the owning chunker; the chunker itself is driven by this thread alone, so the lookup and a re-hash with
+    // another algorithm (an upload plus a launch) run without it and do not serialise the other hashing threads
+    B200Chunker* owner = nullptr;
     {
-        // a range handed out by one of our chunkers: its hash was computed in the chunker's GPU pass
         std::lock_guard<std::mutex> g(g_registry_lock);
         for (B200Chunker* c : g_live)
-        {
-            if (!c->buf || p < c->buf || p >= c->buf + c->size) continue;
-            const uint64_t off = (uint64_t)(p - c->buf);
-            auto it = std::lower_bound(c->chunks.begin(), c->chunks.end(), off, [](const ChunkRec& r, uint64_t o) { return r.offset < o; });
-            if (it != c->chunks.end() && it->offset == off && it->len == length)
+            if (c->buf && p >= c->buf && p < c->buf + c->size)
             {
-                if (c->hash_type != type && rehash_chunker(c, type)) break; // one thread drives one chunker
-                *out = it->hash;
-                return 0;
+                owner = c;
+                break;
             }
-            break;
+    }
+    if (owner)
+    {
+        const uint64_t off = (uint64_t)(p - owner->buf);
+        auto it = std::lower_bound(owner->chunks.begin(), owner->chunks.end(), off, [](const ChunkRec& r, uint64_t o) { return r.offset < o; });
+        if (it != owner->chunks.end() && it->offset == off && it->len == length && (owner->hash_type == type || rehash_chunker(owner, type) == 0))
+        {
+            *out = it->hash;
+            return 0;
         }
     }
     return hash_on_device(type, length, data, out);
@@ -320,7 +338,9 @@ uint64_t hash_end(struct Longtail_HashAPI* api, Longtail_HashAPI_HContext h)
 {
     HashStream* s = reinterpret_cast<HashStream*>(h);
     uint64_t out = 0;
-    hash_on_device(hash_type_of(api), (uint32_t)s->bytes.size(), s->bytes.data(), &out); // EndContext frees the context (lib/blake3/longtail_blake3.c:60-79)
+    // EndContext frees the context and has no error channel (lib/blake3/longtail_blake3.c:60-79): a device failure is at least reported
+    const int err = hash_on_device(hash_type_of(api), (uint32_t)s->bytes.size(), s->bytes.data(), &out);
+    if (err) fprintf(stderr, "longtail_b200: HashAPI.EndContext: device hash failed with %d, returning 0\n", err);
     delete s;
     return out;
 }
@@ -918,6 +938,8 @@ void put_wait_done(struct Longtail_AsyncPutStoredBlockAPI* api, int err)
     w->cv.notify_all();
 }
 
+bool is_b200_compress_store(const struct Longtail_BlockStoreAPI* api) { return api && api->PutStoredBlock == store_put; }
+
 struct WriteSink
 {
     struct Longtail_BlockStoreAPI* store;
@@ -925,6 +947,7 @@ struct WriteSink
     struct Longtail_CancelAPI* cancel;
     Longtail_CancelAPI_HCancelToken token;
     uint32_t total, done;
+    const TLongtail_Hash* expected_hashes; // the store index's block hashes, in block order
 };
 
 // lt_b200_block_sink: the byte image becomes a Longtail_StoredBlock whose index points into it (Longtail_InitStoredBlockFromData,
@@ -933,6 +956,8 @@ int write_content_sink(void* user, const struct lt_b200_stored_block_view* v)
 {
     WriteSink* ws = static_cast<WriteSink*>(user);
     if (ws->cancel && ws->cancel->IsCancelled(ws->cancel, ws->token) == ECANCELED) return ECANCELED;
+    // the block is stored under the hash of ITS chunk hashes; a store index that lists another hash for it does not describe these blocks
+    if (ws->expected_hashes && ws->done < ws->total && ws->expected_hashes[ws->done] != v->block_hash) return EINVAL;
     uint8_t* p = static_cast<uint8_t*>(const_cast<void*>(v->data));
     const uint32_t n = v->chunk_count;
     struct Longtail_BlockIndex bi;
@@ -971,6 +996,9 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
 {
     // same argument validation as src/longtail.c:4781-4786
     if (!source_storage_api || !backing_block_store_api || !job_api || !version_index || !store_index || !assets_folder) return EINVAL;
+    // this verb compresses the blocks itself (their tags say how): the store it writes to is the one BELOW the compress layer.  Chained onto
+    // the B200 compress store the payloads would be compressed twice — refuse that outright
+    if (is_b200_compress_store(backing_block_store_api)) return EINVAL;
     const uint32_t block_count = *store_index->m_BlockCount;
     if (block_count == 0) return 0; // :4788-4792
     const uint32_t hash_type = *version_index->m_HashIdentifier;
@@ -998,25 +1026,31 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
     std::vector<uint64_t> hashes(SC), offsets(SC);
     std::vector<uint32_t> sizes(SC), tags(SC), counts(block_count);
     std::vector<uint8_t> needed(A ? A : 1, 0);
+    // A block is addressed through m_BlockChunksOffsets like WriteContentBlockJob does (:4596-4604); the chunk arrays handed to the device
+    // verb are compacted into block order, so a store index whose offsets are not the running sum of the counts (a subset, a pruned or a
+    // malformed index) is either composed correctly or refused, never read out of bounds
+    uint32_t pos = 0;
     for (uint32_t b = 0; b < block_count; ++b)
     {
         counts[b] = store_index->m_BlockChunkCounts[b];
         if (counts[b] == 0) return EINVAL;
+        const uint32_t first = store_index->m_BlockChunksOffsets[b];
+        if (first > SC || counts[b] > SC - first || counts[b] > SC - pos) return EINVAL;
         const uint32_t tag = store_index->m_BlockTags[b];
         if (tag != 0 && tag != TYPE_LZ4 && !is_zstd_level3(tag)) return ENOTSUP;
-        for (uint32_t k = 0; k < counts[b]; ++k)
+        for (uint32_t k = 0; k < counts[b]; ++k, ++pos)
         {
-            const uint32_t c = store_index->m_BlockChunksOffsets[b] + k;
-            const uint64_t h = store_index->m_ChunkHashes[c];
+            const uint64_t h = store_index->m_ChunkHashes[first + k];
             auto vc = version_chunk.find(h);
             auto w = where.find(h);
             if (vc == version_chunk.end() || w == where.end()) return EINVAL;
-            hashes[c] = h;
-            sizes[c] = version_index->m_ChunkSizes[vc->second];
-            tags[c] = tag;
+            hashes[pos] = h;
+            sizes[pos] = version_index->m_ChunkSizes[vc->second];
+            tags[pos] = tag;
             needed[w->second.first] = 1;
         }
     }
+    const uint32_t written_chunks = pos;
     // arena layout: only the assets that hold a needed chunk
     std::vector<uint64_t> arena_off(A ? A : 1, 0);
     uint64_t total = 0;
@@ -1026,18 +1060,18 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
             arena_off[a] = total;
             total += (version_index->m_AssetSizes[a] + 255u) & ~(uint64_t)255u;
         }
-    for (uint32_t c = 0; c < SC; ++c)
+    for (uint32_t c = 0; c < written_chunks; ++c)
     {
         const auto& w = where[hashes[c]];
         offsets[c] = arena_off[w.first] + w.second;
     }
 
-    std::lock_guard<std::mutex> g(g_gpu);
-    int err = ensure_ctx();
+    std::lock_guard<std::mutex> g(g_verb);
+    int err = ensure_verb_ctx();
     if (err) return err;
     const uint64_t arena_bytes = total + 4096;
     void* arena = nullptr;
-    err = lt_b200_device_alloc(g_ctx, arena_bytes, &arena);
+    err = lt_b200_device_alloc(g_verb_ctx, arena_bytes, &arena);
     if (err) return err;
     // the reader of the index verb: StorageAPI reads fanned out over the caller's JobAPI, paths from the version index
     struct Longtail_FileInfos names;
@@ -1048,7 +1082,7 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
     ReadCtx rc = {source_storage_api, assets_folder, &names, job_api, nullptr, optional_cancel_api, optional_cancel_token, 0, 0};
     const uint64_t stage_bytes = 256ull << 20, piece = 8ull << 20;
     void* stage = nullptr;
-    err = lt_b200_host_alloc_pinned(g_ctx, stage_bytes, &stage);
+    err = lt_b200_host_alloc_pinned(g_verb_ctx, stage_bytes, &stage);
     std::vector<lt_b200_read_job> jobs;
     std::vector<uint64_t> dst_off;
     uint64_t used = 0;
@@ -1056,7 +1090,7 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
         if (jobs.empty()) return 0;
         int e = read_batch(&rc, jobs.data(), (uint32_t)jobs.size());
         for (size_t i = 0; i < jobs.size() && !e; ++i)
-            e = lt_b200_copy_to_device(g_ctx, static_cast<uint8_t*>(arena) + dst_off[i], jobs[i].dst, jobs[i].size);
+            e = lt_b200_copy_to_device(g_verb_ctx, static_cast<uint8_t*>(arena) + dst_off[i], jobs[i].dst, jobs[i].size);
         jobs.clear();
         dst_off.clear();
         used = 0;
@@ -1077,12 +1111,12 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
     if (!err) err = flush();
     if (!err)
     {
-        WriteSink ws = {backing_block_store_api, progress_api, optional_cancel_api, optional_cancel_token, block_count, 0};
-        err = lt_b200_write_given_blocks_device(g_ctx, static_cast<const uint8_t*>(arena), arena_bytes, SC, hashes.data(), sizes.data(), tags.data(),
+        WriteSink ws = {backing_block_store_api, progress_api, optional_cancel_api, optional_cancel_token, block_count, 0, store_index->m_BlockHashes};
+        err = lt_b200_write_given_blocks_device(g_verb_ctx, static_cast<const uint8_t*>(arena), arena_bytes, written_chunks, hashes.data(), sizes.data(), tags.data(),
                                                 offsets.data(), hash_type, block_count, counts.data(), write_content_sink, &ws);
     }
-    if (stage) lt_b200_host_free_pinned(g_ctx, stage);
-    lt_b200_device_free(g_ctx, arena);
+    if (stage) lt_b200_host_free_pinned(g_verb_ctx, stage);
+    lt_b200_device_free(g_verb_ctx, arena);
     return err;
 }
 
@@ -1147,7 +1181,8 @@ extern "C" struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockStoreA
 extern "C" int Longtail_B200_SetDevice(int device_ordinal)
 {
     std::lock_guard<std::mutex> g(g_gpu);
-    if (g_ctx) return EBUSY;
+    std::lock_guard<std::mutex> gv(g_verb);
+    if (g_ctx || g_verb_ctx) return EBUSY;
     g_device = device_ordinal;
     return 0;
 }
@@ -1218,12 +1253,12 @@ extern "C" int Longtail_B200_CreateVersionIndex(struct Longtail_StorageAPI* stor
     for (uint32_t i = 0; i < assets.asset_count; ++i)
         rc.total_jobs += (uint32_t)((assets.sizes[i] + part - 1) / part); // non-empty parts only
 
-    std::lock_guard<std::mutex> g(g_gpu);
-    err = ensure_ctx();
+    std::lock_guard<std::mutex> g(g_verb);
+    err = ensure_verb_ctx();
     if (err) return err;
     const void* data = nullptr;
     uint64_t size = 0;
-    err = lt_b200_index_stream_assets(g_ctx, &assets, optional_asset_tags, hash_type, target_chunk_size, read_batch, &rc, &data, &size);
+    err = lt_b200_index_stream_assets(g_verb_ctx, &assets, optional_asset_tags, hash_type, target_chunk_size, read_batch, &rc, &data, &size);
     if (err) return err;
     struct Longtail_VersionIndex* v = wrap_version_index(data, size);
     if (!v) return ENOMEM;

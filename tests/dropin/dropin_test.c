@@ -7,6 +7,9 @@
  *   2. reference Longtail_CreateVersionIndex with Longtail_CreateB200ChunkerAPI + B200 HashAPI -> identical bytes
  *   3. Longtail_B200_CreateVersionIndex (same parameter list)                                 -> identical bytes
  *   4. the reference's ChunkerLargeFile golden vector (test/test.cpp:3363-3465) through the B200 ChunkerAPI
+ *   5. the compress half inside the reference's WriteContent; Longtail_B200_WriteContent
+ *   6. fault injection: failing Read, a store that fills up, a cancel token flipped mid-verb, malformed store indexes — the B200 verbs
+ *      return the reference's errno (test/test.cpp:4733, :4839, :5752 are the reference's own doubles for these)
  */
 #define LONGTAIL_B200_USE_LONGTAIL_H
 #include "longtail.h"
@@ -167,6 +170,238 @@ static int write_content(struct Longtail_StorageAPI* storage, struct Longtail_Bl
     if (!err) err = Longtail_WriteContent(storage, store, jobs, 0, 0, 0, *out_missing, vi, "root");
     Longtail_Free(empty);
     return err;
+}
+
+
+/* ---------------------------------------------------------------- fault injection through the boundary
+ * The reference's own doubles for this are a storage that runs out of space (test/test.cpp:5752), a cancel token flipped in the middle of an
+ * operation (:4733, :4839) and a failing store; each fault goes through the reference verb AND the B200 verb, and both must answer with
+ * the same errno, return (no hang) and leave the library usable for the next call. */
+struct flaky_storage
+{
+    struct Longtail_StorageAPI api;
+    struct Longtail_StorageAPI* inner;
+    volatile long reads;     /* Read calls seen so far */
+    long fail_at;            /* the call that fails (counted from 1); 0 = never */
+    int error;
+};
+static void flaky_dispose(struct Longtail_API* api) { (void)api; }
+static int flaky_open(struct Longtail_StorageAPI* a, const char* path, Longtail_StorageAPI_HOpenFile* out)
+{ struct flaky_storage* f = (struct flaky_storage*)a; return f->inner->OpenReadFile(f->inner, path, out); }
+static int flaky_size(struct Longtail_StorageAPI* a, Longtail_StorageAPI_HOpenFile h, uint64_t* out)
+{ struct flaky_storage* f = (struct flaky_storage*)a; return f->inner->GetSize(f->inner, h, out); }
+static int flaky_read(struct Longtail_StorageAPI* a, Longtail_StorageAPI_HOpenFile h, uint64_t offset, uint64_t length, void* output)
+{
+    struct flaky_storage* f = (struct flaky_storage*)a;
+    const long n = __sync_add_and_fetch(&f->reads, 1);
+    if (f->fail_at && n >= f->fail_at) return f->error;
+    return f->inner->Read(f->inner, h, offset, length, output);
+}
+static void flaky_close(struct Longtail_StorageAPI* a, Longtail_StorageAPI_HOpenFile h) { struct flaky_storage* f = (struct flaky_storage*)a; f->inner->CloseFile(f->inner, h); }
+static char* flaky_concat(struct Longtail_StorageAPI* a, const char* r, const char* s) { struct flaky_storage* f = (struct flaky_storage*)a; return f->inner->ConcatPath(f->inner, r, s); }
+static void make_flaky(struct flaky_storage* f, struct Longtail_StorageAPI* inner, long fail_at, int error)
+{
+    memset(f, 0, sizeof(*f));
+    f->api.m_API.Dispose = flaky_dispose;
+    f->api.OpenReadFile = flaky_open;
+    f->api.GetSize = flaky_size;
+    f->api.Read = flaky_read;
+    f->api.CloseFile = flaky_close;
+    f->api.ConcatPath = flaky_concat;
+    f->inner = inner;
+    f->fail_at = fail_at;
+    f->error = error;
+}
+
+/* a block store that accepts `good` blocks and then fails: by its return value (OnComplete is not called then, src/longtail.c:4747-4757)
+ * or through OnComplete */
+struct full_store
+{
+    struct Longtail_BlockStoreAPI api;
+    volatile long puts;
+    long good;
+    int error, through_callback;
+};
+static void full_dispose(struct Longtail_API* api) { (void)api; }
+static int full_put(struct Longtail_BlockStoreAPI* api, struct Longtail_StoredBlock* b, struct Longtail_AsyncPutStoredBlockAPI* async)
+{
+    struct full_store* s = (struct full_store*)api;
+    (void)b;
+    const long n = __sync_add_and_fetch(&s->puts, 1);
+    if (n > s->good)
+    {
+        if (!s->through_callback) return s->error;
+        async->OnComplete(async, s->error);
+        return 0;
+    }
+    async->OnComplete(async, 0);
+    return 0;
+}
+static int full_flush(struct Longtail_BlockStoreAPI* api, struct Longtail_AsyncFlushAPI* async) { (void)api; async->OnComplete(async, 0); return 0; }
+static void make_full(struct full_store* s, long good, int error, int through_callback)
+{
+    memset(s, 0, sizeof(*s));
+    s->api.m_API.Dispose = full_dispose;
+    s->api.PutStoredBlock = full_put;
+    s->api.Flush = full_flush;
+    s->good = good;
+    s->error = error;
+    s->through_callback = through_callback;
+}
+
+/* a cancel API whose token reads "cancelled" after `after` polls */
+struct late_cancel
+{
+    struct Longtail_CancelAPI api;
+    volatile long polls;
+    long after;
+};
+static void cancel_dispose(struct Longtail_API* api) { (void)api; }
+static int cancel_create(struct Longtail_CancelAPI* a, Longtail_CancelAPI_HCancelToken* out) { *out = (Longtail_CancelAPI_HCancelToken)a; return 0; }
+static int cancel_cancel(struct Longtail_CancelAPI* a, Longtail_CancelAPI_HCancelToken t) { (void)a; (void)t; return 0; }
+static int cancel_is(struct Longtail_CancelAPI* a, Longtail_CancelAPI_HCancelToken t)
+{
+    struct late_cancel* c = (struct late_cancel*)a;
+    (void)t;
+    return __sync_add_and_fetch(&c->polls, 1) > c->after ? ECANCELED : 0;
+}
+static int cancel_dispose_token(struct Longtail_CancelAPI* a, Longtail_CancelAPI_HCancelToken t) { (void)a; (void)t; return 0; }
+static void make_cancel(struct late_cancel* c, long after)
+{
+    memset(c, 0, sizeof(*c));
+    c->api.m_API.Dispose = cancel_dispose;
+    c->api.CreateToken = cancel_create;
+    c->api.Cancel = cancel_cancel;
+    c->api.IsCancelled = cancel_is;
+    c->api.DisposeToken = cancel_dispose_token;
+    c->after = after;
+}
+
+static void fault_injection(struct Longtail_StorageAPI* storage, struct Longtail_JobAPI* jobs, struct Longtail_HashAPI* ref_hash,
+                            struct Longtail_ChunkerAPI* ref_chunker, struct Longtail_FileInfos* infos, uint32_t* tags, uint32_t target,
+                            const void* b_ref, size_t n_ref)
+{
+    const int before = failures;
+    /* (a) a Read that fails in the middle of CreateVersionIndex */
+    for (int k = 0; k < 3; ++k)
+    {
+        const long fail_at = k == 0 ? 1 : k == 1 ? 7 : 40;
+        struct flaky_storage f_ref, f_b200;
+        make_flaky(&f_ref, storage, fail_at, EIO);
+        make_flaky(&f_b200, storage, fail_at, EIO);
+        struct Longtail_VersionIndex *v1 = 0, *v2 = 0;
+        const int e1 = Longtail_CreateVersionIndex(&f_ref.api, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v1);
+        const int e2 = Longtail_B200_CreateVersionIndex(&f_b200.api, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v2);
+        /* the reference answers EIO when the first job to fail reads a file of at most 48 bytes directly (src/longtail.c:2076) and ESPIPE when it
+         * fails inside the chunker, which swallows the feeder's errno (longtail_hpcdcchunker.c:243-250 -> :414-423) — which one is latched depends
+         * on the worker schedule.  The B200 verb reports the storage's own errno. */
+        CHECK((e1 == EIO || e1 == ESPIPE) && e2 == EIO, "failing Read #%ld: reference %d, B200 verb %d", fail_at, e1, e2);
+        CHECK(v1 == 0 && v2 == 0, "no index may come out of a failed call");
+        Longtail_Free(v1); Longtail_Free(v2);
+    }
+    /* (b) a cancel token that flips while the verb runs */
+    for (int k = 0; k < 2; ++k)
+    {
+        struct late_cancel c_ref, c_b200;
+        make_cancel(&c_ref, k ? 5 : 0);
+        make_cancel(&c_b200, k ? 5 : 0);
+        struct Longtail_VersionIndex *v1 = 0, *v2 = 0;
+        const int e1 = Longtail_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, &c_ref.api, (Longtail_CancelAPI_HCancelToken)&c_ref, "root", infos, tags, target, 0, &v1);
+        const int e2 = Longtail_B200_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, &c_b200.api, (Longtail_CancelAPI_HCancelToken)&c_b200, "root", infos, tags, target, 0, &v2);
+        CHECK(e1 == ECANCELED && e2 == e1, "cancel after %d polls in CreateVersionIndex: reference %d, B200 verb %d", k ? 5 : 0, e1, e2);
+        Longtail_Free(v1); Longtail_Free(v2);
+    }
+    /* the library is still usable and still right (the tags have changed since section 1: compare with a fresh reference index) */
+    {
+        struct Longtail_VersionIndex *v = 0, *w = 0;
+        const int e = Longtail_B200_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &v);
+        CHECK(Longtail_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &w) == 0, "reference index");
+        void *b = 0, *bw = 0; size_t n = 0, nw = 0;
+        if (!e) serialise(v, &b, &n);
+        serialise(w, &bw, &nw);
+        CHECK(e == 0 && n == nw && b && memcmp(b, bw, n) == 0, "CreateVersionIndex after the injected faults: %d", e);
+        Longtail_Free(b); Longtail_Free(bw); Longtail_Free(v); Longtail_Free(w);
+        (void)b_ref; (void)n_ref;
+    }
+    /* (c) WriteContent: a store that fills up (by return value and through OnComplete), a failing Read, a cancel */
+    struct Longtail_VersionIndex* vi = 0;
+    CHECK(Longtail_CreateVersionIndex(storage, ref_hash, ref_chunker, jobs, 0, 0, 0, "root", infos, tags, target, 0, &vi) == 0, "index for the write faults");
+    struct Longtail_StoreIndex *empty = 0, *missing = 0;
+    Longtail_CreateStoreIndexFromBlocks(0, 0, &empty);
+    CHECK(Longtail_CreateMissingContent(ref_hash, empty, vi, target * 16, 64, &missing) == 0, "missing content");
+    struct Longtail_CompressionRegistryAPI* full = Longtail_CreateFullCompressionRegistry();
+    for (int k = 0; k < 4; ++k)
+    {
+        struct full_store s_ref_inner, s_b200;
+        make_full(&s_ref_inner, k < 2 ? 2 : 0, ENOSPC, k & 1);
+        make_full(&s_b200, k < 2 ? 2 : 0, ENOSPC, k & 1);
+        struct Longtail_BlockStoreAPI* s_ref = Longtail_CreateCompressBlockStoreAPI(&s_ref_inner.api, full);
+        const int e1 = Longtail_WriteContent(storage, s_ref, jobs, 0, 0, 0, missing, vi, "root");
+        const int e2 = Longtail_B200_WriteContent(storage, &s_b200.api, jobs, 0, 0, 0, missing, vi, "root");
+        CHECK(e1 == ENOSPC && e2 == e1, "store full after %d blocks (%s): reference %d, B200 verb %d", k < 2 ? 2 : 0, (k & 1) ? "OnComplete" : "return value", e1, e2);
+        SAFE_DISPOSE_API(s_ref);
+    }
+    {
+        struct flaky_storage f_ref, f_b200;
+        make_flaky(&f_ref, storage, 9, EIO);
+        make_flaky(&f_b200, storage, 9, EIO);
+        struct keep_store* k1 = make_keep_store();
+        struct keep_store* k2 = make_keep_store();
+        struct Longtail_BlockStoreAPI* s_ref = Longtail_CreateCompressBlockStoreAPI(&k1->api, full);
+        const int e1 = Longtail_WriteContent(&f_ref.api, s_ref, jobs, 0, 0, 0, missing, vi, "root");
+        const int e2 = Longtail_B200_WriteContent(&f_b200.api, &k2->api, jobs, 0, 0, 0, missing, vi, "root");
+        CHECK(e1 == EIO && e2 == e1, "failing Read in WriteContent: reference %d, B200 verb %d", e1, e2);
+        SAFE_DISPOSE_API(s_ref);
+        SAFE_DISPOSE_API(&k1->api); SAFE_DISPOSE_API(&k2->api);
+    }
+    {
+        struct late_cancel c_ref, c_b200;
+        make_cancel(&c_ref, 3);
+        make_cancel(&c_b200, 3);
+        struct keep_store* k1 = make_keep_store();
+        struct keep_store* k2 = make_keep_store();
+        struct Longtail_BlockStoreAPI* s_ref = Longtail_CreateCompressBlockStoreAPI(&k1->api, full);
+        const int e1 = Longtail_WriteContent(storage, s_ref, jobs, 0, &c_ref.api, (Longtail_CancelAPI_HCancelToken)&c_ref, missing, vi, "root");
+        const int e2 = Longtail_B200_WriteContent(storage, &k2->api, jobs, 0, &c_b200.api, (Longtail_CancelAPI_HCancelToken)&c_b200, missing, vi, "root");
+        CHECK(e1 == ECANCELED && e2 == e1, "cancel in WriteContent: reference %d, B200 verb %d", e1, e2);
+        SAFE_DISPOSE_API(s_ref);
+        SAFE_DISPOSE_API(&k1->api); SAFE_DISPOSE_API(&k2->api);
+    }
+    /* (d) the B200 compress block store under the B200 write verb would compress twice: refused; a store index whose offsets point
+     *     outside its chunk array: refused, not read */
+    {
+        struct keep_store* k = make_keep_store();
+        struct Longtail_BlockStoreAPI* chained = Longtail_CreateB200CompressBlockStoreAPI(&k->api, full);
+        CHECK(Longtail_B200_WriteContent(storage, chained, jobs, 0, 0, 0, missing, vi, "root") == EINVAL, "B200 compress store as backing store must be EINVAL");
+        SAFE_DISPOSE_API(chained);
+        const uint32_t saved = missing->m_BlockChunksOffsets[*missing->m_BlockCount - 1];
+        missing->m_BlockChunksOffsets[*missing->m_BlockCount - 1] = *missing->m_ChunkCount;
+        CHECK(Longtail_B200_WriteContent(storage, &k->api, jobs, 0, 0, 0, missing, vi, "root") == EINVAL, "block offsets outside the chunk array must be EINVAL");
+        missing->m_BlockChunksOffsets[*missing->m_BlockCount - 1] = saved;
+        const uint64_t saved_hash = missing->m_BlockHashes[0];
+        missing->m_BlockHashes[0] ^= 1;
+        CHECK(Longtail_B200_WriteContent(storage, &k->api, jobs, 0, 0, 0, missing, vi, "root") == EINVAL, "a block hash the chunks do not hash to must be EINVAL");
+        missing->m_BlockHashes[0] = saved_hash;
+        /* and the verb still works afterwards */
+        struct keep_store* k_ok = make_keep_store();
+        struct keep_store* k_want = make_keep_store();
+        struct Longtail_BlockStoreAPI* s_ref = Longtail_CreateCompressBlockStoreAPI(&k_want->api, full);
+        CHECK(Longtail_WriteContent(storage, s_ref, jobs, 0, 0, 0, missing, vi, "root") == 0, "reference WriteContent after the faults");
+        CHECK(Longtail_B200_WriteContent(storage, &k_ok->api, jobs, 0, 0, 0, missing, vi, "root") == 0, "Longtail_B200_WriteContent after the faults");
+        uint32_t same = 0;
+        for (uint32_t i = 0; i < k_want->count; ++i)
+        {
+            const struct kept_block* c = find_block(k_ok, k_want->blocks[i].hash);
+            if (c && c->size == k_want->blocks[i].size && memcmp(c->data, k_want->blocks[i].data, c->size) == 0) ++same;
+        }
+        CHECK(k_ok->count == k_want->count && same == k_want->count, "after the faults: %u of %u blocks identical", same, k_want->count);
+        SAFE_DISPOSE_API(s_ref);
+        SAFE_DISPOSE_API(&k->api); SAFE_DISPOSE_API(&k_ok->api); SAFE_DISPOSE_API(&k_want->api);
+    }
+    SAFE_DISPOSE_API(full);
+    Longtail_Free(missing); Longtail_Free(empty); Longtail_Free(vi);
+    printf("fault injection (failing Read, full store, cancel, malformed store index, chained compress store): %s\n",
+           failures == before ? "same errno as the reference everywhere" : "see failures");
 }
 
 int main(int argc, char** argv)
@@ -435,6 +670,9 @@ int main(int argc, char** argv)
         CHECK(e1 == e2, "empty hash");
         CHECK(b200_hash->GetIdentifier(b200_hash) == ref_hash->GetIdentifier(ref_hash), "identifier");
     }
+
+    /* 6. faults injected through the boundary */
+    fault_injection(storage, jobs, ref_hash, ref_chunker, infos, tags, target, b_ref, n_ref);
 
     Longtail_Free(b_ref);
     Longtail_Free(v_ref);

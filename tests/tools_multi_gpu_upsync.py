@@ -4,7 +4,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tests/tools_multi_gpu_upsync.py --gib 0.25 --codec lz4
 
-Every rank holds its own assets of ONE version (configs[2] generator: random / 4-bit / text-like segments, half of them from a pool all
+Every rank holds the bytes of its slice of the job list of ONE version (configs[2] generator: random / 4-bit / text-like segments, half of them from a pool all
 ranks share, so chunks deduplicate ACROSS ranks).  lt_b200_index_sharded (chunk + hash of the rank's jobs, NCCL all-gather of the tables,
 dedup split by hash) and lt_b200_write_blocks_sharded (global block plan, chunk exchange, per-rank WriteContent) run on all ranks; rank 0
 then runs the unmodified reference's single-process upsync over all ranks' bytes: the VersionIndex must be memcmp-identical and the
@@ -50,41 +50,29 @@ def main():
     tag = {"lz4": longtail_b200.COMPRESSION_LZ4, "zstd": longtail_b200.COMPRESSION_ZSTD_DEFAULT, "none": 0}[args.codec]
     part = TARGET * 1024
 
+    # every rank knows the whole version (names, sizes, generator ids) and fills the bytes of the jobs the plan hands it
     if args.single_file:
         per = max(part, int(args.gib * GIB) // part * part)
-        names, sizes = ["pak/data.pak"], [per * world]
-        arena_bytes = per + 4096
-        arena = ctx.device_alloc(arena_bytes)
-        ctx.synth_fill(arena, per, seed=3, asset_id=0, offset=rank * per, class_mode=2)
-        al = longtail_b200.AssetList(names, sizes)
-        first, n = ctx.plan_shards(al, TARGET, world)
-        jobs = ctx.shard_jobs(al, TARGET, int(first[rank]), int(first[rank + 1] - first[rank]))
-        job_offs = (jobs["offset"].astype(np.int64) - rank * per).astype(np.uint64)
-        mine = [ctx.to_host(arena, per)]
+        names, sizes, ids = ["pak/data.pak"], [per * world + 12345], [0]
+        spec = dict(seed=3, class_mode=2)
     else:
         count = 6
-        my_sizes = [int(args.gib * GIB / count) // 256 * 256 + 4096 * (rank + 1) + 77 * i for i in range(count)]  # ragged, different per rank
-        all_sizes = [int(args.gib * GIB / count) // 256 * 256 + 4096 * (r + 1) + 77 * i for r in range(world) for i in range(count)]
+        sizes = [int(args.gib * GIB / count) // 256 * 256 + 4096 * (r + 1) + 77 * i for r in range(world) for i in range(count)]  # ragged
         names = ["r%d/a%02d.bin" % (r, i) for r in range(world) for i in range(count)]
-        sizes = all_sizes
-        offs, off = [], 0
-        for s in my_sizes:
-            offs.append(off)
-            off += (s + 255) & ~255
-        arena_bytes = off + 4096
-        arena = ctx.device_alloc(arena_bytes)
-        pool = max(8, int(args.gib * 256))
-        for i, (o, s) in enumerate(zip(offs, my_sizes)):
-            ctx.synth_fill(arena + o, s, seed=2, asset_id=rank * count + i, class_mode=1, shared_permille=500, pool_segments=pool)
-        al = longtail_b200.AssetList(names, sizes)
-        first, n = ctx.plan_shards(al, TARGET, world)
-        jobs = ctx.shard_jobs(al, TARGET, int(first[rank]), int(first[rank + 1] - first[rank]))
-        local = jobs["asset_index"].astype(np.int64) - rank * count
-        # the byte-balanced plan may hand a rank jobs of a neighbour's assets: this tool keeps it simple and requires asset-aligned slices
-        if local.size and (local.min() < 0 or local.max() >= count):
-            raise SystemExit("rank %d: the shard plan crosses the asset ownership of this test; use equal per-rank sizes" % rank)
-        job_offs = np.asarray(offs, dtype=np.uint64)[local] + jobs["offset"]
-        mine = [ctx.to_host(arena + o, s) for o, s in zip(offs, my_sizes)]
+        ids = list(range(world * count))
+        spec = dict(seed=2, class_mode=1, shared_permille=500, pool_segments=max(8, int(args.gib * 256)))
+    al = longtail_b200.AssetList(names, sizes)
+    first, n = ctx.plan_shards(al, TARGET, world)
+    jobs = ctx.shard_jobs(al, TARGET, int(first[rank]), int(first[rank + 1] - first[rank]))
+    job_offs, off = [], 0
+    for j in jobs:
+        job_offs.append(off)
+        off += (int(j["size"]) + 255) & ~255
+    arena_bytes = off + 4096
+    arena = ctx.device_alloc(arena_bytes)
+    for j, o in zip(jobs, job_offs):
+        ctx.synth_fill(arena + o, int(j["size"]), asset_id=ids[int(j["asset_index"])], offset=int(j["offset"]), **spec)
+    job_offs = np.asarray(job_offs, dtype=np.uint64)
     ctx.synchronize()
 
     tags = [tag] * len(names)
@@ -101,20 +89,26 @@ def main():
     assert n_mine == len(blocks)
     if world > 1:
         gathered_blocks = [None] * world if rank == 0 else None
-        gathered_data = [None] * world if rank == 0 else None
         dist.gather_object(blocks, gathered_blocks, dst=0)
-        dist.gather_object(mine, gathered_data, dst=0)
         vs = [None] * world if rank == 0 else None
         dist.gather_object(bytes(v), vs, dst=0)
     else:
-        gathered_blocks, gathered_data, vs = [blocks], [mine], [bytes(v)]
+        gathered_blocks, vs = [blocks], [bytes(v)]
     if rank == 0:
         ref = ol.Reference()
         checker = ref if ref.available else ol.Oracle()
-        if args.single_file:
-            datas = [np.concatenate([d[0] for d in gathered_data])]
-        else:
-            datas = [d for r in gathered_data for d in r]
+        # the same bytes once more, made on the host by the same generator (include/lt_synth.h)
+        import subprocess
+        lib_path = os.path.join(ROOT, "oracle", "_ref", "libsynth_host.so")
+        if not os.path.exists(lib_path):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        lib = C.CDLL(lib_path)
+        hspec = longtail_b200.SynthSpec(spec["seed"], spec.get("shared_permille", 0), spec.get("pool_segments", 1), spec["class_mode"], 0)
+        datas = []
+        for sz, i in zip(sizes, ids):
+            buf = np.empty(sz, dtype=np.uint8)
+            lib.synth_fill_mt(C.byref(hspec), C.c_uint64(i), C.c_uint64(0), buf.ctypes.data_as(C.c_void_p), C.c_uint64(sz), C.c_uint32(8))
+            datas.append(buf)
         want_blocks, want_v = checker.upsync(list(zip(names, datas)), TARGET, tags=tags)
         assert all(x == want_v for x in vs), "VersionIndex differs from the %s (or between ranks)" % ("reference" if ref.available else "oracle")
         got = [b for r in gathered_blocks for b in r]
