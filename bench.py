@@ -479,6 +479,7 @@ def run_b200(args):
 
         ctx.device_free(arena)  # the verb brings its own arena
         arena = None
+        ctx.trim()              # ... and the workspace of the resident run (write batches, merged tables) is not needed next to it
         step_e2e()
         eacc[:] = 0
         e2e_steps = max(1, min(args.steps, 3))
@@ -499,6 +500,8 @@ def run_b200(args):
     if arena is not None:
         ctx.device_free(arena)
         arena = None
+
+    ctx.trim()
 
     # ================================================================== index_only: configs[1] (N = 1)
     index_only = None

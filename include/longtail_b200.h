@@ -49,6 +49,8 @@ LT_B200_EXPORT void lt_b200_context_destroy(lt_b200_context* context);
 LT_B200_EXPORT const char* lt_b200_last_error(const lt_b200_context* context);
 /* number of kernel launches issued by this context since creation (bench.py reports it as gpu_launches) */
 LT_B200_EXPORT uint64_t lt_b200_launch_count(const lt_b200_context* context);
+/* frees the context's grow-only device workspace (it comes back on demand); the resident chunk table of the last index call is dropped */
+LT_B200_EXPORT int lt_b200_trim(lt_b200_context* context);
 /* blocks until all work queued by this context is done */
 LT_B200_EXPORT int lt_b200_synchronize(lt_b200_context* context);
 /* the CUDA stream (cudaStream_t as void*) this context launches on — for CUDA-event timing by the caller */

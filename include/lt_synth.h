@@ -38,7 +38,7 @@ struct lt_synth_spec
     uint64_t seed;
     uint32_t shared_permille; /* 0..1000: chance that a 1 MiB segment comes from the shared pool */
     uint32_t pool_segments;   /* size of the shared pool in segments (>=1 when shared_permille>0) */
-    uint32_t class_mode;      /* 0: all uniform random; 1: random / 4-bit / text-like by segment */
+    uint32_t class_mode;      /* 0: all uniform random; 1: random / 4-bit / text-like by segment; 2: PAK-like; 16 + c: all of class c */
     uint32_t reserved;
 };
 
@@ -79,7 +79,7 @@ LT_SYNTH_FN void lt_synth_segment(const struct lt_synth_spec* s, uint64_t asset_
     }
     *out_key = key;
     *out_base = base;
-    *out_class = s->class_mode ? (uint32_t)((h >> 40) % 3u) : 0u;
+    *out_class = s->class_mode >= 16u ? (s->class_mode - 16u) % 3u : s->class_mode ? (uint32_t)((h >> 40) % 3u) : 0u; /* 16 + c: every segment of class c */
 }
 
 /* the 16 bytes of 16-byte block `block` (= byte offset / 16 inside the keyed stream) */

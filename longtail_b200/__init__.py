@@ -151,6 +151,7 @@ def load_library():
     lib.lt_b200_context_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.lt_b200_context_destroy.argtypes = [C.c_void_p]
     lib.lt_b200_synchronize.argtypes = [C.c_void_p]
+    lib.lt_b200_trim.argtypes = [C.c_void_p]
     lib.lt_b200_device_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lt_b200_device_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.lt_b200_host_alloc_pinned.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
@@ -335,6 +336,10 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.lt_b200_launch_count(self.handle))
+
+    def trim(self):
+        """free the grow-only device workspace (it comes back on demand)"""
+        self._check(self.lib.lt_b200_trim(self.handle), "trim")
 
     def synchronize(self):
         self._check(self.lib.lt_b200_synchronize(self.handle), "synchronize")

@@ -451,6 +451,26 @@ extern "C" int lt_b200_synchronize(lt_b200_context* c)
     return 0;
 }
 
+// frees the grow-only device workspace of the context (the buffers come back on demand): for callers that move on to a phase with a
+// different memory picture, e.g. from a resident-arena upsync to one that brings its own arena
+extern "C" int lt_b200_trim(lt_b200_context* c)
+{
+    if (!c) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    for (Buf& b : c->ws)
+    {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    c->table_chunks = 0;
+    c->unique_chunks = 0;
+    c->unique_offsets_valid = false;
+    return 0;
+}
+
 extern "C" int lt_b200_profile_enable(lt_b200_context* c, int on)
 {
     if (!c) return EINVAL;

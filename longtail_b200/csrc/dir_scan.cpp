@@ -402,6 +402,7 @@ extern "C" int lt_b200_upsync_host_assets(lt_b200_context* context, const lt_b20
     const uint64_t arena_bytes = total + 4096;
     void* arena = nullptr;
     int err = lt_b200_device_alloc(context, arena_bytes, &arena);
+    if (err == ENOMEM && lt_b200_trim(context) == 0) err = lt_b200_device_alloc(context, arena_bytes, &arena); // workspace of earlier verbs in the way
     if (err) return err; // ENOMEM: shard the asset list across GPUs (lt_b200_index_sharded)
     for (uint32_t i = 0; i < n && !err; ++i)
         if (assets->sizes[i])

@@ -421,17 +421,18 @@ __device__ __forceinline__ void emit_runs(uint8_t* __restrict__ dst, uint32_t op
     }
     else if (lit)
     {
-        // fewer than 256 bytes: at most 8 per lane, all loads in flight before the first store
-        const uint8_t* s = src + from + lane;
-        uint8_t* d = dst + op + lane;
-        const uint32_t rounds = (lit + 31u) >> 5;
-        uint8_t v[8];
-#pragma unroll
-        for (uint32_t i = 0; i < 8; ++i)
-            if (i < rounds && lane + 32u * i < lit) v[i] = s[32u * i];
-#pragma unroll
-        for (uint32_t i = 0; i < 8; ++i)
-            if (i < rounds && lane + 32u * i < lit) d[32u * i] = v[i];
+        // fewer than 256 bytes: two bytes per lane and round, both loads in flight before the stores
+        const uint8_t* s = src + from;
+        uint8_t* d = dst + op;
+        for (uint32_t i = lane; i < lit; i += 64)
+        {
+            const bool two = i + 32u < lit;
+            const uint8_t a = s[i];
+            uint8_t b = 0;
+            if (two) b = s[i + 32u];
+            d[i] = a;
+            if (two) d[i + 32u] = b;
+        }
     }
 }
 
@@ -455,12 +456,6 @@ __device__ __forceinline__ Raw load_raw(const uint8_t* __restrict__ s, uint32_t 
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// The probes of a search that starts at S (lz4.c:1023-1053), in batches of 32: batch k0 (a multiple of 32) holds probes k0 .. k0+31.
-// Every probe of the batch advances by step = (k0 >> 6) + 1, except the first one of a batch with k0 = 64, 128, ... which advances by
-// one less.  So with pf = the position of the batch's first probe, lane l probes pf + l * step - (l && short_first).
-__device__ __forceinline__ uint32_t batch_step(uint32_t k0) { return (k0 >> 6) + 1u; }
-__device__ __forceinline__ uint32_t batch_short_first(uint32_t k0) { return (k0 & 63u) == 0u && k0 != 0u ? 1u : 0u; }
-
 __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t n, uint8_t* __restrict__ dst, uint32_t* table, const uint32_t lane,
                                  CopyJobs& cj)
 {
@@ -481,34 +476,54 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
     Raw rawA = load_raw(src, pA, n);
     for (;;)
     {
-        // ---------------- search (lz4.c:1043-1100): 32 probes per batch, the source words two batches ahead in flight
+        // ---------------- search (lz4.c:1043-1100): 32 probes per batch — lane l takes probe k0 + l of the search that started at S — with
+        // the source words two batches ahead in flight.  The first 65 probes of a search advance by one byte (`lean`): a batch is 32
+        // consecutive positions from `base`, no closed forms needed; most searches of compressible data end there.
         uint32_t k0 = 0;
-        uint32_t pf = S;        // first position of batch k0
-        uint32_t pfC = S + 64u; // first position of batch k0 + 64
+        uint32_t base = S; // lean: position of lane 0's probe
+        bool lean = true;
         uint32_t pB = S + 32u + lane;
         Raw rawB = load_raw(src, pB, n);
         uint32_t ip0 = 0, m0 = 0, fx = 0;
         bool beq = false;
         for (;;)
         {
+            if (lean && k0 + 31u > 64u) // the batch leaves the step-1 stretch: the words in flight are not its positions
+            {
+                lean = false;
+                pA = probe_pos(S, k0 + lane);
+                rawA = load_raw(src, pA, n);
+                pB = probe_pos(S, k0 + 32u + lane);
+                rawB = load_raw(src, pB, n);
+            }
             const uint32_t p = pA;
             const uint32_t sh = (p & 3u) * 8u;
             const uint32_t lo = __funnelshift_r(rawA.a, rawA.b, sh);
             const uint32_t hi = __funnelshift_r(rawA.b, rawA.c, sh);
             pA = pB;
             rawA = rawB;
+            uint32_t pf, p_last, adv_last;
+            if (lean)
             {
-                const uint32_t kc = k0 + 64u, stepC = batch_step(kc), sfC = (kc & 63u) == 0u ? 1u : 0u;
-                pB = pfC + lane * stepC - (lane ? sfC : 0u);
+                pB = pA + 32u; // (re-derived when the search outlives the stretch)
                 rawB = load_raw(src, pB, n);
-                const uint32_t far = pB + 2048u + 256u * stepC; // the stream some ten batches ahead: HBM -> L2
-                if (far < n) prefetch_l2(src + far);
-                pfC += 32u * stepC - sfC;
+                if (lane == 0 && base + 4096u < n) prefetch_l2(src + base + 4096u); // the stream ahead: HBM -> L2
+                pf = base;
+                p_last = base + 31u;
+                adv_last = 1u;
             }
-            const uint32_t step = batch_step(k0), sf = batch_short_first(k0);
-            const uint32_t span = 32u * step - sf; // = the next batch's first position - pf
-            if (pf + span - step >= sweep_base + SWEEP_TRIGGER) sweep_base = sweep_to(table, sweep_base, pf, pf, lane);
-            const bool all_valid = pf + span <= mflimit_plus_one; // else: goto _last_literals inside this batch
+            else
+            {
+                pB = probe_pos(S, k0 + 64u + lane);
+                rawB = load_raw(src, pB, n);
+                const uint32_t far = pB + 2048u + 8u * (pB - pA);
+                if (far < n) prefetch_l2(src + far);
+                pf = probe_pos(S, k0);
+                p_last = probe_pos(S, k0 + 31u);
+                adv_last = probe_advance(k0 + 31u);
+            }
+            if (p_last >= sweep_base + SWEEP_TRIGGER) sweep_base = sweep_to(table, sweep_base, pf, pf, lane);
+            const bool all_valid = p_last + adv_last <= mflimit_plus_one; // else: goto _last_literals inside this batch
             const uint32_t h = hash5((uint64_t)lo | ((uint64_t)hi << 32));
             const uint32_t mine = entry_of(p, lo);
             uint32_t e = 0, r = 0;
@@ -524,15 +539,102 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
                 if (!__any_sync(FULL, pot || r != mine))
                 {
                     k0 += 32;
-                    pf += span;
+                    base += 32;
                     continue;
                 }
             }
             else
             {
-                valid = p < n && p + (lane == 0 && sf ? step - 1u : step) <= mflimit_plus_one;
+                valid = p < n && p + probe_advance(k0 + lane) <= mflimit_plus_one;
                 if (valid) e = table[h];
                 __syncwarp();
+            }
+            // ---- short matches resolved inside the batch.  In a step-1 batch (the first 64 probes of a search: lane l probes pf + l) whose
+            // 32 hashes are distinct, every lane's table entry `e` is exact whatever happens to the other lanes — no lane of the batch
+            // touches its slot.  So all tag matches of the batch can be verified in ONE round trip (each lane compares the 8 bytes at its
+            // candidate with its own), and a match of 4..7 bytes that ends inside the batch is followed by exactly what the batch already
+            // did: the insertion of ip-2 and the probe of ip (lz4.c:1236-1294) are the eager writes / entries of lanes f+L-2 and f+L, and
+            // the next search (step 1 again) continues with lane f+L+1.  The warp therefore walks the verified matches in order, emits
+            // their sequences, takes back the writes of the positions the matches skip, and goes on with the next batch as probes
+            // 32 - c0 .. of the search that started at lane c0 — no per-match round trip, no general path, no restart.  Anything else (a
+            // longer match, a match that extends backwards, one that ends beyond the batch) is handed to the general path at that lane.
+            if (all_valid && lean && pf + 48u <= matchlimit && __ballot_sync(FULL, r != mine) == 0u) // step 1: lane l probes pf + l
+            {
+                const uint32_t age = (p - e) & POS_MASK;
+                const uint32_t cand0 = p - age;
+                const bool pot0 = ((e ^ mine) & HI_MASK) == 0u && age <= LZ4_MAX_DISTANCE;
+                uint32_t mlen = 0;
+                bool backs = false;
+                if (pot0)
+                {
+                    const uint64_t cw = rd64(src, cand0);
+                    const uint32_t x_lo = lo ^ (uint32_t)cw, x_hi = hi ^ (uint32_t)(cw >> 32);
+                    if (x_lo == 0u) mlen = 4u + (x_hi ? (uint32_t)(__ffs(x_hi) - 1) >> 3 : 4u); // 8 = all eight bytes equal: longer than this path takes
+                    backs = cand0 > 0u && src[p - 1u] == src[cand0 - 1u];
+                }
+                const uint32_t V = __ballot_sync(FULL, mlen != 0u);
+                if (V == 0u) // tag matches by chance only: the batch stands as it is
+                {
+                    k0 += 32;
+                    base += 32;
+                    continue;
+                }
+                const uint32_t LONGM = __ballot_sync(FULL, mlen == 8u), BACKM = __ballot_sync(FULL, backs);
+                uint32_t cancel = 0, cur = 0, handoff = 32, prev_end = 0xffffffffu;
+                for (;;)
+                {
+                    const uint32_t m = cur < 32u ? V & ~((1u << cur) - 1u) : 0u;
+                    if (!m) break;
+                    const uint32_t f = (uint32_t)__ffs(m) - 1u;
+                    const uint32_t L = __shfl_sync(FULL, mlen, f);
+                    const bool chained = f == prev_end; // the post-match test of the previous match hit: no literals, no catch-up (lz4.c:1262-1294)
+                    if (((LONGM >> f) & 1u) || (((BACKM >> f) & 1u) && !chained) || f + L > 31u)
+                    {
+                        handoff = f;
+                        break;
+                    }
+                    const uint32_t pfm = pf + f, mf = __shfl_sync(FULL, cand0, f);
+                    const uint32_t lit = pfm - anchor;
+                    const uint32_t token_pos = op++;
+                    if (lit >= 15) op = put_length(dst, op, lit - 15, lane);
+                    emit_runs(dst, op, src, anchor, lit, lane, cj);
+                    op += lit;
+                    if (lane == 0)
+                    {
+                        const uint32_t off = pfm - mf;
+                        dst[op] = (uint8_t)off;
+                        dst[op + 1] = (uint8_t)(off >> 8);
+                        dst[token_pos] = (uint8_t)((lit >= 15 ? 15u : lit) << 4 | (L - 4u));
+                    }
+                    op += 2;
+                    anchor = pfm + L;
+                    // positions f+1 .. f+L-1 are inside the match: only ip-2 = f+L-2 is inserted
+                    cancel |= (((1u << L) - 1u) << f) & ~(1u << f) & ~(1u << (f + L - 2u));
+                    cur = prev_end = f + L;
+                }
+                if (handoff == 32u)
+                {
+                    // every match of the batch is out.  The next search started at lane c0 = prev_end + 1 and lanes c0 .. 31 were its first
+                    // 32 - c0 probes (none of them hit): it simply goes on with the next batch, whose positions — consecutive as before —
+                    // are the ones already in flight
+                    if ((cancel >> lane) & 1u) table[h] = e;
+                    __syncwarp();
+                    const uint32_t c0 = prev_end + 1u;
+                    S = pf + c0;
+                    k0 = 32u - c0;
+                    base = pf + 32u;
+                    continue;
+                }
+                // hand the match at lane `handoff` to the general sequence code: the table as the sequential loop leaves it there
+                {
+                    const uint32_t undo = cancel | (handoff < 31u ? ~((2u << handoff) - 1u) : 0u);
+                    if ((undo >> lane) & 1u) table[h] = e;
+                    __syncwarp();
+                    ip0 = pf + handoff;
+                    m0 = __shfl_sync(FULL, cand0, handoff);
+                    load_match_words(src, ip0, m0, anchor, matchlimit, lane, fx, beq);
+                    break;
+                }
             }
             // ---- general path.  A lane's candidate is the closest lower lane of this batch with the same hash, else the table entry
             // it read before the batch wrote anything.  `same` = the lanes with this lane's hash: found from the eager writes (a lane
@@ -553,13 +655,17 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
                 same = __match_any_sync(FULL, valid ? h : 0x10000u + lane);
             const uint32_t lower = same & lt_mask;
             const int from = lower ? 31 - __clz(lower) : (int)lane;
-            uint32_t lo_from = lo;
-            if (__any_sync(FULL, lower != 0u)) lo_from = __shfl_sync(FULL, lo, from);
+            uint32_t lo_from = lo, p_from = p;
+            if (__any_sync(FULL, lower != 0u))
+            {
+                lo_from = __shfl_sync(FULL, lo, from);
+                p_from = __shfl_sync(FULL, p, from);
+            }
             uint32_t cand;
             bool pot;
             if (lower)
             {
-                cand = pf + from * step - (from ? sf : 0u);
+                cand = p_from;
                 pot = valid && lo_from == lo && p - cand <= LZ4_MAX_DISTANCE;
             }
             else
@@ -574,7 +680,7 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
             while (pots) // the first candidate that really starts with the same 4 bytes (lane 0 of fx compares them)
             {
                 const uint32_t f = (uint32_t)__ffs(pots) - 1u;
-                ip0 = pf + f * step - (f ? sf : 0u);
+                ip0 = __shfl_sync(FULL, p, f);
                 m0 = __shfl_sync(FULL, cand, f);
                 load_match_words(src, ip0, m0, anchor, matchlimit, lane, fx, beq);
                 if ((__ballot_sync(FULL, fx != 0u) & 1u) == 0u)
@@ -605,7 +711,7 @@ __device__ uint32_t encode_block(const uint8_t* __restrict__ src, const uint32_t
                 break;
             }
             k0 += 32;
-            pf += span;
+            base += 32;
         }
         if (finished) break;
 
