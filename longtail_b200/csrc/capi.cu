@@ -36,7 +36,7 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
-    WS_LZ4_TABLES, WS_LZ4_V2, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_CHUNK_SIZES, WS_UFIRST, WS_G_COUNTS, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND, WS_X_RECV, WS_X_TAB, WS_PACK_A, WS_PACK_B, WS_PACK_C, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
+    WS_LZ4_TABLES, WS_LZ4_V2, WS_LZ4_TABLES_B, WS_LZ4_V2_B, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_CHUNK_SIZES, WS_UFIRST, WS_G_COUNTS, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND, WS_X_RECV, WS_X_TAB, WS_PACK_A, WS_PACK_B, WS_PACK_C, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
     WS_COUNT
 };
 
@@ -59,7 +59,7 @@ struct lt_b200_context
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t aux_stream = nullptr; // second compute stream (the global-table LZ4 warps run next to the shared-memory ones)
+    cudaStream_t aux_stream = nullptr; // second compute stream: WriteContent keeps two batches of stored blocks in flight
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaEvent_t compute_done[2] = {nullptr, nullptr};
@@ -189,7 +189,7 @@ int ws_reserve(lt_b200_context* c, int slot, size_t bytes)
     if (b.cap >= bytes && b.p) return 0;
     if (b.p)
     {
-        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaDeviceSynchronize()); // kernels of either compute stream may still use the old buffer
         CU(cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -244,15 +244,16 @@ struct ProfScope
     lt_b200_context* c;
     size_t idx;
     bool on;
-    ProfScope(lt_b200_context* ctx, int id, uint64_t bytes) : c(ctx), idx(0), on(ctx->prof_on)
+    cudaStream_t st;
+    ProfScope(lt_b200_context* ctx, int id, uint64_t bytes, cudaStream_t stream = nullptr) : c(ctx), idx(0), on(ctx->prof_on), st(stream ? stream : ctx->stream)
     {
         if (!on) return;
         lt_b200_context::Span s = {prof_event(c), prof_event(c), id, bytes};
-        cudaEventRecord(s.a, c->stream);
+        cudaEventRecord(s.a, st);
         idx = c->spans.size();
         c->spans.push_back(s);
     }
-    ~ProfScope() { if (on) cudaEventRecord(c->spans[idx].b, c->stream); }
+    ~ProfScope() { if (on) cudaEventRecord(c->spans[idx].b, st); }
 };
 
 void prof_collect(lt_b200_context* c)
@@ -1375,8 +1376,9 @@ namespace {
 // event that marks its kernels done.  With room for two of them the device -> host copies of batch k overlap the kernels of k + 1.
 struct WriteSlot
 {
-    int ws_raw, ws_out, ws_tab, ws_jobs, hs_tab, hs_len;
+    int ws_raw, ws_out, ws_tab, ws_jobs, hs_tab, hs_len, ws_lz4_queue, ws_lz4_tables;
     cudaEvent_t done;
+    cudaStream_t st; // every slot launches on its own stream: the codec kernel of batch k + 1 fills the warp slots batch k's slowest blocks leave idle
     // filled by launch
     uint32_t b0 = 0, nb = 0, n_lz = 0, n_zs = 0;
     std::vector<uint64_t> img_off;  // offset of each block's serialised image (block index + payload) in the out buffer
@@ -1488,18 +1490,25 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     // what the grow-only workspace already holds for these buffers counts as available
     const uint64_t held = c->ws[WS_BLK_RAW].cap + c->ws[WS_BLK_OUT].cap + c->ws[WS_BLK_JOBS].cap + c->ws[WS_BLK_RAW_B].cap + c->ws[WS_BLK_OUT_B].cap +
                           c->ws[WS_BLK_JOBS_B].cap;
-    uint64_t avail = (uint64_t)((free_b + held) * 0.92);
+    uint64_t avail = (uint64_t)((free_b + held) * 0.85); // the rest: launch tables, v1 hash tables, allocator granularity
     // the codec kernels want a batch to fill every resident warp (13 x 148 LZ4 blocks); two batches in flight only when both can be that large
-    const uint64_t full_batch = std::min<uint64_t>(need_all, (uint64_t)13 * c->sm_count * need_max);
-    const bool host_sink_pipeline = !device_sink && avail >= 2 * full_batch + (64ull << 20) && need_all > full_batch;
-    const uint32_t nslots = host_sink_pipeline ? 2u : 1u;
+    // One batch when everything fits (the codec's work queue then balances all blocks over the resident warps).  Otherwise two batches in
+    // flight on two streams: a codec launch ends on its slowest block — stored blocks differ 2x in parse time with their content — and the
+    // next batch's kernels take the warp slots that fall idle meanwhile; with a host sink the device -> host copies of batch k also overlap
+    // the kernels of k + 1.  ZStd batches keep one stream (its launcher owns shared worker slabs).
+    bool any_zstd = false;
+    for (const Block& bl : blocks) any_zstd = any_zstd || is_zstd_level3(bl.tag);
+    const uint32_t nslots = need_all + (64ull << 20) > avail && !any_zstd ? 2u : 1u;
     uint64_t budget = avail / nslots;
     if (budget > (64ull << 30)) budget = 64ull << 30;
     if (budget < need_max + (1ull << 20)) budget = need_max + (1ull << 20);
 
-    WriteSlot slots[2] = {{WS_BLK_RAW, WS_BLK_OUT, WS_BLK_TAB, WS_BLK_JOBS, HS_BLK_TAB, HS_BLK_OUT_LEN, c->copy_done[0]},
-                          {WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_TAB_B, WS_BLK_JOBS_B, HS_BLK_TAB_B, HS_BLK_OUT_LEN_B, c->copy_done[1]}};
-    TRY(ws_reserve(c, WS_LZ4_V2, lz4_v2_scratch_bytes()));
+    WriteSlot slots[2] = {{WS_BLK_RAW, WS_BLK_OUT, WS_BLK_TAB, WS_BLK_JOBS, HS_BLK_TAB, HS_BLK_OUT_LEN, WS_LZ4_V2, WS_LZ4_TABLES, c->copy_done[0], c->stream},
+                          {WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_TAB_B, WS_BLK_JOBS_B, HS_BLK_TAB_B, HS_BLK_OUT_LEN_B, WS_LZ4_V2_B, WS_LZ4_TABLES_B, c->copy_done[1],
+                           c->aux_stream}};
+    // the second stream starts behind the block hashes / chunk tables uploaded above
+    CU(cudaEventRecord(c->aux_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
 
     // launch the kernels of blocks [b0, b1) into slot s
     auto launch = [&](WriteSlot& s, uint32_t b0, uint32_t b1) -> int {
@@ -1566,21 +1575,22 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
             h_lro[q] = raw_off[i]; h_loo[q] = pay_off[i]; h_lrl[q] = blocks[b0 + i].raw; h_ljs[q] = job_at;
             job_at += lz4_copy_job_capacity(blocks[b0 + i].raw);
         }
-        CU(cudaMemcpyAsync(d64, h64, 8 * n64 + 4 * (n32 - 2 * (size_t)s.n_lz), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d64, h64, 8 * n64 + 4 * (n32 - 2 * (size_t)s.n_lz), cudaMemcpyHostToDevice, s.st));
         {
-            ProfScope ps(c, LT_B200_KERNEL_GATHER, raw_bytes);
-            launch_gather_chunks(d_arena, d64, d64 + nc, d32, nullptr, nc, c->stream);
+            ProfScope ps(c, LT_B200_KERNEL_GATHER, raw_bytes, s.st);
+            launch_gather_chunks(d_arena, d64, d64 + nc, d32, nullptr, nc, s.st);
         }
         uint32_t* d_lz_out_len = d32 + nc + 3 * (size_t)nb + 2 * (size_t)s.n_lz;
         if (s.n_lz)
         {
             uint64_t lz_bytes = 0;
             for (uint32_t q = 0; q < s.n_lz; ++q) lz_bytes += h_lrl[q];
-            TRY(ws_reserve(c, WS_LZ4_TABLES, LZ4_TABLE_BYTES_PER_BLOCK * (size_t)s.n_lz));
-            ProfScope ps(c, LT_B200_KERNEL_LZ4, lz_bytes);
+            TRY(ws_reserve(c, s.ws_lz4_tables, LZ4_TABLE_BYTES_PER_BLOCK * (size_t)s.n_lz));
+            TRY(ws_reserve(c, s.ws_lz4_queue, lz4_v2_scratch_bytes()));
+            ProfScope ps(c, LT_B200_KERNEL_LZ4, lz_bytes, s.st);
             CU(launch_lz4_blocks(d_raw, d64 + 2 * (size_t)nc + nb, d32 + nc + 3 * (size_t)nb, d_out, d64 + 2 * (size_t)nc + nb + s.n_lz, d_lz_out_len,
                                  ws<uint3>(c, s.ws_jobs), d32 + nc + 3 * (size_t)nb + s.n_lz, d_lz_out_len + s.n_lz, s.n_lz,
-                                 ws<uint32_t>(c, WS_LZ4_TABLES), ws<void>(c, WS_LZ4_V2), c->sm_count, c->stream));
+                                 ws<uint32_t>(c, s.ws_lz4_tables), ws<void>(c, s.ws_lz4_queue), c->sm_count, s.st));
         }
         if (s.n_zs) // ZStd level 3 over the 'ztd1' / 'ztd2' blocks of the batch: one frame per block
         {
@@ -1596,13 +1606,13 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
             TRY(zstd_launch(c, d_raw, zro, zrl, d_out, zoo, zs_bytes));
         }
         launch_block_headers(d_out, d64 + 2 * (size_t)nc, d32 + nc, d32 + nc + nb, d32 + nc + 2 * (size_t)nb, ws<uint64_t>(c, WS_BLK_HASH_OUT) + b0,
-                             ws<uint64_t>(c, WS_BLK_HASHES), ws<uint32_t>(c, WS_BLK_CHUNK_SIZES), hash_type, nb, c->stream);
+                             ws<uint64_t>(c, WS_BLK_HASHES), ws<uint32_t>(c, WS_BLK_CHUNK_SIZES), hash_type, nb, s.st);
         c->launches += 5;
         TRY(hs_reserve(c, s.hs_len, sizeof(uint32_t) * 2 * (size_t)nb + 16));
         uint32_t* h_out_len = hs<uint32_t>(c, s.hs_len);
-        if (s.n_lz) CU(cudaMemcpyAsync(h_out_len, d_lz_out_len, sizeof(uint32_t) * s.n_lz, cudaMemcpyDeviceToHost, c->stream));
-        if (s.n_zs) CU(cudaMemcpyAsync(h_out_len + nb, ws<void>(c, WS_ZSTD_OUT_LEN), sizeof(uint32_t) * s.n_zs, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaEventRecord(s.done, c->stream));
+        if (s.n_lz) CU(cudaMemcpyAsync(h_out_len, d_lz_out_len, sizeof(uint32_t) * s.n_lz, cudaMemcpyDeviceToHost, s.st));
+        if (s.n_zs) CU(cudaMemcpyAsync(h_out_len + nb, ws<void>(c, WS_ZSTD_OUT_LEN), sizeof(uint32_t) * s.n_zs, cudaMemcpyDeviceToHost, s.st));
+        CU(cudaEventRecord(s.done, s.st));
         s.busy = true;
         return 0;
     };
@@ -1695,21 +1705,51 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
         return 0;
     };
 
-    int rc = 0;
-    uint32_t batch = 0;
-    WriteSlot* prev = nullptr;
-    for (uint32_t b0 = 0; b0 < nblocks && !rc; ++batch)
+    // the batches, and every slot's buffers at the size of the largest one up front: a buffer that had to grow in the middle would stall
+    // both streams
+    std::vector<uint32_t> batch_end;
     {
-        uint64_t used = 0;
-        uint32_t b1 = b0;
-        while (b1 < nblocks)
+        uint64_t max_raw = 0, max_out = 0, max_jobs = 0, max_tab = 0, max_lz = 0;
+        for (uint32_t b0 = 0; b0 < nblocks;)
         {
-            uint64_t r, o, j;
-            block_need(blocks[b1], &r, &o, &j);
-            if (b1 > b0 && used + r + o + j > budget) break;
-            used += r + o + j;
-            ++b1;
+            uint64_t used = 0, raw = 0, out = 0, jobs = 0, nc = 0, nlz = 0;
+            uint32_t b1 = b0;
+            while (b1 < nblocks)
+            {
+                uint64_t r, o, j;
+                block_need(blocks[b1], &r, &o, &j);
+                if (b1 > b0 && used + r + o + j > budget) break;
+                used += r + o + j;
+                raw += r; out += o; jobs += j; nc += blocks[b1].count;
+                nlz += blocks[b1].tag == LT_B200_COMPRESSION_LZ4;
+                ++b1;
+            }
+            const uint64_t nb = b1 - b0;
+            max_raw = std::max(max_raw, raw); max_out = std::max(max_out, out); max_jobs = std::max(max_jobs, jobs); max_lz = std::max(max_lz, nlz);
+            max_tab = std::max(max_tab, 8 * (2 * nc + nb + 2 * nlz) + 4 * (nc + 3 * nb + 4 * nlz) + 64);
+            batch_end.push_back(b1);
+            b0 = b1;
         }
+        const uint32_t use = std::min<uint32_t>(nslots, (uint32_t)batch_end.size());
+        for (uint32_t k = 0; k < use; ++k)
+        {
+            TRY(ws_reserve(c, slots[k].ws_raw, max_raw + (128u << 10)));
+            TRY(ws_reserve(c, slots[k].ws_out, max_out + 64));
+            TRY(ws_reserve(c, slots[k].ws_jobs, max_jobs + sizeof(uint3)));
+            TRY(ws_reserve(c, slots[k].ws_tab, max_tab));
+            TRY(hs_reserve(c, slots[k].hs_tab, max_tab));
+            if (max_lz)
+            {
+                TRY(ws_reserve(c, slots[k].ws_lz4_tables, LZ4_TABLE_BYTES_PER_BLOCK * (size_t)max_lz));
+                TRY(ws_reserve(c, slots[k].ws_lz4_queue, lz4_v2_scratch_bytes()));
+            }
+        }
+    }
+    int rc = 0;
+    WriteSlot* prev = nullptr;
+    for (uint32_t batch = 0, b0 = 0; batch < batch_end.size() && !rc; ++batch)
+    {
+        const uint32_t b1 = batch_end[batch];
         WriteSlot& s = slots[batch % nslots];
         if (nslots == 1 && prev) rc = drain(*prev);
         if (!rc) rc = launch(s, b0, b1);
@@ -1721,9 +1761,13 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     if (rc)
     {
         cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->aux_stream);
         cudaStreamSynchronize(c->copy_stream);
         for (WriteSlot& s : slots) s.busy = false;
     }
+    // whatever the second stream did is done (its batches were drained); later work on the context stream is ordered behind it anyway
+    cudaEventRecord(c->aux_join, c->aux_stream);
+    cudaStreamWaitEvent(c->stream, c->aux_join, 0);
     return rc;
 }
 } // namespace
