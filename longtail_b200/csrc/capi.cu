@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -1783,6 +1784,28 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
 
 namespace {
 
+// LT_B200_TRACE=1: wall-clock phase times of the sharded verbs on stderr (rank 0)
+struct PhaseTrace
+{
+    bool on;
+    const char* verb;
+    double t0, last;
+    char line[512];
+    size_t at = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    PhaseTrace(const char* v, uint32_t rank) : on(rank == 0 && getenv("LT_B200_TRACE") != nullptr), verb(v), t0(now()), last(t0) { line[0] = 0; }
+    void mark(lt_b200_context* c, const char* what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(c->stream);
+        const double t = now();
+        at += (size_t)snprintf(line + at, sizeof(line) - at, " %s %.1f", what, 1e3 * (t - last));
+        if (at > sizeof(line) - 64) at = sizeof(line) - 64;
+        last = t;
+    }
+    ~PhaseTrace() { if (on) fprintf(stderr, "%s: %.1f ms:%s\n", verb, 1e3 * (now() - t0), line); }
+};
+
 struct ShardJob { uint32_t asset; uint64_t offset; uint32_t size; };
 
 // the reference's job list without its empty parts, in asset / part order
@@ -1908,6 +1931,8 @@ extern "C" int lt_b200_index_sharded(lt_b200_context* c, lt_b200_comm* m, const 
     shard_plan(jobs, world, first_job);
     const uint32_t total_jobs = (uint32_t)jobs.size(), j0 = first_job[rank], j1 = first_job[rank + 1];
     if (j1 > j0 && !job_arena_offsets) return EINVAL;
+    PhaseTrace trace("lt_b200_index_sharded", rank);
+    trace.mark(c, "plan");
 
     // ---- this rank's slice: chunk + hash, table left resident
     std::vector<lt_b200_range> ranges(j1 - j0);
@@ -1918,6 +1943,7 @@ extern "C" int lt_b200_index_sharded(lt_b200_context* c, lt_b200_comm* m, const 
     }
     lt_b200_chunk_table table;
     TRY(lt_b200_chunk_ranges(c, d_arena, arena_size, ranges.data(), (uint32_t)ranges.size(), mn, av, mx, hash_type, 0, &table));
+    trace.mark(c, "chunk+hash");
 
     // ---- exchange 1: chunk count of every job (each rank contributes its slice)
     TRY(ws_reserve(c, WS_G_COUNTS, sizeof(uint32_t) * ((size_t)total_jobs + 1)));
@@ -1978,6 +2004,7 @@ extern "C" int lt_b200_index_sharded(lt_b200_context* c, lt_b200_comm* m, const 
         c->launches += 2;
     }
 
+    trace.mark(c, "allgather");
     // ---- the one VersionIndex, on every rank (the host copy only where it is wanted)
     TRY(build_index_from_device_table(c, a, asset_chunks.data(), N, g_hash, g_len, g_tag, hash_type, target_chunk_size, out_buffer, out_size, nullptr, m,
                                       want_host != 0));
@@ -1987,6 +2014,7 @@ extern "C" int lt_b200_index_sharded(lt_b200_context* c, lt_b200_comm* m, const 
         if (m->rank_chunk_start[r] < N)
             CU(cudaMemcpyAsync(&m->rank_unique_start[r], ws<uint32_t>(c, WS_DEDUP_UIDX) + m->rank_chunk_start[r], sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    trace.mark(c, "dedup+layout");
     m->global_chunks = N;
     m->global_unique = c->unique_chunks;
     m->d_arena = d_arena;
@@ -2008,26 +2036,70 @@ extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m,
     if (!U) return 0;
 
     // ---- the same plan on every rank: Longtail_CreateStoreIndex's packing over the unique chunks in VersionIndex order
-    // (src/longtail.c:6796-6860), then contiguous runs of blocks per rank with (nearly) equal payload bytes
-    std::vector<uint32_t> u_len(U), u_tag(U);
-    CU(cudaMemcpyAsync(u_len.data(), ws<void>(c, WS_ULEN), sizeof(uint32_t) * (size_t)U, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(u_tag.data(), ws<void>(c, WS_UTAG), sizeof(uint32_t) * (size_t)U, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    std::vector<uint32_t> blk_first(U), blk_count(U);
-    uint32_t B = 0;
-    TRY(lt_b200_pack_blocks(U, u_len.data(), u_tag.data(), max_block_size, max_chunks_per_block, blk_first.data(), blk_count.data(), &B));
-    std::vector<uint64_t> blk_end_bytes(B);
-    uint64_t total_bytes = 0;
-    for (uint32_t b = 0; b < B; ++b)
+    // (src/longtail.c:6796-6860) — on the device, from the unique table the index build left there — then contiguous runs of blocks per
+    // rank with (nearly) equal payload bytes.  Only the block list (one entry per ~270 chunks) and this rank's own slice come to the host.
+    PhaseTrace trace("lt_b200_write_blocks_sharded", rank);
+    const uint64_t limit = (uint64_t)max_block_size + max_block_size / 10;
+    const uint32_t* d_ulen = ws<uint32_t>(c, WS_ULEN);
+    const uint32_t* d_utag = ws<uint32_t>(c, WS_UTAG);
+    PackBuffers pb;
     {
-        for (uint32_t k = 0; k < blk_count[b]; ++k) total_bytes += u_len[blk_first[b] + k];
-        blk_end_bytes[b] = total_bytes;
+        const size_t n1 = (size_t)U + 1, t32 = scan_tmp_words(U + 1) + 2, t64 = scan64_tmp_words(U) + 2;
+        TRY(ws_reserve(c, WS_PACK_A, 8 * (2 * n1 + t64) + 4 * (9 * n1 + t32) + 256));
+        uint64_t* q = ws<uint64_t>(c, WS_PACK_A);
+        pb.prefix = q; q += n1;
+        pb.blk_end = q; q += n1;
+        pb.tmp64 = q; q += t64;
+        uint32_t* w = reinterpret_cast<uint32_t*>(q);
+        pb.flag = w; w += n1;
+        pb.rscan = w; w += n1;
+        pb.run_start = w; w += n1;
+        pb.next = w; w += n1;
+        pb.jump_a = w; w += n1;
+        pb.jump_b = w; w += n1;
+        pb.mark = w; w += n1;
+        pb.mscan = w; w += n1;
+        pb.blk_first = w; w += n1;
+        pb.tmp32 = w;
     }
+    launch_pack_blocks(d_ulen, d_utag, U, limit, max_chunks_per_block, pb, c->stream);
+    c->launches += 40;
+    uint32_t B = 0;
+    CU(cudaMemcpyAsync(&B, pb.mscan + U, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    std::vector<uint32_t> blk_first((size_t)B + 1);
+    std::vector<uint64_t> blk_end_bytes(B);
+    CU(cudaMemcpyAsync(blk_first.data(), pb.blk_first, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(blk_end_bytes.data(), pb.blk_end, sizeof(uint64_t) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    blk_first[B] = U;
+    trace.mark(c, "pack");
+    const uint64_t total_bytes = B ? blk_end_bytes[B - 1] : 0;
     std::vector<uint32_t> rank_blk(world + 1, B);
     rank_blk[0] = 0;
     for (uint32_t b = 0, r = 1; b < B && r < world; ++b)
         while (r < world && blk_end_bytes[b] * world >= total_bytes * r) rank_blk[r++] = b + 1;
-    auto chunk_lo = [&](uint32_t r) { return rank_blk[r] < B ? blk_first[rank_blk[r]] : U; }; // first unique chunk rank r writes
+    // A rank's blocks should mostly be made of chunks it holds: every byte that is not has to cross NVLink into a receive buffer that takes
+    // device memory away from the block batches.  The first occurrences are not spread evenly (the rank that indexed the shared content
+    // first holds more unique bytes), so the byte-balanced boundaries are pulled back towards the ownership boundaries until no rank
+    // imports more than `cap` bytes per boundary: a little imbalance instead of gigabytes of exchange.
+    {
+        uint64_t cap = 1ull << 30;
+        if (const char* e = getenv("LT_B200_EXCHANGE_CAP_MB")) cap = (uint64_t)strtoull(e, nullptr, 10) << 20;
+        auto bytes_before = [&](uint32_t b) { return b ? blk_end_bytes[b - 1] : 0ull; }; // payload bytes of blocks 0 .. b-1
+        for (uint32_t r = 1; r < world; ++r)
+        {
+            const uint32_t own_b = (uint32_t)(std::lower_bound(blk_first.begin(), blk_first.begin() + B, m->rank_unique_start[r]) - blk_first.begin());
+            uint32_t b = rank_blk[r];
+            if (b > own_b)
+                while (b > own_b && bytes_before(b) - bytes_before(own_b) > cap) --b; // rank r-1 imports blocks own_b .. b-1 from rank r
+            else
+                while (b < own_b && bytes_before(own_b) - bytes_before(b) > cap) ++b; // rank r imports blocks b .. own_b-1 from rank r-1
+            rank_blk[r] = std::max(b, rank_blk[r - 1]);
+        }
+    }
+    auto chunk_lo = [&](uint32_t r) { return blk_first[rank_blk[r]]; }; // first unique chunk rank r writes (U past the last block)
     if (out_total_blocks) *out_total_blocks = B;
     const uint32_t my_b0 = rank_blk[rank], my_b1 = rank_blk[rank + 1];
     const uint32_t cs = chunk_lo(rank), ce = chunk_lo(rank + 1);
@@ -2037,8 +2109,19 @@ extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m,
     const uint32_t us = m->rank_unique_start[rank], ue = m->rank_unique_start[rank + 1];
     std::vector<uint64_t> local_off(my_cn);
     std::vector<uint32_t> u_first(ue > us ? ue - us : 0);
+    std::vector<uint32_t> own_len(ue > us ? ue - us : 0);         // sizes of the unique chunks this rank holds   [us, ue)
+    std::vector<uint32_t> my_len(ce > cs ? ce - cs : 0), my_tag(ce > cs ? ce - cs : 0); // ... and of the ones it writes [cs, ce)
     if (my_cn) CU(cudaMemcpyAsync(local_off.data(), ws<void>(c, WS_CHUNK_OFF), sizeof(uint64_t) * (size_t)my_cn, cudaMemcpyDeviceToHost, c->stream));
-    if (ue > us) CU(cudaMemcpyAsync(u_first.data(), ws<uint32_t>(c, WS_UFIRST) + us, sizeof(uint32_t) * (size_t)(ue - us), cudaMemcpyDeviceToHost, c->stream));
+    if (ue > us)
+    {
+        CU(cudaMemcpyAsync(u_first.data(), ws<uint32_t>(c, WS_UFIRST) + us, sizeof(uint32_t) * (size_t)(ue - us), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(own_len.data(), d_ulen + us, sizeof(uint32_t) * (size_t)(ue - us), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (ce > cs)
+    {
+        CU(cudaMemcpyAsync(my_len.data(), d_ulen + cs, sizeof(uint32_t) * (size_t)(ce - cs), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(my_tag.data(), d_utag + cs, sizeof(uint32_t) * (size_t)(ce - cs), cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
     auto off_of = [&](uint32_t u) { return local_off[u_first[u - us] - my_c0]; }; // arena offset of unique chunk u (mine)
 
@@ -2052,7 +2135,7 @@ extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m,
         if (a < b)
         {
             Seg s = {w, a, b, 0, send_bytes};
-            for (uint32_t u = a; u < b; ++u) s.bytes += u_len[u];
+            for (uint32_t u = a; u < b; ++u) s.bytes += own_len[u - us];
             send_bytes += (s.bytes + 15) & ~15ull;
             sends.push_back(s);
         }
@@ -2060,11 +2143,12 @@ extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m,
         if (ra < rb)
         {
             Seg s = {w, ra, rb, 0, recv_bytes};
-            for (uint32_t u = ra; u < rb; ++u) s.bytes += u_len[u];
+            for (uint32_t u = ra; u < rb; ++u) s.bytes += my_len[u - cs];
             recv_bytes += (s.bytes + 15) & ~15ull;
             recvs.push_back(s);
         }
     }
+    trace.mark(c, "plan");
     if (world > 1)
     {
         TRY(ws_reserve(c, WS_X_SEND, send_bytes + 64));
@@ -2083,8 +2167,8 @@ extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m,
                 {
                     src[i] = off_of(u);
                     dst[i] = w;
-                    len[i] = u_len[u];
-                    w += u_len[u];
+                    len[i] = own_len[u - us];
+                    w += own_len[u - us];
                 }
             }
             TRY(ws_reserve(c, WS_X_TAB, 20 * n + 64));
@@ -2104,6 +2188,7 @@ extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m,
         c->launches += 2;
     }
 
+    trace.mark(c, "exchange");
     // ---- this rank's blocks: chunks [cs, ce) with their bytes at absolute device addresses (own arena or the receive buffer)
     if (out_my_blocks) *out_my_blocks = my_b1 - my_b0;
     if (cs >= ce) return 0;
@@ -2117,15 +2202,18 @@ extern "C" int lt_b200_write_blocks_sharded(lt_b200_context* c, lt_b200_comm* m,
         for (uint32_t u = s.a; u < s.b; ++u)
         {
             addr[u - cs] = w;
-            w += u_len[u];
+            w += my_len[u - cs];
         }
     }
     CU(cudaStreamSynchronize(c->stream));
-    std::vector<uint32_t> counts(blk_count.begin() + my_b0, blk_count.begin() + my_b1);
+    std::vector<uint32_t> counts(my_b1 - my_b0);
+    for (uint32_t b = my_b0; b < my_b1; ++b) counts[b - my_b0] = blk_first[b + 1] - blk_first[b];
     uint32_t most = 1;
     for (uint32_t v : counts) most = std::max(most, v);
-    return write_blocks_impl(c, nullptr, ~0ull, n, hashes.data(), u_len.data() + cs, u_tag.data() + cs, addr.data(), m->hash_type, 0xffffffffu, most,
-                             my_b1 - my_b0, counts.data(), flags, sink, user);
+    const int rc = write_blocks_impl(c, nullptr, ~0ull, n, hashes.data(), my_len.data(), my_tag.data(), addr.data(), m->hash_type, 0xffffffffu, most,
+                                     my_b1 - my_b0, counts.data(), flags, sink, user);
+    trace.mark(c, "write");
+    return rc;
 }
 
 // ================================================================ CompressionAPI batch entry points (host buffers)

@@ -74,6 +74,23 @@ cudaError_t launch_zstd_decode(const uint8_t* d_in, const uint64_t* d_in_off, co
 size_t scan_tmp_words(uint32_t count);
 void launch_exclusive_scan(const uint32_t* d_in, uint32_t count, uint32_t* d_out, uint32_t* d_tmp, cudaStream_t st);
 
+// exclusive prefix sum of count u32 values as u64 sums into out[0..count]; out[count] = total.  tmp: >= scan64_tmp_words(count) u64.
+size_t scan64_tmp_words(uint32_t count);
+void launch_exclusive_scan64(const uint32_t* d_in, uint32_t count, uint64_t* d_out, uint64_t* d_tmp, cudaStream_t st);
+
+// Longtail_CreateStoreIndex's greedy packing (src/longtail.c:6796-6860) of `count` chunks (sizes d_len, tags d_tag, store order) on the
+// device: next(i) for every chunk by binary search in the prefix sums, the block starts marked by pointer doubling from chunk 0.
+// Results: mscan[count] = block count B; blk_first[b] (b < B) = first chunk of block b; blk_end[b] = payload bytes of blocks 0..b;
+// prefix[i] = bytes of chunks 0..i-1.  All arrays hold count + 1 entries (tmp32: scan_tmp_words(count + 1), tmp64: scan64_tmp_words(count)).
+struct PackBuffers
+{
+    uint64_t* prefix;
+    uint64_t* tmp64;
+    uint64_t* blk_end;
+    uint32_t *flag, *rscan, *run_start, *next, *jump_a, *jump_b, *mark, *mscan, *tmp32, *blk_first;
+};
+void launch_pack_blocks(const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, uint64_t limit, uint32_t max_chunks, const PackBuffers& b, cudaStream_t st);
+
 // first-occurrence dedup of chunk hashes (src/longtail.c:2952-2970)
 struct DedupBuffers
 {

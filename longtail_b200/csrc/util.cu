@@ -123,6 +123,185 @@ void launch_fill_u32(uint32_t* d, uint32_t value, size_t count, cudaStream_t st)
     k_fill_u32<<<(unsigned)blocks, 256, 0, st>>>(d, value, count);
 }
 
+// ---------------------------------------------------------------- exclusive scan (u32 values, u64 sums) and greedy block packing
+// Longtail_CreateStoreIndex (src/longtail.c:6796-6860) packs the chunks, in order, into blocks: a block closes on a tag change, at
+// max_chunks chunks, or when the next chunk would push it beyond max_block_size + max_block_size / 10.  Sequential as written, but the
+// block that STARTS at chunk i ends at a place that depends on i alone — next(i) = min(end of i's tag run, i + max_chunks, first j with
+// sum(i..j) > limit) — so next() is computed for every chunk at once (a binary search in the prefix sums), and the chunks reachable from
+// chunk 0 through next() are marked by pointer doubling: log2(count) rounds instead of count steps.
+
+namespace {
+__device__ __forceinline__ uint64_t block_exclusive64(uint64_t v, uint64_t* s_warp, uint64_t* out_total)
+{
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint64_t base = 0, total = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w)
+    {
+        uint64_t t = s_warp[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    __syncthreads();
+    *out_total = total;
+    return base + incl - v;
+}
+} // namespace
+
+__global__ void __launch_bounds__(PS_THREADS) k_scan64_reduce(const uint32_t* __restrict__ in, uint32_t count, uint64_t* __restrict__ block_sums)
+{
+    __shared__ uint64_t s_warp[PS_THREADS / 32];
+    const uint32_t first = blockIdx.x * PS_BLOCK + threadIdx.x * PS_ITEMS;
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i)
+        if (first + i < count) v += in[first + i];
+    uint64_t total;
+    block_exclusive64(v, s_warp, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k_scan64_tops(uint64_t* __restrict__ block_sums, uint32_t nblocks)
+{
+    __shared__ uint64_t s_warp[32];
+    uint64_t carry = 0;
+    for (uint32_t b = 0; b < nblocks; b += 1024)
+    {
+        uint32_t i = b + threadIdx.x;
+        uint64_t v = i < nblocks ? block_sums[i] : 0;
+        uint64_t total;
+        uint64_t ex = block_exclusive64(v, s_warp, &total);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) block_sums[nblocks] = carry;
+}
+__global__ void __launch_bounds__(PS_THREADS) k_scan64_final(const uint32_t* __restrict__ in, uint32_t count, const uint64_t* __restrict__ block_sums,
+                                                             uint32_t nblocks, uint64_t* __restrict__ out)
+{
+    __shared__ uint64_t s_warp[PS_THREADS / 32];
+    const uint32_t first = blockIdx.x * PS_BLOCK + threadIdx.x * PS_ITEMS;
+    uint32_t item[PS_ITEMS];
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i)
+    {
+        item[i] = first + i < count ? in[first + i] : 0;
+        v += item[i];
+    }
+    uint64_t total;
+    uint64_t run = block_sums[blockIdx.x] + block_exclusive64(v, s_warp, &total);
+#pragma unroll
+    for (int i = 0; i < PS_ITEMS; ++i)
+    {
+        if (first + i < count) out[first + i] = run;
+        run += item[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[count] = block_sums[nblocks];
+}
+size_t scan64_tmp_words(uint32_t count) { return (size_t)(count + PS_BLOCK - 1) / PS_BLOCK + 2; }
+void launch_exclusive_scan64(const uint32_t* d_in, uint32_t count, uint64_t* d_out, uint64_t* d_tmp, cudaStream_t st)
+{
+    if (count == 0)
+    {
+        cudaMemsetAsync(d_out, 0, sizeof(uint64_t), st);
+        return;
+    }
+    const uint32_t nblocks = (count + PS_BLOCK - 1) / PS_BLOCK;
+    k_scan64_reduce<<<nblocks, PS_THREADS, 0, st>>>(d_in, count, d_tmp);
+    k_scan64_tops<<<1, 1024, 0, st>>>(d_tmp, nblocks);
+    k_scan64_final<<<nblocks, PS_THREADS, 0, st>>>(d_in, count, d_tmp, nblocks, d_out);
+}
+
+// flag[i] = 1 where a tag run starts
+__global__ void k_pack_run_flags(const uint32_t* __restrict__ tag, uint32_t count, uint32_t* __restrict__ flag)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) flag[i] = (i == 0 || tag[i] != tag[i - 1]) ? 1u : 0u;
+}
+// run_start[r] = first chunk of tag run r (rscan = exclusive scan of flag)
+__global__ void k_pack_run_starts(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rscan, uint32_t count, uint32_t* __restrict__ run_start)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && flag[i]) run_start[rscan[i]] = i;
+}
+// next[i] = where the block that starts at chunk i ends (= where the following block starts); next[count] = count
+__global__ void k_pack_next(const uint64_t* __restrict__ prefix, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rscan,
+                            const uint32_t* __restrict__ run_start, uint32_t count, uint64_t limit, uint32_t max_chunks, uint32_t* __restrict__ next)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > count) return;
+    if (i == count)
+    {
+        next[i] = count;
+        return;
+    }
+    const uint32_t runs = rscan[count];
+    const uint32_t rid = rscan[i] + flag[i] - 1u;
+    uint32_t e = rid + 1u < runs ? run_start[rid + 1u] : count;        // tag change
+    if (max_chunks < e - i) e = i + max_chunks;                        // chunk count
+    // size: chunk j joins while prefix[j + 1] - prefix[i] <= limit; the first chunk always does
+    const uint64_t t = prefix[i] + limit;
+    uint32_t lo = i + 1u, hi = e; // smallest j in [i + 1, e) with prefix[j + 1] > t, else e
+    while (lo < hi)
+    {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        if (prefix[mid + 1u] > t) hi = mid; else lo = mid + 1u;
+    }
+    next[i] = lo;
+}
+// one round of pointer doubling: every marked chunk marks the chunk 2^r blocks ahead; jump_out = jump o jump
+__global__ void k_pack_jump(const uint32_t* __restrict__ jump_in, uint32_t* __restrict__ jump_out, uint32_t* __restrict__ mark, uint32_t count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > count) return;
+    const uint32_t j = jump_in[i];
+    jump_out[i] = jump_in[j];
+    if (i < count && j < count && mark[i]) mark[j] = 1u;
+}
+// blk_first[b] = first chunk of block b, blk_end[b] = payload bytes of blocks 0 .. b (mscan = exclusive scan of mark)
+__global__ void k_pack_emit(const uint32_t* __restrict__ mark, const uint32_t* __restrict__ mscan, const uint32_t* __restrict__ next,
+                            const uint64_t* __restrict__ prefix, uint32_t count, uint32_t* __restrict__ blk_first, uint64_t* __restrict__ blk_end)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count || !mark[i]) return;
+    const uint32_t b = mscan[i];
+    blk_first[b] = i;
+    blk_end[b] = prefix[next[i]];
+}
+
+void launch_pack_blocks(const uint32_t* d_len, const uint32_t* d_tag, uint32_t count, uint64_t limit, uint32_t max_chunks, const PackBuffers& b, cudaStream_t st)
+{
+    if (!count) return;
+    const uint32_t g = (count + 1 + 255) / 256;
+    launch_exclusive_scan64(d_len, count, b.prefix, b.tmp64, st);
+    k_pack_run_flags<<<g, 256, 0, st>>>(d_tag, count, b.flag);
+    launch_exclusive_scan(b.flag, count, b.rscan, b.tmp32, st);
+    k_pack_run_starts<<<g, 256, 0, st>>>(b.flag, b.rscan, count, b.run_start);
+    k_pack_next<<<g, 256, 0, st>>>(b.prefix, b.flag, b.rscan, b.run_start, count, limit, max_chunks, b.next);
+    cudaMemsetAsync(b.mark, 0, sizeof(uint32_t) * (size_t)count, st);
+    const uint32_t one = 1;
+    cudaMemcpyAsync(b.mark, &one, sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    // jump_a starts as next; after r rounds the marked set is everything within 2^r blocks of chunk 0
+    cudaMemcpyAsync(b.jump_a, b.next, sizeof(uint32_t) * ((size_t)count + 1), cudaMemcpyDeviceToDevice, st);
+    uint32_t* in = b.jump_a;
+    uint32_t* out = b.jump_b;
+    for (uint64_t reach = 1; reach < (uint64_t)count + 1; reach <<= 1)
+    {
+        k_pack_jump<<<g, 256, 0, st>>>(in, out, b.mark, count);
+        uint32_t* t = in; in = out; out = t;
+    }
+    launch_exclusive_scan(b.mark, count, b.mscan, b.tmp32, st);
+    k_pack_emit<<<g, 256, 0, st>>>(b.mark, b.mscan, b.next, b.prefix, count, b.blk_first, b.blk_end);
+}
+
 // ---------------------------------------------------------------- first-occurrence dedup
 // The reference keeps, for every distinct chunk hash, the first occurrence in asset/part/chunk order
 // (src/longtail.c:2952-2970, LookupTable_PutUnique).  Order-independent restatement: the representative of a
