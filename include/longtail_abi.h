@@ -4,7 +4,7 @@
  *
  * These are INTERFACE declarations: struct member order and function-pointer signatures are the binary contract
  * between longtail's core (which calls through the structs) and any backend; they are restated here field for
- * field and checked against the real header by tests/dropin/abi_check.c (compiled with -DLONGTAIL_B200_USE_LONGTAIL_H
+ * field and checked against the real header by tests/dropin/abi_table.c (compiled with -DLONGTAIL_B200_USE_LONGTAIL_H
  * wherever /root/reference is available).
  *
  * A consumer that already includes the real longtail.h defines LONGTAIL_B200_USE_LONGTAIL_H before including
@@ -307,6 +307,45 @@ struct Longtail_BlockStoreAPI
                        struct Longtail_AsyncPruneBlocksAPI* async_complete_api);
     int (*GetStats)(struct Longtail_BlockStoreAPI* block_store_api, struct Longtail_BlockStore_Stats* out_stats);
     int (*Flush)(struct Longtail_BlockStoreAPI* block_store_api, struct Longtail_AsyncFlushAPI* async_complete_api);
+};
+
+/* src/longtail.h:826-858: progress / tracing callbacks.  The reference keeps the table it is given in a private static
+ * (Longtail_SetMonitor, src/longtail.c:762-776) that a library outside longtail.c cannot read, so the B200 verbs take the same
+ * struct through Longtail_B200_SetMonitor (include/longtail_b200_api.h). */
+typedef void (*Longtail_MonitorGetStoredBlockPrepare)(const struct Longtail_StoreIndex* store_index, uint32_t block_index);
+typedef void (*Longtail_MonitorGetStoredBlockLoad)(const struct Longtail_StoreIndex* store_index, uint32_t block_index);
+typedef void (*Longtail_MonitorGetStoredBlockLoaded)(const struct Longtail_StoreIndex* store_index, uint32_t block_index, int err);
+typedef void (*Longtail_MonitorGetStoredBlockComplete)(const struct Longtail_StoreIndex* store_index, uint32_t block_index, int err);
+typedef void (*Longtail_MonitorAssetRemove)(const struct Longtail_VersionIndex* source_version_index, uint32_t asset_index, int err);
+typedef void (*Longtail_MonitorAssetOpen)(const struct Longtail_VersionIndex* target_version_index, uint32_t asset_index, int err);
+typedef void (*Longtail_MonitorAssetWrite)(const struct Longtail_StoreIndex* target_store_index, const struct Longtail_VersionIndex* version_index,
+                                           uint32_t asset_index, uint64_t write_offset, uint32_t size, uint32_t chunk_index, uint32_t chunk_index_in_block,
+                                           uint32_t chunk_count_in_block, uint32_t block_index, uint32_t block_data_offset, int err);
+typedef void (*Longtail_MonitorChunkRead)(const struct Longtail_StoreIndex* store_index, const struct Longtail_VersionIndex* target_version_index,
+                                          uint32_t block_index, uint32_t chunk_index, uint32_t chunk_index_in_block, int err);
+typedef void (*Longtail_MonitorBlockCompose)(const struct Longtail_StoreIndex* store_index, uint32_t block_index);
+typedef void (*Longtail_MonitorBlockSave)(const struct Longtail_StoreIndex* store_index, uint32_t block_index, uint64_t block_size);
+typedef void (*Longtail_MonitorBlockSaved)(const struct Longtail_StoreIndex* store_index, uint32_t block_index, int err);
+typedef void (*Longtail_MonitorAssetRead)(const struct Longtail_StoreIndex* store_index, const struct Longtail_VersionIndex* version_index,
+                                          uint32_t asset_index, uint64_t read_offset, uint32_t size, TLongtail_Hash chunk_hash, uint32_t block_index,
+                                          uint32_t block_data_offset, int err);
+typedef void (*Longtail_MonitorAssetClose)(const struct Longtail_VersionIndex* version_index, uint32_t asset_index);
+struct Longtail_Monitor
+{
+    uint64_t StructSize;
+    Longtail_MonitorGetStoredBlockPrepare BlockPrepare;
+    Longtail_MonitorGetStoredBlockLoad BlockLoad;
+    Longtail_MonitorGetStoredBlockLoaded BlockLoaded;
+    Longtail_MonitorGetStoredBlockComplete BlockLoadComplete;
+    Longtail_MonitorAssetRemove AssetRemove;
+    Longtail_MonitorAssetOpen AssetOpen;
+    Longtail_MonitorAssetWrite AssetWrite;
+    Longtail_MonitorChunkRead ChunkRead;
+    Longtail_MonitorBlockCompose BlockCompose;
+    Longtail_MonitorBlockSave BlockSave;
+    Longtail_MonitorBlockSaved BlockSaved;
+    Longtail_MonitorAssetClose AssetClose;
+    Longtail_MonitorAssetRead AssetRead;
 };
 
 #ifdef __cplusplus

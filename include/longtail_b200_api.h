@@ -74,8 +74,9 @@ LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CompressionRegistry_Crea
 
 /* CompressionAPI for the ZStd type ids (lib/zstd/longtail_zstd.c:31-42, :107-140): Compress with settings 'ztd1' / 'ztd2' is
  * ZSTD_compressCCtx(level 3) on the GPU, one frame per call, byte-identical to the reference (vendored zstd 1.5.6);
- * GetMaxCompressedSize is ZSTD_COMPRESSBOUND.  The other quality ids ('ztd3' level 22, 'ztd4' level 8, 'ztd5') and Decompress
- * return ENOTSUP: there is no device kernel for them and no CPU fallback. */
+ * GetMaxCompressedSize is ZSTD_COMPRESSBOUND; Decompress decodes the frames of EVERY ZStd type id on the GPU (k_zstd_decode: frames of all
+ * levels, lib/zstd/longtail_zstd.c:143-176), EINVAL on a malformed frame like the reference.  Compress with the other quality ids ('ztd3'
+ * level 22, 'ztd4' level 8, 'ztd5') returns ENOTSUP: there is no device encoder for them and no CPU fallback. */
 LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CreateB200ZStdCompressionAPI(void);
 /* replaces Longtail_CompressionRegistry_CreateForZstd (lib/zstd/longtail_zstd.c:31) in Longtail_CreateDefaultCompressionRegistry */
 LT_B200_EXPORT struct Longtail_CompressionAPI* Longtail_CompressionRegistry_CreateForB200ZStd(uint32_t compression_type, uint32_t* out_settings);
@@ -103,6 +104,13 @@ LT_B200_EXPORT int Longtail_B200_WriteContent(
     struct Longtail_StorageAPI* source_storage_api, struct Longtail_BlockStoreAPI* backing_block_store_api, struct Longtail_JobAPI* job_api,
     struct Longtail_ProgressAPI* progress_api, struct Longtail_CancelAPI* optional_cancel_api, Longtail_CancelAPI_HCancelToken optional_cancel_token,
     struct Longtail_StoreIndex* store_index, struct Longtail_VersionIndex* version_index, const char* assets_folder);
+
+/* Longtail_SetMonitor (src/longtail.h:860, src/longtail.c:762-776) for the B200 verbs.  Longtail_B200_WriteContent fires, per block of the
+ * store index and in block order, BlockCompose when the block's batch is launched, BlockSave (with the size of the serialised block) when
+ * it is handed to the backing store and BlockSaved with the store's answer — the events of WriteContentBlockJob (src/longtail.c:4586-4753) —
+ * and AssetOpen / AssetClose around the one read of every asset that holds a needed chunk.  AssetRead, which the reference fires per chunk
+ * copy, is not fired: the gather runs on the device.  NULL switches the events off; the table is copied. */
+LT_B200_EXPORT void Longtail_B200_SetMonitor(const struct Longtail_Monitor* monitor);
 
 #ifdef __cplusplus
 }

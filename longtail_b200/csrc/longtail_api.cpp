@@ -940,6 +940,10 @@ void put_wait_done(struct Longtail_AsyncPutStoredBlockAPI* api, int err)
 
 bool is_b200_compress_store(const struct Longtail_BlockStoreAPI* api) { return api && api->PutStoredBlock == store_put; }
 
+// the monitor table of the B200 verbs (Longtail_B200_SetMonitor): a copy, read without a lock by the verb that fires the events
+struct Longtail_Monitor g_monitor;
+bool g_monitor_on = false;
+
 struct WriteSink
 {
     struct Longtail_BlockStoreAPI* store;
@@ -948,6 +952,8 @@ struct WriteSink
     Longtail_CancelAPI_HCancelToken token;
     uint32_t total, done;
     const TLongtail_Hash* expected_hashes; // the store index's block hashes, in block order
+    const struct Longtail_StoreIndex* store_index;
+    uint32_t composed; // blocks whose BlockCompose event has been fired
 };
 
 // lt_b200_block_sink: the byte image becomes a Longtail_StoredBlock whose index points into it (Longtail_InitStoredBlockFromData,
@@ -975,13 +981,25 @@ int write_content_sink(void* user, const struct lt_b200_stored_block_view* v)
     PutWait w;
     w.api.m_API.Dispose = nullptr;
     w.api.OnComplete = put_wait_done;
+    const uint32_t block_index = ws->done;
+    if (g_monitor_on)
+    {
+        // the device composes a whole batch at once: a block counts as composed when the first block of its batch comes out
+        if (g_monitor.BlockCompose && ws->composed <= block_index) g_monitor.BlockCompose(ws->store_index, ws->composed++);
+        if (g_monitor.BlockSave) g_monitor.BlockSave(ws->store_index, block_index, v->size);
+    }
     int err = ws->store->PutStoredBlock(ws->store, &sb, &w.api);
-    if (err) return err; // a non-zero return means OnComplete is not called (src/longtail.c:4747-4757)
+    if (err) // a non-zero return means OnComplete is not called (src/longtail.c:4747-4757)
+    {
+        if (g_monitor_on && g_monitor.BlockSaved) g_monitor.BlockSaved(ws->store_index, block_index, err);
+        return err;
+    }
     {
         std::unique_lock<std::mutex> g(w.m);
         w.cv.wait(g, [&w] { return w.done; });
         err = w.err;
     }
+    if (g_monitor_on && g_monitor.BlockSaved) g_monitor.BlockSaved(ws->store_index, block_index, err);
     ++ws->done;
     if (!err && ws->progress) ws->progress->OnProgress(ws->progress, ws->total, ws->done);
     return err;
@@ -1099,6 +1117,8 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
     for (uint32_t a = 0; a < A && !err; ++a)
     {
         if (!needed[a]) continue;
+        if (g_monitor_on && g_monitor.AssetOpen) g_monitor.AssetOpen(version_index, a, 0);
+        if (g_monitor_on && g_monitor.AssetClose) g_monitor.AssetClose(version_index, a);
         for (uint64_t o = 0; o < version_index->m_AssetSizes[a] && !err; o += piece)
         {
             const uint32_t n = (uint32_t)std::min<uint64_t>(piece, version_index->m_AssetSizes[a] - o);
@@ -1111,7 +1131,7 @@ extern "C" int Longtail_B200_WriteContent(struct Longtail_StorageAPI* source_sto
     if (!err) err = flush();
     if (!err)
     {
-        WriteSink ws = {backing_block_store_api, progress_api, optional_cancel_api, optional_cancel_token, block_count, 0, store_index->m_BlockHashes};
+        WriteSink ws = {backing_block_store_api, progress_api, optional_cancel_api, optional_cancel_token, block_count, 0, store_index->m_BlockHashes, store_index, 0};
         err = lt_b200_write_given_blocks_device(g_verb_ctx, static_cast<const uint8_t*>(arena), arena_bytes, written_chunks, hashes.data(), sizes.data(), tags.data(),
                                                 offsets.data(), hash_type, block_count, counts.data(), write_content_sink, &ws);
     }
@@ -1176,6 +1196,13 @@ extern "C" struct Longtail_BlockStoreAPI* Longtail_CreateB200CompressBlockStoreA
     for (auto& v : s->stats) v = 0;
     s->worker = std::thread(store_worker, s);
     return &s->api;
+}
+
+extern "C" void Longtail_B200_SetMonitor(const struct Longtail_Monitor* monitor)
+{
+    std::lock_guard<std::mutex> g(g_verb);
+    g_monitor_on = monitor != nullptr;
+    if (monitor) g_monitor = *monitor;
 }
 
 extern "C" int Longtail_B200_SetDevice(int device_ordinal)

@@ -277,6 +277,13 @@ static void make_cancel(struct late_cancel* c, long after)
     c->after = after;
 }
 
+static volatile long mon_compose, mon_save, mon_saved, mon_saved_err, mon_open, mon_close;
+static void mon_block_compose(const struct Longtail_StoreIndex* s, uint32_t b) { (void)s; (void)b; __sync_add_and_fetch(&mon_compose, 1); }
+static void mon_block_save(const struct Longtail_StoreIndex* s, uint32_t b, uint64_t size) { (void)s; (void)b; (void)size; __sync_add_and_fetch(&mon_save, 1); }
+static void mon_block_saved(const struct Longtail_StoreIndex* s, uint32_t b, int err) { (void)s; (void)b; __sync_add_and_fetch(&mon_saved, 1); if (err) __sync_add_and_fetch(&mon_saved_err, 1); }
+static void mon_asset_open(const struct Longtail_VersionIndex* v, uint32_t a, int err) { (void)v; (void)a; (void)err; __sync_add_and_fetch(&mon_open, 1); }
+static void mon_asset_close(const struct Longtail_VersionIndex* v, uint32_t a) { (void)v; (void)a; __sync_add_and_fetch(&mon_close, 1); }
+
 static void fault_injection(struct Longtail_StorageAPI* storage, struct Longtail_JobAPI* jobs, struct Longtail_HashAPI* ref_hash,
                             struct Longtail_ChunkerAPI* ref_chunker, struct Longtail_FileInfos* infos, uint32_t* tags, uint32_t target,
                             const void* b_ref, size_t n_ref)
@@ -382,7 +389,13 @@ static void fault_injection(struct Longtail_StorageAPI* storage, struct Longtail
         missing->m_BlockHashes[0] ^= 1;
         CHECK(Longtail_B200_WriteContent(storage, &k->api, jobs, 0, 0, 0, missing, vi, "root") == EINVAL, "a block hash the chunks do not hash to must be EINVAL");
         missing->m_BlockHashes[0] = saved_hash;
-        /* and the verb still works afterwards */
+        /* and the verb still works afterwards — with the monitor events of WriteContentBlockJob (src/longtail.c:4586-4753) switched on */
+        struct Longtail_Monitor mon;
+        memset(&mon, 0, sizeof(mon));
+        mon.StructSize = sizeof(mon);
+        mon.BlockCompose = mon_block_compose; mon.BlockSave = mon_block_save; mon.BlockSaved = mon_block_saved;
+        mon.AssetOpen = mon_asset_open; mon.AssetClose = mon_asset_close;
+        Longtail_B200_SetMonitor(&mon);
         struct keep_store* k_ok = make_keep_store();
         struct keep_store* k_want = make_keep_store();
         struct Longtail_BlockStoreAPI* s_ref = Longtail_CreateCompressBlockStoreAPI(&k_want->api, full);
@@ -395,6 +408,10 @@ static void fault_injection(struct Longtail_StorageAPI* storage, struct Longtail
             if (c && c->size == k_want->blocks[i].size && memcmp(c->data, k_want->blocks[i].data, c->size) == 0) ++same;
         }
         CHECK(k_ok->count == k_want->count && same == k_want->count, "after the faults: %u of %u blocks identical", same, k_want->count);
+        Longtail_B200_SetMonitor(0);
+        CHECK(mon_compose == (long)k_want->count && mon_save == mon_compose && mon_saved == mon_compose && mon_saved_err == 0 && mon_open > 0 && mon_open == mon_close,
+              "monitor events: %ld compose, %ld save, %ld saved (%ld errors), %ld open, %ld close for %u blocks", mon_compose, mon_save, mon_saved, mon_saved_err,
+              mon_open, mon_close, k_want->count);
         SAFE_DISPOSE_API(s_ref);
         SAFE_DISPOSE_API(&k->api); SAFE_DISPOSE_API(&k_ok->api); SAFE_DISPOSE_API(&k_want->api);
     }
