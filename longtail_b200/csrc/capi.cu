@@ -203,7 +203,29 @@ int ws_reserve(lt_b200_context* c, int slot, size_t bytes)
         want = bytes ? bytes : 256;
         e = cudaMalloc(&b.p, want);
     }
-    if (e != cudaSuccess) { b.p = nullptr; return cuda_fail(c, e, "cudaMalloc(workspace)"); }
+    if (e != cudaSuccess)
+    {
+        // the grow-only workspace of the OTHER phase is in the way (the block batches of WriteContent take whatever the arena leaves;
+        // the chunk + hash scratch is ~5 % of the arena): give it back and try once more — it regrows when that phase runs again
+        cudaGetLastError();
+        static const int write_phase[] = {WS_BLK_RAW, WS_BLK_OUT, WS_BLK_JOBS, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B,
+                                          WS_LZ4_TABLES, WS_LZ4_TABLES_B, WS_X_SEND, WS_X_RECV, WS_PACK_A};
+        bool is_write_slot = false;
+        for (int w : write_phase) is_write_slot = is_write_slot || w == slot;
+        if (!is_write_slot)
+        {
+            cudaDeviceSynchronize();
+            for (int w : write_phase)
+            {
+                Buf& o = c->ws[w];
+                if (o.p) cudaFree(o.p);
+                o.p = nullptr;
+                o.cap = 0;
+            }
+            e = cudaMalloc(&b.p, want);
+        }
+    }
+    if (e != cudaSuccess) { b.p = nullptr; cudaGetLastError(); return cuda_fail(c, e, "cudaMalloc(workspace)"); }
     b.cap = want;
     return 0;
 }
@@ -1488,23 +1510,6 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    if (need_all > (uint64_t)(free_b * 0.8))
-    {
-        // not everything fits at once: every GiB more per batch is ~50 more stored blocks in flight.  The scratch of the chunk + hash phase
-        // (tile candidate lists, BLAKE3 chaining values, staging of the walk: ~5 % of the arena) is dead by now and comes back on demand.
-        static const int scratch[] = {WS_TILE_DESC, WS_TILE_COUNT, WS_TILE_SLOTS, WS_CAND, WS_STAGE_OFF, WS_STAGE_LEN, WS_LEAF_COUNT, WS_LEAF_PREFIX, WS_CVS,
-                                      WS_MERGE_A, WS_MERGE_B, WS_SEG_CVS, WS_SEG_LEAF_COUNT, WS_SEG_LEAF_PREFIX, WS_DEDUP_KEYS, WS_DEDUP_VALS, WS_DEDUP_FIRST,
-                                      WS_DEDUP_ISFIRST, WS_ACI, WS_INDEX_OUT, WS_PACK_A, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND};
-        CU(cudaDeviceSynchronize());
-        for (int slot : scratch)
-        {
-            Buf& b = c->ws[slot];
-            if (b.p) cudaFree(b.p);
-            b.p = nullptr;
-            b.cap = 0;
-        }
-        CU(cudaMemGetInfo(&free_b, &total_b));
-    }
     // what the grow-only workspace already holds for these buffers counts as available
     const uint64_t held = c->ws[WS_BLK_RAW].cap + c->ws[WS_BLK_OUT].cap + c->ws[WS_BLK_JOBS].cap + c->ws[WS_BLK_RAW_B].cap + c->ws[WS_BLK_OUT_B].cap +
                           c->ws[WS_BLK_JOBS_B].cap;
