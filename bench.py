@@ -571,6 +571,12 @@ def run_b200(args):
         # + u (codec read) + c*u (codec write), u = unique fraction, c = compression ratio
         u = raw_all / float(world * cs.nbytes)
         c = stored_all / float(max(raw_all, 1))
+        # DRAM traffic of the dominant kernel per launch: (dram__bytes_read + dram__bytes_write) / algorithmic bytes from the `ncu --set full`
+        # captures under profiles/ (k_lz4_blocks_v2: 3.11 GB read + 0.66 GB written for 3.11 GB of block payload, profiles/r02y_lz4v2_ncu.txt;
+        # scan and leaves: profiles/r01p_*_ncu.txt), applied to this run's algorithmic bytes per launch
+        ncu_traffic_ratio = {"k_lz4_blocks": (3.111575e9 + 0.656347e9) / 3.111575e9, "k_blake3_leaves": (8.963703e9 + 0.340567e9) / 8.589934592e9,
+                             "k_hpcdc_scan": (8.609740e9 + 0.019096e9) / 8.589934592e9}
+        traffic = round(kbytes / max(kn, 1) * ncu_traffic_ratio[name]) if name in ncu_traffic_ratio else None
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": "GiB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -585,10 +591,13 @@ def run_b200(args):
             "hbm_roofline_frac_whole_step": round(value * GIB / 1e9 / world / peak, 4),
             "hbm_roofline_frac_whole_step_all_traffic": round(value * GIB / 1e9 / world / peak * (1 + 3 * u + c * u), 4),
             "roofline": {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "traffic_source": "see profiles/r02_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                         "traffic": traffic, "traffic_source": "ncu --set full (profiles/r02y_lz4v2_ncu.txt): DRAM read + write / algorithmic bytes = 1.21 for the "
+                                                                "LZ4 parse (the payload is read once; the tokens, offsets, short literal runs and copy-job "
+                                                                "lists are written), scaled to this run's bytes per launch",
                          "peak_source": peak_src, "per_kernel": per_kernel,
-                         "note": "algorithmic bytes of the codec kernel = the unique payload bytes it reads (SURVEY.md §8d); rank 0's kernels; the LZ4 "
-                                 "parse is a latency-bound serial chain per stored block, see DESIGN.md"},
+                         "note": "algorithmic bytes of the codec kernel = the unique payload bytes it reads (SURVEY.md §8d); rank 0's kernels; a kernel's "
+                                 "time = the union of its launches' intervals (two write batches are in flight on two streams); the LZ4 parse is a "
+                                 "latency-bound serial chain per stored block, see DESIGN.md §4.6"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "index_only": index_only, "zstd_pak": zstd_pak,
         }

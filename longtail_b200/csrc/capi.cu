@@ -279,17 +279,38 @@ struct ProfScope
     ~ProfScope() { if (on) cudaEventRecord(c->spans[idx].b, st); }
 };
 
+// Launches of one kernel may overlap in time (WriteContent keeps two batches in flight on two streams): a kernel's time is the length of
+// the UNION of its launches' intervals, so that bytes / time stays a throughput of the device and never counts a moment twice.
 void prof_collect(lt_b200_context* c)
 {
+    if (c->spans.empty()) return;
+    struct Iv { float a, b; };
+    std::vector<Iv> iv[LT_B200_KERNEL_COUNT];
+    const cudaEvent_t ref = c->spans[0].a;
     for (auto& s : c->spans)
     {
-        float ms = 0;
-        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
+        float ta = 0, tb = 0;
+        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ta, ref, s.a) == cudaSuccess &&
+            cudaEventElapsedTime(&tb, ref, s.b) == cudaSuccess)
         {
-            c->prof_ms[s.id] += ms;
+            iv[s.id].push_back({ta, tb});
             c->prof_launches[s.id] += 1;
             c->prof_bytes[s.id] += s.bytes;
         }
+    }
+    for (int k = 0; k < LT_B200_KERNEL_COUNT; ++k)
+    {
+        std::sort(iv[k].begin(), iv[k].end(), [](const Iv& x, const Iv& y) { return x.a < y.a; });
+        float end = -1e30f;
+        for (const Iv& x : iv[k])
+        {
+            if (x.b <= end) continue;
+            c->prof_ms[k] += x.b - std::max(x.a, end);
+            end = x.b;
+        }
+    }
+    for (auto& s : c->spans)
+    {
         c->event_pool.push_back(s.a);
         c->event_pool.push_back(s.b);
     }
