@@ -37,13 +37,13 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
-    WS_LZ4_TABLES, WS_LZ4_V2, WS_LZ4_TABLES_B, WS_LZ4_V2_B, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_CHUNK_SIZES, WS_UFIRST, WS_G_COUNTS, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND, WS_X_RECV, WS_X_TAB, WS_PACK_A, WS_PACK_B, WS_PACK_C, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
+    WS_LZ4_TABLES, WS_LZ4_V2, WS_LZ4_TABLES_B, WS_LZ4_V2_B, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_RAW_C, WS_BLK_OUT_C, WS_BLK_JOBS_C, WS_BLK_TAB_C, WS_LZ4_TABLES_C, WS_LZ4_V2_C, WS_BLK_RAW_D, WS_BLK_OUT_D, WS_BLK_JOBS_D, WS_BLK_TAB_D, WS_LZ4_TABLES_D, WS_LZ4_V2_D, WS_BLK_CHUNK_SIZES, WS_UFIRST, WS_G_COUNTS, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND, WS_X_RECV, WS_X_TAB, WS_PACK_A, WS_PACK_B, WS_PACK_C, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
     WS_COUNT
 };
 
 enum HostSlot
 {
-    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_BLK_META, HS_BLK_OUT_LEN, HS_BLK_OUT_LEN_B, HS_BLK_TAB, HS_BLK_TAB_B, HS_BLK_STAGE, HS_COUNT
+    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_BLK_META, HS_BLK_OUT_LEN, HS_BLK_OUT_LEN_B, HS_BLK_TAB, HS_BLK_TAB_B, HS_BLK_OUT_LEN_C, HS_BLK_TAB_C, HS_BLK_OUT_LEN_D, HS_BLK_TAB_D, HS_BLK_STAGE, HS_COUNT
 };
 
 struct Buf
@@ -60,8 +60,10 @@ struct lt_b200_context
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t aux_stream = nullptr; // second compute stream: WriteContent keeps two batches of stored blocks in flight
+    cudaStream_t aux_stream = nullptr; // more compute streams: WriteContent keeps up to four batches of stored blocks in flight
+    cudaStream_t aux_stream2[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    cudaEvent_t slot_done[2] = {nullptr, nullptr};
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaEvent_t compute_done[2] = {nullptr, nullptr};
     uint32_t* d_table = nullptr;
@@ -209,7 +211,8 @@ int ws_reserve(lt_b200_context* c, int slot, size_t bytes)
         // the chunk + hash scratch is ~5 % of the arena): give it back and try once more — it regrows when that phase runs again
         cudaGetLastError();
         static const int write_phase[] = {WS_BLK_RAW, WS_BLK_OUT, WS_BLK_JOBS, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B,
-                                          WS_LZ4_TABLES, WS_LZ4_TABLES_B, WS_X_SEND, WS_X_RECV, WS_PACK_A};
+                                          WS_BLK_RAW_C, WS_BLK_OUT_C, WS_BLK_JOBS_C, WS_BLK_TAB_C, WS_BLK_RAW_D, WS_BLK_OUT_D, WS_BLK_JOBS_D, WS_BLK_TAB_D,
+                                          WS_LZ4_TABLES, WS_LZ4_TABLES_B, WS_LZ4_TABLES_C, WS_LZ4_TABLES_D, WS_X_SEND, WS_X_RECV, WS_PACK_A};
         bool is_write_slot = false;
         for (int w : write_phase) is_write_slot = is_write_slot || w == slot;
         if (!is_write_slot)
@@ -445,6 +448,8 @@ extern "C" int lt_b200_context_create(int device_ordinal, lt_b200_context** out_
     }
     for (int i = 0; i < 2; ++i)
     {
+        cudaStreamCreateWithFlags(&c->aux_stream2[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming);
     }
@@ -473,6 +478,8 @@ extern "C" void lt_b200_context_destroy(lt_b200_context* c)
     for (int i = 0; i < 2; ++i)
     {
         if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
+        if (c->slot_done[i]) cudaEventDestroy(c->slot_done[i]);
+        if (c->aux_stream2[i]) { cudaStreamSynchronize(c->aux_stream2[i]); cudaStreamDestroy(c->aux_stream2[i]); }
         if (c->compute_done[i]) cudaEventDestroy(c->compute_done[i]);
     }
     cudaStreamDestroy(c->stream);
@@ -1514,8 +1521,17 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     // serialised image (Longtail_WriteStoredBlockToBuffer, src/longtail.c:4111-4150) is handed to the sink in store order — as a device
     // address (LT_B200_WRITE_DEVICE_SINK) or after one device -> host copy into pinned staging
     auto lz4_bound = [](uint64_t n) { return n + n / 255 + 16; }; // lib/lz4/ext/lz4.h:215
+    auto in_place = [](const Block& bl) { return bl.tag == LT_B200_COMPRESSION_LZ4 && lz4_block_in_place(bl.raw); };
     auto block_need = [&](const Block& bl, uint64_t* raw_need, uint64_t* out_need, uint64_t* job_need) {
         const uint64_t hdr = (20 + 12ull * bl.count + 15) & ~15ull;
+        if (in_place(bl))
+        {
+            // [block index][8][8 pad .. output grows from here ..][gap][raw bytes][16]: see lz4_block_in_place
+            *raw_need = 0;
+            *out_need = hdr + ((16 + lz4_in_place_offset(bl.raw) + bl.raw + 16 + 15) & ~15ull);
+            *job_need = 0;
+            return;
+        }
         const uint64_t pay = bl.tag ? 8 + (is_zstd_level3(bl.tag) ? lt_b200_zstd_bound(bl.raw) : lz4_bound(bl.raw)) : bl.raw;
         *raw_need = bl.tag ? (((uint64_t)bl.raw + 16 + 15) & ~15ull) : 0;
         *out_need = hdr + ((pay + 16 + 15) & ~15ull);
@@ -1532,8 +1548,10 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     // what the grow-only workspace already holds for these buffers counts as available
-    const uint64_t held = c->ws[WS_BLK_RAW].cap + c->ws[WS_BLK_OUT].cap + c->ws[WS_BLK_JOBS].cap + c->ws[WS_BLK_RAW_B].cap + c->ws[WS_BLK_OUT_B].cap +
-                          c->ws[WS_BLK_JOBS_B].cap;
+    uint64_t held = 0;
+    for (int w : {WS_BLK_RAW, WS_BLK_OUT, WS_BLK_JOBS, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_RAW_C, WS_BLK_OUT_C, WS_BLK_JOBS_C, WS_BLK_RAW_D,
+                  WS_BLK_OUT_D, WS_BLK_JOBS_D})
+        held += c->ws[w].cap;
     uint64_t avail = (uint64_t)((free_b + held) * 0.85); // the rest: launch tables, v1 hash tables, allocator granularity
     // the codec kernels want a batch to fill every resident warp (13 x 148 LZ4 blocks); two batches in flight only when both can be that large
     // One batch when everything fits (the codec's work queue then balances all blocks over the resident warps).  Otherwise two batches in
@@ -1542,24 +1560,30 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     // the kernels of k + 1.  ZStd batches keep one stream (its launcher owns shared worker slabs).
     bool any_zstd = false;
     for (const Block& bl : blocks) any_zstd = any_zstd || is_zstd_level3(bl.tag);
-    const uint32_t nslots = need_all + (64ull << 20) > avail && !any_zstd ? 2u : 1u;
+    uint32_t many = 4;
+    if (const char* e = getenv("LT_B200_WRITE_SLOTS")) many = (uint32_t)std::min(4, std::max(1, atoi(e))); // A/B knob
+    const uint32_t nslots = need_all + (64ull << 20) > avail && !any_zstd ? many : 1u;
     uint64_t budget = avail / nslots;
     if (budget > (64ull << 30)) budget = 64ull << 30;
     if (budget < need_max + (1ull << 20)) budget = need_max + (1ull << 20);
 
-    WriteSlot slots[2] = {{WS_BLK_RAW, WS_BLK_OUT, WS_BLK_TAB, WS_BLK_JOBS, HS_BLK_TAB, HS_BLK_OUT_LEN, WS_LZ4_V2, WS_LZ4_TABLES, c->copy_done[0], c->stream},
+    WriteSlot slots[4] = {{WS_BLK_RAW, WS_BLK_OUT, WS_BLK_TAB, WS_BLK_JOBS, HS_BLK_TAB, HS_BLK_OUT_LEN, WS_LZ4_V2, WS_LZ4_TABLES, c->copy_done[0], c->stream},
                           {WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_TAB_B, WS_BLK_JOBS_B, HS_BLK_TAB_B, HS_BLK_OUT_LEN_B, WS_LZ4_V2_B, WS_LZ4_TABLES_B, c->copy_done[1],
-                           c->aux_stream}};
-    // the second stream starts behind the block hashes / chunk tables uploaded above
+                           c->aux_stream},
+                          {WS_BLK_RAW_C, WS_BLK_OUT_C, WS_BLK_TAB_C, WS_BLK_JOBS_C, HS_BLK_TAB_C, HS_BLK_OUT_LEN_C, WS_LZ4_V2_C, WS_LZ4_TABLES_C, c->slot_done[0],
+                           c->aux_stream2[0]},
+                          {WS_BLK_RAW_D, WS_BLK_OUT_D, WS_BLK_TAB_D, WS_BLK_JOBS_D, HS_BLK_TAB_D, HS_BLK_OUT_LEN_D, WS_LZ4_V2_D, WS_LZ4_TABLES_D, c->slot_done[1],
+                           c->aux_stream2[1]}};
+    // the other streams start behind the block hashes / chunk tables uploaded above
     CU(cudaEventRecord(c->aux_fork, c->stream));
-    CU(cudaStreamWaitEvent(c->aux_stream, c->aux_fork, 0));
+    for (uint32_t k = 1; k < nslots; ++k) CU(cudaStreamWaitEvent(slots[k].st, c->aux_fork, 0));
 
     // launch the kernels of blocks [b0, b1) into slot s
     auto launch = [&](WriteSlot& s, uint32_t b0, uint32_t b1) -> int {
         const uint32_t nb = b1 - b0;
         s.b0 = b0; s.nb = nb;
         s.img_off.assign(nb, 0); s.hdr_size.assign(nb, 0); s.lz_idx.clear(); s.zs_idx.clear();
-        uint64_t raw_bytes = 0, out_bytes = 0, job_count = 0;
+        uint64_t raw_bytes = 0, out_bytes = 0, job_count = 0, gather_bytes = 0;
         uint32_t nc = 0;
         std::vector<uint64_t> raw_off(nb), pay_off(nb);
         for (uint32_t i = 0; i < nb; ++i)
@@ -1573,13 +1597,14 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
             s.img_off[i] = pay_off[i] - hdr;
             s.hdr_size[i] = (uint32_t)hdr;
             raw_bytes += r; out_bytes += o; nc += bl.count;
-            if (bl.tag == LT_B200_COMPRESSION_LZ4) { s.lz_idx.push_back(i); job_count += lz4_copy_job_capacity(bl.raw); }
+            if (bl.tag) gather_bytes += bl.raw;
+            if (bl.tag == LT_B200_COMPRESSION_LZ4) { s.lz_idx.push_back(i); job_count += in_place(bl) ? 0u : lz4_copy_job_capacity(bl.raw); }
             else if (bl.tag) s.zs_idx.push_back(i);
         }
         s.n_lz = (uint32_t)s.lz_idx.size(); s.n_zs = (uint32_t)s.zs_idx.size();
         // the LZ4 encoder prefetches the source a few batches of probes ahead: keep that inside the allocation
         TRY(ws_reserve(c, s.ws_raw, raw_bytes + (128u << 10)));
-        TRY(ws_reserve(c, s.ws_out, out_bytes + 64));
+        TRY(ws_reserve(c, s.ws_out, out_bytes + (128u << 10)));
         TRY(ws_reserve(c, s.ws_jobs, sizeof(uint3) * (size_t)(job_count + 1)));
         uint8_t* d_raw = ws<uint8_t>(c, s.ws_raw);
         uint8_t* d_out = ws<uint8_t>(c, s.ws_out);
@@ -1601,7 +1626,9 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
         {
             const Block& bl = blocks[b0 + i];
             // compressed blocks gather into the raw buffer, stored-raw blocks straight into their place in the image
-            uint64_t w = bl.tag ? (uint64_t)(uintptr_t)(d_raw + raw_off[i]) : (uint64_t)(uintptr_t)(d_out + pay_off[i]);
+            uint64_t w = in_place(bl) ? (uint64_t)(uintptr_t)(d_out + pay_off[i] + 16 + lz4_in_place_offset(bl.raw))
+                         : bl.tag     ? (uint64_t)(uintptr_t)(d_raw + raw_off[i])
+                                      : (uint64_t)(uintptr_t)(d_out + pay_off[i]);
             for (uint32_t k = 0; k < bl.count; ++k, ++ci)
             {
                 h_src[ci] = chunk_arena_offsets[bl.first + k];
@@ -1616,12 +1643,16 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
         for (uint32_t q = 0; q < s.n_lz; ++q)
         {
             const uint32_t i = s.lz_idx[q];
-            h_lro[q] = raw_off[i]; h_loo[q] = pay_off[i]; h_lrl[q] = blocks[b0 + i].raw; h_ljs[q] = job_at;
-            job_at += lz4_copy_job_capacity(blocks[b0 + i].raw);
+            const Block& bl = blocks[b0 + i];
+            // source addresses are absolute (the encoder's source base is null): in-place blocks read from their own output slot
+            h_lro[q] = in_place(bl) ? (uint64_t)(uintptr_t)(d_out + pay_off[i] + 16 + lz4_in_place_offset(bl.raw)) : (uint64_t)(uintptr_t)(d_raw + raw_off[i]);
+            h_loo[q] = pay_off[i]; h_lrl[q] = bl.raw;
+            h_ljs[q] = in_place(bl) ? LZ4_JOBS_INLINE : job_at;
+            if (!in_place(bl)) job_at += lz4_copy_job_capacity(bl.raw);
         }
         CU(cudaMemcpyAsync(d64, h64, 8 * n64 + 4 * (n32 - 2 * (size_t)s.n_lz), cudaMemcpyHostToDevice, s.st));
         {
-            ProfScope ps(c, LT_B200_KERNEL_GATHER, raw_bytes, s.st);
+            ProfScope ps(c, LT_B200_KERNEL_GATHER, gather_bytes, s.st);
             launch_gather_chunks(d_arena, d64, d64 + nc, d32, nullptr, nc, s.st);
         }
         uint32_t* d_lz_out_len = d32 + nc + 3 * (size_t)nb + 2 * (size_t)s.n_lz;
@@ -1632,7 +1663,7 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
             TRY(ws_reserve(c, s.ws_lz4_tables, LZ4_TABLE_BYTES_PER_BLOCK * (size_t)s.n_lz));
             TRY(ws_reserve(c, s.ws_lz4_queue, lz4_v2_scratch_bytes()));
             ProfScope ps(c, LT_B200_KERNEL_LZ4, lz_bytes, s.st);
-            CU(launch_lz4_blocks(d_raw, d64 + 2 * (size_t)nc + nb, d32 + nc + 3 * (size_t)nb, d_out, d64 + 2 * (size_t)nc + nb + s.n_lz, d_lz_out_len,
+            CU(launch_lz4_blocks(nullptr, d64 + 2 * (size_t)nc + nb, d32 + nc + 3 * (size_t)nb, d_out, d64 + 2 * (size_t)nc + nb + s.n_lz, d_lz_out_len,
                                  ws<uint3>(c, s.ws_jobs), d32 + nc + 3 * (size_t)nb + s.n_lz, d_lz_out_len + s.n_lz, s.n_lz,
                                  ws<uint32_t>(c, s.ws_lz4_tables), ws<void>(c, s.ws_lz4_queue), c->sm_count, s.st));
         }
@@ -1778,7 +1809,7 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
         for (uint32_t k = 0; k < use; ++k)
         {
             TRY(ws_reserve(c, slots[k].ws_raw, max_raw + (128u << 10)));
-            TRY(ws_reserve(c, slots[k].ws_out, max_out + 64));
+            TRY(ws_reserve(c, slots[k].ws_out, max_out + (128u << 10)));
             TRY(ws_reserve(c, slots[k].ws_jobs, max_jobs + sizeof(uint3)));
             TRY(ws_reserve(c, slots[k].ws_tab, max_tab));
             TRY(hs_reserve(c, slots[k].hs_tab, max_tab));
@@ -1789,29 +1820,32 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
             }
         }
     }
+    // batch k goes into slot k % nslots once batch k - nslots has been handed to the sink: nslots batches are in flight, and while the
+    // host waits for the oldest one the codec kernels of the younger ones take the warp slots its slowest blocks leave idle
     int rc = 0;
-    WriteSlot* prev = nullptr;
-    for (uint32_t batch = 0, b0 = 0; batch < batch_end.size() && !rc; ++batch)
+    const uint32_t nbatches = (uint32_t)batch_end.size();
+    for (uint32_t batch = 0, b0 = 0; batch < nbatches && !rc; ++batch)
     {
         const uint32_t b1 = batch_end[batch];
         WriteSlot& s = slots[batch % nslots];
-        if (nslots == 1 && prev) rc = drain(*prev);
+        rc = drain(s);
         if (!rc) rc = launch(s, b0, b1);
-        if (!rc && nslots == 2 && prev) rc = drain(*prev); // overlaps the kernels just launched
-        prev = &s;
         b0 = b1;
     }
-    if (!rc && prev) rc = drain(*prev);
+    for (uint32_t k = 0; k < nslots && !rc; ++k) rc = drain(slots[(nbatches + k) % nslots]); // oldest first: store order
     if (rc)
     {
         cudaStreamSynchronize(c->stream);
-        cudaStreamSynchronize(c->aux_stream);
+        for (uint32_t k = 1; k < 4; ++k) cudaStreamSynchronize(slots[k].st);
         cudaStreamSynchronize(c->copy_stream);
         for (WriteSlot& s : slots) s.busy = false;
     }
-    // whatever the second stream did is done (its batches were drained); later work on the context stream is ordered behind it anyway
-    cudaEventRecord(c->aux_join, c->aux_stream);
-    cudaStreamWaitEvent(c->stream, c->aux_join, 0);
+    // whatever the other streams did is done (their batches were drained); later work on the context stream is ordered behind it anyway
+    for (uint32_t k = 1; k < nslots; ++k)
+    {
+        cudaEventRecord(c->aux_join, slots[k].st);
+        cudaStreamWaitEvent(c->stream, c->aux_join, 0);
+    }
     return rc;
 }
 } // namespace

@@ -39,6 +39,12 @@ cudaError_t launch_meow_segments(const uint8_t* d_base, const uint64_t* d_off, c
 
 // ---- lz4.cu
 uint32_t lz4_copy_job_capacity(uint32_t raw_len);
+// In-place layout of the write path: a block the shared-memory-table encoder takes is gathered to the END of its own output slot and
+// compressed towards the front (the output never reaches source bytes the parse can still refer to when the source starts
+// lz4_in_place_offset() bytes behind the output; literal runs are then copied by the parsing warp, copy_job_start = LZ4_JOBS_INLINE).
+bool lz4_block_in_place(uint32_t raw_len);
+uint64_t lz4_in_place_offset(uint32_t raw_len);
+constexpr uint32_t LZ4_JOBS_INLINE = 0xffffffffu;
 cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, const uint32_t* d_in_len, uint8_t* d_out,
                               const uint64_t* d_out_off, const uint32_t* d_out_cap, uint32_t* d_out_len, uint32_t block_count, cudaStream_t st);
 // d_v2_scratch: lz4_v2_scratch_bytes() bytes (the work-queue head of the shared-memory-table encoder)

@@ -406,10 +406,36 @@ __device__ __forceinline__ void load_match_words(const uint8_t* __restrict__ src
     if (ip0 > anchor + lane && m0 > lane) beq = src[ip0 - 1u - lane] == src[m0 - 1u - lane];
 }
 
+// dst[0..n) = src[0..n) by one warp: 16-byte stores assembled from the (arbitrarily aligned) source with funnel shifts
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, uint32_t lane)
+{
+    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
+    if (lane < head) d[lane] = s[lane];
+    const uint8_t* s2 = s + head;
+    uint4* d4 = reinterpret_cast<uint4*>(d + head);
+    const uint32_t vecs = n - head >= 20u ? (n - head - 4u) >> 4 : 0u; // the funnel reads one word ahead: stay 4 bytes clear of the end
+    const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - ((uintptr_t)s2 & 3u));
+#pragma unroll 4
+    for (uint32_t v = lane; v < vecs; v += 32)
+    {
+        const uint32_t* w = sw + 4 * v;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        d4[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    for (uint32_t i = head + vecs * 16u + lane; i < n; i += 32) d[i] = s[i];
+}
+
 __device__ __forceinline__ void emit_runs(uint8_t* __restrict__ dst, uint32_t op, const uint8_t* __restrict__ src, uint32_t from, uint32_t lit,
                                               uint32_t lane, CopyJobs& cj)
 {
-    if (lit >= DEFER_MIN)
+    if (lit >= DEFER_MIN && !cj.jobs)
+    {
+        // in-place layout (the source sits at the end of the destination slot): nothing may be deferred, the output overtakes
+        // source bytes more than 64 KiB behind the parse.  The copy runs forward, 512 bytes per round, far below the gap.
+        warp_copy(dst + op, src + from, lit, lane);
+    }
+    else if (lit >= DEFER_MIN)
     {
         const uint32_t pieces = (lit + JOB_PIECE - 1u) / JOB_PIECE;
         for (uint32_t i = lane; i < pieces; i += 32)
@@ -914,7 +940,8 @@ k_lz4_blocks_v2(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict
         if (!lz4_v2_takes(n)) continue;
         const uint8_t* src = raw_base + raw_off[b];
         uint8_t* dst = out_base + out_off[b];
-        CopyJobs cj = {copy_jobs + copy_job_start[b], 0};
+        const uint32_t job_start = copy_job_start[b];
+        CopyJobs cj = {job_start == LZ4_JOBS_INLINE ? nullptr : copy_jobs + job_start, 0};
         const uint32_t c = v2::encode_block(src, n, dst + 8, s_shared_table, lane, cj);
         if (lane == 0)
         {
@@ -925,26 +952,6 @@ k_lz4_blocks_v2(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict
         }
         __syncwarp();
     }
-}
-
-// dst[0..n) = src[0..n) by one warp: 16-byte stores assembled from the (arbitrarily aligned) source with funnel shifts
-__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, uint32_t lane)
-{
-    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
-    if (lane < head) d[lane] = s[lane];
-    const uint8_t* s2 = s + head;
-    uint4* d4 = reinterpret_cast<uint4*>(d + head);
-    const uint32_t vecs = n - head >= 20u ? (n - head - 4u) >> 4 : 0u; // the funnel reads one word ahead: stay 4 bytes clear of the end
-    const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3u) * 8u;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - ((uintptr_t)s2 & 3u));
-#pragma unroll 2
-    for (uint32_t v = lane; v < vecs; v += 32)
-    {
-        const uint32_t* w = sw + 4 * v;
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        d4[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-    }
-    for (uint32_t i = head + vecs * 16u + lane; i < n; i += 32) d[i] = s[i];
 }
 
 // the deferred literal runs of the encoders: grid = (block, slice).  A block with many jobs (v2: pieces of <= 64 KiB) hands them to
@@ -967,7 +974,7 @@ k_lz4_copy(const uint8_t* __restrict__ raw_base, const uint64_t* __restrict__ ra
         for (uint32_t j = blockIdx.y * LZ4_COPY_WARPS + warp; j < njobs; j += LZ4_COPY_SLICES * LZ4_COPY_WARPS)
         {
             const uint3 job = jobs[j];
-            warp_copy(dst + job.x, src + job.y, job.z, lane);
+            v2::warp_copy(dst + job.x, src + job.y, job.z, lane);
         }
         return;
     }
@@ -1149,6 +1156,14 @@ cudaError_t launch_lz4_decode(const uint8_t* d_in, const uint64_t* d_in_off, con
 }
 
 uint32_t lz4_copy_job_capacity(uint32_t raw_len) { return raw_len / v2::DEFER_MIN + 2; }
+
+static bool lz4_v2_enabled()
+{
+    const char* e = getenv("LT_B200_LZ4_V1");
+    return !(e && e[0] == '1');
+}
+bool lz4_block_in_place(uint32_t raw_len) { return lz4_v2_enabled() && raw_len >= LZ4_64K_LIMIT && raw_len <= v2::MAX_N; }
+uint64_t lz4_in_place_offset(uint32_t raw_len) { return ((uint64_t)raw_len / 255 + 16 + 65536 + 256 + 15) & ~15ull; }
 
 size_t lz4_v2_scratch_bytes() { return 256; }
 
