@@ -72,10 +72,11 @@ __device__ __noinline__ void scan_group_exact_now(uint32_t in_addr, uint32_t out
 // overflowed, which k_hpcdc_walk resolves exactly.
 constexpr uint32_t SCAN_PEND_MAX = 3;
 
-// Sixteen positions of the rolling hash.  ring[] holds the table ADDRESS of each of the last 48 bytes (one register each, slots
-// are compile-time constants): the PRMT that extracts a byte and forms its table address runs once per byte, when the byte
-// enters the window; when it leaves, 48 positions later, its rotl(T,16) is read from the same address + 128
-// (longtail_hpcdcchunker.c:295-297).
+// Sixteen positions of the rolling hash.  ring[] holds the table VALUE of each of the last 48 bytes (one register each, slots
+// are compile-time constants): one PRMT extracts a byte and forms its table address, one shared-memory load per byte fetches T
+// when the byte enters the window; when it leaves, 48 positions later, its rotl(T,16) is one more PRMT on the kept register
+// (longtail_hpcdcchunker.c:295-297).  Measured equal to a second lookup at address + 128 (26.3 vs 25.9 ms on 64 GiB): the loop is
+// bound by instruction issue (seven per byte either way), not by the shared-memory pipe.
 template <int SLOT, bool SPARSE>
 __device__ __forceinline__ void scan_step16(uint32_t (&ring)[SCAN_WINDOW], uint32_t& h, uint32_t& npend, uint32_t pad_addr, uint32_t in_addr,
                                             uint32_t out_addr, uint32_t first_bit, const ChunkParams& cp, uint32_t tab_lane, uint32_t bits_addr)
@@ -90,9 +91,9 @@ __device__ __forceinline__ void scan_step16(uint32_t (&ring)[SCAN_WINDOW], uint3
 #pragma unroll
         for (int k = 8 * g; k < 8 * g + 8; ++k)
         {
-            const uint32_t a = __byte_perm(wi[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4));
-            h = rotl32(h, 1) ^ lds32_off128(ring[SLOT + k]) ^ lds32(a);
-            ring[SLOT + k] = a;
+            const uint32_t t = lds32(__byte_perm(wi[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4)));
+            h = rotl32(h, 1) ^ __byte_perm(ring[SLOT + k], 0u, 0x1032) ^ t;
+            ring[SLOT + k] = t;
             best = min(best, h * cp.d_odd_inv + cp.d_odd_inv); // (h+1)/odd(d) exact-division test, superset of :298
         }
         if (best <= cp.d_odd_thr)
@@ -132,9 +133,9 @@ __device__ __noinline__ uint32_t scan_segment(uint32_t my, uint32_t prev, uint32
 #pragma unroll
         for (int k = 0; k < 16; ++k)
         {
-            const uint32_t a = __byte_perm(ws[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4));
-            h ^= rotl32(lds32(a), (47 - (16 * j + k)) & 31);
-            ring[16 * j + k] = a;
+            const uint32_t t = lds32(__byte_perm(ws[k >> 2], tab_lane, 0x7604 | ((k & 3) << 4)));
+            h ^= rotl32(t, (47 - (16 * j + k)) & 31);
+            ring[16 * j + k] = t;
         }
     }
 

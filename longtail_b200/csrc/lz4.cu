@@ -406,22 +406,36 @@ __device__ __forceinline__ void load_match_words(const uint8_t* __restrict__ src
     if (ip0 > anchor + lane && m0 > lane) beq = src[ip0 - 1u - lane] == src[m0 - 1u - lane];
 }
 
-// dst[0..n) = src[0..n) by one warp: 16-byte stores assembled from the (arbitrarily aligned) source with funnel shifts
+// dst[0..n) = src[0..n) by one warp: 16-byte stores assembled from two aligned 16-byte loads of the (arbitrarily aligned) source
+template <uint32_t WS>
+__device__ __forceinline__ uint4 shift_words(const uint4 a, const uint4 b, uint32_t sh)
+{
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    return make_uint4(__funnelshift_r(w[WS], w[WS + 1], sh), __funnelshift_r(w[WS + 1], w[WS + 2], sh), __funnelshift_r(w[WS + 2], w[WS + 3], sh),
+                      __funnelshift_r(w[WS + 3], w[WS + 4], sh));
+}
+template <uint32_t WS>
+__device__ __forceinline__ void warp_copy_vecs(uint4* __restrict__ d4, const uint4* __restrict__ sv, uint32_t vecs, uint32_t sh, uint32_t lane)
+{
+#pragma unroll 4
+    for (uint32_t v = lane; v < vecs; v += 32) d4[v] = shift_words<WS>(sv[v], sv[v + 1], sh);
+}
 __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, uint32_t lane)
 {
     const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
     if (lane < head) d[lane] = s[lane];
     const uint8_t* s2 = s + head;
     uint4* d4 = reinterpret_cast<uint4*>(d + head);
-    const uint32_t vecs = n - head >= 20u ? (n - head - 4u) >> 4 : 0u; // the funnel reads one word ahead: stay 4 bytes clear of the end
-    const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3u) * 8u;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - ((uintptr_t)s2 & 3u));
-#pragma unroll 4
-    for (uint32_t v = lane; v < vecs; v += 32)
+    // a vector reads the 32 aligned source bytes around it: stay that far clear of the end
+    const uint32_t vecs = n - head >= 48u ? (n - head - 32u) >> 4 : 0u;
+    const uint32_t mis = (uint32_t)((uintptr_t)s2 & 15u), sh = (mis & 3u) * 8u;
+    const uint4* sv = reinterpret_cast<const uint4*>(s2 - mis);
+    switch (mis >> 2)
     {
-        const uint32_t* w = sw + 4 * v;
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        d4[v] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    case 0: warp_copy_vecs<0>(d4, sv, vecs, sh, lane); break;
+    case 1: warp_copy_vecs<1>(d4, sv, vecs, sh, lane); break;
+    case 2: warp_copy_vecs<2>(d4, sv, vecs, sh, lane); break;
+    default: warp_copy_vecs<3>(d4, sv, vecs, sh, lane); break;
     }
     for (uint32_t i = head + vecs * 16u + lane; i < n; i += 32) d[i] = s[i];
 }
