@@ -17,8 +17,8 @@ Workloads (config.workload names the one `value` is measured on):
 
 A step = one full pass over the workload.
   value  inputs resident in HBM, stored blocks left in HBM (device sink): CUDA events on the context stream, max over ranks
-  e2e    the same verbs with the asset bytes in pinned HOST memory and every stored block copied to pinned host memory:
-         lt_b200_upsync_host_assets, wall clock
+  e2e    the same work with the asset bytes in pinned HOST memory and every stored block copied to pinned host memory:
+         lt_b200_upsync_stream_host_assets (one streaming pass; --e2e-mode resident = lt_b200_upsync_host_assets), wall clock
   roofline / cpu_baseline  as the task contract describes; see DESIGN.md §Measurement
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/libref_shim.so: Longtail_CreateVersionIndex + CreateMissingContent +
@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--e2e-gib", type=float, default=None, help="host-resident part of the asset set for the e2e leg (default: all that fits host RAM)")
     ap.add_argument("--cpu-gib", type=float, default=16.0, help="bounded sample of the reference arm per step (BASELINE.md: a fixed 16 GiB prefix)")
     ap.add_argument("--verify-gib", type=float, default=1.0, help="N > 1: per-rank size of the multi-GPU parity run against the reference (0 = skip)")
+    ap.add_argument("--e2e-mode", default="stream", choices=["stream", "resident"], help="e2e verb: one streaming pass (default) or H2D of everything first")
+    ap.add_argument("--e2e-batch-gib", type=float, default=16.0, help="batch size of the streaming e2e pass")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the reference runs (parity and cpu_baseline)")
     return ap.parse_args()
@@ -440,13 +442,17 @@ def run_b200(args):
         vi = longtail_b200.parse_version_index(v) if rank == 0 else None
         up.write((count_fn, count_user), True, vi)
         state["vi"] = vi
+        state["index_bytes"] = len(v) if rank == 0 else 0
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    one_step = None
     for _ in range(max(args.warmup, 3)):
         step_resident()
+        if one_step is None:
+            one_step = acc.copy()  # {blocks, stored bytes, raw bytes, xor of block hashes} of ONE pass: what the e2e pass must reproduce
     acc[:] = 0
     launches0 = ctx.launch_count
     ctx.profile_reset()
@@ -473,14 +479,26 @@ def run_b200(args):
         efn, euser, eacc = ctx.counting_sink()
         ibytes = [0]
 
+        streaming = args.e2e_mode == "stream"
+
         def step_e2e():
-            v, _ = ctx.upsync_host_assets(e2e_assets, host_datas, e2e_tags, (efn, euser), TARGET_CHUNK_SIZE, MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK, copy=False)
+            if streaming:
+                v, _ = ctx.upsync_stream_host_assets(e2e_assets, host_datas, e2e_tags, (efn, euser), TARGET_CHUNK_SIZE, MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK,
+                                                     batch_bytes=int(args.e2e_batch_gib * GIB), copy=False)
+            else:
+                v, _ = ctx.upsync_host_assets(e2e_assets, host_datas, e2e_tags, (efn, euser), TARGET_CHUNK_SIZE, MAX_BLOCK_SIZE, MAX_CHUNKS_PER_BLOCK, copy=False)
             ibytes[0] = len(v)
 
         ctx.device_free(arena)  # the verb brings its own arena
         arena = None
         ctx.trim()              # ... and the workspace of the resident run (write batches, merged tables) is not needed next to it
         step_e2e()
+        same = None
+        if world == 1 and host_count == cs.count:
+            # the whole version went through: the pass from host memory must have written the resident pass's blocks
+            same = bool((eacc == one_step).all()) and ibytes[0] == int(state["index_bytes"])
+            if not same:
+                raise SystemExit("e2e pass differs from the resident pass: %s vs %s, index %d vs %d bytes" % (eacc, one_step, ibytes[0], state["index_bytes"]))
         eacc[:] = 0
         e2e_steps = max(1, min(args.steps, 3))
         barrier()
@@ -491,9 +509,16 @@ def run_b200(args):
         wall = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": round(world * host_bytes * e2e_steps / wall / GIB, 3), "unit": "GiB/s", "h2d_bytes_per_step": host_bytes,
                "d2h_bytes_per_step": int(eacc[1]) // e2e_steps + ibytes[0], "steps": e2e_steps,
-               "note": "lt_b200_upsync_host_assets per GPU over %d assets (%.1f GiB) in pinned host memory: one H2D copy per asset, CreateVersionIndex, "
-                       "WriteContent with every StoredBlock copied to pinned host staging; wall clock, max over ranks%s"
-                       % (host_count, host_bytes / GIB, "" if host_count == cs.count else " (host RAM bounds the host-resident part of the set)")}
+               "verb": "lt_b200_upsync_stream_host_assets" if streaming else "lt_b200_upsync_host_assets",
+               "same_blocks_as_resident_pass": same,
+               "note": ("one streaming pass per GPU over %d assets (%.1f GiB) in pinned host memory: batches of %.0f GiB travel host -> device while the "
+                        "previous batch is chunked, hashed, deduplicated, packed and compressed and its StoredBlocks are copied to pinned host staging; "
+                        "wall clock, max over ranks%s" % (host_count, host_bytes / GIB, args.e2e_batch_gib,
+                                                          "" if host_count == cs.count else " (host RAM bounds the host-resident part of the set)"))
+               if streaming else
+               ("lt_b200_upsync_host_assets per GPU over %d assets (%.1f GiB) in pinned host memory: one H2D copy per asset, CreateVersionIndex, "
+                "WriteContent with every StoredBlock copied to pinned host staging; wall clock, max over ranks%s"
+                % (host_count, host_bytes / GIB, "" if host_count == cs.count else " (host RAM bounds the host-resident part of the set)"))}
     if host_buf is not None:
         ctx.pinned_free(host_buf)
         host_buf, host_datas = None, []

@@ -361,6 +361,19 @@ LT_B200_EXPORT int lt_b200_upsync_host_assets(lt_b200_context* context, const st
                                               uint32_t flags, lt_b200_block_sink sink, void* user, const void** out_version_index,
                                               uint64_t* out_size, uint32_t* out_chunks_written);
 
+/* The same upsync in ONE streaming pass, for host-resident assets of any total size (the version never has to fit the device): batches of
+ * whole parts (`batch_bytes` each, 0 = 16 GiB, never less than one part of target_chunk_size * 1024 bytes) travel host -> device into
+ * two arenas; while batch k + 1 is on the bus batch k is chunked + hashed, its chunks are matched against the hashes seen so far
+ * (first occurrence wins, src/longtail.c:2952-2970; the set starts with `existing_hashes`, Longtail_CreateMissingContent :7257-7340),
+ * and every stored block the greedy packing (:6796-6860) can no longer change is compressed and handed to `sink` — so host -> device
+ * and device -> host copies overlap.  VersionIndex, stored blocks and their order are identical to lt_b200_upsync_host_assets'. */
+LT_B200_EXPORT int lt_b200_upsync_stream_host_assets(lt_b200_context* context, const struct lt_b200_assets* assets,
+                                                     const uint8_t* const* asset_data, const uint32_t* asset_tags, uint32_t hash_type,
+                                                     uint32_t target_chunk_size, uint32_t max_block_size, uint32_t max_chunks_per_block,
+                                                     uint32_t existing_count, const uint64_t* existing_hashes, uint32_t flags,
+                                                     uint64_t batch_bytes, lt_b200_block_sink sink, void* user,
+                                                     const void** out_version_index, uint64_t* out_size, uint32_t* out_chunks_written);
+
 /* ---- multi-GPU: one process per GPU of one node, NCCL over NVLink / NVSwitch.  The reference has no distributed
  * runtime (its only parallelism is the bikeshed thread pool behind Longtail_JobAPI); what is sharded here is its own job unit, one
  * (asset, part) pair with parts of target_chunk_size * 1024 bytes (src/longtail.c:2396-2457): parts never share chunker state, so ranks

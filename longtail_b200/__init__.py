@@ -178,6 +178,9 @@ def load_library():
     lib.lt_b200_upsync_host_assets.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    lib.lt_b200_upsync_stream_host_assets.argtypes = [C.c_void_p, C.POINTER(Assets), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                      C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p,
+                                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     lib.lt_b200_comm_unique_id.argtypes = [C.c_void_p]
     lib.lt_b200_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     lib.lt_b200_comm_destroy.argtypes = [C.c_void_p]
@@ -506,6 +509,21 @@ class Context:
                                                         0 if eh is None else int(eh.size), None if eh is None else eh.ctypes.data_as(C.c_void_p),
                                                         WRITE_DEVICE_SINK if device_sink else 0, c_sink[0], c_sink[1], C.byref(buf), C.byref(size),
                                                         C.byref(written)), "upsync_host_assets")
+        return self._result(buf, size, copy), written.value
+
+    def upsync_stream_host_assets(self, assets, datas, tags, c_sink, target_chunk_size=32768, max_block_size=8388608, max_chunks_per_block=1024,
+                                  hash_type=HASH_BLAKE3, existing_hashes=None, device_sink=False, batch_bytes=0, copy=True):
+        """upsync_host_assets as one streaming pass (batches of batch_bytes; the version need not fit the device); same results"""
+        st = assets.as_struct()
+        ptrs = (C.c_void_p * max(len(datas), 1))(*[d.ctypes.data if d.size else None for d in datas])
+        tg = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint32)
+        eh = None if existing_hashes is None else np.ascontiguousarray(existing_hashes, dtype=np.uint64)
+        buf, size, written = C.c_void_p(), C.c_uint64(0), C.c_uint32(0)
+        self._check(self.lib.lt_b200_upsync_stream_host_assets(self.handle, C.byref(st), ptrs, None if tg is None else tg.ctypes.data_as(C.c_void_p),
+                                                               int(hash_type), int(target_chunk_size), int(max_block_size), int(max_chunks_per_block),
+                                                               0 if eh is None else int(eh.size), None if eh is None else eh.ctypes.data_as(C.c_void_p),
+                                                               WRITE_DEVICE_SINK if device_sink else 0, C.c_uint64(int(batch_bytes)), c_sink[0], c_sink[1],
+                                                               C.byref(buf), C.byref(size), C.byref(written)), "upsync_stream_host_assets")
         return self._result(buf, size, copy), written.value
 
     # ---- multi-GPU (one process per GPU; include/longtail_b200.h "multi-GPU")

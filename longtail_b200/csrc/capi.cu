@@ -37,13 +37,13 @@ enum WsSlot
     WS_PATHS, WS_INDEX_OUT, WS_ARENA_A, WS_ARENA_B, WS_ACC_HASH, WS_ACC_LEN, WS_ACC_TAG,
     WS_UOFF, WS_BLK_HASHES, WS_BLK_SEG_OFF, WS_BLK_SEG_LEN, WS_BLK_HASH_OUT, WS_BLK_SRC_OFF, WS_BLK_DST_OFF, WS_BLK_LEN, WS_BLK_RAW, WS_BLK_OUT,
     WS_BLK_RAW_OFF, WS_BLK_RAW_LEN, WS_BLK_OUT_OFF, WS_BLK_OUT_LEN, WS_BLK_JOBS, WS_BLK_JOB_START, WS_BLK_JOB_COUNT, WS_QUEUE_HEAD, WS_MERGE_A, WS_MERGE_B, WS_MERGE_COUNTS, WS_MEOW_TABLE,
-    WS_LZ4_TABLES, WS_LZ4_V2, WS_LZ4_TABLES_B, WS_LZ4_V2_B, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_RAW_C, WS_BLK_OUT_C, WS_BLK_JOBS_C, WS_BLK_TAB_C, WS_LZ4_TABLES_C, WS_LZ4_V2_C, WS_BLK_RAW_D, WS_BLK_OUT_D, WS_BLK_JOBS_D, WS_BLK_TAB_D, WS_LZ4_TABLES_D, WS_LZ4_V2_D, WS_BLK_CHUNK_SIZES, WS_UFIRST, WS_G_COUNTS, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND, WS_X_RECV, WS_X_TAB, WS_PACK_A, WS_PACK_B, WS_PACK_C, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
+    WS_LZ4_TABLES, WS_LZ4_V2, WS_LZ4_TABLES_B, WS_LZ4_V2_B, WS_BLK_RAW_B, WS_BLK_OUT_B, WS_BLK_JOBS_B, WS_BLK_TAB, WS_BLK_TAB_B, WS_BLK_RAW_C, WS_BLK_OUT_C, WS_BLK_JOBS_C, WS_BLK_TAB_C, WS_LZ4_TABLES_C, WS_LZ4_V2_C, WS_BLK_RAW_D, WS_BLK_OUT_D, WS_BLK_JOBS_D, WS_BLK_TAB_D, WS_LZ4_TABLES_D, WS_LZ4_V2_D, WS_BLK_CHUNK_SIZES, WS_UPLOAD_SEGS_A, WS_UPLOAD_SEGS_B, WS_UFIRST, WS_G_COUNTS, WS_G_HASH, WS_G_LEN, WS_G_TAG, WS_X_SEND, WS_X_RECV, WS_X_TAB, WS_PACK_A, WS_PACK_B, WS_PACK_C, WS_ZSTD_WORKERS, WS_ZSTD_RAW_OFF, WS_ZSTD_RAW_LEN, WS_ZSTD_OUT_OFF, WS_ZSTD_OUT_LEN, WS_ZSTD_DEC_WORKERS,
     WS_COUNT
 };
 
 enum HostSlot
 {
-    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_BLK_META, HS_BLK_OUT_LEN, HS_BLK_OUT_LEN_B, HS_BLK_TAB, HS_BLK_TAB_B, HS_BLK_OUT_LEN_C, HS_BLK_TAB_C, HS_BLK_OUT_LEN_D, HS_BLK_TAB_D, HS_BLK_STAGE, HS_COUNT
+    HS_PARTS, HS_SMALL, HS_RANGE_COUNTS, HS_CHUNK_HASH, HS_CHUNK_LEN, HS_CHUNK_TAG, HS_CHUNK_OFF, HS_SEG, HS_INDEX_OUT, HS_STAGE_A, HS_STAGE_B, HS_BLK_META, HS_BLK_OUT_LEN, HS_BLK_OUT_LEN_B, HS_BLK_TAB, HS_BLK_TAB_B, HS_BLK_OUT_LEN_C, HS_BLK_TAB_C, HS_BLK_OUT_LEN_D, HS_BLK_TAB_D, HS_BLK_STAGE, HS_UPLOAD_SEGS_A, HS_UPLOAD_SEGS_B, HS_COUNT
 };
 
 struct Buf
@@ -64,6 +64,8 @@ struct lt_b200_context
     cudaStream_t aux_stream2[2] = {nullptr, nullptr};
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     cudaEvent_t slot_done[2] = {nullptr, nullptr};
+    cudaStream_t upload_stream = nullptr; // host -> device copies of the streaming upsync (its device -> host copies own copy_stream)
+    cudaEvent_t upload_done[2] = {nullptr, nullptr}, arena_free[2] = {nullptr, nullptr};
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaEvent_t compute_done[2] = {nullptr, nullptr};
     uint32_t* d_table = nullptr;
@@ -449,10 +451,13 @@ extern "C" int lt_b200_context_create(int device_ordinal, lt_b200_context** out_
     for (int i = 0; i < 2; ++i)
     {
         cudaStreamCreateWithFlags(&c->aux_stream2[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->upload_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->arena_free[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->compute_done[i], cudaEventDisableTiming);
     }
+    cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking);
     c->sm_count = prop.multiProcessorCount;
     if (make_scan_layout(&c->scan_layout, c->stream) != cudaSuccess)
     {
@@ -479,6 +484,8 @@ extern "C" void lt_b200_context_destroy(lt_b200_context* c)
     {
         if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
         if (c->slot_done[i]) cudaEventDestroy(c->slot_done[i]);
+        if (c->upload_done[i]) cudaEventDestroy(c->upload_done[i]);
+        if (c->arena_free[i]) cudaEventDestroy(c->arena_free[i]);
         if (c->aux_stream2[i]) { cudaStreamSynchronize(c->aux_stream2[i]); cudaStreamDestroy(c->aux_stream2[i]); }
         if (c->compute_done[i]) cudaEventDestroy(c->compute_done[i]);
     }
@@ -487,6 +494,7 @@ extern "C" void lt_b200_context_destroy(lt_b200_context* c)
     if (c->aux_fork) cudaEventDestroy(c->aux_fork);
     if (c->aux_join) cudaEventDestroy(c->aux_join);
     cudaStreamDestroy(c->copy_stream);
+    if (c->upload_stream) { cudaStreamSynchronize(c->upload_stream); cudaStreamDestroy(c->upload_stream); }
     delete c;
 }
 
@@ -1425,6 +1433,8 @@ namespace {
 
 // One batch of stored blocks in flight: its device buffers, its launch tables (one pinned host image, one device image) and the
 // event that marks its kernels done.  With room for two of them the device -> host copies of batch k overlap the kernels of k + 1.
+constexpr uint32_t WRITE_PIPELINED = 0x80000000u; // internal flag of write_blocks_impl, not part of the C ABI
+
 struct WriteSlot
 {
     int ws_raw, ws_out, ws_tab, ws_jobs, hs_tab, hs_len, ws_lz4_queue, ws_lz4_tables;
@@ -1562,8 +1572,12 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     for (const Block& bl : blocks) any_zstd = any_zstd || is_zstd_level3(bl.tag);
     uint32_t many = 4;
     if (const char* e = getenv("LT_B200_WRITE_SLOTS")) many = (uint32_t)std::min(4, std::max(1, atoi(e))); // A/B knob
-    const uint32_t nslots = need_all + (64ull << 20) > avail && !any_zstd ? many : 1u;
+    // WRITE_PIPELINED (the streaming upsync, whose sink is a device -> host copy): split even a batch that fits, so that the copies of the
+    // first quarter start when its blocks are done instead of when the slowest block of the whole batch is
+    const bool pipelined = (flags & WRITE_PIPELINED) != 0 && !any_zstd && !device_sink && nblocks >= 64;
+    const uint32_t nslots = (need_all + (64ull << 20) > avail || pipelined) && !any_zstd ? many : 1u;
     uint64_t budget = avail / nslots;
+    if (pipelined && budget > need_all / nslots + need_max) budget = need_all / nslots + need_max;
     if (budget > (64ull << 30)) budget = 64ull << 30;
     if (budget < need_max + (1ull << 20)) budget = need_max + (1ull << 20);
 
@@ -1849,6 +1863,234 @@ int write_blocks_impl(lt_b200_context* c, const uint8_t* d_arena, uint64_t arena
     return rc;
 }
 } // namespace
+
+// ================================================================ streaming upsync: one pass over host-resident assets of any total size
+//
+// cmd/main.c:UpSync (:972-1153) without holding the version on the device.  Batches of whole parts travel host -> device into two
+// arenas; while batch k + 1 is on the bus, batch k is chunked + hashed, its chunks are looked up in a host-side set of the hashes seen so
+// far (first occurrence wins, src/longtail.c:2952-2970; the set starts with `existing_hashes` = Longtail_CreateMissingContent :7257-7340),
+// the new chunks join the pending list, Longtail_CreateStoreIndex's greedy packing (:6796-6860) runs over that list and every block
+// that can no longer change — all but the last — is compressed and handed to the sink.  The last block's chunks are carried (copied
+// device -> device) into the next batch's arena.  The blocks and their order are those of the resident verbs: the packing is a left to
+// right scan, so cutting the chunk list at block boundaries does not change it.  The VersionIndex is laid out at the end from the
+// accumulated chunk table.  PCIe runs in both directions at once: uploads on their own stream, stored blocks leave on the copy stream.
+extern "C" int lt_b200_upsync_stream_host_assets(lt_b200_context* c, const lt_b200_assets* a, const uint8_t* const* asset_data,
+                                                 const uint32_t* asset_tags, uint32_t hash_type, uint32_t target_chunk_size,
+                                                 uint32_t max_block_size, uint32_t max_chunks_per_block, uint32_t existing_count,
+                                                 const uint64_t* existing_hashes, uint32_t flags, uint64_t batch_bytes, lt_b200_block_sink sink,
+                                                 void* user, const void** out_version_index, uint64_t* out_size, uint32_t* out_chunks_written)
+{
+    if (!c || !sink || !out_version_index || !out_size || (existing_count && !existing_hashes)) return EINVAL;
+    CU(cudaSetDevice(c->device));
+    c->err[0] = 0;
+    TRY(validate_assets(c, a));
+    if (a->asset_count && !asset_data) return EINVAL;
+    if (max_chunks_per_block == 0) return EINVAL;
+    if (target_chunk_size == 0 || target_chunk_size > (1u << 20)) return fail(c, EINVAL, "target_chunk_size %u outside (0, 1 MiB]", target_chunk_size);
+    uint32_t mn, av, mx;
+    target_to_params(target_chunk_size, &mn, &av, &mx);
+    const uint64_t part_size = (uint64_t)target_chunk_size * 1024;
+
+    // the job list of ChunkAssets (src/longtail.c:2399-2457), empty parts dropped
+    struct Job { uint32_t asset; uint64_t start; uint32_t size; };
+    std::vector<Job> jobs;
+    uint64_t total_bytes = 0;
+    for (uint32_t i = 0; i < a->asset_count; ++i)
+    {
+        const uint64_t size = a->sizes[i];
+        if (size && !asset_data[i]) return fail(c, EINVAL, "asset %u has no data", i);
+        for (uint64_t start = 0; start < size; start += part_size) jobs.push_back({i, start, (uint32_t)std::min<uint64_t>(part_size, size - start)});
+        total_bytes += size;
+    }
+    if (batch_bytes == 0) batch_bytes = 16ull << 30;
+    if (batch_bytes < part_size) batch_bytes = part_size;
+    if (batch_bytes > total_bytes + 256ull * jobs.size() + 4096) batch_bytes = total_bytes + 256ull * jobs.size() + 4096;
+    // room in front of every arena for the chunks of the block still open when the previous batch ended
+    const uint64_t block_limit = (uint64_t)max_block_size + max_block_size / 10;
+    const uint64_t carry_cap = (std::max<uint64_t>(block_limit, mx) + 16ull * max_chunks_per_block + 4096 + 255) & ~255ull;
+    const uint64_t max_chunks = total_bytes / mn + 2 * (uint64_t)jobs.size() + 16;
+    if (max_chunks > 0xffffffffull) return fail(c, E2BIG, "more than 2^32 chunks");
+    TRY(ws_reserve(c, WS_ACC_HASH, sizeof(uint64_t) * (size_t)max_chunks));
+    TRY(ws_reserve(c, WS_ACC_LEN, sizeof(uint32_t) * (size_t)max_chunks));
+    TRY(ws_reserve(c, WS_ACC_TAG, sizeof(uint32_t) * (size_t)max_chunks));
+    std::vector<uint32_t> asset_chunks(a->asset_count, 0);
+
+    // the hashes seen so far: open addressing, linear probing; 0 is kept aside
+    size_t set_cap = 1024;
+    while (set_cap < 2 * (max_chunks + existing_count)) set_cap <<= 1;
+    std::vector<uint64_t> set(set_cap, 0);
+    bool seen_zero = false;
+    auto insert = [&](uint64_t h) -> bool { // true: first time
+        if (h == 0) { const bool first = !seen_zero; seen_zero = true; return first; }
+        size_t at = (size_t)((h * 0x9E3779B97F4A7C15ull) >> 20) & (set_cap - 1);
+        while (set[at]) { if (set[at] == h) return false; at = (at + 1) & (set_cap - 1); }
+        set[at] = h;
+        return true;
+    };
+    for (uint32_t i = 0; i < existing_count; ++i) insert(existing_hashes[i]);
+
+    struct Batch { size_t first = 0, last = 0; std::vector<lt_b200_range> ranges; uint64_t bytes = 0; };
+    auto plan = [&](size_t first) {
+        Batch b;
+        b.first = first;
+        size_t j = first;
+        while (j < jobs.size())
+        {
+            const uint64_t padded = ((uint64_t)jobs[j].size + 255) & ~255ull;
+            if (b.bytes + padded > batch_bytes && j > first) break;
+            b.ranges.push_back({b.bytes, jobs[j].size, asset_tags ? asset_tags[jobs[j].asset] : 0u});
+            b.bytes += padded;
+            ++j;
+        }
+        b.last = j;
+        return b;
+    };
+    const int arena_slot[2] = {WS_ARENA_A, WS_ARENA_B};
+    // Assets in pinned (device-mapped) host memory are read by a kernel (launch_upload_segments: the copy engine stays free for the small
+    // table uploads of the kernels working on the previous batch); anything else goes through cudaMemcpyAsync.
+    std::vector<const uint8_t*> mapped(a->asset_count, nullptr);
+    if (!getenv("LT_B200_UPLOAD_MEMCPY")) // A/B knob
+        for (uint32_t i = 0; i < a->asset_count; ++i)
+        {
+            cudaPointerAttributes attr;
+            if (a->sizes[i] && cudaPointerGetAttributes(&attr, asset_data[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer &&
+                (((uintptr_t)attr.devicePointer) & 15u) == 0)
+                mapped[i] = static_cast<const uint8_t*>(attr.devicePointer);
+            else
+                cudaGetLastError();
+        }
+    auto upload = [&](const Batch& b, int which) -> int {
+        uint8_t* d = ws<uint8_t>(c, arena_slot[which]) + carry_cap;
+        const size_t nj = b.last - b.first;
+        TRY(hs_reserve(c, which ? HS_UPLOAD_SEGS_B : HS_UPLOAD_SEGS_A, sizeof(UploadSeg) * (nj + 1)));
+        TRY(ws_reserve(c, which ? WS_UPLOAD_SEGS_B : WS_UPLOAD_SEGS_A, sizeof(UploadSeg) * (nj + 1)));
+        UploadSeg* h_segs = hs<UploadSeg>(c, which ? HS_UPLOAD_SEGS_B : HS_UPLOAD_SEGS_A);
+        UploadSeg* d_segs = ws<UploadSeg>(c, which ? WS_UPLOAD_SEGS_B : WS_UPLOAD_SEGS_A);
+        CU(cudaStreamWaitEvent(c->upload_stream, c->arena_free[which], 0)); // the arena's previous batch has been consumed
+        uint32_t nsegs = 0;
+        for (size_t j = b.first; j < b.last; ++j)
+        {
+            uint8_t* dst = d + b.ranges[j - b.first].arena_offset;
+            const uint8_t* m = mapped[jobs[j].asset];
+            if (m && (jobs[j].start & 15u) == 0)
+                h_segs[nsegs++] = {m + jobs[j].start, dst, jobs[j].size};
+            else
+                CU(cudaMemcpyAsync(dst, asset_data[jobs[j].asset] + jobs[j].start, jobs[j].size, cudaMemcpyHostToDevice, c->upload_stream));
+        }
+        if (nsegs)
+        {
+            CU(cudaMemcpyAsync(d_segs, h_segs, sizeof(UploadSeg) * nsegs, cudaMemcpyHostToDevice, c->upload_stream));
+            launch_upload_segments(d_segs, nsegs, c->upload_stream);
+            CU(cudaGetLastError());
+            c->launches += 1;
+        }
+        CU(cudaEventRecord(c->upload_done[which], c->upload_stream));
+        return 0;
+    };
+
+    // the pending chunks: new to the store, not yet in a closed block
+    std::vector<uint64_t> p_hash, p_addr;
+    std::vector<uint32_t> p_size, p_tag, blk_first, blk_count;
+    uint64_t acc = 0, written = 0;
+    // LT_B200_TRACE=1: where the host thread's wall clock goes (waiting for the bus, chunk + hash, host dedup, pack + compress + sink)
+    const bool trace = getenv("LT_B200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_wait = 0, t_chunk = 0, t_dedup = 0, t_write = 0;
+    const double t_start = now();
+    if (!jobs.empty())
+    {
+        const uint64_t arena_bytes = carry_cap + batch_bytes + 4096;
+        for (int w = 0; w < 2; ++w)
+        {
+            if (w == 1 && batch_bytes >= total_bytes) break; // one batch: one arena
+            TRY(ws_reserve(c, arena_slot[w], arena_bytes));
+        }
+        CU(cudaEventRecord(c->arena_free[0], c->stream));
+        CU(cudaEventRecord(c->arena_free[1], c->stream));
+        Batch cur = plan(0);
+        int which = 0;
+        TRY(upload(cur, which));
+        while (true)
+        {
+            Batch next;
+            const bool has_next = cur.last < jobs.size();
+            if (has_next)
+            {
+                next = plan(cur.last);
+                TRY(ws_reserve(c, arena_slot[which ^ 1], arena_bytes));
+                TRY(upload(next, which ^ 1));
+            }
+            CU(cudaStreamWaitEvent(c->stream, c->upload_done[which], 0));
+            if (trace) { const double t = now(); CU(cudaEventSynchronize(c->upload_done[which])); t_wait += now() - t; }
+            uint8_t* d_batch = ws<uint8_t>(c, arena_slot[which]) + carry_cap;
+            lt_b200_chunk_table table;
+            double t_mark = now();
+            TRY(lt_b200_chunk_ranges(c, d_batch, batch_bytes + 4096, cur.ranges.data(), (uint32_t)cur.ranges.size(), mn, av, mx, hash_type, 1, &table));
+            t_chunk += now() - t_mark; t_mark = now();
+            if (acc + table.chunk_count > max_chunks) return fail(c, EFAULT, "chunk accumulation overflow");
+            if (table.chunk_count)
+            {
+                CU(cudaMemcpyAsync(ws<uint64_t>(c, WS_ACC_HASH) + acc, ws<void>(c, WS_CHUNK_HASH), sizeof(uint64_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaMemcpyAsync(ws<uint32_t>(c, WS_ACC_LEN) + acc, ws<void>(c, WS_CHUNK_LEN), sizeof(uint32_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+                CU(cudaMemcpyAsync(ws<uint32_t>(c, WS_ACC_TAG) + acc, ws<void>(c, WS_CHUNK_TAG), sizeof(uint32_t) * (size_t)table.chunk_count, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            for (size_t j = cur.first; j < cur.last; ++j) asset_chunks[jobs[j].asset] += table.range_chunk_counts[j - cur.first];
+            acc += table.chunk_count;
+            for (uint32_t i = 0; i < table.chunk_count; ++i)
+                if (insert(table.chunk_hashes[i]))
+                {
+                    p_hash.push_back(table.chunk_hashes[i]);
+                    p_size.push_back(table.chunk_sizes[i]);
+                    p_tag.push_back(table.chunk_tags[i]);
+                    p_addr.push_back((uint64_t)(uintptr_t)(d_batch + table.chunk_offsets[i]));
+                }
+            t_dedup += now() - t_mark; t_mark = now();
+            // close what can be closed
+            const uint32_t pending = (uint32_t)p_hash.size();
+            uint32_t nblk = 0;
+            blk_first.resize(pending ? pending : 1); blk_count.resize(pending ? pending : 1);
+            if (pending) TRY(lt_b200_pack_blocks(pending, p_size.data(), p_tag.data(), max_block_size, max_chunks_per_block, blk_first.data(), blk_count.data(), &nblk));
+            const uint32_t closed_blocks = has_next && nblk ? nblk - 1 : nblk;
+            const uint32_t closed_chunks = closed_blocks == nblk ? pending : blk_first[closed_blocks];
+            if (closed_chunks)
+            {
+                TRY(write_blocks_impl(c, nullptr, ~0ull, closed_chunks, p_hash.data(), p_size.data(), p_tag.data(), p_addr.data(), hash_type, max_block_size,
+                                      max_chunks_per_block, closed_blocks, blk_count.data(), flags | WRITE_PIPELINED, sink, user));
+                written += closed_chunks;
+            }
+            t_write += now() - t_mark;
+            // carry the open block's chunks into the front of the other arena
+            const uint32_t open_chunks = pending - closed_chunks;
+            if (open_chunks)
+            {
+                uint8_t* d_carry = ws<uint8_t>(c, arena_slot[which ^ 1]);
+                uint64_t at = 0;
+                for (uint32_t k = 0; k < open_chunks; ++k)
+                {
+                    const uint32_t i = closed_chunks + k;
+                    if (at + p_size[i] > carry_cap) return fail(c, EFAULT, "open block exceeds the carry room");
+                    CU(cudaMemcpyAsync(d_carry + at, (const void*)(uintptr_t)p_addr[i], p_size[i], cudaMemcpyDeviceToDevice, c->stream));
+                    p_hash[k] = p_hash[i]; p_size[k] = p_size[i]; p_tag[k] = p_tag[i];
+                    p_addr[k] = (uint64_t)(uintptr_t)(d_carry + at);
+                    at += ((uint64_t)p_size[i] + 15) & ~15ull;
+                }
+            }
+            p_hash.resize(open_chunks); p_size.resize(open_chunks); p_tag.resize(open_chunks); p_addr.resize(open_chunks);
+            CU(cudaEventRecord(c->arena_free[which], c->stream));
+            if (!has_next) break;
+            cur = std::move(next);
+            which ^= 1;
+        }
+    }
+    if (out_chunks_written) *out_chunks_written = (uint32_t)written;
+    const double t_loop = now();
+    const int rc = build_index_from_device_table(c, a, asset_chunks.data(), (uint32_t)acc, ws<uint64_t>(c, WS_ACC_HASH), ws<uint32_t>(c, WS_ACC_LEN),
+                                                 ws<uint32_t>(c, WS_ACC_TAG), hash_type, target_chunk_size, out_version_index, out_size);
+    if (trace)
+        fprintf(stderr, "lt_b200_upsync_stream_host_assets: %.1f ms: upload wait %.1f chunk+hash %.1f dedup %.1f pack+compress+sink %.1f index %.1f\n",
+                1e3 * (now() - t_start), 1e3 * t_wait, 1e3 * t_chunk, 1e3 * t_dedup, 1e3 * t_write, 1e3 * (now() - t_loop));
+    return rc;
+}
 
 // ================================================================ multi-GPU: one process per GPU, NCCL over NVLink
 //

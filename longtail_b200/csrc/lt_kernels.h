@@ -57,6 +57,9 @@ constexpr size_t LZ4_TABLE_BYTES_PER_BLOCK = 32768; // d_tables: one hash table 
 void launch_block_headers(uint8_t* d_out, const uint64_t* d_img_off, const uint32_t* d_blk_first, const uint32_t* d_blk_count,
                           const uint32_t* d_blk_tag, const uint64_t* d_blk_hash, const uint64_t* d_chunk_hashes, const uint32_t* d_chunk_sizes,
                           uint32_t hash_type, uint32_t nb, cudaStream_t st);
+// bytes [src, src + len) of device-mapped pinned host memory -> [dst, dst + len) of device memory, both 16-byte aligned; read by the SMs
+struct UploadSeg { const uint8_t* src; uint8_t* dst; uint64_t len; };
+void launch_upload_segments(const UploadSeg* d_segs, uint32_t count, cudaStream_t st);
 void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, const uint64_t* d_dst_off, const uint32_t* d_len,
                           uint8_t* d_out, uint32_t count, cudaStream_t st);
 

@@ -1220,4 +1220,41 @@ void launch_gather_chunks(const uint8_t* d_arena, const uint64_t* d_src_off, con
     k_gather_chunks<<<count, 256, 0, st>>>(d_arena, d_src_off, d_dst_off, d_len, d_out, count);
 }
 
+// host -> device upload by the SMs: the sources are pinned host memory mapped into the device's address space, read over PCIe with
+// 16-byte loads.  Unlike cudaMemcpyAsync this does not occupy the host -> device copy engine, whose queue is first in first out across
+// streams: the small table uploads of the kernels that run meanwhile would otherwise wait behind gigabytes of asset bytes.
+// A small persistent grid (PCIe needs ~100 KiB in flight, not SMs): 64 KiB tiles of all segments dealt round robin to the CTAs, so the
+// kernels working on the previous batch keep the machine.  Sources and destinations 16-byte aligned.
+constexpr uint32_t UPLOAD_CTAS = 64, UPLOAD_THREADS = 128, UPLOAD_TILE_VECS = 4096;
+__global__ void __launch_bounds__(UPLOAD_THREADS)
+k_upload_segments(const UploadSeg* __restrict__ segs, uint32_t count)
+{
+    uint64_t tile_base = 0;
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        const UploadSeg sg = segs[i];
+        const uint64_t vecs = sg.len >> 4;
+        const uint64_t tiles = (vecs + UPLOAD_TILE_VECS - 1) / UPLOAD_TILE_VECS;
+        const uint4* s = reinterpret_cast<const uint4*>(sg.src);
+        uint4* d = reinterpret_cast<uint4*>(sg.dst);
+        // my first tile of this segment: the smallest t with (tile_base + t) % gridDim.x == blockIdx.x
+        uint64_t t = (blockIdx.x + gridDim.x - (uint32_t)(tile_base % gridDim.x)) % gridDim.x;
+        for (; t < tiles; t += gridDim.x)
+        {
+            const uint64_t lo = t * UPLOAD_TILE_VECS, hi = min(vecs, lo + UPLOAD_TILE_VECS);
+#pragma unroll 8
+            for (uint64_t v = lo + threadIdx.x; v < hi; v += UPLOAD_THREADS) __stcs(d + v, __ldcs(s + v));
+        }
+        if ((uint32_t)(tile_base % gridDim.x) == blockIdx.x)
+            for (uint64_t b = (vecs << 4) + threadIdx.x; b < sg.len; b += UPLOAD_THREADS) sg.dst[b] = sg.src[b];
+        tile_base += tiles;
+    }
+}
+
+void launch_upload_segments(const UploadSeg* d_segs, uint32_t count, cudaStream_t st)
+{
+    if (!count) return;
+    k_upload_segments<<<UPLOAD_CTAS, UPLOAD_THREADS, 0, st>>>(d_segs, count);
+}
+
 } // namespace ltb

@@ -61,6 +61,55 @@ def test_upsync_host_assets_fresh_and_incremental(oracle, reference, tag):
         ctx.close()
 
 
+@pytest.mark.parametrize("target,block,per_block,batch,pinned", [(32768, 8388608, 1024, 0, False), (4096, 262144, 64, 4 << 20, False),
+                                                                 (4096, 100000, 7, 8 << 20, True), (8192, 1 << 20, 1024, 8 << 20, True)])
+def test_upsync_stream_host_assets(oracle, reference, target, block, per_block, batch, pinned):
+    """the streaming pass (batches of `batch` bytes, open block carried from arena to arena) writes the reference's blocks in its order;
+    pinned: the assets sit in pinned host memory (every other one 16-byte aligned: read by the upload kernel, the rest by cudaMemcpyAsync)"""
+    import longtail_b200
+    ctx = longtail_b200.Context(0)
+    host = None
+    try:
+        assets = _assets()
+        if pinned:
+            host = ctx.pinned_alloc(sum(d.size + 64 for _, d in assets) + 64)
+            at, placed = 0, []
+            for i, (p, d) in enumerate(assets):
+                at = (at + 15) & ~15
+                if i % 2:
+                    at += 3
+                host[at:at + d.size] = d
+                placed.append((p, host[at:at + d.size]))
+                at += d.size
+            assets = placed
+        tags = [(ol.COMP_LZ4 if i % 4 else 0) if i % 5 else ol.COMP_ZSTD_DEFAULT for i in range(len(assets))]
+        al = longtail_b200.AssetList([p for p, _ in assets], [d.size for _, d in assets])
+        checker = reference if reference is not None else oracle
+        want_blocks, want_v = checker.upsync(assets, target, max_block_size=block, max_chunks_per_block=per_block, tags=tags)
+        blocks, sink = _collect()
+        cb = longtail_b200.BLOCK_SINK(sink)
+        v, written = ctx.upsync_stream_host_assets(al, [d for _, d in assets], tags, (C.cast(cb, C.c_void_p), None), target_chunk_size=target,
+                                                   max_block_size=block, max_chunks_per_block=per_block, batch_bytes=batch)
+        assert v == want_v
+        assert [h for h, _ in blocks] == [h for h, _ in want_blocks]
+        assert blocks == want_blocks
+        vi = longtail_b200.parse_version_index(v)
+        assert written == vi["chunk_count"]
+        if reference is not None:
+            have = vi["chunk_hashes"][1::3].copy()
+            want2, _ = reference.upsync(assets, target, max_block_size=block, max_chunks_per_block=per_block, tags=tags, existing_hashes=have)
+            blocks2, sink2 = _collect()
+            cb2 = longtail_b200.BLOCK_SINK(sink2)
+            v2, written2 = ctx.upsync_stream_host_assets(al, [d for _, d in assets], tags, (C.cast(cb2, C.c_void_p), None), target_chunk_size=target,
+                                                         max_block_size=block, max_chunks_per_block=per_block, batch_bytes=batch, existing_hashes=have)
+            assert v2 == want_v and written2 == vi["chunk_count"] - have.size
+            assert blocks2 == want2
+    finally:
+        if host is not None:
+            ctx.pinned_free(host)
+        ctx.close()
+
+
 def test_device_sink_leaves_identical_images_in_hbm(oracle, reference):
     """LT_B200_WRITE_DEVICE_SINK: `data` of every view is a device address; copied back, the images are the reference's StoredBlocks"""
     import longtail_b200
