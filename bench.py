@@ -597,9 +597,9 @@ def run_b200(args):
         u = raw_all / float(world * cs.nbytes)
         c = stored_all / float(max(raw_all, 1))
         # DRAM traffic of the dominant kernel per launch: (dram__bytes_read + dram__bytes_write) / algorithmic bytes from the `ncu --set full`
-        # captures under profiles/ (k_lz4_blocks_v2: 3.11 GB read + 0.66 GB written for 3.11 GB of block payload, profiles/r02y_lz4v2_ncu.txt;
-        # scan and leaves: profiles/r01p_*_ncu.txt), applied to this run's algorithmic bytes per launch
-        ncu_traffic_ratio = {"k_lz4_blocks": (3.111575e9 + 0.656347e9) / 3.111575e9, "k_blake3_leaves": (8.963703e9 + 0.340567e9) / 8.589934592e9,
+        # captures under profiles/ (k_lz4_blocks_v2, in-place layout: 2.38 GB read + 2.09 GB written for 2.147 GB of block payload,
+        # profiles/r03q_lz4v2_inplace_ncu.txt; scan and leaves: profiles/r01p_*_ncu.txt), applied to this run's algorithmic bytes per launch
+        ncu_traffic_ratio = {"k_lz4_blocks": (2.382096e9 + 2.089249e9) / 2.147483648e9, "k_blake3_leaves": (8.963703e9 + 0.340567e9) / 8.589934592e9,
                              "k_hpcdc_scan": (8.609740e9 + 0.019096e9) / 8.589934592e9}
         traffic = round(kbytes / max(kn, 1) * ncu_traffic_ratio[name]) if name in ncu_traffic_ratio else None
         line = {
@@ -616,9 +616,9 @@ def run_b200(args):
             "hbm_roofline_frac_whole_step": round(value * GIB / 1e9 / world / peak, 4),
             "hbm_roofline_frac_whole_step_all_traffic": round(value * GIB / 1e9 / world / peak * (1 + 3 * u + c * u), 4),
             "roofline": {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "traffic_source": "ncu --set full (profiles/r02y_lz4v2_ncu.txt): DRAM read + write / algorithmic bytes = 1.21 for the "
-                                                                "LZ4 parse (the payload is read once; the tokens, offsets, short literal runs and copy-job "
-                                                                "lists are written), scaled to this run's bytes per launch",
+                         "traffic": traffic, "traffic_source": "ncu --set full (profiles/r03q_lz4v2_inplace_ncu.txt): DRAM read + write / algorithmic bytes = 2.08 for the "
+                                                                "in-place LZ4 encoder (the payload is read once, 1.11x with re-reads that miss L2; the whole "
+                                                                "LZ4 stream, 0.97x, is written by the same kernel), scaled to this run's bytes per launch",
                          "peak_source": peak_src, "per_kernel": per_kernel,
                          "note": "algorithmic bytes of the codec kernel = the unique payload bytes it reads (SURVEY.md §8d); rank 0's kernels; a kernel's "
                                  "time = the union of its launches' intervals (two write batches are in flight on two streams); the LZ4 parse is a "
