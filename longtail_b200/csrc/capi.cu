@@ -1988,6 +1988,8 @@ extern "C" int lt_b200_upsync_stream_host_assets(lt_b200_context* c, const lt_b2
         return 0;
     };
 
+    // whatever way this call ends, no upload may still be reading the caller's memory afterwards
+    struct UploadGuard { lt_b200_context* c; ~UploadGuard() { cudaStreamSynchronize(c->upload_stream); } } upload_guard{c};
     // the pending chunks: new to the store, not yet in a closed block
     std::vector<uint64_t> p_hash, p_addr;
     std::vector<uint32_t> p_size, p_tag, blk_first, blk_count;

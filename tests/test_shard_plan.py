@@ -73,3 +73,39 @@ def test_pack_blocks_matches_oracle_upsync(oracle):
     for b, (h, blob) in enumerate(blocks):  # block index: u64 hash, u32 hash id, u32 chunk count, u32 tag
         _, _, cnt, tag = struct.unpack_from("<QIII", blob, 0)
         assert cnt == count[b] and tag == ctags[first[b]]
+
+
+def _pack(lib, sizes, tags, max_block, per_block):
+    import ctypes as C
+    n = len(sizes)
+    s = np.ascontiguousarray(sizes, dtype=np.uint32)
+    t = np.ascontiguousarray(tags, dtype=np.uint32)
+    first, count = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint32)
+    nb = C.c_uint32(0)
+    assert lib.lt_b200_pack_blocks(C.c_uint32(n), s.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.c_uint32(max_block), C.c_uint32(per_block),
+                                   first.ctypes.data_as(C.c_void_p), count.ctypes.data_as(C.c_void_p), C.byref(nb)) == 0
+    return count[:nb.value].tolist()
+
+
+@pytest.mark.parametrize("seed,max_block,per_block", [(1, 65536, 48), (2, 100000, 7), (3, 8388608, 1024), (4, 40000, 3)])
+def test_packing_is_stable_under_streaming(seed, max_block, per_block):
+    """what lt_b200_upsync_stream_host_assets relies on: the greedy packing (src/longtail.c:6796-6860) is a left to right scan, so packing
+    the chunks as they arrive, closing every block but the last of each round and carrying that one's chunks into the next round, gives
+    the blocks of ONE packing over the whole list — whatever the batch cuts are (empty rounds and one-chunk rounds included)"""
+    lib = longtail_b200.load_library()
+    rng = np.random.RandomState(seed)
+    n = 5000
+    sizes = rng.randint(1, 30000, size=n).astype(np.uint32)
+    tags = np.repeat(rng.choice(np.array([0, 0x6c7a3432, 0x7a746432], np.uint32), size=n // 50 + 1), 50)[:n]
+    want = _pack(lib, sizes, tags, max_block, per_block)
+    cuts = sorted(set([0, n] + rng.randint(0, n, size=40).tolist() + [17, 17, 18]))
+    got, pending = [], []  # pending = indices of the chunks of the open block
+    for a, b in zip(cuts[:-1] + [n], cuts[1:] + [n]):  # the last round (n, n) adds nothing and closes everything
+        pending += list(range(a, b))
+        last = (a, b) == (n, n)
+        counts = _pack(lib, sizes[pending], tags[pending], max_block, per_block) if pending else []
+        closed = counts if last else counts[:-1]
+        got += closed
+        pending = pending[sum(closed):]
+        assert sum(sizes[pending].astype(np.uint64)) <= max_block + max_block // 10 or len(pending) == 1
+    assert not pending and got == want
