@@ -459,7 +459,7 @@ int lto_lz4_compress(const uint8_t* src, uint64_t size, uint8_t* dst, uint64_t c
                 token = op++;
                 if (lit >= 15) { *token = 0xF0; op = lz4_put_length(op, lit - 15); }
                 else *token = (uint8_t)(lit << 4);
-                memcpy(op, src + anchor, lit);
+                memmove(op, src + anchor, lit); /* memmove: the in-place test (tests/test_oracle.py) runs with dst in front of src in ONE buffer */
                 op += lit;
             }
         next_match:
@@ -498,7 +498,7 @@ int lto_lz4_compress(const uint8_t* src, uint64_t size, uint8_t* dst, uint64_t c
         uint64_t last = n - anchor;
         if (last >= 15) { *op++ = 0xF0; op = lz4_put_length(op, last - 15); }
         else *op++ = (uint8_t)(last << 4);
-        memcpy(op, src + anchor, last);
+        memmove(op, src + anchor, last);
         op += last;
     }
     *out_size = (uint64_t)(op - dst);

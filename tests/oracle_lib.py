@@ -146,6 +146,19 @@ class Oracle:
         assert err == 0, err
         return dst[:n.value].tobytes()
 
+    def lz4_compress_in_place(self, data, src_offset):
+        """the same encoder with source and destination in ONE buffer: output from byte 0, source at src_offset (the layout of the device
+        write path, longtail_b200/csrc/lz4.cu lz4_in_place_offset) -> compressed bytes"""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        buf = np.zeros(src_offset + data.size + 16, dtype=np.uint8)
+        buf[src_offset:src_offset + data.size] = data
+        n = C.c_uint64(0)
+        base = buf.ctypes.data
+        err = self.lib.lto_lz4_compress(C.cast(base + src_offset, _u8p), C.c_uint64(data.size), C.cast(base, _u8p),
+                                        C.c_uint64(self.lib.lto_lz4_bound(data.size)), C.byref(n))
+        assert err == 0, err
+        return buf[:n.value].tobytes()
+
     def lz4_decompress(self, comp, raw_size):
         comp = np.frombuffer(comp, dtype=np.uint8)
         dst = np.zeros(max(raw_size, 1), dtype=np.uint8)

@@ -150,6 +150,27 @@ def test_lz4_vs_reference(oracle, reference, n, kind):
     assert oracle.lz4_compress(x) == reference.compress(ol.COMP_LZ4, x)
 
 
+def _in_place_offset(n):
+    """longtail_b200/csrc/lz4.cu lz4_in_place_offset: how far behind the output start the source of an in-place block sits"""
+    return (n // 255 + 16 + 65536 + 256 + 15) & ~15
+
+
+@pytest.mark.parametrize("n,kind", [(65547, "nib"), (70000, "text"), (300000, "rec"), (2 << 20, "text"), (3 << 20, "nib"), (2 << 20, "rand"),
+                                    (1 << 20, "zero"), (5 << 20, "mix")])
+def test_lz4_in_place_margin(oracle, n, kind):
+    """the layout of the device write path: source at the END of the block's own output slot, lz4_in_place_offset(n)
+    bytes behind the output start.  The reference's parse only reads source bytes >= anchor - 65 536 and has written at most
+    consumed * (1 + 1/255) + 16 bytes by then, so the output never reaches a byte it still reads: compressing in ONE buffer gives the
+    bytes of the ordinary call.  (The margin is what makes that true: with 64 KiB less the text case below would read its own output.)"""
+    if kind == "mix":
+        x = np.concatenate([synth_bytes(5, n // 4, k) for k in ("rand", "text", "nib", "rec")])
+    else:
+        x = synth_bytes(1200 + n, n, kind)
+    want = oracle.lz4_compress(x)
+    assert oracle.lz4_compress_in_place(x, 8 + _in_place_offset(x.size)) == want
+    assert oracle.lz4_decompress(want, x.size) == x.tobytes()
+
+
 @pytest.mark.parametrize("n,kind", [(100, "rec"), (5000, "rec"), (70000, "rec"), (140000, "text"), (270000, "rec"), (3 << 20, "rec"), (1 << 20, "nib"),
                                     (600000, "zero"), (9 << 20, "rec")])
 def test_zstd_vs_reference(oracle, reference, n, kind):
